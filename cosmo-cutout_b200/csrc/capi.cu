@@ -1,0 +1,1046 @@
+/*
+ * capi.cu -- implementation of include/cosmo_cutout_b200.h: contexts, HBM column residency, kernel launches,
+ * result staging and the NCCL count exchange.  No CPU compute path exists here: every cutout entry point
+ * launches the sm_100a kernels of kernels.cuh or fails.
+ */
+#include "../../include/cosmo_cutout_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h> /* types and enums only; the library itself is dlopen()ed on first use */
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "prefilter.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA, "%s failed: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+    } while (0)
+
+/* ---------------------------------------------------------------- NCCL, loaded lazily */
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.handle) return CC_OK;
+    const char* names[] = {getenv("CC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(CC_ERR_NCCL, "cannot dlopen libnccl.so.2 (%s); set CC_NCCL_LIB", dlerror());
+#define SYM(field, name)                                                       \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                                 \
+    if (!g_nccl.field) return fail(CC_ERR_NCCL, "libnccl lacks symbol %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommInitAll, "ncclCommInitAll");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.handle = h;
+    return CC_OK;
+}
+#define NC(call)                                                                                  \
+    do {                                                                                          \
+        ncclResult_t r_ = (call);                                                                 \
+        if (r_ != ncclSuccess) return fail(CC_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+/* ---------------------------------------------------------------- device buffer that only grows */
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return CC_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(CC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        }
+        bytes = need;
+        return CC_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+enum { COL_X, COL_Y, COL_Z, COL_VX, COL_VY, COL_VZ, COL_A, COL_ID, COL_ROT, COL_REP, N_IN_COLS };
+const size_t IN_COL_SIZE[N_IN_COLS] = {4, 4, 4, 4, 4, 4, 4, 8, 4, 4};
+enum { OC_X, OC_Y, OC_Z, OC_VX, OC_VY, OC_VZ, OC_RED, OC_TH, OC_PH, OC_ID, OC_ROT, OC_REP, OC_THU, OC_IDX, N_OUT_COLS };
+const size_t OUT_COL_SIZE[N_OUT_COLS] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 8, 4, 4, 4, 8};
+
+enum Pending { P_NONE = 0, P_CONST = 1, P_HALO = 2 };
+
+}  // namespace
+
+struct cc_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr, ev_total1 = nullptr;
+    int64_t launches = 0;
+
+    /* resident step */
+    bool step_valid = false, step_owned = false;
+    int64_t n = 0, index_base = 0;
+    const void* col[N_IN_COLS] = {};
+    DevBuf col_buf[N_IN_COLS];
+
+    /* survivors */
+    DevBuf out_buf[N_OUT_COLS];
+    int64_t out_cap = 0;
+
+    /* scan scratch: [tile_state ... | ticket | result(2) ] */
+    DevBuf scratch;
+    /* use case 2 scratch */
+    DevBuf pre_buf, halo_buf, rec_a, rec_b, rank_buf, counts_buf, seg_buf, cursor_buf, misc_buf;
+    int64_t rec_cap = 0;
+
+    /* pinned host mirror for small read-backs */
+    unsigned long long* h_small = nullptr; /* [16 + 2*H_cap + ...] */
+    size_t h_small_elems = 0;
+
+    /* pending cutout */
+    Pending pending = P_NONE;
+    bool synced = false;
+    float p_th[2] = {}, p_ph[2] = {};
+    std::vector<cc_halo> p_halos;
+    int p_pos_only = 0;
+    int64_t p_n_limit = -1;
+    int nhalos = 0; /* of the pending/last cutout (1 for use case 1) */
+    std::vector<int64_t> counts, rough, seg_begin;
+    int64_t stats[4] = {};
+    bool have_times = false;
+
+    /* streamed step (pinned host -> HBM double buffering) */
+    bool streamed = false;
+    cc_cols_in host_cols = {};
+    cck::ColsIn gcols = {};      /* where survivor columns are gathered from */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    DevBuf stage[2][3];
+    int64_t stream_chunk = 16 << 20; /* particles per staged chunk */
+
+    /* communicator */
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    DevBuf gather_buf, offsets_buf;
+};
+
+namespace {
+
+cck::ColsIn cols_in_of(const cc_ctx* c) {
+    cck::ColsIn ci;
+    ci.x = (const float*)c->col[COL_X]; ci.y = (const float*)c->col[COL_Y]; ci.z = (const float*)c->col[COL_Z];
+    ci.vx = (const float*)c->col[COL_VX]; ci.vy = (const float*)c->col[COL_VY]; ci.vz = (const float*)c->col[COL_VZ];
+    ci.a = (const float*)c->col[COL_A]; ci.id = (const long long*)c->col[COL_ID];
+    ci.rot = (const int*)c->col[COL_ROT]; ci.rep = (const int*)c->col[COL_REP];
+    return ci;
+}
+cck::ColsOut cols_out_of(const cc_ctx* c) {
+    cck::ColsOut o;
+    o.x = (float*)c->out_buf[OC_X].p; o.y = (float*)c->out_buf[OC_Y].p; o.z = (float*)c->out_buf[OC_Z].p;
+    o.vx = (float*)c->out_buf[OC_VX].p; o.vy = (float*)c->out_buf[OC_VY].p; o.vz = (float*)c->out_buf[OC_VZ].p;
+    o.redshift = (float*)c->out_buf[OC_RED].p; o.theta = (float*)c->out_buf[OC_TH].p; o.phi = (float*)c->out_buf[OC_PH].p;
+    o.id = (long long*)c->out_buf[OC_ID].p; o.rot = (int*)c->out_buf[OC_ROT].p; o.rep = (int*)c->out_buf[OC_REP].p;
+    o.theta_u = (float*)c->out_buf[OC_THU].p; o.index = (long long*)c->out_buf[OC_IDX].p;
+    return o;
+}
+
+int ensure_out_cap(cc_ctx* c, int64_t cap) {
+    if (cap <= c->out_cap) return CC_OK;
+    cap = std::max<int64_t>(cap, 1024);
+    for (int i = 0; i < N_OUT_COLS; ++i) {
+        int rc = c->out_buf[i].ensure((size_t)cap * OUT_COL_SIZE[i]);
+        if (rc) { c->out_cap = 0; return rc; }
+    }
+    c->out_cap = cap;
+    return CC_OK;
+}
+
+int ensure_small(cc_ctx* c, size_t elems) {
+    if (elems <= c->h_small_elems) return CC_OK;
+    if (c->h_small) cudaFreeHost(c->h_small);
+    c->h_small = nullptr;
+    c->h_small_elems = 0;
+    CU(cudaMallocHost((void**)&c->h_small, elems * sizeof(unsigned long long)));
+    c->h_small_elems = elems;
+    return CC_OK;
+}
+
+bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+int use_device(cc_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return CC_OK;
+}
+
+/* ---------------------------------------------------------------- scan sources
+ * A cutout scans x,y,z either from the resident step or, for a streamed step, from a staging slot that holds
+ * one chunk; the columns gathered for survivors come from `gcols` (resident columns, or the pinned+mapped
+ * host columns of a streamed step). */
+struct Chunk {
+    const float *x, *y, *z; /* device pointers to the chunk's first particle */
+    int64_t n;              /* particles in the chunk */
+    int64_t start;          /* index of the chunk's first particle inside the step */
+    bool first, last;
+};
+
+/* scratch layout of use case 1: [ result: 4 x u64 | ticket (+pad): 32 B | tile_state: ntiles x u64 ] */
+const size_t K1_HDR = 64;
+
+int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
+    const unsigned long long ntiles64 = (unsigned long long)((ch.n + cck::K1_TILE - 1) / cck::K1_TILE);
+    if (ntiles64 > 0xfffffff0ull) return fail(CC_ERR_ARG, "chunk too large (%lld particles)", (long long)ch.n);
+    const unsigned int ntiles = (unsigned int)ntiles64;
+    const size_t bytes = K1_HDR + ((size_t)ntiles + 8) * sizeof(unsigned long long);
+    int rc = c->scratch.ensure(bytes);
+    if (rc) return rc;
+    if (ch.first) CU(cudaMemsetAsync(c->scratch.p, 0, bytes, c->stream));
+    else CU(cudaMemsetAsync((char*)c->scratch.p + 32, 0, bytes - 32, c->stream)); /* keep the running totals */
+    cck::ConstArgs a;
+    a.in = c->gcols;
+    /* survivor columns other than x,y,z are indexed by the chunk-local particle index */
+    a.in.vx += ch.start; a.in.vy += ch.start; a.in.vz += ch.start; a.in.a += ch.start; a.in.id += ch.start;
+    a.in.rot += ch.start; a.in.rep += ch.start;
+    a.in.x = ch.x; a.in.y = ch.y; a.in.z = ch.z;
+    a.out = cols_out_of(c);
+    a.out.theta_u = nullptr;
+    a.n = ch.n;
+    a.cap = c->out_cap;
+    a.index_base = c->index_base + ch.start;
+    a.th_lo = c->p_th[0]; a.th_hi = c->p_th[1]; a.ph_lo = c->p_ph[0]; a.ph_hi = c->p_ph[1];
+    ccpf::uc1_bounds(c->p_th, c->p_ph, &a.chi2, &a.clo2, &a.tlo, &a.thi);
+    a.result = (unsigned long long*)c->scratch.p;
+    a.ticket = (unsigned int*)((char*)c->scratch.p + 32);
+    a.tile_state = (unsigned long long*)((char*)c->scratch.p + K1_HDR);
+    a.ntiles = ntiles;
+    if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
+    if (ntiles > 0) {
+        const unsigned int grid = std::min<unsigned int>(ntiles, (unsigned int)c->sm_count * 3u);
+        const bool vec = aligned16(a.in.x) && aligned16(a.in.y) && aligned16(a.in.z);
+        if (vec) cck::k1_cutout_const<true><<<grid, cck::K1_THREADS, 0, c->stream>>>(a);
+        else cck::k1_cutout_const<false><<<grid, cck::K1_THREADS, 0, c->stream>>>(a);
+        CU(cudaGetLastError());
+        c->launches += 1;
+    }
+    if (ch.last) {
+        CU(cudaEventRecord(c->ev_scan1, c->stream));
+        CU(cudaEventRecord(c->ev_total1, c->stream));
+        CU(cudaMemcpyAsync(c->h_small, a.result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        c->have_times = true;
+    }
+    return CC_OK;
+}
+
+int prepare_const(cc_ctx* c) {
+    if (c->out_cap == 0) {
+        /* first guess: 1/16 of the step; cc_cutout_sync grows it to the exact count and re-runs on overflow */
+        int rc = ensure_out_cap(c, std::max<int64_t>(c->n / 16, 1 << 16));
+        if (rc) return rc;
+    }
+    return CC_OK;
+}
+
+/* ---------------------------------------------------------------- use case 2 launch */
+int64_t halo_scan_limit(const cc_ctx* c) {
+    int64_t n_scan = c->n;
+    if (c->p_n_limit >= 0) n_scan = std::max<int64_t>(0, std::min<int64_t>(c->n, c->p_n_limit - c->index_base));
+    return n_scan;
+}
+
+int prepare_halo(cc_ctx* c) {
+    const int H = (int)c->p_halos.size();
+    if (c->n > 0xffffffffll) return fail(CC_ERR_ARG, "step too large for one shard (%lld particles)", (long long)c->n);
+    int rc;
+    if ((rc = c->pre_buf.ensure((size_t)H * sizeof(float4)))) return rc;
+    if ((rc = c->halo_buf.ensure((size_t)H * sizeof(cck::HaloDev)))) return rc;
+    if ((rc = c->counts_buf.ensure((size_t)(2 * H) * 8))) return rc;
+    if ((rc = c->seg_buf.ensure((size_t)(H + 1) * 8))) return rc;
+    if ((rc = c->cursor_buf.ensure((size_t)H * 8))) return rc;
+    if ((rc = c->misc_buf.ensure(64))) return rc;
+    if (c->rec_cap == 0) c->rec_cap = 1 << 20;
+    if ((rc = c->rec_a.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
+    if ((rc = c->rec_b.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
+    if ((rc = c->rank_buf.ensure((size_t)c->rec_cap * 4))) return rc;
+    if ((rc = ensure_out_cap(c, c->rec_cap))) return rc;
+    if ((rc = ensure_small(c, 16 + 3 * (size_t)H + 1))) return rc;
+
+    /* host: exact + pre-filter parameters */
+    std::vector<float4> pre(H);
+    std::vector<cck::HaloDev> hd(H);
+    for (int h = 0; h < H; ++h) {
+        const cc_halo& s = c->p_halos[h];
+        float p4[4];
+        ccpf::uc2_bounds(s.theta_rough, s.phi_rough, p4);
+        pre[h] = make_float4(p4[0], p4[1], p4[2], p4[3]);
+        cck::HaloDev& d = hd[h];
+        memset(&d, 0, sizeof(d));
+        for (int i = 0; i < 9; ++i) d.R[i] = s.R[i];
+        d.th_lo = s.theta_cut[0]; d.th_hi = s.theta_cut[1]; d.ph_lo = s.phi_cut[0]; d.ph_hi = s.phi_cut[1];
+        d.rth_lo = s.theta_rough[0]; d.rth_hi = s.theta_rough[1]; d.rph_lo = s.phi_rough[0]; d.rph_hi = s.phi_rough[1];
+    }
+    /* pageable -> device copies are staged by the runtime before returning, so the vectors may die */
+    CU(cudaMemcpyAsync(c->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->halo_buf.p, hd.data(), (size_t)H * sizeof(cck::HaloDev), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->counts_buf.p, 0, (size_t)(2 * H) * 8, c->stream));
+    CU(cudaMemsetAsync(c->cursor_buf.p, 0, (size_t)H * 8, c->stream));
+    CU(cudaMemsetAsync(c->misc_buf.p, 0, 64, c->stream));
+    return CC_OK;
+}
+
+int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
+    const int H = (int)c->p_halos.size();
+    unsigned long long* rec_count = (unsigned long long*)c->misc_buf.p;
+    unsigned long long* n_cand = rec_count + 1;
+    if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
+    /* the n_limit clamp (tail drop of the reference's load balancer) applies to step-local indices */
+    const int64_t n_scan = std::max<int64_t>(0, std::min<int64_t>(ch.n, halo_scan_limit(c) - ch.start));
+    const bool vec = aligned16(ch.x) && aligned16(ch.y) && aligned16(ch.z);
+    for (int h0 = 0; h0 < H && n_scan > 0; h0 += cck::K2_MAX_HALOS) {
+        cck::HaloArgs a;
+        a.x = ch.x; a.y = ch.y; a.z = ch.z;
+        a.n = n_scan;
+        a.local_base = ch.start;
+        a.nhalos = std::min(cck::K2_MAX_HALOS, H - h0);
+        a.halo0 = h0;
+        a.pre = (const float4*)c->pre_buf.p + h0;
+        a.halos = (const cck::HaloDev*)c->halo_buf.p + h0;
+        a.recs = (cck::Rec*)c->rec_a.p;
+        a.rec_cap = (unsigned long long)c->rec_cap;
+        a.rec_count = rec_count;
+        a.counts = (unsigned long long*)c->counts_buf.p;
+        a.n_cand = n_cand;
+        a.total_halos = H;
+        const long long nquads = (n_scan + 3) / 4;
+        const long long want = (nquads + cck::K2_THREADS - 1) / cck::K2_THREADS;
+        const unsigned int grid = (unsigned int)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * 8));
+        if (vec) cck::k2_cutout_halo<true><<<grid, cck::K2_THREADS, 0, c->stream>>>(a);
+        else cck::k2_cutout_halo<false><<<grid, cck::K2_THREADS, 0, c->stream>>>(a);
+        CU(cudaGetLastError());
+        c->launches += 1;
+    }
+    if (ch.last) {
+        CU(cudaEventRecord(c->ev_scan1, c->stream));
+        cck::k3_scan_counts<<<1, 256, 0, c->stream>>>((const unsigned long long*)c->counts_buf.p,
+                                                      (unsigned long long*)c->seg_buf.p, H);
+        CU(cudaGetLastError());
+        c->launches += 1;
+        CU(cudaMemcpyAsync(c->h_small, c->misc_buf.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_small + 2, c->counts_buf.p, (size_t)(2 * H) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_small + 2 + 2 * H, c->seg_buf.p, (size_t)(H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return CC_OK;
+}
+
+/* ---------------------------------------------------------------- whole-step drivers */
+int run_resident(cc_ctx* c) {
+    int rc = (c->pending == P_CONST) ? prepare_const(c) : prepare_halo(c);
+    if (rc) return rc;
+    c->gcols = cols_in_of(c);
+    Chunk ch;
+    ch.x = c->gcols.x; ch.y = c->gcols.y; ch.z = c->gcols.z;
+    ch.n = c->n; ch.start = 0; ch.first = true; ch.last = true;
+    return (c->pending == P_CONST) ? launch_const_chunk(c, ch) : launch_halo_chunk(c, ch);
+}
+
+/* pinned host -> HBM, double-buffered: the copy stream fills slot s while the cutout kernel consumes slot s^1 */
+int run_streamed(cc_ctx* c) {
+    int rc = (c->pending == P_CONST) ? prepare_const(c) : prepare_halo(c);
+    if (rc) return rc;
+    const int64_t n = c->n;
+    const int64_t chunk = std::max<int64_t>(cck::K1_TILE, (c->stream_chunk / cck::K1_TILE) * cck::K1_TILE);
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; ++s) {
+            CU(cudaEventCreateWithFlags(&c->ev_copied[s], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_consumed[s], cudaEventDisableTiming));
+        }
+    }
+    const int64_t slot_elems = std::min<int64_t>(chunk, std::max<int64_t>(n, 1));
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < 3; ++k)
+            if ((rc = c->stage[s][k].ensure((size_t)slot_elems * 4))) return rc;
+    /* the copy stream must not overwrite a slot that kernels of an earlier call may still read */
+    CU(cudaEventRecord(c->ev_consumed[0], c->stream));
+    CU(cudaEventRecord(c->ev_consumed[1], c->stream));
+    const int64_t nchunks = std::max<int64_t>(1, (n + chunk - 1) / chunk);
+    for (int64_t i = 0; i < nchunks; ++i) {
+        const int s = (int)(i & 1);
+        const int64_t start = i * chunk, len = std::min<int64_t>(chunk, n - start);
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[s], 0));
+        const float* src[3] = {c->host_cols.x, c->host_cols.y, c->host_cols.z};
+        for (int k = 0; k < 3 && len > 0; ++k)
+            CU(cudaMemcpyAsync(c->stage[s][k].p, src[k] + start, (size_t)len * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copied[s], c->copy_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
+        Chunk ch;
+        ch.x = (const float*)c->stage[s][0].p; ch.y = (const float*)c->stage[s][1].p; ch.z = (const float*)c->stage[s][2].p;
+        ch.n = len; ch.start = start; ch.first = (i == 0); ch.last = (i == nchunks - 1);
+        rc = (c->pending == P_CONST) ? launch_const_chunk(c, ch) : launch_halo_chunk(c, ch);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev_consumed[s], c->stream));
+    }
+    return CC_OK;
+}
+
+int run_pending(cc_ctx* c) { return c->streamed ? run_streamed(c) : run_resident(c); }
+
+/* second half of use case 2, once the record count is known on the host */
+int finish_halo(cc_ctx* c, unsigned long long nrec) {
+    const int H = (int)c->p_halos.size();
+    if (nrec > 0) {
+        cck::BucketArgs b;
+        b.recs = (const cck::Rec*)c->rec_a.p;
+        b.nrec = nrec;
+        b.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        b.cursor = (unsigned long long*)c->cursor_buf.p;
+        b.out = (cck::Rec*)c->rec_b.p;
+        const unsigned int g1 = (unsigned int)std::min<unsigned long long>((nrec + 255) / 256, (unsigned long long)c->sm_count * 8);
+        cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
+        CU(cudaGetLastError());
+        cck::RankArgs r;
+        r.recs = (const cck::Rec*)c->rec_b.p;
+        r.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        r.rank = (unsigned int*)c->rank_buf.p;
+        r.H = H;
+        unsigned long long max_seg = 0;
+        for (int h = 0; h < H; ++h) max_seg = std::max<unsigned long long>(max_seg, (unsigned long long)c->counts[h]);
+        const unsigned int gx = (unsigned int)std::max<unsigned long long>(1, std::min<unsigned long long>((max_seg + cck::K3_THREADS - 1) / cck::K3_THREADS, 1024));
+        for (int h0 = 0; h0 < H; h0 += 32768) {
+            cck::RankArgs rr = r;
+            rr.seg_begin = r.seg_begin + h0;
+            rr.H = std::min(32768, H - h0);
+            /* rank[] is indexed by absolute record position, seg_begin values are absolute: only the halo base shifts */
+            cck::k3_rank<<<dim3(gx, (unsigned int)rr.H), cck::K3_THREADS, 0, c->stream>>>(rr);
+            CU(cudaGetLastError());
+            c->launches += 1;
+        }
+        cck::GatherArgs g;
+        g.recs = (const cck::Rec*)c->rec_b.p;
+        g.rank = (const unsigned int*)c->rank_buf.p;
+        g.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        g.nrec = nrec;
+        g.in = c->gcols;
+        g.out = cols_out_of(c);
+        g.index_base = c->index_base;
+        g.pos_only = c->p_pos_only;
+        cck::k3_gather_halo<<<g1, 256, 0, c->stream>>>(g);
+        CU(cudaGetLastError());
+        c->launches += 2;
+    }
+    CU(cudaEventRecord(c->ev_total1, c->stream));
+    c->have_times = true;
+    return CC_OK;
+}
+
+int check_sm100(int device, int* sm_count) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CC_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU; this library has no other path",
+                    device, prop.name, prop.major, prop.minor);
+    *sm_count = prop.multiProcessorCount;
+    return CC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cc_version(void) { return "cosmo-cutout_b200 0.1 (sm_100a)"; }
+const char* cc_last_error(void) { return g_err.c_str(); }
+
+int cc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int cc_create(int device, cc_ctx** out) {
+    if (!out) return fail(CC_ERR_ARG, "cc_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CC_ERR_CUDA, "no CUDA device available (%s); cosmo-cutout_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(CC_ERR_ARG, "cc_create: device %d out of range [0,%d)", device, ndev);
+    int sms = 0;
+    int rc = check_sm100(device, &sms);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    cc_ctx* c = new cc_ctx();
+    c->device = device;
+    c->sm_count = sms;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_scan0) != cudaSuccess || cudaEventCreate(&c->ev_scan1) != cudaSuccess ||
+        cudaEventCreate(&c->ev_total1) != cudaSuccess) {
+        delete c;
+        return fail(CC_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    rc = ensure_small(c, 64);
+    if (rc) { cc_destroy(c); return rc; }
+    *out = c;
+    return CC_OK;
+}
+
+void cc_destroy(cc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto& b : c->col_buf) b.release();
+    for (auto& b : c->out_buf) b.release();
+    DevBuf* rest[] = {&c->scratch, &c->pre_buf, &c->halo_buf, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
+                      &c->seg_buf, &c->cursor_buf, &c->misc_buf, &c->gather_buf, &c->offsets_buf};
+    for (DevBuf* b : rest) b->release();
+    for (auto& sl : c->stage) for (auto& b : sl) b.release();
+    for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->ev_scan0) cudaEventDestroy(c->ev_scan0);
+    if (c->ev_scan1) cudaEventDestroy(c->ev_scan1);
+    if (c->ev_total1) cudaEventDestroy(c->ev_total1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* cc_stream(cc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+/* ------------------------------------------------------------------ step residency */
+static int step_alloc(cc_ctx* c, int64_t n, bool with_vel) {
+    for (int i = 0; i < N_IN_COLS; ++i) {
+        const bool vel = (i == COL_VX || i == COL_VY || i == COL_VZ || i == COL_ROT || i == COL_REP);
+        if (vel && !with_vel) { c->col[i] = nullptr; continue; }
+        int rc = c->col_buf[i].ensure(std::max<size_t>((size_t)n * IN_COL_SIZE[i], 16));
+        if (rc) return rc;
+        c->col[i] = c->col_buf[i].p;
+    }
+    return CC_OK;
+}
+
+int cc_step_release(cc_ctx* c) {
+    if (!c) return fail(CC_ERR_ARG, "ctx is NULL");
+    int rc = use_device(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& b : c->col_buf) b.release();
+    for (auto& p : c->col) p = nullptr;
+    c->step_valid = false;
+    c->step_owned = false;
+    c->n = 0;
+    c->pending = P_NONE;
+    return CC_OK;
+}
+
+int cc_step_upload(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_base) {
+    if (!c || !host || n < 0) return fail(CC_ERR_ARG, "cc_step_upload: bad argument");
+    if (!host->x || !host->y || !host->z || !host->a || !host->id) return fail(CC_ERR_ARG, "cc_step_upload: x,y,z,a,id are required");
+    const bool with_vel = host->vx && host->vy && host->vz && host->rotation && host->replication;
+    int rc = use_device(c);
+    if (rc) return rc;
+    if ((rc = step_alloc(c, n, with_vel))) return rc;
+    const void* src[N_IN_COLS] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->a, host->id, host->rotation, host->replication};
+    for (int i = 0; i < N_IN_COLS; ++i)
+        if (c->col[i] && n > 0)
+            CU(cudaMemcpyAsync(const_cast<void*>(c->col[i]), src[i], (size_t)n * IN_COL_SIZE[i], cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n = n;
+    c->index_base = index_base;
+    c->step_valid = true;
+    c->step_owned = true;
+    c->pending = P_NONE;
+    return CC_OK;
+}
+
+int cc_step_attach(cc_ctx* c, int64_t n, const cc_cols_in* dev, int64_t index_base) {
+    if (!c || !dev || n < 0) return fail(CC_ERR_ARG, "cc_step_attach: bad argument");
+    if (!dev->x || !dev->y || !dev->z || !dev->a || !dev->id) return fail(CC_ERR_ARG, "cc_step_attach: x,y,z,a,id are required");
+    const void* src[N_IN_COLS] = {dev->x, dev->y, dev->z, dev->vx, dev->vy, dev->vz, dev->a, dev->id, dev->rotation, dev->replication};
+    for (int i = 0; i < N_IN_COLS; ++i) c->col[i] = src[i];
+    c->n = n;
+    c->index_base = index_base;
+    c->step_valid = true;
+    c->step_owned = false;
+    c->pending = P_NONE;
+    return CC_OK;
+}
+
+int cc_step_synth(cc_ctx* c, int64_t n, uint64_t seed, int64_t index_base, int kind, float box) {
+    if (!c || n < 0) return fail(CC_ERR_ARG, "cc_step_synth: bad argument");
+    int rc = use_device(c);
+    if (rc) return rc;
+    if ((rc = step_alloc(c, n, true))) return rc;
+    cck::SynthCols s;
+    s.x = (float*)c->col[COL_X]; s.y = (float*)c->col[COL_Y]; s.z = (float*)c->col[COL_Z];
+    s.vx = (float*)c->col[COL_VX]; s.vy = (float*)c->col[COL_VY]; s.vz = (float*)c->col[COL_VZ];
+    s.a = (float*)c->col[COL_A]; s.id = (long long*)c->col[COL_ID]; s.rot = (int*)c->col[COL_ROT]; s.rep = (int*)c->col[COL_REP];
+    if (n > 0) {
+        cck::k_synth<<<c->sm_count * 8, 256, 0, c->stream>>>(s, n, seed, index_base, kind, box);
+        CU(cudaGetLastError());
+        c->launches += 1;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->n = n;
+    c->index_base = index_base;
+    c->step_valid = true;
+    c->step_owned = true;
+    c->pending = P_NONE;
+    return CC_OK;
+}
+
+int cc_synth_host(int64_t n, uint64_t seed, int64_t index_base, int kind, float box, float* x, float* y, float* z,
+                  float* vx, float* vy, float* vz, float* a, int64_t* id, int32_t* rotation, int32_t* replication) {
+    if (n < 0 || !x || !y || !z) return fail(CC_ERR_ARG, "cc_synth_host: bad argument");
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float fx, fy, fz, fvx, fvy, fvz, fa;
+        long long fid;
+        int frot, frep;
+        cck::synth_one(seed, index_base + i, kind, box, fx, fy, fz, fvx, fvy, fvz, fa, fid, frot, frep);
+        x[i] = fx; y[i] = fy; z[i] = fz;
+        if (vx) vx[i] = fvx;
+        if (vy) vy[i] = fvy;
+        if (vz) vz[i] = fvz;
+        if (a) a[i] = fa;
+        if (id) id[i] = fid;
+        if (rotation) rotation[i] = frot;
+        if (replication) replication[i] = frep;
+    }
+    return CC_OK;
+}
+
+int cc_step_download(cc_ctx* c, int64_t first, int64_t count, float* x, float* y, float* z, float* vx, float* vy,
+                     float* vz, float* a, int64_t* id, int32_t* rotation, int32_t* replication) {
+    if (!c || !c->step_valid) return fail(CC_ERR_STATE, "cc_step_download: no resident step");
+    if (first < 0 || count < 0 || first + count > c->n) return fail(CC_ERR_ARG, "cc_step_download: range out of bounds");
+    int rc = use_device(c);
+    if (rc) return rc;
+    void* dst[N_IN_COLS] = {x, y, z, vx, vy, vz, a, id, rotation, replication};
+    for (int i = 0; i < N_IN_COLS; ++i)
+        if (dst[i] && c->col[i] && count > 0)
+            CU(cudaMemcpyAsync(dst[i], (const char*)c->col[i] + (size_t)first * IN_COL_SIZE[i], (size_t)count * IN_COL_SIZE[i],
+                               cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return CC_OK;
+}
+
+int64_t cc_step_size(cc_ctx* c) { return (c && c->step_valid) ? c->n : -1; }
+
+/* ------------------------------------------------------------------ cutout */
+int cc_cutout_const(cc_ctx* c, const float theta_cut[2], const float phi_cut[2]) {
+    if (!c || !theta_cut || !phi_cut) return fail(CC_ERR_ARG, "cc_cutout_const: bad argument");
+    if (!c->step_valid) return fail(CC_ERR_STATE, "cc_cutout_const: no resident step");
+    if (!c->col[COL_VX] || !c->col[COL_VY] || !c->col[COL_VZ] || !c->col[COL_ROT] || !c->col[COL_REP])
+        return fail(CC_ERR_STATE, "cc_cutout_const: use case 1 writes all 12 columns (processLC.cpp:291-307); the step lacks vx/vy/vz/rotation/replication");
+    int rc = use_device(c);
+    if (rc) return rc;
+    c->p_th[0] = theta_cut[0]; c->p_th[1] = theta_cut[1];
+    c->p_ph[0] = phi_cut[0]; c->p_ph[1] = phi_cut[1];
+    c->nhalos = 1;
+    c->pending = P_CONST;
+    c->synced = false;
+    c->streamed = false;
+    return run_pending(c);
+}
+
+int cc_cutout_halo(cc_ctx* c, int nhalos, const cc_halo* halos, int pos_only, int64_t n_limit_global) {
+    if (!c || nhalos < 0 || (nhalos > 0 && !halos)) return fail(CC_ERR_ARG, "cc_cutout_halo: bad argument");
+    if (!c->step_valid) return fail(CC_ERR_STATE, "cc_cutout_halo: no resident step");
+    if (!pos_only && (!c->col[COL_VX] || !c->col[COL_VY] || !c->col[COL_VZ] || !c->col[COL_ROT] || !c->col[COL_REP]))
+        return fail(CC_ERR_STATE, "cc_cutout_halo: step lacks vx/vy/vz/rotation/replication; pass pos_only=1");
+    int rc = use_device(c);
+    if (rc) return rc;
+    c->p_halos.assign(halos, halos + nhalos);
+    c->p_pos_only = pos_only ? 1 : 0;
+    c->p_n_limit = n_limit_global;
+    c->nhalos = nhalos;
+    c->pending = P_HALO;
+    c->synced = false;
+    c->streamed = false;
+    if (nhalos == 0) { c->counts.clear(); c->rough.clear(); c->seg_begin.assign(1, 0); c->synced = true; return CC_OK; }
+    return run_pending(c);
+}
+
+int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
+    if (!c) return fail(CC_ERR_ARG, "ctx is NULL");
+    if (c->pending == P_NONE) return fail(CC_ERR_STATE, "cc_cutout_sync: no cutout pending");
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (!c->synced) {
+        if (c->pending == P_CONST) {
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                CU(cudaStreamSynchronize(c->stream));
+                const int64_t k = (int64_t)c->h_small[0];
+                if (k <= c->out_cap) break;
+                /* survivors exceeded the output capacity: grow to the exact count and run the pass again */
+                if ((rc = ensure_out_cap(c, k + k / 64))) return rc;
+                if ((rc = run_pending(c))) return rc;
+            }
+            c->counts.assign(1, (int64_t)c->h_small[0]);
+            c->rough.assign(1, 0);
+            c->seg_begin.assign(2, 0);
+            c->seg_begin[1] = c->counts[0];
+            c->stats[0] = c->n; c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = c->counts[0]; c->stats[3] = 0;
+        } else {
+            const int H = c->nhalos;
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                CU(cudaStreamSynchronize(c->stream));
+                const int64_t nrec = (int64_t)c->h_small[0];
+                if (nrec <= c->rec_cap) break;
+                c->rec_cap = nrec + nrec / 64;
+                if ((rc = run_pending(c))) return rc;
+            }
+            const int64_t nrec = (int64_t)c->h_small[0];
+            c->counts.resize(H); c->rough.resize(H); c->seg_begin.resize(H + 1);
+            int64_t tot = 0, tot_rough = 0;
+            for (int h = 0; h < H; ++h) {
+                c->counts[h] = (int64_t)c->h_small[2 + h];
+                c->rough[h] = (int64_t)c->h_small[2 + H + h];
+                tot += c->counts[h]; tot_rough += c->rough[h];
+            }
+            for (int h = 0; h <= H; ++h) c->seg_begin[h] = (int64_t)c->h_small[2 + 2 * H + h];
+            if (tot != nrec) return fail(CC_ERR_CUDA, "internal: record count %lld != sum of halo counts %lld", (long long)nrec, (long long)tot);
+            c->stats[0] = halo_scan_limit(c); c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = tot; c->stats[3] = tot_rough;
+            if ((rc = finish_halo(c, (unsigned long long)nrec))) return rc;
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        c->synced = true;
+    }
+    for (int h = 0; h < c->nhalos; ++h) {
+        if (counts) counts[h] = c->counts[h];
+        if (rough_counts) rough_counts[h] = c->rough[h];
+    }
+    return CC_OK;
+}
+
+int cc_cutout_fetch(cc_ctx* c, int halo, int64_t first, int64_t count, const cc_cols_out* host) {
+    if (!c || !host) return fail(CC_ERR_ARG, "cc_cutout_fetch: bad argument");
+    if (c->pending == P_NONE || !c->synced) return fail(CC_ERR_STATE, "cc_cutout_fetch: call cc_cutout_sync first");
+    if (halo < 0 || halo >= c->nhalos) return fail(CC_ERR_ARG, "cc_cutout_fetch: halo %d out of range", halo);
+    if (first < 0 || count < 0 || first + count > c->counts[halo]) return fail(CC_ERR_ARG, "cc_cutout_fetch: rows out of range");
+    int rc = use_device(c);
+    if (rc) return rc;
+    const int64_t row0 = c->seg_begin[halo] + first;
+    void* dst[N_OUT_COLS] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->redshift, host->theta, host->phi,
+                             host->id, host->rotation, host->replication, host->theta_u, host->index};
+    const bool pos_only = (c->pending == P_HALO) && c->p_pos_only;
+    for (int i = 0; i < N_OUT_COLS; ++i) {
+        if (!dst[i] || count == 0) continue;
+        if (pos_only && (i == OC_VX || i == OC_VY || i == OC_VZ || i == OC_ROT || i == OC_REP))
+            return fail(CC_ERR_ARG, "cc_cutout_fetch: velocity/rotation/replication were not gathered (pos_only)");
+        if (c->pending == P_CONST && i == OC_THU) return fail(CC_ERR_ARG, "cc_cutout_fetch: theta_u exists only for halo cutouts");
+        CU(cudaMemcpyAsync(dst[i], (const char*)c->out_buf[i].p + (size_t)row0 * OUT_COL_SIZE[i], (size_t)count * OUT_COL_SIZE[i],
+                           cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return CC_OK;
+}
+
+int cc_cutout_device_cols(cc_ctx* c, int halo, cc_cols_out* dev, int64_t* row0, int64_t* count) {
+    if (!c || !dev) return fail(CC_ERR_ARG, "cc_cutout_device_cols: bad argument");
+    if (c->pending == P_NONE || !c->synced) return fail(CC_ERR_STATE, "cc_cutout_device_cols: call cc_cutout_sync first");
+    if (halo < 0 || halo >= c->nhalos) return fail(CC_ERR_ARG, "halo out of range");
+    const cck::ColsOut o = cols_out_of(c);
+    dev->x = o.x; dev->y = o.y; dev->z = o.z; dev->vx = o.vx; dev->vy = o.vy; dev->vz = o.vz;
+    dev->redshift = o.redshift; dev->theta = o.theta; dev->phi = o.phi; dev->id = (int64_t*)o.id;
+    dev->rotation = o.rot; dev->replication = o.rep; dev->theta_u = o.theta_u; dev->index = (int64_t*)o.index;
+    if (row0) *row0 = c->seg_begin[halo];
+    if (count) *count = c->counts[halo];
+    return CC_OK;
+}
+
+/* ------------------------------------------------------------------ streamed step */
+namespace {
+/* a streamed step needs host columns the GPU can address: pinned (cudaHostAlloc / cudaHostRegister) memory */
+int map_host_col(const void* h, const char* name, bool required, const void** dev) {
+    *dev = nullptr;
+    if (!h) return required ? fail(CC_ERR_ARG, "streamed cutout: column %s is required", name) : CC_OK;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, h);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(CC_ERR_ARG, "streamed cutout: cannot query column %s", name); }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { *dev = h; return CC_OK; }
+    if (at.type != cudaMemoryTypeHost)
+        return fail(CC_ERR_ARG, "streamed cutout: column %s is pageable host memory; allocate it with cc_host_alloc or pin it "
+                    "with cc_host_register (or use cc_step_upload for pageable data)", name);
+    void* d = nullptr;
+    e = cudaHostGetDevicePointer(&d, const_cast<void*>(h), 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(CC_ERR_CUDA, "cudaHostGetDevicePointer(%s): %s", name, cudaGetErrorString(e)); }
+    *dev = d;
+    return CC_OK;
+}
+
+int begin_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_base, bool need_vel) {
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->step_owned) { /* a streamed step replaces the resident one */
+        if ((rc = cc_step_release(c))) return rc;
+    }
+    const void* h[N_IN_COLS] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->a, host->id, host->rotation, host->replication};
+    const char* names[N_IN_COLS] = {"x", "y", "z", "vx", "vy", "vz", "a", "id", "rotation", "replication"};
+    const void* d[N_IN_COLS];
+    for (int i = 0; i < N_IN_COLS; ++i) {
+        const bool vel = (i == COL_VX || i == COL_VY || i == COL_VZ || i == COL_ROT || i == COL_REP);
+        if ((rc = map_host_col(h[i], names[i], vel ? need_vel : true, &d[i]))) return rc;
+    }
+    c->host_cols = *host;
+    c->gcols.x = (const float*)d[COL_X]; c->gcols.y = (const float*)d[COL_Y]; c->gcols.z = (const float*)d[COL_Z];
+    c->gcols.vx = (const float*)d[COL_VX]; c->gcols.vy = (const float*)d[COL_VY]; c->gcols.vz = (const float*)d[COL_VZ];
+    c->gcols.a = (const float*)d[COL_A]; c->gcols.id = (const long long*)d[COL_ID];
+    c->gcols.rot = (const int*)d[COL_ROT]; c->gcols.rep = (const int*)d[COL_REP];
+    for (int i = 0; i < N_IN_COLS; ++i) c->col[i] = nullptr;
+    c->step_valid = false;
+    c->n = n;
+    c->index_base = index_base;
+    c->streamed = true;
+    c->synced = false;
+    return CC_OK;
+}
+}  // namespace
+
+int cc_cutout_const_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_base,
+                             const float theta_cut[2], const float phi_cut[2]) {
+    if (!c || !host || n < 0 || !theta_cut || !phi_cut) return fail(CC_ERR_ARG, "cc_cutout_const_streamed: bad argument");
+    int rc = begin_streamed(c, n, host, index_base, true);
+    if (rc) return rc;
+    c->p_th[0] = theta_cut[0]; c->p_th[1] = theta_cut[1];
+    c->p_ph[0] = phi_cut[0]; c->p_ph[1] = phi_cut[1];
+    c->nhalos = 1;
+    c->pending = P_CONST;
+    return run_pending(c);
+}
+
+int cc_cutout_halo_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_base, int nhalos,
+                            const cc_halo* halos, int pos_only, int64_t n_limit_global) {
+    if (!c || !host || n < 0 || nhalos < 0 || (nhalos > 0 && !halos)) return fail(CC_ERR_ARG, "cc_cutout_halo_streamed: bad argument");
+    int rc = begin_streamed(c, n, host, index_base, !pos_only);
+    if (rc) return rc;
+    c->p_halos.assign(halos, halos + nhalos);
+    c->p_pos_only = pos_only ? 1 : 0;
+    c->p_n_limit = n_limit_global;
+    c->nhalos = nhalos;
+    c->pending = P_HALO;
+    if (nhalos == 0) { c->counts.clear(); c->rough.clear(); c->seg_begin.assign(1, 0); c->synced = true; return CC_OK; }
+    return run_pending(c);
+}
+
+/* ------------------------------------------------------------------ pinned host memory */
+int cc_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(CC_ERR_ARG, "ptr is NULL");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return CC_OK;
+}
+int cc_host_free(void* ptr) {
+    CU(cudaFreeHost(ptr));
+    return CC_OK;
+}
+int cc_host_register(void* ptr, size_t bytes) {
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return CC_OK;
+}
+int cc_host_unregister(void* ptr) {
+    CU(cudaHostUnregister(ptr));
+    return CC_OK;
+}
+
+/* ------------------------------------------------------------------ communicator + count exchange */
+int cc_comm_unique_id(void* id128) {
+    if (!id128) return fail(CC_ERR_ARG, "id is NULL");
+    int rc = nccl_load();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == CC_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return CC_OK;
+}
+
+int cc_comm_init(cc_ctx* c, int nranks, int rank, const void* id128) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(CC_ERR_ARG, "cc_comm_init: bad argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    if ((rc = use_device(c))) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NC(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    c->nranks = nranks;
+    c->rank = rank;
+    return CC_OK;
+}
+
+int cc_comm_init_all(cc_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return fail(CC_ERR_ARG, "cc_comm_init_all: bad argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+    NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[i]; ctxs[i]->nranks = n; ctxs[i]->rank = i; }
+    return CC_OK;
+}
+
+int cc_comm_rank(cc_ctx* c) { return c ? c->rank : -1; }
+int cc_comm_size(cc_ctx* c) { return c ? c->nranks : -1; }
+
+int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64_t* offsets) {
+    if (!c) return fail(CC_ERR_ARG, "ctx is NULL");
+    int rc = cc_cutout_sync(c, nullptr, nullptr);
+    if (rc) return rc;
+    const int H = c->nhalos, R = c->nranks;
+    if (H == 0) return CC_OK;
+    if ((rc = c->counts_buf.ensure((size_t)2 * H * 8))) return rc;
+    if ((rc = c->gather_buf.ensure((size_t)R * 2 * H * 8))) return rc;
+    if ((rc = c->offsets_buf.ensure((size_t)H * 8))) return rc;
+    if ((rc = ensure_small(c, 16 + (size_t)R * 2 * H + H))) return rc;
+    /* device-resident send buffer: {counts[H], rough[H]} (use case 2 already has it; use case 1 fills it here) */
+    if (c->pending == P_CONST) {
+        c->h_small[8] = (unsigned long long)c->counts[0];
+        c->h_small[9] = 0;
+        CU(cudaMemcpyAsync(c->counts_buf.p, c->h_small + 8, 16, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (c->comm) {
+        NC(g_nccl.AllGather(c->counts_buf.p, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, c->stream));
+    } else {
+        CU(cudaMemcpyAsync(c->gather_buf.p, c->counts_buf.p, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    cck::k4_offsets<<<(H + 255) / 256, 256, 0, c->stream>>>((const unsigned long long*)c->gather_buf.p,
+                                                          (unsigned long long*)c->offsets_buf.p, H, c->rank);
+    CU(cudaGetLastError());
+    c->launches += 1;
+    unsigned long long* hg = c->h_small + 16;
+    CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < R; ++r)
+        for (int h = 0; h < H; ++h) {
+            if (all_counts) all_counts[(size_t)r * H + h] = (int64_t)hg[(size_t)r * 2 * H + h];
+            if (all_rough) all_rough[(size_t)r * H + h] = (int64_t)hg[(size_t)r * 2 * H + H + h];
+        }
+    if (offsets)
+        for (int h = 0; h < H; ++h) offsets[h] = (int64_t)hg[(size_t)R * 2 * H + h];
+    return CC_OK;
+}
+
+/* ------------------------------------------------------------------ measurement */
+double cc_last_scan_ms(cc_ctx* c) {
+    if (!c || !c->have_times) return -1.0;
+    cudaSetDevice(c->device);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1.0;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev_scan0, c->ev_scan1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return ms;
+}
+double cc_last_total_ms(cc_ctx* c) {
+    if (!c || !c->have_times || !c->synced) return -1.0;
+    cudaSetDevice(c->device);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1.0;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev_scan0, c->ev_total1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return ms;
+}
+int64_t cc_launch_count(cc_ctx* c) { return c ? c->launches : 0; }
+int cc_last_stats(cc_ctx* c, int64_t out[4]) {
+    if (!c || !out) return fail(CC_ERR_ARG, "bad argument");
+    if (!c->synced) return fail(CC_ERR_STATE, "no synced cutout");
+    for (int i = 0; i < 4; ++i) out[i] = c->stats[i];
+    return CC_OK;
+}
+
+/* ------------------------------------------------------------------ test hooks */
+int cc_debug_eval(cc_ctx* c, int op, int64_t n, const float* in0, const float* in1, const float* in2, float* out0) {
+    if (!c || n < 0 || !in0 || !out0 || op < 0 || op > 5) return fail(CC_ERR_ARG, "cc_debug_eval: bad argument");
+    if ((op == 2 && (!in1 || !in2)) || ((op == 3 || op == 4) && !in1)) return fail(CC_ERR_ARG, "cc_debug_eval: missing input");
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (n == 0) return CC_OK;
+    DevBuf d0, d1, d2, dout;
+    const size_t bytes = (size_t)n * 4;
+    if ((rc = d0.ensure(bytes)) || (rc = dout.ensure(bytes))) { d0.release(); dout.release(); return rc; }
+    if (in1 && (rc = d1.ensure(bytes))) { d0.release(); dout.release(); return rc; }
+    if (in2 && (rc = d2.ensure(bytes))) { d0.release(); d1.release(); dout.release(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(d0.p, in0, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && in1) e = cudaMemcpyAsync(d1.p, in1, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && in2) e = cudaMemcpyAsync(d2.p, in2, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        cck::k_debug_eval<<<c->sm_count * 8, 256, 0, c->stream>>>(op, n, (const float*)d0.p, (const float*)d1.p, (const float*)d2.p, (float*)dout.p);
+        e = cudaGetLastError();
+        c->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out0, dout.p, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d0.release(); d1.release(); d2.release(); dout.release();
+    if (e != cudaSuccess) return fail(CC_ERR_CUDA, "cc_debug_eval: %s", cudaGetErrorString(e));
+    return CC_OK;
+}
+
+int cc_debug_eval_host(int op, int64_t n, const float* in0, const float* in1, const float* in2, float* out0) {
+    if (n < 0 || !in0 || !out0 || op < 0 || op > 5) return fail(CC_ERR_ARG, "cc_debug_eval_host: bad argument");
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float r;
+        switch (op) {
+            case 0: r = ccref::acosf_ref(in0[i]); break;
+            case 1: r = ccref::atanf_ref(in0[i]); break;
+            case 2: r = ccref::theta_arcsec(in0[i], in1[i], in2[i]); break;
+            case 3: r = ccref::phi_arcsec_plain(in0[i], in1[i]); break;
+            case 4: r = ccref::phi_arcsec_guarded(in0[i], in1[i]); break;
+            default: r = ccref::a_to_z(in0[i]); break;
+        }
+        out0[i] = r;
+    }
+    return CC_OK;
+}
+
+}  // extern "C"

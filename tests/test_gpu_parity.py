@@ -1,0 +1,319 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against the oracle
+(oracle/liboracle.so, pinned to the real reference by tests/test_oracle_vs_ref.py) on the same seeded inputs.
+Bar: byte-exact for every column, the survivor set and its order."""
+import numpy as np
+import pytest
+
+import harness as H
+from __graft_entry__ import load_package
+
+cc = load_package()
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cc.Context(0)
+    yield c
+    c.close()
+
+
+def _same_float_bits(a, b):
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
+
+
+# ------------------------------------------------------------------------------------------------ arithmetic
+def test_device_libm_equals_host_restatement_on_all_floats(ctx):
+    """device acosf/atanf restatement == host build of the same header on all 2^32 inputs (the host build is
+    checked against glibc on all 2^32 inputs by the CPU suite)"""
+    chunk = 1 << 26
+    for op in (0, 1):
+        for c0 in range(0, 1 << 32, chunk):
+            x = np.arange(c0, c0 + chunk, dtype=np.uint64).astype(np.uint32).view(np.float32)
+            d = ctx.debug_eval(op, x)
+            h = cc.debug_eval_host(op, x)
+            assert _same_float_bits(d, h), (op, c0)
+
+
+def test_device_libm_equals_glibc_sample(ctx):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-1.0, 1.0, 2_000_000), rng.normal(0, 50, 2_000_000),
+                        [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, np.inf, -np.inf, 1e-30, 3e7, 4e7, 0.4375, 0.6875, 1.1875,
+                         2.4375]]).astype(np.float32)
+    assert _same_float_bits(ctx.debug_eval(0, x), H.oracle_libm("acosf", x))
+    assert _same_float_bits(ctx.debug_eval(1, x), H.oracle_libm("atanf", x))
+
+
+def test_device_theta_phi_equals_oracle(ctx):
+    cols = H.concat_cols(H.shell_fixture(1_000_000, seed=3), H.shell_fixture(1_000_000, seed=4, octant=False),
+                         H.edge_fixture((306000, 320400), (0, 14400)))
+    x, y, z = cols["x"], cols["y"], cols["z"]
+    th1, ph1 = H.oracle_theta_phi(x, y, z, guards=False)
+    th2, ph2 = H.oracle_theta_phi(x, y, z, guards=True)
+    assert _same_float_bits(ctx.debug_eval(2, x, y, z), th1)
+    assert _same_float_bits(ctx.debug_eval(3, x, y), ph1)
+    assert _same_float_bits(ctx.debug_eval(4, x, y), ph2)
+    a = cols["a"]
+    want = cc.debug_eval_host(5, a)
+    assert ctx.debug_eval(5, a).tobytes() == want.tobytes()
+
+
+def test_synth_device_equals_host(ctx):
+    for kind in (0, 1):
+        n = 3_000_001
+        ctx.synth(n, seed=99, index_base=12345, kind=kind, box=250.0)
+        d = ctx.download(0, n)
+        h = cc.synth_host(n, seed=99, index_base=12345, kind=kind, box=250.0)
+        for k in cc.IN_COLS:
+            assert d[k].tobytes() == h[k].tobytes(), (kind, k)
+
+
+# ------------------------------------------------------------------------------------------------ use case 1
+WINDOWS = [((87, 2), (2, 2)), ((90, 20), (0, 20)), ((45, 1), (45, 1)), ((3, 3), (60, 30)), ((89.9, 0.2), (89.5, 0.6)),
+           ((45, 50), (45, 50)), ((0.5, 0.4), (10, 5)), ((120, 10), (20, 5))]
+
+
+@pytest.mark.parametrize("tc,pc", WINDOWS)
+def test_const_equals_oracle(ctx, tc, pc):
+    theta_cut, phi_cut = cc.cli_bounds(*tc), cc.cli_bounds(*pc)
+    cols = H.concat_cols(H.shell_fixture(700_000, seed=11), H.edge_fixture(theta_cut, phi_cut, octant_only=True),
+                         H.shell_fixture(300_123, seed=12, octant=False), H.edge_fixture(theta_cut, phi_cut, seed=9))
+    ctx.upload(cols)
+    ctx.cutout_const(theta_cut, phi_cut)
+    counts, rough = ctx.sync()
+    got = ctx.fetch(0, names=cc.OUT_COLS + ("index",))
+    want = H.oracle_cutout_const(cols, theta_cut, phi_cut)
+    assert int(counts[0]) == want["id"].shape[0]
+    H.assert_cols_equal(got, want, what=f"const {tc} {pc}: ")
+    # `index` really is the input position of each survivor, in increasing order (stable compaction)
+    assert np.array_equal(cols["id"][got["index"]], got["id"]) and np.all(np.diff(got["index"]) > 0)
+    st = ctx.stats()
+    assert st["survivors"] == int(counts[0]) and st["candidates"] >= st["survivors"]
+
+
+def test_const_kat_10m(ctx):
+    """cfg1 of BASELINE.json: the survey-time known answers of the patched reference"""
+    import hashlib
+    cols = H.shell_fixture(10_000_000, seed=20261019)
+    ctx.upload(cols)
+    for (tc, pc, k, h_id, h_th) in (((87, 2), (2, 2), 30889, "4ce6a39d99f49613", "2047f5c587dafe29"),
+                                     ((90, 20), (0, 20), 759498, "182f9c350d689719", "64e730ea83c6f615")):
+        ctx.cutout_const(cc.cli_bounds(*tc), cc.cli_bounds(*pc))
+        counts, _ = ctx.sync()
+        got = ctx.fetch(0)
+        assert int(counts[0]) == k
+        assert hashlib.sha256(got["id"].tobytes()).hexdigest()[:16] == h_id
+        assert hashlib.sha256(got["theta"].tobytes()).hexdigest()[:16] == h_th
+        want = H.oracle_cutout_const(cols, cc.cli_bounds(*tc), cc.cli_bounds(*pc))
+        H.assert_cols_equal(got, want, what="kat: ")
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 2047, 2048, 2049, 4096 + 17])
+def test_const_ragged_sizes(ctx, n):
+    theta_cut, phi_cut = cc.cli_bounds(45, 44), cc.cli_bounds(45, 44)
+    cols = H.slice_cols(H.shell_fixture(10_000, seed=2), 0, n)
+    ctx.upload(cols)
+    ctx.cutout_const(theta_cut, phi_cut)
+    counts, _ = ctx.sync()
+    want = H.oracle_cutout_const(cols, theta_cut, phi_cut)
+    assert int(counts[0]) == want["id"].shape[0]
+    H.assert_cols_equal(ctx.fetch(0), want)
+
+
+def test_const_everything_survives_and_capacity_regrows(ctx):
+    """window covering the whole octant: K == N, far beyond the initial output capacity"""
+    cols = H.shell_fixture(1_500_000, seed=8)
+    theta_cut, phi_cut = np.array([-10.0, 400000.0], np.float32), np.array([-10.0, 400000.0], np.float32)
+    ctx.upload(cols)
+    ctx.cutout_const(theta_cut, phi_cut)
+    counts, _ = ctx.sync()
+    want = H.oracle_cutout_const(cols, theta_cut, phi_cut)
+    assert int(counts[0]) == want["id"].shape[0] == 1_500_000
+    H.assert_cols_equal(ctx.fetch(0), want)
+
+
+def test_const_unaligned_device_columns(ctx):
+    """attach columns whose device addresses are not 16-byte aligned: the scalar-load kernel variant"""
+    import torch
+    cols = H.shell_fixture(300_000, seed=13)
+    n = 300_000 - 3
+    keep, ptrs = [], {}
+    for k in cc.IN_COLS:
+        t = torch.from_numpy(cols[k]).cuda()
+        keep.append(t)
+        ptrs[k] = t.data_ptr() + 3 * t.element_size()
+    torch.cuda.synchronize()
+    sub = H.slice_cols(cols, 3, 300_000)
+    theta_cut, phi_cut = cc.cli_bounds(60, 10), cc.cli_bounds(30, 10)
+    ctx.attach(n, ptrs)
+    ctx.cutout_const(theta_cut, phi_cut)
+    ctx.sync()
+    H.assert_cols_equal(ctx.fetch(0), H.oracle_cutout_const(sub, theta_cut, phi_cut))
+
+
+def test_const_shards_concatenate_to_single_rank_order(ctx):
+    """index sharding (one contiguous range per GPU): concatenating the shard outputs in rank order equals the
+    single-rank output, so file offsets = exclusive scan of counts"""
+    cols = H.shell_fixture(1_000_003, seed=21)
+    theta_cut, phi_cut = cc.cli_bounds(70, 15), cc.cli_bounds(40, 15)
+    want = H.oracle_cutout_const(cols, theta_cut, phi_cut)
+    parts = []
+    bounds = [0, 250_000, 500_001, 777_777, 1_000_003]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        ctx.upload(H.slice_cols(cols, lo, hi), index_base=lo)
+        ctx.cutout_const(theta_cut, phi_cut)
+        ctx.sync()
+        parts.append(ctx.fetch(0, names=cc.OUT_COLS + ("index",)))
+    got = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    H.assert_cols_equal(got, want)
+    assert np.array_equal(got["index"], got["id"])  # shell_fixture ids are the global index
+
+
+# ------------------------------------------------------------------------------------------------ use case 2
+HALOS = [((150, 20, 12), 10.0), ((150, 20, 12), 120.0), ((30, 170, 100), 30.0), ((100, 100, 100), 5.0),
+         ((10, 10, 250), 60.0), ((200, 1, 1), 20.0), ((120, -60, 40), 45.0), ((-90, 80, -150), 60.0),
+         ((1, 2, 300), 240.0), ((0.5, -0.5, -200), 90.0)]
+
+
+@pytest.fixture(scope="module")
+def halo_cols():
+    h = H.oracle_halo_setup((150, 20, 12), 120.0)
+    return H.concat_cols(H.shell_fixture(600_000, seed=21), H.shell_fixture(600_000, seed=22, octant=False),
+                         H.edge_fixture(h.theta_rough, h.phi_rough, seed=5), H.edge_fixture(h.theta_cut, h.phi_cut, seed=6))
+
+
+@pytest.mark.parametrize("pos_only", [False, True])
+def test_halo_batch_equals_oracle(ctx, halo_cols, pos_only):
+    """all halos in ONE pass; each halo's survivors, their (theta_u, index) order, columns and rough count"""
+    infos = [cc.halo_setup(p, b) for p, b in HALOS]
+    up = dict(halo_cols)
+    if pos_only:
+        for k in ("vx", "vy", "vz", "rotation", "replication"):
+            up[k] = None
+    ctx.upload(up)
+    ctx.cutout_halo([i.halo for i in infos], pos_only=pos_only)
+    counts, rough = ctx.sync()
+    names = cc.OUT_COLS_POSONLY if pos_only else cc.OUT_COLS
+    total = 0
+    for h, (p, b) in enumerate(HALOS):
+        want, want_rough = H.oracle_cutout_halo(halo_cols, H.oracle_halo_setup(p, b), pos_only=pos_only)
+        assert int(counts[h]) == want["id"].shape[0], (p, b)
+        assert int(rough[h]) == want_rough, (p, b)
+        H.assert_cols_equal(ctx.fetch(h), want, names, what=f"halo {p} {b}: ")
+        total += int(counts[h])
+    assert total > 1000
+
+
+def test_halo_sort_keys_and_tail_drop(ctx, halo_cols):
+    p, b = (150, 20, 12), 120.0
+    info = cc.halo_setup(p, b)
+    n = halo_cols["x"].shape[0]
+    ctx.upload(halo_cols)
+    # n_limit: only a prefix of the step is considered (the reference's Q7 tail drop at Np > 2^24)
+    limit = n - 100_000
+    ctx.cutout_halo([info.halo], n_limit_global=limit)
+    ctx.sync()
+    got = ctx.fetch(0, names=cc.OUT_COLS + ("theta_u", "index"))
+    want, _ = H.oracle_cutout_halo(H.slice_cols(halo_cols, 0, limit), H.oracle_halo_setup(p, b))
+    H.assert_cols_equal(got, want)
+    d_th, d_ix = np.diff(got["theta_u"]), np.diff(got["index"])
+    assert np.all((d_th > 0) | ((d_th == 0) & (d_ix > 0)))  # processLC.cpp:1214-1221: stable sort on theta_u
+    th_u, _ = H.oracle_theta_phi(halo_cols["x"], halo_cols["y"], halo_cols["z"], guards=True)
+    assert np.array_equal(th_u[got["index"]].view(np.uint32), got["theta_u"].view(np.uint32))
+
+
+def test_halo_many_halos_one_pass(ctx):
+    """more halos than one launch batch (K2_MAX_HALOS = 1024)"""
+    rng = np.random.default_rng(5)
+    cols = H.shell_fixture(400_000, seed=31)
+    pos = rng.uniform(20, 250, (1100, 3)).astype(np.float32)
+    infos = [cc.halo_setup(p, 30.0) for p in pos]
+    ctx.upload(cols)
+    ctx.cutout_halo([i.halo for i in infos])
+    counts, rough = ctx.sync()
+    for h in list(range(0, 1100, 97)) + [1023, 1024, 1099]:
+        want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(pos[h], 30.0))
+        assert int(counts[h]) == want["id"].shape[0] and int(rough[h]) == want_rough
+        H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {h}: ")
+
+
+def test_halo_empty_inputs(ctx):
+    info = cc.halo_setup((150, 20, 12), 10.0)
+    ctx.upload(H.slice_cols(H.shell_fixture(10, seed=1), 0, 0))
+    ctx.cutout_halo([info.halo])
+    counts, rough = ctx.sync()
+    assert int(counts[0]) == 0 and int(rough[0]) == 0
+    ctx.upload(H.shell_fixture(1000, seed=1))
+    ctx.cutout_halo([])
+    counts, rough = ctx.sync()
+    assert counts.shape[0] == 0
+
+
+# ------------------------------------------------------------------------------------------------ streamed
+def _pinned(cols):
+    out, addrs = {}, []
+    for k in cc.IN_COLS:
+        a, addr = cc.pinned_empty(cols[k].shape[0], cols[k].dtype)
+        a[:] = cols[k]
+        out[k] = a
+        addrs.append(addr)
+    return out, addrs
+
+
+def test_streamed_equals_oracle(ctx):
+    """pinned host -> HBM double-buffered path, several chunks (16 Mi particles per chunk) + a ragged tail"""
+    n = (16 << 20) * 2 + 12_345
+    cols = cc.synth_host(n, seed=77, kind=0, box=300.0)
+    pin, addrs = _pinned(cols)
+    try:
+        theta_cut, phi_cut = cc.cli_bounds(87, 2), cc.cli_bounds(2, 2)
+        ctx.cutout_const_streamed(pin, theta_cut, phi_cut)
+        ctx.sync()
+        H.assert_cols_equal(ctx.fetch(0), H.oracle_cutout_const(cols, theta_cut, phi_cut), what="streamed const: ")
+        info = cc.halo_setup((150, 20, 12), 60.0)
+        limit = cc.ref_scatter_kept(n, 1)
+        ctx.cutout_halo_streamed(pin, [info.halo], n_limit_global=limit)
+        counts, rough = ctx.sync()
+        want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup((150, 20, 12), 60.0))
+        assert int(rough[0]) == want_rough
+        H.assert_cols_equal(ctx.fetch(0), want, what="streamed halo: ")
+    finally:
+        del pin
+        for a in addrs:
+            cc.pinned_free(a)
+
+
+def test_streamed_rejects_pageable(ctx):
+    cols = H.shell_fixture(1000, seed=1)
+    with pytest.raises(cc.CutoutError, match="pageable"):
+        ctx.cutout_const_streamed(cols, cc.cli_bounds(87, 2), cc.cli_bounds(2, 2))
+
+
+# ------------------------------------------------------------------------------------------------ large
+def test_large_resident_const_100m(ctx):
+    """BASELINE-size step (100 M particles, device-generated): survivor count and columns equal the oracle run on
+    the same (host-regenerated) particles; the tail drop of use case 2 equals the reference's (4 particles)"""
+    n = 100_000_000
+    ctx.synth(n, seed=20261019, kind=0, box=300.0)
+    theta_cut, phi_cut = cc.cli_bounds(87, 2), cc.cli_bounds(2, 2)
+    ctx.cutout_const(theta_cut, phi_cut)
+    counts, _ = ctx.sync()
+    got = ctx.fetch(0, names=cc.OUT_COLS + ("index",))
+    host = cc.synth_host(n, seed=20261019, kind=0, box=300.0)
+    want = H.oracle_cutout_const(host, theta_cut, phi_cut)
+    assert int(counts[0]) == want["id"].shape[0] > 100_000
+    H.assert_cols_equal(got, want, what="100M const: ")
+    info = cc.halo_setup((150, 20, 12), 10.0)
+    ctx.cutout_halo([info.halo], n_limit_global=cc.ref_scatter_kept(n, 1))
+    counts, rough = ctx.sync()
+    got = ctx.fetch(0, names=cc.OUT_COLS + ("index",))
+    assert ctx.stats()["scanned"] == n - 4
+    # oracle on the particles that can matter: everything whose exact theta_u lies in the rough annulus
+    th_u, _ = H.oracle_theta_phi(host["x"], host["y"], host["z"], guards=True)
+    sel = np.nonzero((th_u >= info.halo.theta_rough[0]) & (th_u < info.halo.theta_rough[1]))[0]
+    sel = sel[sel < n - 4]
+    sub = {k: np.ascontiguousarray(host[k][sel]) for k in cc.IN_COLS}
+    want, want_rough = H.oracle_cutout_halo(sub, H.oracle_halo_setup((150, 20, 12), 10.0))
+    assert int(rough[0]) == want_rough
+    H.assert_cols_equal({k: got[k] for k in cc.OUT_COLS}, want, what="100M halo: ")

@@ -1,0 +1,113 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every declared symbol, the
+host set-up functions reproduce the oracle (and through it the reference) bit for bit, the fdlibm restatement
+the kernels execute equals the host glibc on every float, and compute entry points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import harness as H
+from __graft_entry__ import REPO, load_package
+
+cc = load_package()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(REPO, "include", "cosmo_cutout_b200.h")).read()
+    declared = set(re.findall(r"\b(cc_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"cc_ctx"}
+    assert declared == set(cc.SYMBOLS), declared ^ set(cc.SYMBOLS)
+    L = cc.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in L.cc_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    if cc.lib().cc_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cc.CutoutError, match="no CUDA device|no CPU fallback"):
+        cc.Context(0)
+
+
+def test_product_does_not_link_oracle():
+    out = subprocess.check_output(["ldd", cc.LIB_PATH]).decode()
+    assert "oracle" not in out and "cutout_ref" not in out
+    for root, _, files in os.walk(os.path.join(REPO, "cosmo-cutout_b200")):
+        if "build" in root or "__pycache__" in root:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py", "Makefile")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert "liboracle" not in txt and "oracle/" not in txt and "cutout_oracle" not in txt, (root, f)
+
+
+def test_halo_setup_equals_oracle():
+    rng = np.random.default_rng(17)
+    pts = [(150, 20, 12), (1, 0, 0), (0, 1, 0), (0, 0, 1), (5, 5, 5), (-3, 2, 1), (200, 1, 1), (10, 10, 250)]
+    pts += [tuple(rng.uniform(-300, 300, 3)) for _ in range(300)]
+    for p in pts:
+        for box in (5.0, 10.0, 30.0, 120.0):
+            a = cc.halo_setup(p, box)
+            o = H.oracle_halo_setup(p, box)
+            for nme in ("halo_r", "half_box_rad", "beta"):
+                assert np.float32(getattr(a, nme)).tobytes() == np.float32(getattr(o, nme)).tobytes(), (p, box, nme)
+            for nme in ("k", "K", "R", "R_inv", "corners_rot", "corners_sph"):
+                assert bytes(getattr(a, nme)) == bytes(getattr(o, nme)), (p, box, nme)
+            for nme in ("theta_cut", "phi_cut", "theta_rough", "phi_rough"):
+                assert bytes(getattr(a.halo, nme)) == bytes(getattr(o, nme)), (p, box, nme)
+            assert bytes(a.halo.R) == bytes(o.R)
+
+
+def test_cli_bounds_and_tail_drop_equal_oracle():
+    for c, h in ((87, 2), (2, 2), (90, 20), (0, 20), (45.5, 0.25), (89.9, 0.2), (3, 3)):
+        assert cc.cli_bounds(c, h).tobytes() == H.oracle_cli_bounds(c, h).tobytes()
+    o = H.oracle()
+    for n_p in (0, 1, 2, 1000, 2 ** 24 - 1, 2 ** 24, 2 ** 24 + 1, 2 ** 24 + 3, 20_000_001, 33_554_433, 100_000_000,
+                1_000_000_000):
+        for ranks in (1, 2, 8):
+            assert cc.ref_scatter_kept(n_p, ranks) == o.oracle_scatter_kept(n_p, ranks), (n_p, ranks)
+    assert cc.ref_scatter_kept(100_000_000, 1) == 100_000_000 - 4
+
+
+def test_restated_libm_equals_glibc_everywhere(tmp_path):
+    """all 2^32 float inputs, ~15 s on 8 cores: the device code executes exactly this operation sequence"""
+    exe = str(tmp_path / "check_libm")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-ffp-contract=off", "-fopenmp",
+                           "-I" + os.path.join(REPO, "cosmo-cutout_b200", "csrc"), "-x", "c++",
+                           os.path.join(REPO, "tests", "native", "check_libm_restate.cpp"), "-o", exe, "-lm"])
+    out = subprocess.check_output([exe, "1"]).decode()
+    assert "acosf mismatches=0 atanf mismatches=0 checked=4294967296" in out, out
+
+
+def test_host_build_of_device_arithmetic_equals_oracle():
+    cols = H.concat_cols(H.shell_fixture(200_000, seed=3), H.shell_fixture(200_000, seed=4, octant=False),
+                         H.edge_fixture((306000, 320400), (0, 14400)))
+    x, y, z = cols["x"], cols["y"], cols["z"]
+    th1, ph1 = H.oracle_theta_phi(x, y, z, guards=False)
+    th2, ph2 = H.oracle_theta_phi(x, y, z, guards=True)
+
+    def same(a, b):
+        return np.array_equal(a.view(np.uint32)[~np.isnan(a)], b.view(np.uint32)[~np.isnan(b)]) and \
+            np.array_equal(np.isnan(a), np.isnan(b))
+    assert same(cc.debug_eval_host(2, x, y, z), th1)
+    assert same(cc.debug_eval_host(3, x, y), ph1)
+    assert same(cc.debug_eval_host(4, x, y), ph2)
+    a = np.ascontiguousarray(cols["a"][:2000])
+    want = np.array([H.oracle().oracle_aToZ(float(v)) for v in a], dtype=np.float32)
+    assert cc.debug_eval_host(5, a).tobytes() == want.tobytes()
+
+
+def test_synth_host_is_deterministic_and_sliceable():
+    a = cc.synth_host(10_000, seed=42, index_base=0, kind=0, box=300.0)
+    b = cc.synth_host(4_000, seed=42, index_base=3_000, kind=0, box=300.0)
+    for k in cc.IN_COLS:
+        assert a[k][3_000:7_000].tobytes() == b[k].tobytes(), k
+    assert (a["x"] > 0).all() and (a["y"] > 0).all() and (a["z"] > 0).all() and (a["x"] <= 300).all()
+    c = cc.synth_host(10_000, seed=42, index_base=0, kind=1, box=300.0)
+    assert (c["x"] < 0).any() and (np.abs(c["x"]) < 300).all()
+    assert np.array_equal(a["id"], np.arange(10_000))
+    assert a["rotation"].min() >= 0 and a["rotation"].max() <= 5 and a["replication"].max() < 2 ** 20
