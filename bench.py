@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the lightcone cutout hot path (BASELINE.json metric: Gparticles/s filtered, and the
+achieved fraction of the HBM roofline), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg4|const1b|cfg5] [--impl reference]
+
+A "step" is one complete cutout of one synthetic lightcone step: scan of x,y,z (pre-filter + exact reference
+arithmetic), compaction/ordering, column gather of the survivors and -- for N > 1 -- the NCCL all-gather of the
+per-GPU survivor counts that yields each GPU's file offsets.  Default workload = BASELINE.json configs[1]:
+use case 2 halo cutout (--halo 150 20 12 --boxLength 10), 100 M-particle step per GPU (weak scaling: every GPU
+holds its own 100 M-particle index shard of a N*100 M-particle step).
+
+Printed JSON (one line, rank 0):
+  value      whole-job Gparticles/s with the step resident in HBM (CUDA events on the cutout stream, max over ranks)
+  e2e        same metric through the C ABI with HOST (pinned) columns: x,y,z streamed H2D double-buffered inside
+             the timed region, survivors copied back to host inside the timed region
+  roofline   dominant kernel (the scan): algorithmic bytes (12 B per particle scanned + 84 B per survivor;
+             44 B with posOnly) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the real reference (oracle/_ref, single rank = 1 core, as shipped it has no threading) on a
+             bounded sample of the same workload, timed on this box's host
+--impl reference: the reference's own CPU implementation on all host cores (one single-rank reference process per
+core on disjoint index slices -- the reference's own decomposition is one MPI rank per core), same metric/config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+WORKLOADS = {
+    # name: (use case, particles per GPU, description, parameters)
+    "cfg2": dict(uc=2, n=100_000_000, halos=[((150.0, 20.0, 12.0), 10.0)], kind=0, box=300.0,
+                 desc="BASELINE cfg2: use case 2 halo cutout --halo 150 20 12 --boxLength 10, 100M-particle synthetic step per GPU"),
+    "cfg1": dict(uc=1, n=10_000_000, theta=(87.0, 2.0), phi=(2.0, 2.0), kind=0, box=300.0,
+                 desc="BASELINE cfg1: use case 1 theta=87+-2 phi=2+-2 deg, 10M-particle synthetic step per GPU"),
+    "const1b": dict(uc=1, n=1_000_000_000, theta=(87.0, 2.0), phi=(2.0, 2.0), kind=0, box=300.0,
+                    desc="north-star size: use case 1 theta=87+-2 phi=2+-2 deg, 1B-particle resident step per GPU"),
+    "cfg4": dict(uc=1, n=500_000_000, theta=(90.0, 20.0), phi=(0.0, 20.0), kind=0, box=300.0,
+                 desc="BASELINE cfg4: wide field theta=90+-20 phi=0+-20 deg, 500M-particle resident shell per GPU"),
+    "cfg5": dict(uc=2, n=125_000_000, halos="random1000", kind=0, box=300.0,
+                 desc="BASELINE cfg5: 1000 halo cutouts (boxLength 15) in one pass, 125M-particle resident shard per GPU"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for (t, line) in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                if t0 - 0.1 <= t <= t1 + 0.1:
+                    sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            if t0 - 0.1 <= t <= t1 + 0.1:
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        if not sm:  # timed region shorter than the sampling period: take everything seen
+            for (_, line) in self.rows:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def halo_list(cc, wl):
+    if wl["halos"] == "random1000":
+        rng = np.random.default_rng(1000)
+        pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
+        return [(tuple(float(v) for v in p), 15.0) for p in pos]
+    return wl["halos"]
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    cc = load_package()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"note: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = WORKLOADS[args.workload]
+    n = int(args.particles) if args.particles else wl["n"]
+    n_total = n * world
+    ctx = cc.Context(local_rank)
+    if world > 1:  # our own communicator for the count exchange; torch.distributed only ships the id
+        ident = [cc.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        ctx.comm_init(world, rank, ident[0])
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    ctx.synth(n, seed=20261019, index_base=rank * n, kind=wl["kind"], box=wl["box"])
+    if wl["uc"] == 1:
+        tc, pc = cc.cli_bounds(*wl["theta"]), cc.cli_bounds(*wl["phi"])
+        halos, pos_only = None, False
+        bytes_per_survivor = 84
+    else:
+        halos = [cc.halo_setup(p, b).halo for (p, b) in halo_list(cc, wl)]
+        pos_only = False
+        bytes_per_survivor = 84
+        n_limit = cc.ref_scatter_kept(n_total, 1)  # the reference's tail drop
+
+    def step():
+        if wl["uc"] == 1:
+            ctx.cutout_const(tc, pc)
+        else:
+            ctx.cutout_halo(halos, pos_only=pos_only, n_limit_global=n_limit)
+        if world > 1:
+            ctx.exchange_counts()
+        else:
+            ctx.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        time.sleep(0.25)
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms, survivors, scanned = [], 0, 0
+    barrier()
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        scan_ms.append(ctx.last_scan_ms())
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    launches = ctx.launch_count() - launches0
+    st = ctx.stats()
+    survivors, scanned = st["survivors"], st["scanned"]
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # ---- e2e: HOST (pinned) columns through the C ABI, H2D + D2H inside the timed region
+    e2e_n = int(args.e2e_particles) if args.e2e_particles else min(n, 100_000_000)
+    ctx.release()
+    host = {}
+    addrs = []
+    for k in cc.IN_COLS:
+        a, addr = cc.pinned_empty(e2e_n, cc.COL_DTYPES[k])
+        host[k] = a
+        addrs.append(addr)
+    import ctypes as C
+    cc._check(cc.lib().cc_synth_host(e2e_n, 20261019, rank * e2e_n, wl["kind"], C.c_float(wl["box"]),
+                                     *[host[k].ctypes.data_as(C.c_void_p) for k in cc.IN_COLS]))
+    e2e_limit = cc.ref_scatter_kept(e2e_n * world, 1)
+
+    def e2e_step():
+        if wl["uc"] == 1:
+            ctx.cutout_const_streamed(host, tc, pc, index_base=rank * e2e_n)
+        else:
+            ctx.cutout_halo_streamed(host, halos, pos_only=pos_only, n_limit_global=e2e_limit, index_base=rank * e2e_n)
+        if world > 1:
+            ctx.exchange_counts()
+        counts, _ = ctx.sync()
+        nbytes = 0
+        for h in range(len(counts)):
+            if counts[h]:
+                out = ctx.fetch(h, count=int(counts[h]))
+                nbytes += sum(v.nbytes for v in out.values())
+        return int(counts.sum()), nbytes
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    tw0 = time.perf_counter()
+    ev0.record(stream)
+    d2h = 0
+    for _ in range(e2e_steps):
+        k_e2e, d2h = e2e_step()
+    ev1.record(stream)
+    barrier()
+    tw1 = time.perf_counter()
+    e2e_ms = max(ev0.elapsed_time(ev1), (tw1 - tw0) * 1e3)
+    for a in addrs:
+        pass  # pinned buffers are freed with the process (numpy views still reference them)
+
+    # ---- max over ranks
+    times = torch.tensor([ms_total, e2e_ms, float(np.mean(scan_ms))], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(launches), float(survivors), float(scanned)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms, scan_avg_ms = [float(v) for v in times.tolist()]
+    launches, survivors_all, scanned_all = [int(v) for v in cnt.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_per_step = ms_total / args.steps
+        value = n_total / (ms_per_step * 1e-3) / 1e9
+        # roofline of the dominant kernel, per launch on this GPU (rank 0's shard)
+        alg_bytes = 12.0 * scanned + bytes_per_survivor * survivors
+        achieved = alg_bytes / (float(np.mean(scan_ms)) * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 reference arithmetic + f64 arcsec scaling (bit-exact); u64 compaction",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "particles_per_gpu": n, "particles_total": n_total,
+                       "survivors_total": survivors_all, "l2": "inputs (12 B x particles per GPU) exceed the 126 MB L2; no flush needed",
+                       "timing": "CUDA events on the cutout stream around all timed steps, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k2_cutout_halo" if wl["uc"] == 2 else "k1_cutout_const",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(float(np.mean(scan_ms)), 4)},
+            "e2e": {"value": round(e2e_n * world / (e2e_ms / e2e_steps * 1e-3) / 1e9, 4), "unit": "Gparticles/s",
+                    "h2d_bytes_per_step": 12 * e2e_n, "d2h_bytes_per_step": d2h, "particles_per_gpu": e2e_n,
+                    "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
+                    "api": "cc_cutout_halo_streamed/cc_cutout_const_streamed + cc_cutout_sync + cc_cutout_fetch on pinned host columns"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, wl, single_core=True)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(task):
+    """one single-rank reference process on one contiguous index slice (runs in a child process)"""
+    (wl_name, first, count, seed, repeat) = task
+    import harness as H
+    from __graft_entry__ import load_package
+    cc = load_package()
+    wl = WORKLOADS[wl_name]
+    cols = cc.synth_host(count, seed, index_base=first, kind=wl["kind"], box=wl["box"])
+    kind = "reference" if H.ref_available() else "port"
+    dts = []
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        if kind == "reference":
+            with H.RefRun(cols) as r:
+                if wl["uc"] == 1:
+                    out = r.const(cc.cli_bounds(*wl["theta"]), cc.cli_bounds(*wl["phi"]))
+                    k = out["id"].shape[0]
+                else:
+                    k = 0
+                    for (p, b) in halo_list(cc, wl)[:1]:
+                        out = r.halo(p, b)
+                        k += out["id"].shape[0]
+        else:
+            if wl["uc"] == 1:
+                k = H.oracle_cutout_const(cols, cc.cli_bounds(*wl["theta"]), cc.cli_bounds(*wl["phi"]))["id"].shape[0]
+            else:
+                p, b = halo_list(cc, wl)[0]
+                k = H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, b))[0]["id"].shape[0]
+        dts.append(time.perf_counter() - t0)
+    return kind, dts, k
+
+
+def cpu_baseline(args, wl, single_core):
+    import multiprocessing as mp
+    sample = int(args.cpu_sample) if args.cpu_sample else (10_000_000 if wl["uc"] == 2 else 100_000_000)
+    sample = min(sample, wl["n"])
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1) as pool:
+        kind, dts, k = pool.map(_ref_worker, [(args.workload, 0, sample, 20261019, 1)])[0]
+    v = sample / dts[0] / 1e9
+    return {"value": round(v, 6), "unit": "Gparticles/s", "cores": 1, "kind": kind,
+            "sample": f"first {sample} particles of the workload's step, one reference rank (the reference has no "
+                      f"threading: 1 rank = 1 core), whole processLC call incl. in-memory column read and file write; "
+                      f"{dts[0]:.2f} s, {k} survivors"}
+
+
+def run_reference(args):
+    """the reference's own CPU implementation on all host cores: one single-rank process per core, each on its own
+    contiguous index slice (that is how the reference itself decomposes: one MPI rank per core)"""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cores = len(os.sched_getaffinity(0))
+    per = int(args.cpu_sample) if args.cpu_sample else (2_000_000 if wl["uc"] == 2 else 20_000_000)
+    ctx = mp.get_context("spawn")
+    tasks = [(args.workload, i * per, per, 20261019, 1) for i in range(cores)]
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, tasks[:cores])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = pool.map(_ref_worker, tasks)
+        dt = time.perf_counter() - t0
+    kind = res[0][0]
+    # rate of the compute inside the workers (excludes process start-up and synthetic column generation)
+    slowest = max(max(r[1]) for r in res)
+    v = cores * per / slowest / 1e9
+    out = {"impl": "reference", "metric": "Gparticles/s filtered", "value": round(v, 6), "unit": "Gparticles/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(slowest * 1e3, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 libm + f64 scaling (CPU)",
+           "data": "synthetic",
+           "config": {"workload": wl["desc"], "sample_particles_per_step": cores * per},
+           "cpu_baseline": {"value": round(v, 6), "unit": "Gparticles/s", "cores": cores, "kind": kind,
+                            "sample": f"{cores} single-rank reference processes x {per} particles each (disjoint index "
+                                      f"slices of the workload's step), slowest process {slowest:.2f} s per step; wall "
+                                      f"{dt / max(args.steps, 1):.2f} s per step incl. column generation"},
+           "e2e": {"value": round(v, 6), "unit": "Gparticles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", default=None, help="override particles per GPU")
+    ap.add_argument("--e2e-particles", default=None)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -182,7 +182,6 @@ def pinned_empty(n, dtype):
     _check(lib().cc_host_alloc(C.byref(p), nbytes))
     buf = (C.c_char * nbytes).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(n))
-    arr._cc_base = p.value  # noqa
     return arr, p.value
 
 

@@ -1,0 +1,31 @@
+/*
+ * host/processLC.h -- the two cutout entry points of the reference (src/processLC.h:41-48), same names, argument
+ * order and meaning, re-implemented over the C ABI of include/cosmo_cutout_b200.h.
+ *
+ * Differences a caller can observe are listed in INTEGRATION.md; the on-disk results (one raw little-endian file
+ * per column under <out><prefix>Cutout<step>/, properties.csv) are byte-identical to a single-rank run of the
+ * reference.  `myrank`/`numranks` keep their position: this implementation is one host process driving
+ * `numranks` GPUs (rank r of the reference's output layout = GPU r's contiguous index shard), so it must be
+ * called with myrank == 0.
+ */
+#ifndef CC_HOST_PROCESSLC_H
+#define CC_HOST_PROCESSLC_H
+
+#include <string>
+#include <vector>
+
+#define PI 3.14159265 /* reference processLC.h:35 */
+#define ARCSEC 3600.0 /* reference processLC.h:36 */
+
+/* use case 1: constant angular bounds {lo, hi} in arcsec (reference processLC.cpp:15-429) */
+void processLC(std::string dir_name, std::string out_dir, std::vector<std::string> step_strings,
+               std::vector<float> theta_bounds, std::vector<float> phi_bounds, int myrank, int numranks,
+               bool verbose, bool timeit, bool overwrite, bool positionOnly);
+
+/* use case 2: halo-centred square cutouts of `boxLength` arcmin (reference processLC.cpp:440-1757) */
+void processLC(std::string dir_name, std::vector<std::string> out_dirs, std::vector<std::string> step_strings,
+               std::vector<float> halo_pos, std::vector<float> halo_props, float boxLength, int myrank,
+               int numranks, bool verbose, bool timeit, bool overwrite, bool positionOnly,
+               bool forceWriteProps, bool propsOnly);
+
+#endif
