@@ -202,6 +202,8 @@ def run_ours(args):
 
     # ---- e2e: HOST (pinned) columns through the C ABI, H2D + D2H inside the timed region
     e2e_n = int(args.e2e_particles) if args.e2e_particles else min(n, 100_000_000)
+    if args.no_e2e:
+        e2e_n = 1 << 20
     ctx.release()
     host = {}
     addrs = []
@@ -392,6 +394,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -58,6 +58,7 @@ SYMBOLS = (
     "cc_cutout_const_streamed", "cc_cutout_halo_streamed", "cc_host_alloc", "cc_host_free", "cc_host_register",
     "cc_host_unregister",
     "cc_comm_unique_id", "cc_comm_init", "cc_comm_init_all", "cc_exchange_counts", "cc_comm_rank", "cc_comm_size",
+    "cc_shard_range", "cc_merge_order",
     "cc_last_scan_ms", "cc_last_total_ms", "cc_launch_count", "cc_last_stats",
     "cc_debug_eval", "cc_debug_eval_host",
 )
@@ -109,6 +110,9 @@ def lib():
         L.cc_exchange_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cc_comm_rank.argtypes = [C.c_void_p]
         L.cc_comm_size.argtypes = [C.c_void_p]
+        L.cc_shard_range.restype = None
+        L.cc_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.cc_merge_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cc_last_scan_ms.restype = C.c_double
         L.cc_last_scan_ms.argtypes = [C.c_void_p]
         L.cc_last_total_ms.restype = C.c_double
@@ -158,6 +162,25 @@ def cli_bounds(center_deg, half_deg):
 
 def ref_scatter_kept(n, numranks=1):
     return int(lib().cc_ref_scatter_kept(int(n), int(numranks)))
+
+
+def shard_range(n, nranks, rank):
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    lib().cc_shard_range(int(n), int(nranks), int(rank), C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
+def merge_order(theta_u_parts, index_parts):
+    """cc_merge_order: merged row order of per-rank (theta_u, index)-sorted survivor lists -> (src_rank, src_row)"""
+    n = len(theta_u_parts)
+    counts = np.array([t.shape[0] for t in theta_u_parts], dtype=np.int64)
+    tp = (C.c_void_p * n)(*[t.ctypes.data for t in theta_u_parts])
+    ip = (C.c_void_p * n)(*[t.ctypes.data for t in index_parts])
+    tot = int(counts.sum())
+    src_rank = np.zeros(tot, dtype=np.int32)
+    src_row = np.zeros(tot, dtype=np.int64)
+    _check(lib().cc_merge_order(n, _ptr(counts), tp, ip, _ptr(src_rank), _ptr(src_row)))
+    return src_rank, src_row
 
 
 def synth_host(n, seed, index_base=0, kind=0, box=300.0):

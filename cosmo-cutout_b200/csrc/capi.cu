@@ -127,6 +127,7 @@ struct cc_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr, ev_total1 = nullptr;
     int64_t launches = 0;
+    int k1_occupancy[2] = {0, 0};
 
     /* resident step */
     bool step_valid = false, step_owned = false;
@@ -234,7 +235,7 @@ struct Chunk {
     bool first, last;
 };
 
-/* scratch layout of use case 1: [ result: 4 x u64 | ticket (+pad): 32 B | tile_state: ntiles x u64 ] */
+/* scratch layout of use case 1: [ result: 4 x u64 | pad: 32 B | tile_state: ntiles x u64 ] */
 const size_t K1_HDR = 64;
 
 int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
@@ -260,16 +261,22 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
     a.th_lo = c->p_th[0]; a.th_hi = c->p_th[1]; a.ph_lo = c->p_ph[0]; a.ph_hi = c->p_ph[1];
     ccpf::uc1_bounds(c->p_th, c->p_ph, &a.chi2, &a.clo2, &a.tlo, &a.thi);
     a.result = (unsigned long long*)c->scratch.p;
-    a.ticket = (unsigned int*)((char*)c->scratch.p + 32);
     a.tile_state = (unsigned long long*)((char*)c->scratch.p + K1_HDR);
     a.ntiles = ntiles;
     if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
     if (ntiles > 0) {
-        const unsigned int grid = std::min<unsigned int>(ntiles, (unsigned int)c->sm_count * 3u);
+        /* cooperative launch: every warp of the grid must be resident, the look-back relies on it (kernels.cuh) */
         const bool vec = aligned16(a.in.x) && aligned16(a.in.y) && aligned16(a.in.z);
-        if (vec) cck::k1_cutout_const<true><<<grid, cck::K1_THREADS, 0, c->stream>>>(a);
-        else cck::k1_cutout_const<false><<<grid, cck::K1_THREADS, 0, c->stream>>>(a);
-        CU(cudaGetLastError());
+        void* fn = vec ? (void*)cck::k1_cutout_const<true> : (void*)cck::k1_cutout_const<false>;
+        int& occ = c->k1_occupancy[vec ? 1 : 0];
+        if (occ == 0) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cck::K1_THREADS, 0));
+            if (occ < 1) return fail(CC_ERR_CUDA, "k1_cutout_const cannot be resident on this device");
+        }
+        const unsigned int want = (ntiles + cck::K1_WARPS - 1) / cck::K1_WARPS;
+        const unsigned int grid = std::min<unsigned int>(want, (unsigned int)(c->sm_count * occ));
+        void* params[] = {(void*)&a};
+        CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(cck::K1_THREADS), params, 0, c->stream));
         c->launches += 1;
     }
     if (ch.last) {

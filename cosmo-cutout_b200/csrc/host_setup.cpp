@@ -11,6 +11,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "../../include/cosmo_cutout_b200.h"
 
 namespace {
@@ -180,6 +183,50 @@ int64_t cc_ref_scatter_kept(int64_t np, int numranks) {
         else hi = mid;
     }
     return lo;
+}
+
+void cc_shard_range(int64_t n, int nranks, int rank, int64_t* lo, int64_t* hi) {
+    if (n < 0) n = 0;
+    if (nranks < 1) nranks = 1;
+    /* 128-bit product: n * rank can exceed 2^63 only for absurd sizes, but stay exact anyway */
+    *lo = (int64_t)(((__int128)n * rank) / nranks);
+    *hi = (int64_t)(((__int128)n * (rank + 1)) / nranks);
+}
+
+int cc_merge_order(int nranks, const int64_t* counts, const float* const* theta_u, const int64_t* const* index,
+                   int32_t* src_rank, int64_t* src_row) {
+    if (nranks < 1 || !counts || !theta_u || !index || !src_rank || !src_row) return CC_ERR_ARG;
+    /* k-way merge; theta_u >= 0 and never NaN for a survivor, so its bit pattern orders like its value */
+    struct Head { uint32_t key; int64_t idx; int32_t r; int64_t row; };
+    std::vector<Head> heap;
+    auto less = [](const Head& a, const Head& b) { /* min-heap through std::*_heap's max-heap convention */
+        return a.key != b.key ? a.key > b.key : a.idx > b.idx;
+    };
+    auto head_of = [&](int r, int64_t row) {
+        Head h;
+        memcpy(&h.key, &theta_u[r][row], 4);
+        h.idx = index[r][row];
+        h.r = r;
+        h.row = row;
+        return h;
+    };
+    for (int r = 0; r < nranks; ++r)
+        if (counts[r] > 0) heap.push_back(head_of(r, 0));
+    std::make_heap(heap.begin(), heap.end(), less);
+    int64_t o = 0;
+    while (!heap.empty()) {
+        std::pop_heap(heap.begin(), heap.end(), less);
+        const Head h = heap.back();
+        heap.pop_back();
+        src_rank[o] = h.r;
+        src_row[o] = h.row;
+        ++o;
+        if (h.row + 1 < counts[h.r]) {
+            heap.push_back(head_of(h.r, h.row + 1));
+            std::push_heap(heap.begin(), heap.end(), less);
+        }
+    }
+    return CC_OK;
 }
 
 }  // extern "C"

@@ -62,10 +62,22 @@ __device__ __forceinline__ float a_to_z_dev(float a) {
 }
 
 /* ================================================================================================
- * K1  use case 1
+ * K1  use case 1: warp-autonomous tiles
+ *
+ * Every warp owns tiles of 256 consecutive particles (8 per lane: two coalesced float4 chunks per column) and
+ * runs the whole chain for a tile by itself -- load, pre-filter, ballot/popc compaction of the candidates into
+ * its private shared-memory queue, exact reference arithmetic on the queued candidates, ballot/popc compaction
+ * of the survivors, decoupled look-back over the per-tile states for the global row offset, 12-column gather.
+ * There is no block-level barrier anywhere, so a warp stalled on a long-latency phase (fp64 divide chain, the
+ * scattered gather loads, a look-back wait) never holds up the 30+ other warps of its SM that keep HBM busy.
+ *
+ * Tiles are assigned statically (tile = iteration * total_warps + global_warp): the look-back of tile t only
+ * waits on tiles < t, which belong to warps that are resident and never wait on higher tiles -- provided every
+ * warp of the grid IS resident, which is why the kernel is launched cooperatively with an occupancy-sized grid.
  * ================================================================================================ */
 constexpr int K1_THREADS = 256;
-constexpr int K1_TILE = 2048; /* particles per tile = 8 per thread: two coalesced float4 chunks of 1024 */
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_TILE = 256; /* particles per warp tile */
 constexpr unsigned long long TS_AGG = 1ull << 62;
 constexpr unsigned long long TS_PREFIX = 2ull << 62;
 constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
@@ -79,7 +91,6 @@ struct ConstArgs {
     float th_lo, th_hi, ph_lo, ph_hi; /* exact, strict (processLC.cpp:287-288) */
     float chi2, clo2, tlo, thi;       /* pre-filter (prefilter.h) */
     unsigned long long* tile_state;   /* [ntiles], zeroed before launch */
-    unsigned int* ticket;             /* zeroed before launch */
     unsigned long long* result;       /* [0] survivors so far: read as the row base of tile 0 (zero for a resident
                                          step, the running total for a streamed one), written back by the last
                                          tile; [1] pre-filter candidates */
@@ -96,31 +107,29 @@ __device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const Co
     return (z2 < a.chi2 * r2) & (z2 > a.clo2 * r2) & (y > a.tlo * x) & (y < a.thi * x);
 }
 
+struct K1WarpQueue { /* one per warp */
+    float x[K1_TILE], y[K1_TILE], z[K1_TILE], th[K1_TILE], ph[K1_TILE];
+    unsigned char idx[K1_TILE];
+};
+
 template <bool VEC>
-__global__ void __launch_bounds__(K1_THREADS, 3) k1_cutout_const(const ConstArgs a) {
-    __shared__ float q_x[K1_TILE], q_y[K1_TILE], q_z[K1_TILE], q_th[K1_TILE], q_ph[K1_TILE];
-    __shared__ unsigned short q_i[K1_TILE];
-    __shared__ unsigned int s_bits[K1_TILE / 32], s_wpre[K1_TILE / 32];
-    __shared__ unsigned int s_warp_tot[K1_THREADS / 32];
-    __shared__ unsigned int s_tile;
-    __shared__ unsigned long long s_base;
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_cutout_const(const ConstArgs a) {
+    __shared__ K1WarpQueue s_q[K1_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    K1WarpQueue& q = s_q[warp];
+    const unsigned int total_warps = gridDim.x * K1_WARPS;
+    const unsigned int lane_lt = (1u << lane) - 1u;
+    unsigned long long n_cand = 0;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long n_cand_local = 0;
-
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    unsigned int tile = s_tile;
-
-    while (tile < a.ntiles) {
+    for (unsigned int tile = blockIdx.x * K1_WARPS + warp; tile < a.ntiles; tile += total_warps) {
         const long long base = (long long)tile * K1_TILE;
-        /* ---- load 8 particles: chunk A = [base+4*tid, +4), chunk B = [base+1024+4*tid, +4) ---- */
+        /* ---- load 8 particles: chunk A = [base+4*lane, +4), chunk B = [base+128+4*lane, +4) ---- */
         float px[8], py[8], pz[8];
         unsigned int valid = 0xffu;
         if (VEC && base + K1_TILE <= a.n) {
-            const float4 xa = ldg_stream4(a.in.x + base + 4 * tid), xb = ldg_stream4(a.in.x + base + 1024 + 4 * tid);
-            const float4 ya = ldg_stream4(a.in.y + base + 4 * tid), yb = ldg_stream4(a.in.y + base + 1024 + 4 * tid);
-            const float4 za = ldg_stream4(a.in.z + base + 4 * tid), zb = ldg_stream4(a.in.z + base + 1024 + 4 * tid);
+            const float4 xa = ldg_stream4(a.in.x + base + 4 * lane), xb = ldg_stream4(a.in.x + base + 128 + 4 * lane);
+            const float4 ya = ldg_stream4(a.in.y + base + 4 * lane), yb = ldg_stream4(a.in.y + base + 128 + 4 * lane);
+            const float4 za = ldg_stream4(a.in.z + base + 4 * lane), zb = ldg_stream4(a.in.z + base + 128 + 4 * lane);
             px[0] = xa.x; px[1] = xa.y; px[2] = xa.z; px[3] = xa.w; px[4] = xb.x; px[5] = xb.y; px[6] = xb.z; px[7] = xb.w;
             py[0] = ya.x; py[1] = ya.y; py[2] = ya.z; py[3] = ya.w; py[4] = yb.x; py[5] = yb.y; py[6] = yb.z; py[7] = yb.w;
             pz[0] = za.x; pz[1] = za.y; pz[2] = za.z; pz[3] = za.w; pz[4] = zb.x; pz[5] = zb.y; pz[6] = zb.z; pz[7] = zb.w;
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k1_cutout_const(const ConstArgs
             valid = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const long long g = base + (j >> 2) * 1024 + 4 * tid + (j & 3);
+                const long long g = base + (j >> 2) * 128 + 4 * lane + (j & 3);
                 if (g < a.n) {
                     px[j] = __ldcs(a.in.x + g); py[j] = __ldcs(a.in.y + g); pz[j] = __ldcs(a.in.z + g);
                     valid |= 1u << j;
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k1_cutout_const(const ConstArgs
 #pragma unroll
         for (int j = 0; j < 8; ++j) m |= (unsigned)k1_prefilter(px[j], py[j], pz[j], a) << j;
         m &= valid;
-        /* ---- ordered candidate compaction into the shared queue (order: chunk, thread, element) ---- */
+        /* ---- ordered candidate compaction into the warp's queue (order: chunk, lane, element = input order) ---- */
         const unsigned int cnt = __popc(m & 0xfu) | (__popc(m >> 4) << 16);
         unsigned int inc = cnt;
 #pragma unroll
@@ -150,127 +159,112 @@ __global__ void __launch_bounds__(K1_THREADS, 3) k1_cutout_const(const ConstArgs
             const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += t;
         }
-        if (lane == 31) s_warp_tot[warp] = inc;
-        __syncthreads();
-        unsigned int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < K1_THREADS / 32; ++w) {
-            const unsigned int t = s_warp_tot[w];
-            if (w < warp) before += t;
-            total += t;
-        }
+        const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
         const unsigned int totalA = total & 0xffffu, C = totalA + (total >> 16);
-        const unsigned int ex = before + inc - cnt;
-        unsigned int posA = ex & 0xffffu, posB = totalA + (ex >> 16);
+        unsigned long long exclusive = 0;
+        unsigned int bits[K1_TILE / 32];
+        unsigned int K = 0;
+        if (C) { /* warp-uniform */
+            const unsigned int ex = inc - cnt;
+            unsigned int posA = ex & 0xffffu, posB = totalA + (ex >> 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (m & (1u << j)) {
-                q_x[posA] = px[j]; q_y[posA] = py[j]; q_z[posA] = pz[j];
-                q_i[posA] = (unsigned short)(4 * tid + j);
-                ++posA;
-            }
-#pragma unroll
-        for (int j = 4; j < 8; ++j)
-            if (m & (1u << j)) {
-                q_x[posB] = px[j]; q_y[posB] = py[j]; q_z[posB] = pz[j];
-                q_i[posB] = (unsigned short)(1024 + 4 * tid + (j - 4));
-                ++posB;
-            }
-        __syncthreads();
-        /* ---- exact path for the candidates, densely packed: the reference's arithmetic ---- */
-        for (unsigned int j0 = warp * 32; j0 < C; j0 += K1_THREADS) {
-            const unsigned int j = j0 + lane;
-            bool pass = false;
-            if (j < C) {
-                const float x = q_x[j], y = q_y[j], z = q_z[j];
-                if (x > 0.0f && y > 0.0f && z > 0.0f) { /* processLC.cpp:279 */
-                    const float th = ccref::theta_arcsec(x, y, z);
-                    const float ph = ccref::phi_arcsec_plain(x, y);
-                    pass = th > a.th_lo && th < a.th_hi && ph > a.ph_lo && ph < a.ph_hi; /* :287-288 */
-                    q_th[j] = th;
-                    q_ph[j] = ph;
+            for (int j = 0; j < 4; ++j)
+                if (m & (1u << j)) {
+                    q.x[posA] = px[j]; q.y[posA] = py[j]; q.z[posA] = pz[j];
+                    q.idx[posA] = (unsigned char)(4 * lane + j);
+                    ++posA;
                 }
-            }
-            const unsigned int b = __ballot_sync(0xffffffffu, pass);
-            if (lane == 0) s_bits[j0 >> 5] = b;
-        }
-        __syncthreads();
-        /* ---- warp 0: survivors per 32-candidate word, tile total, decoupled look-back ---- */
-        if (warp == 0) {
-            const unsigned int nwords = (C + 31) >> 5;
-            const unsigned int w0 = (2u * lane < nwords) ? s_bits[2 * lane] : 0u;
-            const unsigned int w1 = (2u * lane + 1 < nwords) ? s_bits[2 * lane + 1] : 0u;
-            const unsigned int c0 = __popc(w0), c = c0 + __popc(w1);
-            unsigned int ksum = c;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned int t = __shfl_up_sync(0xffffffffu, ksum, d);
-                if (lane >= d) ksum += t;
-            }
-            s_wpre[2 * lane] = ksum - c;
-            s_wpre[2 * lane + 1] = ksum - c + c0;
-            const unsigned long long K = __shfl_sync(0xffffffffu, ksum, 31);
-            unsigned long long exclusive = 0;
-            if (tile == 0) {
-                exclusive = ld_relaxed_u64(a.result); /* rows written by earlier chunks of a streamed step */
-                if (lane == 0) st_relaxed_u64(a.tile_state, TS_PREFIX | (exclusive + K));
-            } else {
-                if (lane == 0) st_relaxed_u64(a.tile_state + tile, TS_AGG | K);
-                long long look = (long long)tile - 1;
-                while (true) {
-                    const long long idx = look - lane;
-                    unsigned long long st = TS_PREFIX; /* before tile 0: prefix 0 */
-                    if (idx >= 0) {
-                        st = ld_relaxed_u64(a.tile_state + idx);
-                        while ((st >> 62) == 0) st = ld_relaxed_u64(a.tile_state + idx);
+            for (int j = 4; j < 8; ++j)
+                if (m & (1u << j)) {
+                    q.x[posB] = px[j]; q.y[posB] = py[j]; q.z[posB] = pz[j];
+                    q.idx[posB] = (unsigned char)(128 + 4 * lane + (j - 4));
+                    ++posB;
+                }
+            __syncwarp();
+            /* ---- exact path on the densely packed candidates: the reference's arithmetic ---- */
+#pragma unroll
+            for (int w = 0; w < K1_TILE / 32; ++w) {
+                bits[w] = 0;
+                if ((unsigned)(w * 32) < C) {
+                    const unsigned int j = w * 32 + lane;
+                    bool pass = false;
+                    if (j < C) {
+                        const float x = q.x[j], y = q.y[j], z = q.z[j];
+                        if (x > 0.0f && y > 0.0f && z > 0.0f) { /* processLC.cpp:279 */
+                            const float th = ccref::theta_arcsec(x, y, z);
+                            const float ph = ccref::phi_arcsec_plain(x, y);
+                            pass = th > a.th_lo && th < a.th_hi && ph > a.ph_lo && ph < a.ph_hi; /* :287-288 */
+                            q.th[j] = th;
+                            q.ph[j] = ph;
+                        }
                     }
-                    const unsigned int pmask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-                    const int first = pmask ? (__ffs(pmask) - 1) : 31;
-                    unsigned long long v = (lane <= first) ? (st & TS_MASK) : 0ull;
+                    bits[w] = __ballot_sync(0xffffffffu, pass);
+                    K += __popc(bits[w]);
+                }
+            }
+            n_cand += C;
+        }
+        /* ---- decoupled look-back: row offset of this tile's first survivor ---- */
+        if (tile == 0) {
+            exclusive = ld_relaxed_u64(a.result); /* rows written by earlier chunks of a streamed step */
+            if (lane == 0) st_relaxed_u64(a.tile_state, TS_PREFIX | (exclusive + K));
+        } else {
+            if (lane == 0) st_relaxed_u64(a.tile_state + tile, TS_AGG | (unsigned long long)K);
+            long long look = (long long)tile - 1;
+            while (true) {
+                const long long idx = look - lane;
+                unsigned long long st = TS_PREFIX; /* before tile 0: prefix 0 (tile 0 itself carries the base) */
+                if (idx >= 0) {
+                    st = ld_relaxed_u64(a.tile_state + idx);
+                    while ((st >> 62) == 0) st = ld_relaxed_u64(a.tile_state + idx);
+                }
+                const unsigned int pmask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                const int first = pmask ? (__ffs(pmask) - 1) : 31;
+                unsigned long long v = (lane <= first) ? (st & TS_MASK) : 0ull;
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    exclusive += v;
-                    if (pmask) break;
-                    look -= 32;
-                }
-                if (lane == 0) st_relaxed_u64(a.tile_state + tile, TS_PREFIX | (exclusive + K));
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                exclusive += v;
+                if (pmask) break;
+                look -= 32;
             }
-            if (lane == 0) {
-                s_base = exclusive;
-                if (tile == a.ntiles - 1) a.result[0] = exclusive + K;
-                s_tile = atomicAdd(a.ticket, 1u); /* next tile for this CTA */
-            }
+            if (lane == 0) st_relaxed_u64(a.tile_state + tile, TS_PREFIX | (exclusive + K));
         }
-        __syncthreads();
+        if (tile == a.ntiles - 1 && lane == 0) a.result[0] = exclusive + K;
         /* ---- gather: survivors in input order; 12 columns (processLC.cpp:291-307) ---- */
-        const unsigned long long obase = s_base;
-        const unsigned int next_tile = s_tile;
-        for (unsigned int j = tid; j < C; j += K1_THREADS) {
-            const unsigned int bits = s_bits[j >> 5];
-            if ((bits >> (j & 31)) & 1u) {
-                const long long r = (long long)(obase + s_wpre[j >> 5] + __popc(bits & ((1u << (j & 31)) - 1u)));
-                if (r < a.cap) {
-                    const long long g = base + q_i[j];
-                    a.out.theta[r] = q_th[j];
-                    a.out.phi[r] = q_ph[j];
-                    a.out.x[r] = q_x[j];
-                    a.out.y[r] = q_y[j];
-                    a.out.z[r] = q_z[j];
-                    a.out.vx[r] = a.in.vx[g];
-                    a.out.vy[r] = a.in.vy[g];
-                    a.out.vz[r] = a.in.vz[g];
-                    a.out.redshift[r] = a_to_z_dev(a.in.a[g]);
-                    a.out.id[r] = a.in.id[g];
-                    a.out.rot[r] = a.in.rot[g];
-                    a.out.rep[r] = a.in.rep[g];
-                    if (a.out.index) a.out.index[r] = a.index_base + g;
+        if (K) { /* warp-uniform */
+            unsigned int before = 0;
+#pragma unroll
+            for (int w = 0; w < K1_TILE / 32; ++w) {
+                if ((unsigned)(w * 32) < C) {
+                    const unsigned int b = bits[w];
+                    if ((b >> lane) & 1u) {
+                        const unsigned int j = w * 32 + lane;
+                        const long long r = (long long)(exclusive + before + __popc(b & lane_lt));
+                        if (r < a.cap) {
+                            const long long g = base + q.idx[j];
+                            a.out.theta[r] = q.th[j];
+                            a.out.phi[r] = q.ph[j];
+                            a.out.x[r] = q.x[j];
+                            a.out.y[r] = q.y[j];
+                            a.out.z[r] = q.z[j];
+                            a.out.vx[r] = a.in.vx[g];
+                            a.out.vy[r] = a.in.vy[g];
+                            a.out.vz[r] = a.in.vz[g];
+                            a.out.redshift[r] = a_to_z_dev(a.in.a[g]);
+                            a.out.id[r] = a.in.id[g];
+                            a.out.rot[r] = a.in.rot[g];
+                            a.out.rep[r] = a.in.rep[g];
+                            if (a.out.index) a.out.index[r] = a.index_base + g;
+                        }
+                    }
+                    before += __popc(b);
                 }
             }
         }
-        if (tid == 0) n_cand_local += C;
-        tile = next_tile;
+        __syncwarp(); /* the queue is rewritten by the next tile */
     }
-    if (tid == 0 && n_cand_local) atomicAdd(a.result + 1, n_cand_local);
+    if (lane == 0 && n_cand) atomicAdd(a.result + 1, n_cand);
 }
 
 /* ================================================================================================

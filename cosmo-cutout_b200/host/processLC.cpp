@@ -79,8 +79,10 @@ void for_each_gpu(int numranks, F f) {
 
 /* contiguous index shard of GPU r */
 void shard_range(size_t n, int numranks, int r, size_t* lo, size_t* hi) {
-    *lo = n * (size_t)r / (size_t)numranks;
-    *hi = n * (size_t)(r + 1) / (size_t)numranks;
+    int64_t a, b;
+    cc_shard_range((int64_t)n, numranks, r, &a, &b);
+    *lo = (size_t)a;
+    *hi = (size_t)b;
 }
 
 /* ---------------------------------------------------------------- survivors on the host */
@@ -439,24 +441,17 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
             if (numranks == 1) {
                 files.write_block(parts[0], parts[0].n, 0);
             } else {
-                struct Ref { uint32_t key; int64_t index; int r; size_t j; };
-                vector<Ref> order;
-                order.reserve((size_t)tot);
-                for (int r = 0; r < numranks; ++r)
-                    for (size_t j = 0; j < parts[(size_t)r].n; ++j) {
-                        uint32_t bits;
-                        memcpy(&bits, &parts[(size_t)r].theta_u[j], 4);
-                        order.push_back(Ref{bits, parts[(size_t)r].index[j], r, j});
-                    }
-                /* theta_u >= 0, so its bit pattern orders like its value */
-                std::sort(order.begin(), order.end(), [](const Ref& a, const Ref& b) {
-                    return a.key != b.key ? a.key < b.key : a.index < b.index;
-                });
+                vector<int32_t> src_rank((size_t)tot);
+                vector<int64_t> src_row((size_t)tot);
+                vector<const float*> keys_t((size_t)numranks);
+                vector<const int64_t*> keys_i((size_t)numranks);
+                for (int r = 0; r < numranks; ++r) { keys_t[(size_t)r] = parts[(size_t)r].theta_u.data(); keys_i[(size_t)r] = parts[(size_t)r].index.data(); }
+                check(cc_merge_order(numranks, np_count.data(), keys_t.data(), keys_i.data(), src_rank.data(), src_row.data()));
                 Survivors m;
                 m.resize((size_t)tot, !positionOnly, false);
-                for (size_t o = 0; o < order.size(); ++o) {
-                    const Survivors& s = parts[(size_t)order[o].r];
-                    const size_t j = order[o].j;
+                for (size_t o = 0; o < (size_t)tot; ++o) {
+                    const Survivors& s = parts[(size_t)src_rank[o]];
+                    const size_t j = (size_t)src_row[o];
                     m.x[o] = s.x[j]; m.y[o] = s.y[j]; m.z[o] = s.z[j]; m.redshift[o] = s.redshift[j];
                     m.theta[o] = s.theta[j]; m.phi[o] = s.phi[j]; m.id[o] = s.id[j];
                     if (!positionOnly) {

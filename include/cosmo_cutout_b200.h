@@ -163,6 +163,17 @@ int cc_exchange_counts(cc_ctx* ctx, int64_t* all_counts, int64_t* all_rough, int
 int cc_comm_rank(cc_ctx* ctx);
 int cc_comm_size(cc_ctx* ctx);
 
+/* ------------------------------------------------------------------ multi-GPU: host-side plan (no GPU needed)
+ * Contiguous index shard of rank r out of nranks over n particles: [lo, hi).  Replaces the reference's
+ * per-rank GenericIO blocks + load-balancing redistribution (processLC.cpp:974-1125, util.cpp:97-110). */
+void cc_shard_range(int64_t n, int nranks, int rank, int64_t* lo, int64_t* hi);
+/* Use case 2, several ranks: every rank's survivors of a halo arrive ordered by (theta_u, index); a single-rank
+ * reference run orders the WHOLE step that way (stable arg-sort, processLC.cpp:1214-1221), so the file order is
+ * the merge of the per-rank lists on those keys.  theta_u[r], index[r]: rank r's key columns (counts[r] rows).
+ * Output: for merged row i, src_rank[i] / src_row[i] say where it comes from.  Rows total = sum(counts). */
+int cc_merge_order(int nranks, const int64_t* counts, const float* const* theta_u, const int64_t* const* index,
+                   int32_t* src_rank, int64_t* src_row);
+
 /* ------------------------------------------------------------------ measurement */
 /* Device time (CUDA events on the context's stream) of the scan kernel of the last cutout, and of the
  * whole enqueued cutout (scan + sort + gather).  ms; negative if none.  Implies a stream synchronize. */
