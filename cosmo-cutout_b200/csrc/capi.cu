@@ -128,6 +128,9 @@ struct cc_ctx {
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr, ev_total1 = nullptr;
     int64_t launches = 0;
     int k1_occupancy[2] = {0, 0};
+    int k2_occupancy[2] = {0, 0};
+    unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
+    DevBuf t_idx, t_th, t_ph;
 
     /* resident step */
     bool step_valid = false, step_owned = false;
@@ -235,54 +238,103 @@ struct Chunk {
     bool first, last;
 };
 
-/* scratch layout of use case 1: [ result: 4 x u64 | pad: 32 B | tile_state: ntiles x u64 ] */
+/* scratch layout of use case 1:
+ *   [ result: 4 x u64 | ticket u32 (+pad to 64 B) | block_state: nblocks x u64 | tile_info: ntiles x u64 |
+ *     tile_base: ntiles x u32 | cta_used: grid x u32 ]
+ * result[0] survivors so far (carried across the chunks of a streamed step), [1] pre-filter candidates,
+ * [2] carry seen by the current chunk's gather, [3] max records any CTA wanted (temp-region overflow check) */
 const size_t K1_HDR = 64;
 
+int k1_grid_limit(cc_ctx* c, bool vec, unsigned int* out) {
+    int& occ = c->k1_occupancy[vec ? 1 : 0];
+    if (occ == 0) {
+        const void* fn = vec ? (const void*)cck::k1_scan<true> : (const void*)cck::k1_scan<false>;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cck::SCAN_THREADS, 0));
+        if (occ < 1) return fail(CC_ERR_CUDA, "k1_scan cannot be resident on this device");
+    }
+    *out = (unsigned int)(c->sm_count * occ);
+    return CC_OK;
+}
+
 int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
-    const unsigned long long ntiles64 = (unsigned long long)((ch.n + cck::K1_TILE - 1) / cck::K1_TILE);
-    if (ntiles64 > 0xfffffff0ull) return fail(CC_ERR_ARG, "chunk too large (%lld particles)", (long long)ch.n);
+    const unsigned long long ntiles64 = (unsigned long long)((ch.n + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
+    if (ch.n > 0xfffffff0ll) return fail(CC_ERR_ARG, "chunk too large (%lld particles)", (long long)ch.n);
     const unsigned int ntiles = (unsigned int)ntiles64;
-    const size_t bytes = K1_HDR + ((size_t)ntiles + 8) * sizeof(unsigned long long);
-    int rc = c->scratch.ensure(bytes);
+    const unsigned int nblocks = (ntiles + cck::TSCAN_BLOCK - 1) / cck::TSCAN_BLOCK;
+    const bool vec = aligned16(ch.x) && aligned16(ch.y) && aligned16(ch.z);
+    unsigned int grid_max = 0;
+    int rc = k1_grid_limit(c, vec, &grid_max);
     if (rc) return rc;
-    if (ch.first) CU(cudaMemsetAsync(c->scratch.p, 0, bytes, c->stream));
-    else CU(cudaMemsetAsync((char*)c->scratch.p + 32, 0, bytes - 32, c->stream)); /* keep the running totals */
-    cck::ConstArgs a;
-    a.in = c->gcols;
-    /* survivor columns other than x,y,z are indexed by the chunk-local particle index */
-    a.in.vx += ch.start; a.in.vy += ch.start; a.in.vz += ch.start; a.in.a += ch.start; a.in.id += ch.start;
-    a.in.rot += ch.start; a.in.rep += ch.start;
-    a.in.x = ch.x; a.in.y = ch.y; a.in.z = ch.z;
-    a.out = cols_out_of(c);
-    a.out.theta_u = nullptr;
-    a.n = ch.n;
-    a.cap = c->out_cap;
-    a.index_base = c->index_base + ch.start;
-    a.th_lo = c->p_th[0]; a.th_hi = c->p_th[1]; a.ph_lo = c->p_ph[0]; a.ph_hi = c->p_ph[1];
-    ccpf::uc1_bounds(c->p_th, c->p_ph, &a.chi2, &a.clo2, &a.tlo, &a.thi);
-    a.result = (unsigned long long*)c->scratch.p;
-    a.tile_state = (unsigned long long*)((char*)c->scratch.p + K1_HDR);
-    a.ntiles = ntiles;
+    const unsigned int grid = std::max(1u, std::min((ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, grid_max));
+    /* scratch */
+    const size_t off_state = K1_HDR;
+    const size_t off_info = off_state + ((size_t)nblocks + 8) * 8;
+    const size_t off_base = off_info + ((size_t)ntiles + 8) * 8;
+    const size_t off_used = off_base + (((size_t)ntiles + 8) * 4 + 7) / 8 * 8;
+    const size_t bytes = off_used + ((size_t)grid_max + 8) * 4;
+    if ((rc = c->scratch.ensure(bytes))) return rc;
+    /* temp records: one private region per CTA */
+    if (c->region_cap == 0) c->region_cap = (unsigned int)std::min<int64_t>(0x7fffffff, c->out_cap + c->out_cap / 4) / grid_max + 256;
+    const size_t temp_elems = (size_t)grid_max * c->region_cap;
+    if ((rc = c->t_idx.ensure(temp_elems * 4)) || (rc = c->t_th.ensure(temp_elems * 4)) || (rc = c->t_ph.ensure(temp_elems * 4))) return rc;
+    char* sp = (char*)c->scratch.p;
+    if (ch.first) CU(cudaMemsetAsync(sp, 0, off_info, c->stream));                     /* totals + ticket + block states */
+    else CU(cudaMemsetAsync(sp + 32, 0, off_info - 32, c->stream));                    /* keep the running totals */
+    unsigned long long* result = (unsigned long long*)sp;
     if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
     if (ntiles > 0) {
-        /* cooperative launch: every warp of the grid must be resident, the look-back relies on it (kernels.cuh) */
-        const bool vec = aligned16(a.in.x) && aligned16(a.in.y) && aligned16(a.in.z);
-        void* fn = vec ? (void*)cck::k1_cutout_const<true> : (void*)cck::k1_cutout_const<false>;
-        int& occ = c->k1_occupancy[vec ? 1 : 0];
-        if (occ == 0) {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cck::K1_THREADS, 0));
-            if (occ < 1) return fail(CC_ERR_CUDA, "k1_cutout_const cannot be resident on this device");
-        }
-        const unsigned int want = (ntiles + cck::K1_WARPS - 1) / cck::K1_WARPS;
-        const unsigned int grid = std::min<unsigned int>(want, (unsigned int)(c->sm_count * occ));
-        void* params[] = {(void*)&a};
-        CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(cck::K1_THREADS), params, 0, c->stream));
-        c->launches += 1;
+        cck::ScanArgs a;
+        a.x = ch.x; a.y = ch.y; a.z = ch.z;
+        a.n = ch.n;
+        a.th_lo = c->p_th[0]; a.th_hi = c->p_th[1]; a.ph_lo = c->p_ph[0]; a.ph_hi = c->p_ph[1];
+        ccpf::uc1_bounds(c->p_th, c->p_ph, &a.chi2, &a.clo2, &a.tlo, &a.thi);
+        a.t_idx = (unsigned int*)c->t_idx.p; a.t_th = (float*)c->t_th.p; a.t_ph = (float*)c->t_ph.p;
+        a.region_cap = c->region_cap;
+        a.cta_used = (unsigned int*)(sp + off_used);
+        a.tile_info = (unsigned long long*)(sp + off_info);
+        a.result = result;
+        a.ntiles = ntiles;
+        if (vec) cck::k1_scan<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+        else cck::k1_scan<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+        CU(cudaGetLastError());
+        if (ch.last) CU(cudaEventRecord(c->ev_scan1, c->stream));
+
+        cck::TileScanArgs t;
+        t.tile_info = a.tile_info;
+        t.tile_base = (unsigned int*)(sp + off_base);
+        t.block_state = (unsigned long long*)(sp + off_state);
+        t.ticket = (unsigned int*)(sp + 32);
+        t.result = result;
+        t.ntiles = ntiles;
+        t.nblocks = nblocks;
+        cck::k1_tile_scan<<<nblocks, cck::TSCAN_THREADS, 0, c->stream>>>(t);
+        CU(cudaGetLastError());
+
+        cck::GatherConstArgs g;
+        g.in = c->gcols;
+        /* survivor columns other than x,y,z are indexed by the chunk-local particle index */
+        g.in.vx += ch.start; g.in.vy += ch.start; g.in.vz += ch.start; g.in.a += ch.start; g.in.id += ch.start;
+        g.in.rot += ch.start; g.in.rep += ch.start;
+        g.in.x = ch.x; g.in.y = ch.y; g.in.z = ch.z;
+        g.out = cols_out_of(c);
+        g.out.theta_u = nullptr;
+        g.t_idx = a.t_idx; g.t_th = a.t_th; g.t_ph = a.t_ph;
+        g.cta_used = a.cta_used;
+        g.tile_info = a.tile_info;
+        g.tile_base = t.tile_base;
+        g.result = result;
+        g.region_cap = c->region_cap;
+        g.cap = c->out_cap;
+        g.index_base = c->index_base + ch.start;
+        cck::k1_gather<<<dim3(4, grid), 256, 0, c->stream>>>(g);
+        CU(cudaGetLastError());
+        c->launches += 3;
+    } else if (ch.last) {
+        CU(cudaEventRecord(c->ev_scan1, c->stream));
     }
     if (ch.last) {
-        CU(cudaEventRecord(c->ev_scan1, c->stream));
         CU(cudaEventRecord(c->ev_total1, c->stream));
-        CU(cudaMemcpyAsync(c->h_small, a.result, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_small, result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         c->have_times = true;
     }
     return CC_OK;
@@ -367,11 +419,16 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         a.counts = (unsigned long long*)c->counts_buf.p;
         a.n_cand = n_cand;
         a.total_halos = H;
-        const long long nquads = (n_scan + 3) / 4;
-        const long long want = (nquads + cck::K2_THREADS - 1) / cck::K2_THREADS;
-        const unsigned int grid = (unsigned int)std::max<long long>(1, std::min<long long>(want, (long long)c->sm_count * 8));
-        if (vec) cck::k2_cutout_halo<true><<<grid, cck::K2_THREADS, 0, c->stream>>>(a);
-        else cck::k2_cutout_halo<false><<<grid, cck::K2_THREADS, 0, c->stream>>>(a);
+        a.ntiles = (unsigned int)((n_scan + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
+        int& occ = c->k2_occupancy[vec ? 1 : 0];
+        if (occ == 0) {
+            const void* fn = vec ? (const void*)cck::k2_cutout_halo<true> : (const void*)cck::k2_cutout_halo<false>;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cck::SCAN_THREADS, 0));
+            if (occ < 1) occ = 1;
+        }
+        const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
+        if (vec) cck::k2_cutout_halo<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+        else cck::k2_cutout_halo<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
         CU(cudaGetLastError());
         c->launches += 1;
     }
@@ -404,7 +461,7 @@ int run_streamed(cc_ctx* c) {
     int rc = (c->pending == P_CONST) ? prepare_const(c) : prepare_halo(c);
     if (rc) return rc;
     const int64_t n = c->n;
-    const int64_t chunk = std::max<int64_t>(cck::K1_TILE, (c->stream_chunk / cck::K1_TILE) * cck::K1_TILE);
+    const int64_t chunk = std::max<int64_t>(cck::SCAN_TILE, (c->stream_chunk / cck::SCAN_TILE) * cck::SCAN_TILE);
     if (!c->copy_stream) {
         CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (int s = 0; s < 2; ++s) {
@@ -550,7 +607,7 @@ void cc_destroy(cc_ctx* c) {
     for (auto& b : c->col_buf) b.release();
     for (auto& b : c->out_buf) b.release();
     DevBuf* rest[] = {&c->scratch, &c->pre_buf, &c->halo_buf, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
-                      &c->seg_buf, &c->cursor_buf, &c->misc_buf, &c->gather_buf, &c->offsets_buf};
+                      &c->seg_buf, &c->cursor_buf, &c->misc_buf, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph};
     for (DevBuf* b : rest) b->release();
     for (auto& sl : c->stage) for (auto& b : sl) b.release();
     for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
@@ -727,12 +784,15 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
     if (rc) return rc;
     if (!c->synced) {
         if (c->pending == P_CONST) {
-            for (int attempt = 0; attempt < 3; ++attempt) {
+            for (int attempt = 0; attempt < 4; ++attempt) {
                 CU(cudaStreamSynchronize(c->stream));
                 const int64_t k = (int64_t)c->h_small[0];
-                if (k <= c->out_cap) break;
-                /* survivors exceeded the output capacity: grow to the exact count and run the pass again */
-                if ((rc = ensure_out_cap(c, k + k / 64))) return rc;
+                const uint64_t max_used = c->h_small[3];
+                if (k <= c->out_cap && max_used <= c->region_cap) break;
+                if (attempt == 3) return fail(CC_ERR_CUDA, "internal: survivor buffers still too small after regrowth");
+                /* survivors exceeded the output rows or a CTA's temp region: grow to what was needed, run again */
+                if (k > c->out_cap && (rc = ensure_out_cap(c, k + k / 64))) return rc;
+                if (max_used > c->region_cap) c->region_cap = (unsigned int)std::min<uint64_t>(0xfffffff0u, max_used + max_used / 8 + 256);
                 if ((rc = run_pending(c))) return rc;
             }
             c->counts.assign(1, (int64_t)c->h_small[0]);

@@ -61,43 +61,85 @@ __device__ __forceinline__ float a_to_z_dev(float a) {
     return ccref::a_to_z(a);
 }
 
-/* ================================================================================================
- * K1  use case 1: warp-autonomous tiles
- *
- * Every warp owns tiles of 256 consecutive particles (8 per lane: two coalesced float4 chunks per column) and
- * runs the whole chain for a tile by itself -- load, pre-filter, ballot/popc compaction of the candidates into
- * its private shared-memory queue, exact reference arithmetic on the queued candidates, ballot/popc compaction
- * of the survivors, decoupled look-back over the per-tile states for the global row offset, 12-column gather.
- * There is no block-level barrier anywhere, so a warp stalled on a long-latency phase (fp64 divide chain, the
- * scattered gather loads, a look-back wait) never holds up the 30+ other warps of its SM that keep HBM busy.
- *
- * Tiles are assigned statically (tile = iteration * total_warps + global_warp): the look-back of tile t only
- * waits on tiles < t, which belong to warps that are resident and never wait on higher tiles -- provided every
- * warp of the grid IS resident, which is why the kernel is launched cooperatively with an occupancy-sized grid.
- * ================================================================================================ */
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_TILE = 256; /* particles per warp tile */
-constexpr unsigned long long TS_AGG = 1ull << 62;
-constexpr unsigned long long TS_PREFIX = 2ull << 62;
-constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
+/* approximate reciprocal / reciprocal square root for the pre-filter only (arguments are range-checked, so
+ * flushing subnormals is harmless and the slow-path fix-up code of the non-ftz forms is avoided) */
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-struct ConstArgs {
-    ColsIn in;
-    ColsOut out;
-    long long n;          /* particles in this shard */
-    long long cap;        /* rows available in `out` */
-    long long index_base; /* global index of in[0] */
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_TILE = 256; /* particles per warp tile: 8 per lane = two coalesced float4 chunks per column */
+
+/* load one warp tile: chunk A = [base+4*lane, +4), chunk B = [base+128+4*lane, +4); returns the valid mask */
+template <bool VEC>
+__device__ __forceinline__ unsigned int load_tile(const float* __restrict__ x, const float* __restrict__ y,
+                                                  const float* __restrict__ z, long long base, long long n, int lane,
+                                                  float (&px)[8], float (&py)[8], float (&pz)[8]) {
+    if (VEC && base + SCAN_TILE <= n) {
+        const float4 xa = ldg_stream4(x + base + 4 * lane), xb = ldg_stream4(x + base + 128 + 4 * lane);
+        const float4 ya = ldg_stream4(y + base + 4 * lane), yb = ldg_stream4(y + base + 128 + 4 * lane);
+        const float4 za = ldg_stream4(z + base + 4 * lane), zb = ldg_stream4(z + base + 128 + 4 * lane);
+        px[0] = xa.x; px[1] = xa.y; px[2] = xa.z; px[3] = xa.w; px[4] = xb.x; px[5] = xb.y; px[6] = xb.z; px[7] = xb.w;
+        py[0] = ya.x; py[1] = ya.y; py[2] = ya.z; py[3] = ya.w; py[4] = yb.x; py[5] = yb.y; py[6] = yb.z; py[7] = yb.w;
+        pz[0] = za.x; pz[1] = za.y; pz[2] = za.z; pz[3] = za.w; pz[4] = zb.x; pz[5] = zb.y; pz[6] = zb.z; pz[7] = zb.w;
+        return 0xffu;
+    }
+    unsigned int valid = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const long long g = base + (j >> 2) * 128 + 4 * lane + (j & 3);
+        if (g < n) {
+            px[j] = __ldcs(x + g); py[j] = __ldcs(y + g); pz[j] = __ldcs(z + g);
+            valid |= 1u << j;
+        } else {
+            px[j] = py[j] = pz[j] = 1.0f;
+        }
+    }
+    return valid;
+}
+/* index inside the tile of element j of this lane */
+__device__ __forceinline__ unsigned int tile_local(int lane, int j) { return (unsigned)((j >> 2) * 128 + 4 * lane + (j & 3)); }
+
+/* ================================================================================================
+ * K1  use case 1, three phases
+ *
+ *   k1_scan       the bandwidth-bound pass.  Every warp owns tiles of 256 consecutive particles and runs the whole
+ *                 chain for a tile by itself: coalesced float4 loads of x,y,z -> pre-filter -> ballot/popc
+ *                 compaction of the candidates into the warp's shared-memory queue -> exact reference arithmetic
+ *                 on the queued candidates -> ballot/popc compaction of the survivors -> (index, theta, phi)
+ *                 records appended to the CTA's private region of a temp buffer (shared-memory cursor, no global
+ *                 atomics) + one 8-byte (position, count) word per tile.  No block barrier, no inter-tile wait:
+ *                 a warp stalled in the fp64 divide chain never holds up the loads of the other 31 warps of its SM.
+ *   k1_tile_scan  exclusive scan of the per-tile counts: single pass, decoupled look-back across blocks.
+ *   k1_gather     one thread per survivor record: row = carry + tile_base[tile] + rank -> 12-column gather,
+ *                 survivors stay in input order (processLC.cpp:291-307).
+ *
+ * (A first version chained the look-back through the particle tiles themselves; with 3 KB tiles the chain can
+ *  only advance ~32 tiles per L2 round trip and capped the pass at ~14 % of HBM bandwidth -- profiles/r01.)
+ * ================================================================================================ */
+struct ScanArgs {
+    const float *x, *y, *z;
+    long long n;                      /* particles in this chunk */
     float th_lo, th_hi, ph_lo, ph_hi; /* exact, strict (processLC.cpp:287-288) */
     float chi2, clo2, tlo, thi;       /* pre-filter (prefilter.h) */
-    unsigned long long* tile_state;   /* [ntiles], zeroed before launch */
-    unsigned long long* result;       /* [0] survivors so far: read as the row base of tile 0 (zero for a resident
-                                         step, the running total for a streamed one), written back by the last
-                                         tile; [1] pre-filter candidates */
+    unsigned int* t_idx;              /* temp records: particle index inside the chunk */
+    float *t_th, *t_ph;               /*               theta, phi (arcsec) */
+    unsigned int region_cap;          /* records per CTA region */
+    unsigned int* cta_used;           /* [grid] records the CTA appended (> region_cap means overflow) */
+    unsigned long long* tile_info;    /* [ntiles] (temp position << 32) | survivors of the tile */
+    unsigned long long* result;       /* [1] += pre-filter candidates, [3] = max records any CTA wanted */
     unsigned int ntiles;
 };
 
-__device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const ConstArgs& a) {
+__device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const ScanArgs& a) {
     const float mn = fminf(x, fminf(y, z));
     const float mx = fmaxf(x, fmaxf(y, z));
     if (!(mn > 0.0f)) return false;                            /* octant test, processLC.cpp:279 */
@@ -107,86 +149,64 @@ __device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const Co
     return (z2 < a.chi2 * r2) & (z2 > a.clo2 * r2) & (y > a.tlo * x) & (y < a.thi * x);
 }
 
-struct K1WarpQueue { /* one per warp */
-    float x[K1_TILE], y[K1_TILE], z[K1_TILE], th[K1_TILE], ph[K1_TILE];
-    unsigned char idx[K1_TILE];
+struct K1WarpQueue { /* one per warp: candidates of the current tile */
+    float x[SCAN_TILE], y[SCAN_TILE], z[SCAN_TILE], th[SCAN_TILE], ph[SCAN_TILE];
+    unsigned char idx[SCAN_TILE];
 };
 
 template <bool VEC>
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_cutout_const(const ConstArgs a) {
-    __shared__ K1WarpQueue s_q[K1_WARPS];
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k1_scan(const ScanArgs a) {
+    __shared__ K1WarpQueue s_q[SCAN_WARPS];
+    __shared__ unsigned int s_cursor;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     K1WarpQueue& q = s_q[warp];
-    const unsigned int total_warps = gridDim.x * K1_WARPS;
+    const unsigned int total_warps = gridDim.x * SCAN_WARPS;
     const unsigned int lane_lt = (1u << lane) - 1u;
+    const unsigned long long region0 = (unsigned long long)blockIdx.x * a.region_cap;
     unsigned long long n_cand = 0;
+    if (threadIdx.x == 0) s_cursor = 0;
+    __syncthreads();
 
-    for (unsigned int tile = blockIdx.x * K1_WARPS + warp; tile < a.ntiles; tile += total_warps) {
-        const long long base = (long long)tile * K1_TILE;
-        /* ---- load 8 particles: chunk A = [base+4*lane, +4), chunk B = [base+128+4*lane, +4) ---- */
+    for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
+        const long long base = (long long)tile * SCAN_TILE;
         float px[8], py[8], pz[8];
-        unsigned int valid = 0xffu;
-        if (VEC && base + K1_TILE <= a.n) {
-            const float4 xa = ldg_stream4(a.in.x + base + 4 * lane), xb = ldg_stream4(a.in.x + base + 128 + 4 * lane);
-            const float4 ya = ldg_stream4(a.in.y + base + 4 * lane), yb = ldg_stream4(a.in.y + base + 128 + 4 * lane);
-            const float4 za = ldg_stream4(a.in.z + base + 4 * lane), zb = ldg_stream4(a.in.z + base + 128 + 4 * lane);
-            px[0] = xa.x; px[1] = xa.y; px[2] = xa.z; px[3] = xa.w; px[4] = xb.x; px[5] = xb.y; px[6] = xb.z; px[7] = xb.w;
-            py[0] = ya.x; py[1] = ya.y; py[2] = ya.z; py[3] = ya.w; py[4] = yb.x; py[5] = yb.y; py[6] = yb.z; py[7] = yb.w;
-            pz[0] = za.x; pz[1] = za.y; pz[2] = za.z; pz[3] = za.w; pz[4] = zb.x; pz[5] = zb.y; pz[6] = zb.z; pz[7] = zb.w;
-        } else {
-            valid = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const long long g = base + (j >> 2) * 128 + 4 * lane + (j & 3);
-                if (g < a.n) {
-                    px[j] = __ldcs(a.in.x + g); py[j] = __ldcs(a.in.y + g); pz[j] = __ldcs(a.in.z + g);
-                    valid |= 1u << j;
-                } else {
-                    px[j] = py[j] = pz[j] = 0.0f;
-                }
-            }
-        }
+        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
         /* ---- pre-filter ---- */
         unsigned int m = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) m |= (unsigned)k1_prefilter(px[j], py[j], pz[j], a) << j;
         m &= valid;
-        /* ---- ordered candidate compaction into the warp's queue (order: chunk, lane, element = input order) ---- */
-        const unsigned int cnt = __popc(m & 0xfu) | (__popc(m >> 4) << 16);
-        unsigned int inc = cnt;
+        unsigned long long info = 0;
+        if (__any_sync(0xffffffffu, m != 0)) {
+            /* ---- ordered candidate compaction into the warp's queue (chunk, lane, element = input order) ---- */
+            const unsigned int cnt = __popc(m & 0xfu) | (__popc(m >> 4) << 16);
+            unsigned int inc = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
-        const unsigned int totalA = total & 0xffffu, C = totalA + (total >> 16);
-        unsigned long long exclusive = 0;
-        unsigned int bits[K1_TILE / 32];
-        unsigned int K = 0;
-        if (C) { /* warp-uniform */
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
+            const unsigned int totalA = total & 0xffffu, C = totalA + (total >> 16);
             const unsigned int ex = inc - cnt;
             unsigned int posA = ex & 0xffffu, posB = totalA + (ex >> 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
                 if (m & (1u << j)) {
-                    q.x[posA] = px[j]; q.y[posA] = py[j]; q.z[posA] = pz[j];
-                    q.idx[posA] = (unsigned char)(4 * lane + j);
-                    ++posA;
-                }
-#pragma unroll
-            for (int j = 4; j < 8; ++j)
-                if (m & (1u << j)) {
-                    q.x[posB] = px[j]; q.y[posB] = py[j]; q.z[posB] = pz[j];
-                    q.idx[posB] = (unsigned char)(128 + 4 * lane + (j - 4));
-                    ++posB;
+                    unsigned int& pos = (j < 4) ? posA : posB;
+                    q.x[pos] = px[j]; q.y[pos] = py[j]; q.z[pos] = pz[j];
+                    q.idx[pos] = (unsigned char)tile_local(lane, j);
+                    ++pos;
                 }
             __syncwarp();
+            n_cand += C;
             /* ---- exact path on the densely packed candidates: the reference's arithmetic ---- */
+            unsigned int K = 0;
+            unsigned int bits[SCAN_TILE / 32];
 #pragma unroll
-            for (int w = 0; w < K1_TILE / 32; ++w) {
+            for (int w = 0; w < SCAN_TILE / 32; ++w) {
                 bits[w] = 0;
-                if ((unsigned)(w * 32) < C) {
+                if ((unsigned)(w * 32) < C) { /* warp-uniform */
                     const unsigned int j = w * 32 + lane;
                     bool pass = false;
                     if (j < C) {
@@ -203,75 +223,188 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_cutout_const(const ConstArgs
                     K += __popc(bits[w]);
                 }
             }
-            n_cand += C;
+            /* ---- survivors, in input order, to the CTA's region of the temp buffer ---- */
+            unsigned int pos0 = 0;
+            if (K) { /* warp-uniform */
+                if (lane == 0) pos0 = atomicAdd(&s_cursor, K);
+                pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                unsigned int before = 0;
+#pragma unroll
+                for (int w = 0; w < SCAN_TILE / 32; ++w) {
+                    if ((unsigned)(w * 32) < C) {
+                        const unsigned int b = bits[w];
+                        if ((b >> lane) & 1u) {
+                            const unsigned int j = w * 32 + lane;
+                            const unsigned long long slot = (unsigned long long)pos0 + before + __popc(b & lane_lt);
+                            if (slot < a.region_cap) {
+                                a.t_idx[region0 + slot] = (unsigned int)(base + q.idx[j]);
+                                a.t_th[region0 + slot] = q.th[j];
+                                a.t_ph[region0 + slot] = q.ph[j];
+                            }
+                        }
+                        before += __popc(b);
+                    }
+                }
+            }
+            info = ((region0 + pos0) << 32) | K;
+            __syncwarp(); /* the queue is rewritten by the next tile */
         }
-        /* ---- decoupled look-back: row offset of this tile's first survivor ---- */
-        if (tile == 0) {
-            exclusive = ld_relaxed_u64(a.result); /* rows written by earlier chunks of a streamed step */
-            if (lane == 0) st_relaxed_u64(a.tile_state, TS_PREFIX | (exclusive + K));
+        if (lane == 0) a.tile_info[tile] = info;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.cta_used[blockIdx.x] = s_cursor;
+        atomicMax(a.result + 3, (unsigned long long)s_cursor);
+    }
+    if (lane == 0 && n_cand) atomicAdd(a.result + 1, n_cand);
+}
+
+/* ---- phase B: exclusive scan of the tile counts (single pass, decoupled look-back across blocks) ---- */
+constexpr int TSCAN_THREADS = 256;
+constexpr int TSCAN_ITEMS = 16; /* tiles per thread */
+constexpr int TSCAN_BLOCK = TSCAN_THREADS * TSCAN_ITEMS;
+constexpr unsigned long long TS_AGG = 1ull << 62;
+constexpr unsigned long long TS_PREFIX = 2ull << 62;
+constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
+
+struct TileScanArgs {
+    const unsigned long long* tile_info; /* [ntiles] low 32 bits = count */
+    unsigned int* tile_base;             /* [ntiles] exclusive prefix inside the chunk */
+    unsigned long long* block_state;     /* [nblocks] zeroed before launch */
+    unsigned int* ticket;                /* zeroed before launch */
+    unsigned long long* result;          /* [0] survivors so far (in: carry, out: carry + chunk total), [2] = carry */
+    unsigned int ntiles, nblocks;
+};
+
+__global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs a) {
+    __shared__ unsigned int s_warp[TSCAN_THREADS / 32];
+    __shared__ unsigned int s_block;
+    __shared__ unsigned long long s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_block = atomicAdd(a.ticket, 1u); /* blocks enter the chain in ticket order: no deadlock */
+    __syncthreads();
+    const unsigned int blk = s_block;
+    const unsigned int first = blk * TSCAN_BLOCK + tid * TSCAN_ITEMS;
+    unsigned int c[TSCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int i = 0; i < TSCAN_ITEMS; ++i) {
+        c[i] = (first + i < a.ntiles) ? (unsigned int)(a.tile_info[first + i] & 0xffffffffull) : 0u;
+        sum += c[i];
+    }
+    unsigned int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned int before = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < TSCAN_THREADS / 32; ++w) {
+        const unsigned int t = s_warp[w];
+        if (w < warp) before += t;
+        block_total += t;
+    }
+    if (warp == 0) { /* decoupled look-back: ballot for the first published prefix, popc-free sum by shuffles */
+        unsigned long long exclusive = 0;
+        if (blk == 0) {
+            if (lane == 0) st_relaxed_u64(a.block_state, TS_PREFIX | block_total);
         } else {
-            if (lane == 0) st_relaxed_u64(a.tile_state + tile, TS_AGG | (unsigned long long)K);
-            long long look = (long long)tile - 1;
+            if (lane == 0) st_relaxed_u64(a.block_state + blk, TS_AGG | block_total);
+            long long look = (long long)blk - 1;
             while (true) {
                 const long long idx = look - lane;
-                unsigned long long st = TS_PREFIX; /* before tile 0: prefix 0 (tile 0 itself carries the base) */
+                unsigned long long st = TS_PREFIX;
                 if (idx >= 0) {
-                    st = ld_relaxed_u64(a.tile_state + idx);
-                    while ((st >> 62) == 0) st = ld_relaxed_u64(a.tile_state + idx);
+                    st = ld_relaxed_u64(a.block_state + idx);
+                    while ((st >> 62) == 0) st = ld_relaxed_u64(a.block_state + idx);
                 }
                 const unsigned int pmask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-                const int first = pmask ? (__ffs(pmask) - 1) : 31;
-                unsigned long long v = (lane <= first) ? (st & TS_MASK) : 0ull;
+                const int firstp = pmask ? (__ffs(pmask) - 1) : 31;
+                unsigned long long v = (lane <= firstp) ? (st & TS_MASK) : 0ull;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
                 exclusive += v;
                 if (pmask) break;
                 look -= 32;
             }
-            if (lane == 0) st_relaxed_u64(a.tile_state + tile, TS_PREFIX | (exclusive + K));
+            if (lane == 0) st_relaxed_u64(a.block_state + blk, TS_PREFIX | (exclusive + block_total));
         }
-        if (tile == a.ntiles - 1 && lane == 0) a.result[0] = exclusive + K;
-        /* ---- gather: survivors in input order; 12 columns (processLC.cpp:291-307) ---- */
-        if (K) { /* warp-uniform */
-            unsigned int before = 0;
-#pragma unroll
-            for (int w = 0; w < K1_TILE / 32; ++w) {
-                if ((unsigned)(w * 32) < C) {
-                    const unsigned int b = bits[w];
-                    if ((b >> lane) & 1u) {
-                        const unsigned int j = w * 32 + lane;
-                        const long long r = (long long)(exclusive + before + __popc(b & lane_lt));
-                        if (r < a.cap) {
-                            const long long g = base + q.idx[j];
-                            a.out.theta[r] = q.th[j];
-                            a.out.phi[r] = q.ph[j];
-                            a.out.x[r] = q.x[j];
-                            a.out.y[r] = q.y[j];
-                            a.out.z[r] = q.z[j];
-                            a.out.vx[r] = a.in.vx[g];
-                            a.out.vy[r] = a.in.vy[g];
-                            a.out.vz[r] = a.in.vz[g];
-                            a.out.redshift[r] = a_to_z_dev(a.in.a[g]);
-                            a.out.id[r] = a.in.id[g];
-                            a.out.rot[r] = a.in.rot[g];
-                            a.out.rep[r] = a.in.rep[g];
-                            if (a.out.index) a.out.index[r] = a.index_base + g;
-                        }
-                    }
-                    before += __popc(b);
-                }
+        if (lane == 0) {
+            s_excl = exclusive;
+            if (blk == a.nblocks - 1) { /* chunk total known: roll the carry */
+                const unsigned long long carry = a.result[0];
+                a.result[2] = carry;
+                a.result[0] = carry + exclusive + block_total;
             }
         }
-        __syncwarp(); /* the queue is rewritten by the next tile */
     }
-    if (lane == 0 && n_cand) atomicAdd(a.result + 1, n_cand);
+    __syncthreads();
+    unsigned int run = (unsigned int)s_excl + before + inc - sum;
+#pragma unroll
+    for (int i = 0; i < TSCAN_ITEMS; ++i) {
+        if (first + i < a.ntiles) a.tile_base[first + i] = run;
+        run += c[i];
+    }
+}
+
+/* ---- phase C: one thread per survivor record ---- */
+struct GatherConstArgs {
+    ColsIn in;   /* x,y,z: the scanned chunk; the other columns: pointers already offset to the chunk start */
+    ColsOut out;
+    const unsigned int* t_idx;
+    const float *t_th, *t_ph;
+    const unsigned int* cta_used;     /* [nregions] */
+    const unsigned long long* tile_info;
+    const unsigned int* tile_base;
+    const unsigned long long* result; /* [2] = carry: rows written by earlier chunks of a streamed step */
+    unsigned int region_cap;
+    long long cap;                    /* rows available in `out` */
+    long long index_base;             /* global index of the chunk's first particle */
+};
+
+/* grid = (blocks per region, regions) */
+__global__ void __launch_bounds__(256) k1_gather(const GatherConstArgs a) {
+    const unsigned long long carry = a.result[2];
+    const unsigned int region = blockIdx.y;
+    const unsigned int used = min(a.cta_used[region], a.region_cap);
+    const unsigned long long slot0 = (unsigned long long)region * a.region_cap;
+    for (unsigned int off = blockIdx.x * blockDim.x + threadIdx.x; off < used; off += gridDim.x * blockDim.x) {
+        const unsigned long long slot = slot0 + off;
+        const unsigned int idx = a.t_idx[slot];
+        const unsigned int tile = idx / SCAN_TILE;
+        const unsigned long long pos0 = a.tile_info[tile] >> 32;
+        const long long r = (long long)(carry + a.tile_base[tile] + (slot - pos0));
+        if (r >= a.cap) continue;
+        const long long g = idx;
+        a.out.theta[r] = a.t_th[slot];
+        a.out.phi[r] = a.t_ph[slot];
+        a.out.x[r] = a.in.x[g];
+        a.out.y[r] = a.in.y[g];
+        a.out.z[r] = a.in.z[g];
+        a.out.vx[r] = a.in.vx[g];
+        a.out.vy[r] = a.in.vy[g];
+        a.out.vz[r] = a.in.vz[g];
+        a.out.redshift[r] = a_to_z_dev(a.in.a[g]);
+        a.out.id[r] = a.in.id[g];
+        a.out.rot[r] = a.in.rot[g];
+        a.out.rep[r] = a.in.rep[g];
+        if (a.out.index) a.out.index[r] = a.index_base + g;
+    }
 }
 
 /* ================================================================================================
- * K2  use case 2: one pass, a batch of halos
+ * K2  use case 2: one pass, a batch of halos, warp-autonomous tiles
+ *
+ * Per particle (once): r^2, cos(theta_u) ~ z * rsqrt(r^2), tan(phi_u) ~ y * rcp(x), range flag.
+ * Per particle and halo: four compares against the halo's widened (cos, tan) window.  Whatever passes is pushed
+ * as a (particle, halo) pair into the warp's shared-memory queue; after the halo loop the warp drains the queue
+ * with all lanes busy: exact un-rotated angles -> rough test -> R.v -> exact rotated angles -> fine test ->
+ * survivor record (order is restored by k3_*).
  * ================================================================================================ */
-constexpr int K2_THREADS = 256;
 constexpr int K2_MAX_HALOS = 1024; /* halos per launch (pre-filter parameters live in shared memory) */
+constexpr int K2_QCAP = 512;       /* queued (particle, halo) pairs per warp (>= 2 tiles) */
 
 struct HaloDev { /* exact parameters of one halo */
     float R[9];
@@ -280,7 +413,7 @@ struct HaloDev { /* exact parameters of one halo */
     float pad[3];
 };
 struct Rec {                /* one survivor */
-    unsigned long long key; /* (bits of theta_u) << 32 | local particle index: the reference's sort order */
+    unsigned long long key; /* (bits of theta_u) << 32 | particle index in the step: the reference's sort order */
     unsigned int halo;
     float th, ph;           /* rotated, halo-centric angles (processLC.cpp:1446-1447) */
     unsigned int pad;
@@ -299,20 +432,18 @@ struct HaloArgs {
     unsigned long long* counts;      /* [2*H_total]: survivors per halo, then rough survivors per halo */
     unsigned long long* n_cand;      /* pre-filter candidates (stat) */
     int total_halos;
+    unsigned int ntiles;
 };
 
-/* exact path for one (particle, halo) pair; noinline keeps the scan loop small.  Arguments are passed by
- * value (registers) so the kernel parameter block never has to be copied to local memory. */
-__device__ __noinline__ void k2_exact(const HaloDev* __restrict__ Hp, unsigned int halo_global, Rec* recs,
-                                      unsigned long long rec_cap, unsigned long long* rec_count,
-                                      unsigned long long* counts, int total_halos, unsigned long long* n_cand,
-                                      float x, float y, float z, unsigned int local_n) {
+/* exact path for one (particle, halo) pair */
+__device__ __forceinline__ void k2_exact(const HaloArgs& a, int h, float x, float y, float z, unsigned int local_n) {
+    const HaloDev* __restrict__ Hp = a.halos + h;
+    const unsigned int hg = (unsigned int)(a.halo0 + h);
     const float thu = ccref::theta_arcsec(x, y, z);       /* processLC.cpp:899-900 */
     const float phu = ccref::phi_arcsec_guarded(x, y);    /* :903-908 */
-    atomicAdd(n_cand, 1ull);
     if (!(thu >= Hp->rth_lo && thu < Hp->rth_hi)) return; /* :1334-1340 (two lower_bounds) */
     if (!(phu > Hp->rph_lo && phu < Hp->rph_hi)) return;  /* :1400 */
-    atomicAdd(counts + total_halos + halo_global, 1ull);  /* rough_cutout_size, :1436 */
+    atomicAdd(a.counts + a.total_halos + hg, 1ull);       /* rough_cutout_size, :1436 */
     float R[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = Hp->R[i];
@@ -321,80 +452,104 @@ __device__ __noinline__ void k2_exact(const HaloDev* __restrict__ Hp, unsigned i
     const float th = ccref::theta_arcsec(rx, ry, rz);     /* :1425-1426 */
     const float ph = ccref::phi_arcsec_guarded(rx, ry);   /* :1430-1435 */
     if (th > Hp->th_lo && th < Hp->th_hi && ph > Hp->ph_lo && ph < Hp->ph_hi) { /* :1439-1440 */
-        atomicAdd(counts + halo_global, 1ull);
-        const unsigned long long slot = atomicAdd(rec_count, 1ull);
-        if (slot < rec_cap) {
+        atomicAdd(a.counts + hg, 1ull);
+        const unsigned long long slot = atomicAdd(a.rec_count, 1ull);
+        if (slot < a.rec_cap) {
             Rec r;
             r.key = ((unsigned long long)(unsigned int)__float_as_int(thu) << 32) | local_n;
-            r.halo = halo_global;
+            r.halo = hg;
             r.th = th;
             r.ph = ph;
             r.pad = 0;
-            recs[slot] = r;
+            a.recs[slot] = r;
         }
     }
 }
 
+struct K2WarpQueue {
+    unsigned int particle[K2_QCAP]; /* index inside the chunk */
+    unsigned short halo[K2_QCAP];
+};
+
+/* all lanes of the warp: run the queued (particle, halo) pairs through the exact path */
+__device__ __forceinline__ void k2_drain(const HaloArgs& a, const K2WarpQueue& q, unsigned int count, int lane) {
+    __syncwarp();
+    for (unsigned int j = lane; j < count; j += 32) {
+        const unsigned int g = q.particle[j];
+        k2_exact(a, q.halo[j], a.x[g], a.y[g], a.z[g], (unsigned int)(a.local_base + g));
+    }
+    __syncwarp();
+}
+
 template <bool VEC>
-__global__ void __launch_bounds__(K2_THREADS, 4) k2_cutout_halo(const HaloArgs a) {
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs a) {
     __shared__ float4 s_pre[K2_MAX_HALOS];
-    for (int h = threadIdx.x; h < a.nhalos; h += K2_THREADS) s_pre[h] = a.pre[h];
+    __shared__ K2WarpQueue s_q[SCAN_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    K2WarpQueue& q = s_q[warp];
+    for (int h = threadIdx.x; h < a.nhalos; h += SCAN_THREADS) s_pre[h] = a.pre[h];
     __syncthreads();
-    const long long nquads = (a.n + 3) >> 2;
-    for (long long q = (long long)blockIdx.x * K2_THREADS + threadIdx.x; q < nquads;
-         q += (long long)gridDim.x * K2_THREADS) {
-        const long long g0 = q << 2;
-        float px[4], py[4], pz[4];
-        unsigned int valid = 0xfu;
-        if (VEC && g0 + 4 <= a.n) {
-            const float4 vx = ldg_stream4(a.x + g0), vy = ldg_stream4(a.y + g0), vz = ldg_stream4(a.z + g0);
-            px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
-            py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
-            pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
-        } else {
-            valid = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (g0 + j < a.n) {
-                    px[j] = __ldcs(a.x + g0 + j); py[j] = __ldcs(a.y + g0 + j); pz[j] = __ldcs(a.z + g0 + j);
-                    valid |= 1u << j;
-                } else {
-                    px[j] = py[j] = pz[j] = 1.0f;
-                }
-            }
-        }
-        /* per-particle quantities shared by all halos: r = |v| (approx), t = y/x (approx), range flag */
-        float pr[4], pt[4];
+    const unsigned int total_warps = gridDim.x * SCAN_WARPS;
+    unsigned long long n_cand = 0;
+    unsigned int qcount = 0; /* warp-uniform */
+
+    for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
+        const long long base = (long long)tile * SCAN_TILE;
+        float px[8], py[8], pz[8];
+        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+        /* per-particle quantities shared by all halos; out-of-range particles are always candidates */
+        float pc[8], pt[8];
         unsigned int insane = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float ax = fabsf(px[j]), ay = fabsf(py[j]), az = fabsf(pz[j]);
-            const float mx = fmaxf(ax, fmaxf(ay, az));
-            /* x must be in range for the approximate reciprocal; r needs only the largest component */
-            if (!(ax >= CC_SANE_LO && mx <= CC_SANE_HI)) insane |= 1u << j;
+        for (int j = 0; j < 8; ++j) {
             const float r2 = fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j]));
-            pr[j] = r2 * rsqrtf(r2);
-            pt[j] = __fdividef(py[j], px[j]);
+            /* |x| in range keeps rcp accurate and r^2 away from underflow; r^2 <= 2^80 keeps it finite */
+            if (!((fabsf(px[j]) >= CC_SANE_LO) & (r2 <= 1.2089258e24f))) insane |= 1u << j;
+            pc[j] = pz[j] * rsqrt_fast(r2);
+            pt[j] = py[j] * rcp_fast(px[j]);
         }
         insane &= valid;
         for (int h = 0; h < a.nhalos; ++h) {
             const float4 P = s_pre[h];
-            unsigned int m = 0;
+            bool mine = insane != 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool c = (pz[j] <= P.x * pr[j]) & (pz[j] >= P.y * pr[j]) & (pt[j] >= P.z) & (pt[j] <= P.w);
-                m |= (unsigned)c << j;
-            }
-            m = (m & valid) | insane;
-            if (m) {
+            for (int j = 0; j < 8; ++j)
+                mine |= (pc[j] <= P.x) & (pc[j] >= P.y) & (pt[j] >= P.z) & (pt[j] <= P.w);
+            if (__any_sync(0xffffffffu, mine)) { /* rare, warp-uniform: queue the (particle, halo) pairs */
+                unsigned int m = insane;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (m & (1u << j))
-                        k2_exact(a.halos + h, (unsigned int)(a.halo0 + h), a.recs, a.rec_cap, a.rec_count, a.counts,
-                                 a.total_halos, a.n_cand, px[j], py[j], pz[j], (unsigned int)(a.local_base + g0 + j));
+                for (int j = 0; j < 8; ++j)
+                    m |= (unsigned)((pc[j] <= P.x) & (pc[j] >= P.y) & (pt[j] >= P.z) & (pt[j] <= P.w)) << j;
+                m &= valid;
+                const unsigned int c = __popc(m);
+                unsigned int inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                unsigned int pos = qcount + inc - c;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (m & (1u << j)) {
+                        q.particle[pos] = (unsigned int)(base + tile_local(lane, j));
+                        q.halo[pos] = (unsigned short)h;
+                        ++pos;
+                    }
+                qcount += __shfl_sync(0xffffffffu, inc, 31);
+                if (qcount > K2_QCAP - SCAN_TILE) { /* the next push may add up to a whole tile */
+                    k2_drain(a, q, qcount, lane);
+                    n_cand += qcount;
+                    qcount = 0;
+                }
             }
         }
     }
+    if (qcount) {
+        k2_drain(a, q, qcount, lane);
+        n_cand += qcount;
+    }
+    if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
 }
 
 /* ================================================================================================
