@@ -184,13 +184,14 @@ def run_ours(args):
         time.sleep(0.25)
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms, survivors, scanned = [], 0, 0
+    scan_ms, pass_ms, survivors, scanned = [], [], 0, 0
     barrier()
     t0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
         scan_ms.append(ctx.last_scan_ms())
+        pass_ms.append(ctx.last_total_ms())
     ev1.record(stream)
     barrier()
     t1 = time.time()
@@ -260,9 +261,15 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         ms_per_step = ms_total / args.steps
         value = n_total / (ms_per_step * 1e-3) / 1e9
-        # roofline of the dominant kernel, per launch on this GPU (rank 0's shard)
-        alg_bytes = 12.0 * scanned + bytes_per_survivor * survivors
+        # roofline of the dominant kernel (the scan), per launch on this GPU (rank 0's shard): it reads x,y,z of
+        # every particle (12 B) and writes one 12-byte (index, theta, phi) record per survivor (use case 1) or one
+        # 24-byte record per survivor (use case 2); the whole pass (scan + ordering + 12-column gather) moves
+        # 12 B per particle + 84 B per survivor and is reported next to it
+        rec_bytes = 12 if wl["uc"] == 1 else 24
+        alg_bytes = 12.0 * scanned + rec_bytes * survivors
         achieved = alg_bytes / (float(np.mean(scan_ms)) * 1e-3) / 1e9
+        pass_bytes = 12.0 * scanned + bytes_per_survivor * survivors
+        pass_gbs = pass_bytes / (float(np.mean(pass_ms)) * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -281,8 +288,11 @@ def run_ours(args):
                        "timing": "CUDA events on the cutout stream around all timed steps, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k2_cutout_halo" if wl["uc"] == 2 else "k1_cutout_const",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(float(np.mean(scan_ms)), 4)},
+                         "kernel": "k2_cutout_halo" if wl["uc"] == 2 else "k1_scan",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(float(np.mean(scan_ms)), 4),
+                         "whole_pass": {"bytes": pass_bytes, "ms": round(float(np.mean(pass_ms)), 4),
+                                        "achieved": round(pass_gbs, 1), "frac": round(pass_gbs / peak, 4),
+                                        "what": "scan + ordering + gather kernels, 12 B/particle + 84 B/survivor"}},
             "e2e": {"value": round(e2e_n * world / (e2e_ms / e2e_steps * 1e-3) / 1e9, 4), "unit": "Gparticles/s",
                     "h2d_bytes_per_step": 12 * e2e_n, "d2h_bytes_per_step": d2h, "particles_per_gpu": e2e_n,
                     "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),

@@ -130,7 +130,7 @@ struct cc_ctx {
     int k1_occupancy[2] = {0, 0};
     int k2_occupancy[2] = {0, 0};
     unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
-    DevBuf t_idx, t_th, t_ph;
+    DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z, t_row;
 
     /* resident step */
     bool step_valid = false, step_owned = false;
@@ -146,6 +146,10 @@ struct cc_ctx {
     DevBuf scratch;
     /* use case 2 scratch */
     DevBuf pre_buf, halo_buf, rec_a, rec_b, rank_buf, counts_buf, seg_buf, cursor_buf, misc_buf;
+    DevBuf bin_start_buf, bin_items_buf, ovf_particle_buf, ovf_halo_buf;
+    std::vector<size_t> bin_items_off; /* per launch batch: first item */
+    int64_t ovf_cap = 0;
+    bool use_bins = false;
     int64_t rec_cap = 0;
 
     /* pinned host mirror for small read-backs */
@@ -276,7 +280,9 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
     /* temp records: one private region per CTA */
     if (c->region_cap == 0) c->region_cap = (unsigned int)std::min<int64_t>(0x7fffffff, c->out_cap + c->out_cap / 4) / grid_max + 256;
     const size_t temp_elems = (size_t)grid_max * c->region_cap;
-    if ((rc = c->t_idx.ensure(temp_elems * 4)) || (rc = c->t_th.ensure(temp_elems * 4)) || (rc = c->t_ph.ensure(temp_elems * 4))) return rc;
+    DevBuf* temps[] = {&c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row};
+    for (DevBuf* t : temps)
+        if ((rc = t->ensure(temp_elems * 4))) return rc;
     char* sp = (char*)c->scratch.p;
     if (ch.first) CU(cudaMemsetAsync(sp, 0, off_info, c->stream));                     /* totals + ticket + block states */
     else CU(cudaMemsetAsync(sp + 32, 0, off_info - 32, c->stream));                    /* keep the running totals */
@@ -289,6 +295,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         a.th_lo = c->p_th[0]; a.th_hi = c->p_th[1]; a.ph_lo = c->p_ph[0]; a.ph_hi = c->p_ph[1];
         ccpf::uc1_bounds(c->p_th, c->p_ph, &a.chi2, &a.clo2, &a.tlo, &a.thi);
         a.t_idx = (unsigned int*)c->t_idx.p; a.t_th = (float*)c->t_th.p; a.t_ph = (float*)c->t_ph.p;
+        a.t_x = (float*)c->t_x.p; a.t_y = (float*)c->t_y.p; a.t_z = (float*)c->t_z.p;
         a.region_cap = c->region_cap;
         a.cta_used = (unsigned int*)(sp + off_used);
         a.tile_info = (unsigned long long*)(sp + off_info);
@@ -301,7 +308,8 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
 
         cck::TileScanArgs t;
         t.tile_info = a.tile_info;
-        t.tile_base = (unsigned int*)(sp + off_base);
+        t.t_row = (unsigned int*)c->t_row.p;
+        t.temp_cap = (unsigned long long)temp_elems;
         t.block_state = (unsigned long long*)(sp + off_state);
         t.ticket = (unsigned int*)(sp + 32);
         t.result = result;
@@ -315,13 +323,11 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         /* survivor columns other than x,y,z are indexed by the chunk-local particle index */
         g.in.vx += ch.start; g.in.vy += ch.start; g.in.vz += ch.start; g.in.a += ch.start; g.in.id += ch.start;
         g.in.rot += ch.start; g.in.rep += ch.start;
-        g.in.x = ch.x; g.in.y = ch.y; g.in.z = ch.z;
         g.out = cols_out_of(c);
         g.out.theta_u = nullptr;
-        g.t_idx = a.t_idx; g.t_th = a.t_th; g.t_ph = a.t_ph;
+        g.t_idx = a.t_idx; g.t_row = t.t_row; g.t_th = a.t_th; g.t_ph = a.t_ph;
+        g.t_x = a.t_x; g.t_y = a.t_y; g.t_z = a.t_z;
         g.cta_used = a.cta_used;
-        g.tile_info = a.tile_info;
-        g.tile_base = t.tile_base;
         g.result = result;
         g.region_cap = c->region_cap;
         g.cap = c->out_cap;
@@ -371,7 +377,7 @@ int prepare_halo(cc_ctx* c) {
     if ((rc = c->rec_b.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
     if ((rc = c->rank_buf.ensure((size_t)c->rec_cap * 4))) return rc;
     if ((rc = ensure_out_cap(c, c->rec_cap))) return rc;
-    if ((rc = ensure_small(c, 16 + 3 * (size_t)H + 1))) return rc;
+    if ((rc = ensure_small(c, 24 + 3 * (size_t)H + 1))) return rc;
 
     /* host: exact + pre-filter parameters */
     std::vector<float4> pre(H);
@@ -386,6 +392,44 @@ int prepare_halo(cc_ctx* c) {
         for (int i = 0; i < 9; ++i) d.R[i] = s.R[i];
         d.th_lo = s.theta_cut[0]; d.th_hi = s.theta_cut[1]; d.ph_lo = s.phi_cut[0]; d.ph_hi = s.phi_cut[1];
         d.rth_lo = s.theta_rough[0]; d.rth_hi = s.theta_rough[1]; d.rph_lo = s.phi_rough[0]; d.rph_hi = s.phi_rough[1];
+    }
+    /* many halos: cos(theta_u) bin index per launch batch (kernels.cuh, k2_cutout_halo_binned) */
+    c->use_bins = H >= 8 && !getenv("CC_NO_BINS");
+    if (c->use_bins) {
+        const int NB = cck::K2_NBINS;
+        const int nbatch = (H + cck::K2_MAX_HALOS - 1) / cck::K2_MAX_HALOS;
+        std::vector<unsigned int> starts((size_t)nbatch * (NB + 1));
+        std::vector<unsigned short> items;
+        c->bin_items_off.assign((size_t)nbatch, 0);
+        for (int bi = 0; bi < nbatch; ++bi) {
+            const int h0 = bi * cck::K2_MAX_HALOS, hn = std::min(cck::K2_MAX_HALOS, H - h0);
+            std::vector<std::vector<unsigned short>> lists((size_t)NB);
+            for (int h = 0; h < hn; ++h) {
+                const double chi = pre[h0 + h].x, clo = pre[h0 + h].y;
+                if (!(clo <= chi)) continue; /* empty or NaN window: only out-of-range particles reach the exact path */
+                double lo = std::floor((std::max(clo, -1.0) + 1.0) * (0.5 * NB)) - 1.0;
+                double hi = std::floor((std::min(chi, 1.0) + 1.0) * (0.5 * NB)) + 1.0;
+                const int blo = (int)std::max(0.0, std::min((double)NB - 1, lo)), bhi = (int)std::max(0.0, std::min((double)NB - 1, hi));
+                for (int b = blo; b <= bhi; ++b) lists[(size_t)b].push_back((unsigned short)h);
+            }
+            c->bin_items_off[(size_t)bi] = items.size();
+            unsigned int run = 0;
+            for (int b = 0; b < NB; ++b) {
+                starts[(size_t)bi * (NB + 1) + b] = run;
+                items.insert(items.end(), lists[(size_t)b].begin(), lists[(size_t)b].end());
+                run += (unsigned int)lists[(size_t)b].size();
+            }
+            starts[(size_t)bi * (NB + 1) + NB] = run;
+        }
+        if (c->ovf_cap == 0) c->ovf_cap = 1 << 22;
+        if ((rc = c->bin_start_buf.ensure(starts.size() * 4))) return rc;
+        if ((rc = c->bin_items_buf.ensure(std::max<size_t>(items.size(), 8) * 2))) return rc;
+        if ((rc = c->ovf_particle_buf.ensure((size_t)c->ovf_cap * 4))) return rc;
+        if ((rc = c->ovf_halo_buf.ensure((size_t)c->ovf_cap * 2))) return rc;
+        CU(cudaMemcpyAsync(c->bin_start_buf.p, starts.data(), starts.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!items.empty())
+            CU(cudaMemcpyAsync(c->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream)); /* `starts`/`items` are pageable and die here */
     }
     /* pageable -> device copies are staged by the runtime before returning, so the vectors may die */
     CU(cudaMemcpyAsync(c->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -427,10 +471,29 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             if (occ < 1) occ = 1;
         }
         const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
-        if (vec) cck::k2_cutout_halo<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
-        else cck::k2_cutout_halo<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
-        CU(cudaGetLastError());
-        c->launches += 1;
+        if (c->use_bins) {
+            cck::HaloBinArgs b;
+            b.h = a;
+            const int bi = h0 / cck::K2_MAX_HALOS;
+            b.bin_start = (const unsigned int*)c->bin_start_buf.p + (size_t)bi * (cck::K2_NBINS + 1);
+            b.bin_items = (const unsigned short*)c->bin_items_buf.p + c->bin_items_off[(size_t)bi];
+            b.ovf_particle = (unsigned int*)c->ovf_particle_buf.p;
+            b.ovf_halo = (unsigned short*)c->ovf_halo_buf.p;
+            b.ovf_cap = (unsigned long long)c->ovf_cap;
+            b.ovf_count = rec_count + 2;
+            if (vec) cck::k2_cutout_halo_binned<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
+            else cck::k2_cutout_halo_binned<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
+            CU(cudaGetLastError());
+            cck::k2_overflow<<<c->sm_count * 4, 256, 0, c->stream>>>(b);
+            CU(cudaGetLastError());
+            CU(cudaMemsetAsync(rec_count + 2, 0, 8, c->stream)); /* the overflow queue is per launch */
+            c->launches += 2;
+        } else {
+            if (vec) cck::k2_cutout_halo<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+            else cck::k2_cutout_halo<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+            CU(cudaGetLastError());
+            c->launches += 1;
+        }
     }
     if (ch.last) {
         CU(cudaEventRecord(c->ev_scan1, c->stream));
@@ -438,9 +501,9 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
                                                       (unsigned long long*)c->seg_buf.p, H);
         CU(cudaGetLastError());
         c->launches += 1;
-        CU(cudaMemcpyAsync(c->h_small, c->misc_buf.p, 16, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(c->h_small + 2, c->counts_buf.p, (size_t)(2 * H) * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(c->h_small + 2 + 2 * H, c->seg_buf.p, (size_t)(H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_small, c->misc_buf.p, 32, cudaMemcpyDeviceToHost, c->stream)); /* rec_count, n_cand, -, ovf_max */
+        CU(cudaMemcpyAsync(c->h_small + 8, c->counts_buf.p, (size_t)(2 * H) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_small + 8 + 2 * H, c->seg_buf.p, (size_t)(H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     }
     return CC_OK;
 }
@@ -584,6 +647,10 @@ int cc_create(int device, cc_ctx** out) {
     int rc = check_sm100(device, &sms);
     if (rc) return rc;
     CU(cudaSetDevice(device));
+    if (const char* e = getenv("CC_L2_FETCH")) { /* experiment knob: 32 / 64 / 128 bytes */
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+        cudaGetLastError();
+    }
     cc_ctx* c = new cc_ctx();
     c->device = device;
     c->sm_count = sms;
@@ -607,7 +674,8 @@ void cc_destroy(cc_ctx* c) {
     for (auto& b : c->col_buf) b.release();
     for (auto& b : c->out_buf) b.release();
     DevBuf* rest[] = {&c->scratch, &c->pre_buf, &c->halo_buf, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
-                      &c->seg_buf, &c->cursor_buf, &c->misc_buf, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph};
+                      &c->seg_buf, &c->cursor_buf, &c->misc_buf, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row,
+                      &c->bin_start_buf, &c->bin_items_buf, &c->ovf_particle_buf, &c->ovf_halo_buf};
     for (DevBuf* b : rest) b->release();
     for (auto& sl : c->stage) for (auto& b : sl) b.release();
     for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
@@ -802,22 +870,24 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             c->stats[0] = c->n; c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = c->counts[0]; c->stats[3] = 0;
         } else {
             const int H = c->nhalos;
-            for (int attempt = 0; attempt < 3; ++attempt) {
+            for (int attempt = 0; attempt < 4; ++attempt) {
                 CU(cudaStreamSynchronize(c->stream));
-                const int64_t nrec = (int64_t)c->h_small[0];
-                if (nrec <= c->rec_cap) break;
-                c->rec_cap = nrec + nrec / 64;
+                const int64_t nrec = (int64_t)c->h_small[0], ovf_max = (int64_t)c->h_small[3];
+                if (nrec <= c->rec_cap && ovf_max <= c->ovf_cap) break;
+                if (attempt == 3) return fail(CC_ERR_CUDA, "internal: halo survivor buffers still too small after regrowth");
+                if (nrec > c->rec_cap) c->rec_cap = nrec + nrec / 64;
+                if (ovf_max > c->ovf_cap) c->ovf_cap = ovf_max + ovf_max / 8;
                 if ((rc = run_pending(c))) return rc;
             }
             const int64_t nrec = (int64_t)c->h_small[0];
             c->counts.resize(H); c->rough.resize(H); c->seg_begin.resize(H + 1);
             int64_t tot = 0, tot_rough = 0;
             for (int h = 0; h < H; ++h) {
-                c->counts[h] = (int64_t)c->h_small[2 + h];
-                c->rough[h] = (int64_t)c->h_small[2 + H + h];
+                c->counts[h] = (int64_t)c->h_small[8 + h];
+                c->rough[h] = (int64_t)c->h_small[8 + H + h];
                 tot += c->counts[h]; tot_rough += c->rough[h];
             }
-            for (int h = 0; h <= H; ++h) c->seg_begin[h] = (int64_t)c->h_small[2 + 2 * H + h];
+            for (int h = 0; h <= H; ++h) c->seg_begin[h] = (int64_t)c->h_small[8 + 2 * H + h];
             if (tot != nrec) return fail(CC_ERR_CUDA, "internal: record count %lld != sum of halo counts %lld", (long long)nrec, (long long)tot);
             c->stats[0] = halo_scan_limit(c); c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = tot; c->stats[3] = tot_rough;
             if ((rc = finish_halo(c, (unsigned long long)nrec))) return rc;

@@ -132,6 +132,8 @@ struct ScanArgs {
     float chi2, clo2, tlo, thi;       /* pre-filter (prefilter.h) */
     unsigned int* t_idx;              /* temp records: particle index inside the chunk */
     float *t_th, *t_ph;               /*               theta, phi (arcsec) */
+    float *t_x, *t_y, *t_z;           /*               the position (already in registers here: saves three
+                                                       scattered 4-byte reads per survivor in the gather) */
     unsigned int region_cap;          /* records per CTA region */
     unsigned int* cta_used;           /* [grid] records the CTA appended (> region_cap means overflow) */
     unsigned long long* tile_info;    /* [ntiles] (temp position << 32) | survivors of the tile */
@@ -139,14 +141,18 @@ struct ScanArgs {
     unsigned int ntiles;
 };
 
+/* branch-free on purpose: eight of these run back to back per lane and divergent early-outs cost more than the
+ * arithmetic they skip.  NaN coordinates fail `mn > 0` only if all three are NaN; a NaN in one coordinate makes
+ * either the window compares false (rejected, like the reference: x>0 && y>0 && z>0 is false for a NaN) or the
+ * particle a candidate, and the exact path rejects it. */
 __device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const ScanArgs& a) {
     const float mn = fminf(x, fminf(y, z));
     const float mx = fmaxf(x, fmaxf(y, z));
-    if (!(mn > 0.0f)) return false;                            /* octant test, processLC.cpp:279 */
-    if (!(mn >= CC_SANE_LO && mx <= CC_SANE_HI)) return true;  /* let the exact path decide */
     const float r2 = fmaf(z, z, fmaf(y, y, x * x));
     const float z2 = z * z;
-    return (z2 < a.chi2 * r2) & (z2 > a.clo2 * r2) & (y > a.tlo * x) & (y < a.thi * x);
+    const bool window = (z2 < a.chi2 * r2) & (z2 > a.clo2 * r2) & (y > a.tlo * x) & (y < a.thi * x);
+    const bool insane = !((mn >= CC_SANE_LO) & (mx <= CC_SANE_HI)); /* let the exact path decide */
+    return (mn > 0.0f) & (window | insane);                         /* octant test, processLC.cpp:279 */
 }
 
 struct K1WarpQueue { /* one per warp: candidates of the current tile */
@@ -240,6 +246,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k1_scan(const ScanArgs a) {
                                 a.t_idx[region0 + slot] = (unsigned int)(base + q.idx[j]);
                                 a.t_th[region0 + slot] = q.th[j];
                                 a.t_ph[region0 + slot] = q.ph[j];
+                                a.t_x[region0 + slot] = q.x[j];
+                                a.t_y[region0 + slot] = q.y[j];
+                                a.t_z[region0 + slot] = q.z[j];
                             }
                         }
                         before += __popc(b);
@@ -268,8 +277,9 @@ constexpr unsigned long long TS_PREFIX = 2ull << 62;
 constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
 
 struct TileScanArgs {
-    const unsigned long long* tile_info; /* [ntiles] low 32 bits = count */
-    unsigned int* tile_base;             /* [ntiles] exclusive prefix inside the chunk */
+    const unsigned long long* tile_info; /* [ntiles] (temp position << 32) | count */
+    unsigned int* t_row;                 /* per temp record: output row inside the chunk (streamed by the gather) */
+    unsigned long long temp_cap;         /* records the temp buffer holds (regions x region_cap) */
     unsigned long long* block_state;     /* [nblocks] zeroed before launch */
     unsigned int* ticket;                /* zeroed before launch */
     unsigned long long* result;          /* [0] survivors so far (in: carry, out: carry + chunk total), [2] = carry */
@@ -344,27 +354,30 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
     unsigned int run = (unsigned int)s_excl + before + inc - sum;
 #pragma unroll
     for (int i = 0; i < TSCAN_ITEMS; ++i) {
-        if (first + i < a.ntiles) a.tile_base[first + i] = run;
+        if (c[i]) { /* rows of this tile's records: consecutive, in input order */
+            const unsigned long long pos0 = a.tile_info[first + i] >> 32;
+            for (unsigned int k = 0; k < c[i]; ++k)
+                if (pos0 + k < a.temp_cap) a.t_row[pos0 + k] = run + k;
+        }
         run += c[i];
     }
 }
 
 /* ---- phase C: one thread per survivor record ---- */
 struct GatherConstArgs {
-    ColsIn in;   /* x,y,z: the scanned chunk; the other columns: pointers already offset to the chunk start */
+    ColsIn in;   /* columns other than x,y,z: pointers already offset to the chunk start */
     ColsOut out;
-    const unsigned int* t_idx;
-    const float *t_th, *t_ph;
+    const unsigned int *t_idx, *t_row;
+    const float *t_th, *t_ph, *t_x, *t_y, *t_z;
     const unsigned int* cta_used;     /* [nregions] */
-    const unsigned long long* tile_info;
-    const unsigned int* tile_base;
     const unsigned long long* result; /* [2] = carry: rows written by earlier chunks of a streamed step */
     unsigned int region_cap;
     long long cap;                    /* rows available in `out` */
     long long index_base;             /* global index of the chunk's first particle */
 };
 
-/* grid = (blocks per region, regions) */
+/* grid = (blocks per region, regions); every per-record input is a coalesced stream, only the seven columns
+ * that the scan never touched (vx,vy,vz,a,id,rotation,replication) are gathered */
 __global__ void __launch_bounds__(256) k1_gather(const GatherConstArgs a) {
     const unsigned long long carry = a.result[2];
     const unsigned int region = blockIdx.y;
@@ -372,17 +385,14 @@ __global__ void __launch_bounds__(256) k1_gather(const GatherConstArgs a) {
     const unsigned long long slot0 = (unsigned long long)region * a.region_cap;
     for (unsigned int off = blockIdx.x * blockDim.x + threadIdx.x; off < used; off += gridDim.x * blockDim.x) {
         const unsigned long long slot = slot0 + off;
-        const unsigned int idx = a.t_idx[slot];
-        const unsigned int tile = idx / SCAN_TILE;
-        const unsigned long long pos0 = a.tile_info[tile] >> 32;
-        const long long r = (long long)(carry + a.tile_base[tile] + (slot - pos0));
+        const long long r = (long long)(carry + a.t_row[slot]);
         if (r >= a.cap) continue;
-        const long long g = idx;
+        const long long g = a.t_idx[slot];
         a.out.theta[r] = a.t_th[slot];
         a.out.phi[r] = a.t_ph[slot];
-        a.out.x[r] = a.in.x[g];
-        a.out.y[r] = a.in.y[g];
-        a.out.z[r] = a.in.z[g];
+        a.out.x[r] = a.t_x[slot];
+        a.out.y[r] = a.t_y[slot];
+        a.out.z[r] = a.t_z[slot];
         a.out.vx[r] = a.in.vx[g];
         a.out.vy[r] = a.in.vy[g];
         a.out.vz[r] = a.in.vz[g];
@@ -550,6 +560,115 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs
         n_cand += qcount;
     }
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
+}
+
+/* ---- many halos: a coarse cos(theta_u) bin index over the halos of the launch ------------------------------------
+ * With hundreds of halos per pass the loop "every particle x every halo" is compute-bound.  The host sorts the
+ * halos of a launch into K2_NBINS equal-width bins of cos(theta_u) (each halo is listed in every bin its widened
+ * [clo, chi] interval touches, +-1 bin of slack); a particle then only tests the halos listed in its own bin
+ * (~1 % of them for cluster-sized boxes).  This plays the role of the reference's theta-sorted index
+ * (processLC.cpp:1214-1221, :1334-1340) without sorting 12 B/particle data.  Pairs that pass go to the warp queue;
+ * pairs that do not fit go to a global overflow queue drained by k2_overflow. */
+constexpr int K2_NBINS = 2048;
+constexpr int K2B_QCAP = 256; /* warp queue of the binned kernel (the rest goes to the global overflow queue) */
+struct K2BWarpQueue {
+    unsigned int particle[K2B_QCAP];
+    unsigned short halo[K2B_QCAP];
+};
+
+struct HaloBinArgs {
+    HaloArgs h;
+    const unsigned int* bin_start;    /* [K2_NBINS + 1] */
+    const unsigned short* bin_items;  /* halo index inside the launch */
+    unsigned int* ovf_particle;       /* overflow pairs: particle index inside the chunk */
+    unsigned short* ovf_halo;
+    unsigned long long ovf_cap;
+    unsigned long long* ovf_count;    /* may exceed ovf_cap: detected on the host */
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo_binned(const HaloBinArgs b) {
+    __shared__ float4 s_pre[K2_MAX_HALOS];
+    __shared__ unsigned int s_bin[K2_NBINS + 1];
+    __shared__ K2BWarpQueue s_q[SCAN_WARPS];
+    __shared__ unsigned int s_qcount[SCAN_WARPS];
+    const HaloArgs& a = b.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    K2BWarpQueue& q = s_q[warp];
+    for (int h = threadIdx.x; h < a.nhalos; h += SCAN_THREADS) s_pre[h] = a.pre[h];
+    for (int i = threadIdx.x; i <= K2_NBINS; i += SCAN_THREADS) s_bin[i] = b.bin_start[i];
+    if (lane == 0) s_qcount[warp] = 0;
+    __syncthreads();
+    const unsigned int total_warps = gridDim.x * SCAN_WARPS;
+    unsigned long long n_cand = 0;
+
+    for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
+        const long long base = (long long)tile * SCAN_TILE;
+        float px[8], py[8], pz[8];
+        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!(valid & (1u << j))) continue;
+            const float r2 = fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j]));
+            const bool insane = !((fabsf(px[j]) >= CC_SANE_LO) & (r2 <= 1.2089258e24f));
+            const float c = pz[j] * rsqrt_fast(r2);
+            const float t = py[j] * rcp_fast(px[j]);
+            const unsigned int g = (unsigned int)(base + tile_local(lane, j));
+            unsigned int k0, k1;
+            if (insane) { /* the exact path decides, against every halo of the launch */
+                k0 = 0; k1 = (unsigned int)a.nhalos;
+            } else {
+                int bin = (int)((c + 1.0f) * (0.5f * K2_NBINS));
+                bin = max(0, min(K2_NBINS - 1, bin));
+                k0 = s_bin[bin]; k1 = s_bin[bin + 1];
+            }
+            for (unsigned int k = k0; k < k1; ++k) {
+                const unsigned int h = insane ? k : (unsigned int)b.bin_items[k];
+                const float4 P = s_pre[h];
+                if (insane | ((c <= P.x) & (c >= P.y) & (t >= P.z) & (t <= P.w))) {
+                    const unsigned int pos = atomicAdd(&s_qcount[warp], 1u);
+                    if (pos < K2B_QCAP) {
+                        q.particle[pos] = g;
+                        q.halo[pos] = (unsigned short)h;
+                    } else {
+                        const unsigned long long o = atomicAdd(b.ovf_count, 1ull);
+                        if (o < b.ovf_cap) {
+                            b.ovf_particle[o] = g;
+                            b.ovf_halo[o] = (unsigned short)h;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        const unsigned int cnt = min(s_qcount[warp], (unsigned int)K2B_QCAP);
+        if (cnt) { /* warp-uniform */
+            for (unsigned int jq = lane; jq < cnt; jq += 32) {
+                const unsigned int gq = q.particle[jq];
+                k2_exact(a, q.halo[jq], a.x[gq], a.y[gq], a.z[gq], (unsigned int)(a.local_base + gq));
+            }
+            __syncwarp();
+            n_cand += cnt;
+            if (lane == 0) s_qcount[warp] = 0;
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
+}
+
+/* pairs that did not fit a warp queue */
+__global__ void __launch_bounds__(256) k2_overflow(const HaloBinArgs b) {
+    const unsigned long long wanted = *b.ovf_count;
+    const unsigned long long n = min(wanted, b.ovf_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && wanted) atomicMax(b.ovf_count + 1, wanted); /* host: overflow check */
+    unsigned long long mine = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned int g = b.ovf_particle[i];
+        k2_exact(b.h, b.ovf_halo[i], b.h.x[g], b.h.y[g], b.h.z[g], (unsigned int)(b.h.local_base + g));
+        ++mine;
+    }
+    if (mine) atomicAdd(b.h.n_cand, mine);
 }
 
 /* ================================================================================================
