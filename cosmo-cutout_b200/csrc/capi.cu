@@ -128,6 +128,7 @@ struct cc_ctx {
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr, ev_total1 = nullptr;
     int64_t launches = 0;
     int k1_occupancy[2] = {0, 0};
+    int k1_minb = 4; /* CTAs per SM the scan kernel is compiled for (CC_K1_MINB=3: more registers, no spill) */
     int k2_occupancy[2] = {0, 0};
     unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
     DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z, t_row;
@@ -150,6 +151,7 @@ struct cc_ctx {
     std::vector<size_t> bin_items_off; /* per launch batch: first item */
     int64_t ovf_cap = 0;
     bool use_bins = false;
+    std::vector<cc_halo> index_key; /* halos the resident cell index was built for */
     int64_t rec_cap = 0;
 
     /* pinned host mirror for small read-backs */
@@ -249,11 +251,16 @@ struct Chunk {
  * [2] carry seen by the current chunk's gather, [3] max records any CTA wanted (temp-region overflow check) */
 const size_t K1_HDR = 64;
 
+typedef void (*k1_scan_fn)(const cck::ScanArgs);
+k1_scan_fn k1_scan_variant(const cc_ctx* c, bool vec) {
+    if (c->k1_minb == 3) return vec ? cck::k1_scan<true, 3> : cck::k1_scan<false, 3>;
+    return vec ? cck::k1_scan<true, 4> : cck::k1_scan<false, 4>;
+}
+
 int k1_grid_limit(cc_ctx* c, bool vec, unsigned int* out) {
     int& occ = c->k1_occupancy[vec ? 1 : 0];
     if (occ == 0) {
-        const void* fn = vec ? (const void*)cck::k1_scan<true> : (const void*)cck::k1_scan<false>;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cck::SCAN_THREADS, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k1_scan_variant(c, vec), cck::SCAN_THREADS, 0));
         if (occ < 1) return fail(CC_ERR_CUDA, "k1_scan cannot be resident on this device");
     }
     *out = (unsigned int)(c->sm_count * occ);
@@ -301,8 +308,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         a.tile_info = (unsigned long long*)(sp + off_info);
         a.result = result;
         a.ntiles = ntiles;
-        if (vec) cck::k1_scan<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
-        else cck::k1_scan<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+        k1_scan_variant(c, vec)<<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
         CU(cudaGetLastError());
         if (ch.last) CU(cudaEventRecord(c->ev_scan1, c->stream));
 
@@ -393,43 +399,65 @@ int prepare_halo(cc_ctx* c) {
         d.th_lo = s.theta_cut[0]; d.th_hi = s.theta_cut[1]; d.ph_lo = s.phi_cut[0]; d.ph_hi = s.phi_cut[1];
         d.rth_lo = s.theta_rough[0]; d.rth_hi = s.theta_rough[1]; d.rph_lo = s.phi_rough[0]; d.rph_hi = s.phi_rough[1];
     }
-    /* many halos: cos(theta_u) bin index per launch batch (kernels.cuh, k2_cutout_halo_binned) */
+    /* many halos: (cos theta, sin phi) cell index per launch batch (kernels.cuh, k2_cutout_halo_cells) */
     c->use_bins = H >= 8 && !getenv("CC_NO_BINS");
     if (c->use_bins) {
-        const int NB = cck::K2_NBINS;
+        const int G = cck::K2_GRID;
+        const size_t ncell = (size_t)G * G;
         const int nbatch = (H + cck::K2_MAX_HALOS - 1) / cck::K2_MAX_HALOS;
-        std::vector<unsigned int> starts((size_t)nbatch * (NB + 1));
-        std::vector<unsigned short> items;
-        c->bin_items_off.assign((size_t)nbatch, 0);
-        for (int bi = 0; bi < nbatch; ++bi) {
-            const int h0 = bi * cck::K2_MAX_HALOS, hn = std::min(cck::K2_MAX_HALOS, H - h0);
-            std::vector<std::vector<unsigned short>> lists((size_t)NB);
-            for (int h = 0; h < hn; ++h) {
-                const double chi = pre[h0 + h].x, clo = pre[h0 + h].y;
-                if (!(clo <= chi)) continue; /* empty or NaN window: only out-of-range particles reach the exact path */
-                double lo = std::floor((std::max(clo, -1.0) + 1.0) * (0.5 * NB)) - 1.0;
-                double hi = std::floor((std::min(chi, 1.0) + 1.0) * (0.5 * NB)) + 1.0;
-                const int blo = (int)std::max(0.0, std::min((double)NB - 1, lo)), bhi = (int)std::max(0.0, std::min((double)NB - 1, hi));
-                for (int b = blo; b <= bhi; ++b) lists[(size_t)b].push_back((unsigned short)h);
+        for (int h = 0; h < H; ++h) { /* the cell kernel tests sin(phi), not tan(phi) */
+            float p4[4];
+            ccpf::uc2_bounds_cells(c->p_halos[h].theta_rough, c->p_halos[h].phi_rough, p4);
+            pre[h] = make_float4(p4[0], p4[1], p4[2], p4[3]);
+        }
+        const bool same = c->index_key.size() == c->p_halos.size() &&
+                          memcmp(c->index_key.data(), c->p_halos.data(), c->p_halos.size() * sizeof(cc_halo)) == 0;
+        if (!same) { /* rasterise every halo's window, then a counting sort into CSR lists */
+            struct Box { int c0, c1, s0, s1; };
+            auto cell_of = [G](double v) { return std::floor((v + 1.0) * (0.5 * G)); };
+            std::vector<unsigned int> starts((size_t)nbatch * (ncell + 1));
+            std::vector<unsigned short> items;
+            c->bin_items_off.assign((size_t)nbatch, 0);
+            for (int bi = 0; bi < nbatch; ++bi) {
+                const int h0 = bi * cck::K2_MAX_HALOS, hn = std::min(cck::K2_MAX_HALOS, H - h0);
+                unsigned int* st = starts.data() + (size_t)bi * (ncell + 1);
+                std::vector<Box> boxes((size_t)hn);
+                for (int h = 0; h < hn; ++h) {
+                    const float4 P = pre[h0 + h];
+                    Box bx = {0, -1, 0, -1}; /* empty */
+                    if (P.y <= P.x && P.z <= P.w) {
+                        auto clampi = [G](double v) { return (int)std::max(0.0, std::min((double)G - 1, v)); };
+                        bx.c0 = clampi(cell_of(std::max<double>(P.y, -1.0)) - 1.0);
+                        bx.c1 = clampi(cell_of(std::min<double>(P.x, 1.0)) + 1.0);
+                        bx.s0 = clampi(cell_of(std::max<double>(P.z, -1.0)) - 1.0);
+                        bx.s1 = clampi(cell_of(std::min<double>(P.w, 1.0)) + 1.0);
+                    }
+                    boxes[(size_t)h] = bx;
+                    for (int ic = bx.c0; ic <= bx.c1; ++ic)
+                        for (int is = bx.s0; is <= bx.s1; ++is) st[(size_t)ic * G + is + 1] += 1;
+                }
+                for (size_t i = 0; i < ncell; ++i) st[i + 1] += st[i]; /* st[i] = first item of cell i */
+                const size_t base_item = items.size();
+                c->bin_items_off[(size_t)bi] = base_item;
+                items.resize(base_item + st[ncell]);
+                std::vector<unsigned int> fill(st, st + ncell);
+                for (int h = 0; h < hn; ++h) {
+                    const Box& bx = boxes[(size_t)h];
+                    for (int ic = bx.c0; ic <= bx.c1; ++ic)
+                        for (int is = bx.s0; is <= bx.s1; ++is) items[base_item + fill[(size_t)ic * G + is]++] = (unsigned short)h;
+                }
             }
-            c->bin_items_off[(size_t)bi] = items.size();
-            unsigned int run = 0;
-            for (int b = 0; b < NB; ++b) {
-                starts[(size_t)bi * (NB + 1) + b] = run;
-                items.insert(items.end(), lists[(size_t)b].begin(), lists[(size_t)b].end());
-                run += (unsigned int)lists[(size_t)b].size();
-            }
-            starts[(size_t)bi * (NB + 1) + NB] = run;
+            if ((rc = c->bin_start_buf.ensure(starts.size() * 4))) return rc;
+            if ((rc = c->bin_items_buf.ensure(std::max<size_t>(items.size(), 8) * 2))) return rc;
+            CU(cudaMemcpyAsync(c->bin_start_buf.p, starts.data(), starts.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            if (!items.empty())
+                CU(cudaMemcpyAsync(c->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream)); /* `starts`/`items` are pageable and die here */
+            c->index_key = c->p_halos;
         }
         if (c->ovf_cap == 0) c->ovf_cap = 1 << 22;
-        if ((rc = c->bin_start_buf.ensure(starts.size() * 4))) return rc;
-        if ((rc = c->bin_items_buf.ensure(std::max<size_t>(items.size(), 8) * 2))) return rc;
         if ((rc = c->ovf_particle_buf.ensure((size_t)c->ovf_cap * 4))) return rc;
         if ((rc = c->ovf_halo_buf.ensure((size_t)c->ovf_cap * 2))) return rc;
-        CU(cudaMemcpyAsync(c->bin_start_buf.p, starts.data(), starts.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        if (!items.empty())
-            CU(cudaMemcpyAsync(c->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream)); /* `starts`/`items` are pageable and die here */
     }
     /* pageable -> device copies are staged by the runtime before returning, so the vectors may die */
     CU(cudaMemcpyAsync(c->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -475,14 +503,14 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             cck::HaloBinArgs b;
             b.h = a;
             const int bi = h0 / cck::K2_MAX_HALOS;
-            b.bin_start = (const unsigned int*)c->bin_start_buf.p + (size_t)bi * (cck::K2_NBINS + 1);
-            b.bin_items = (const unsigned short*)c->bin_items_buf.p + c->bin_items_off[(size_t)bi];
+            b.cell_start = (const unsigned int*)c->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID + 1);
+            b.cell_items = (const unsigned short*)c->bin_items_buf.p + c->bin_items_off[(size_t)bi];
             b.ovf_particle = (unsigned int*)c->ovf_particle_buf.p;
             b.ovf_halo = (unsigned short*)c->ovf_halo_buf.p;
             b.ovf_cap = (unsigned long long)c->ovf_cap;
             b.ovf_count = rec_count + 2;
-            if (vec) cck::k2_cutout_halo_binned<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
-            else cck::k2_cutout_halo_binned<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
+            if (vec) cck::k2_cutout_halo_cells<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
+            else cck::k2_cutout_halo_cells<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
             CU(cudaGetLastError());
             cck::k2_overflow<<<c->sm_count * 4, 256, 0, c->stream>>>(b);
             CU(cudaGetLastError());
@@ -652,6 +680,7 @@ int cc_create(int device, cc_ctx** out) {
         cudaGetLastError();
     }
     cc_ctx* c = new cc_ctx();
+    if (const char* e = getenv("CC_K1_MINB")) c->k1_minb = atoi(e) == 3 ? 3 : 4;
     c->device = device;
     c->sm_count = sms;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||

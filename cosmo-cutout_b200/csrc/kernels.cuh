@@ -160,8 +160,8 @@ struct K1WarpQueue { /* one per warp: candidates of the current tile */
     unsigned char idx[SCAN_TILE];
 };
 
-template <bool VEC>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k1_scan(const ScanArgs a) {
+template <bool VEC, int MINB>
+__global__ void __launch_bounds__(SCAN_THREADS, MINB) k1_scan(const ScanArgs a) {
     __shared__ K1WarpQueue s_q[SCAN_WARPS];
     __shared__ unsigned int s_cursor;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -173,10 +173,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k1_scan(const ScanArgs a) {
     if (threadIdx.x == 0) s_cursor = 0;
     __syncthreads();
 
-    for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
+    /* software pipeline: the next tile's six LDG.128 are in flight while this tile is processed, so a warp that
+     * drops into the (long, latency-bound) exact path still keeps HBM busy */
+    unsigned int tile = blockIdx.x * SCAN_WARPS + warp;
+    float nx[8], ny[8], nz[8];
+    unsigned int nvalid = 0;
+    if (tile < a.ntiles) nvalid = load_tile<VEC>(a.x, a.y, a.z, (long long)tile * SCAN_TILE, a.n, lane, nx, ny, nz);
+    for (; tile < a.ntiles; tile += total_warps) {
         const long long base = (long long)tile * SCAN_TILE;
         float px[8], py[8], pz[8];
-        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+        const unsigned int valid = nvalid;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { px[j] = nx[j]; py[j] = ny[j]; pz[j] = nz[j]; }
+        if (tile + total_warps < a.ntiles)
+            nvalid = load_tile<VEC>(a.x, a.y, a.z, (long long)(tile + total_warps) * SCAN_TILE, a.n, lane, nx, ny, nz);
         /* ---- pre-filter ---- */
         unsigned int m = 0;
 #pragma unroll
@@ -562,24 +572,26 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
 }
 
-/* ---- many halos: a coarse cos(theta_u) bin index over the halos of the launch ------------------------------------
- * With hundreds of halos per pass the loop "every particle x every halo" is compute-bound.  The host sorts the
- * halos of a launch into K2_NBINS equal-width bins of cos(theta_u) (each halo is listed in every bin its widened
- * [clo, chi] interval touches, +-1 bin of slack); a particle then only tests the halos listed in its own bin
- * (~1 % of them for cluster-sized boxes).  This plays the role of the reference's theta-sorted index
- * (processLC.cpp:1214-1221, :1334-1340) without sorting 12 B/particle data.  Pairs that pass go to the warp queue;
- * pairs that do not fit go to a global overflow queue drained by k2_overflow. */
-constexpr int K2_NBINS = 2048;
-constexpr int K2B_QCAP = 256; /* warp queue of the binned kernel (the rest goes to the global overflow queue) */
+/* ---- many halos: a (cos theta_u, sin phi_u) cell index over the halos of the launch ----------------------------
+ * With hundreds of halos per pass the loop "every particle x every halo" is compute-bound (and a 1-D theta index
+ * still leaves ~1 % of the halos per particle: profiles/r01).  The host rasterises each halo's widened rough
+ * window [clo,chi] x [slo,shi] into a K2_GRID x K2_GRID grid over (c, s) in [-1,1]^2 (+-1 cell of slack) and builds
+ * a CSR list of halos per cell.  A particle computes c = z/r and s = sin(phi_u) = y*sign(x)/sqrt(x^2+y^2), looks up
+ * its cell (one 8-byte read from an L2-resident table) and tests only the halos listed there -- for cluster-sized
+ * boxes most cells are empty.  This plays the role of the reference's theta-sorted index (processLC.cpp:1214-1221,
+ * :1334-1340) without sorting or re-reading 12 B/particle data.  Pairs that pass go to the warp queue; pairs that
+ * do not fit go to a global overflow queue drained by k2_overflow. */
+constexpr int K2_GRID = 1024;
+constexpr int K2B_QCAP = 256; /* warp queue of the cell kernel (the rest goes to the global overflow queue) */
 struct K2BWarpQueue {
     unsigned int particle[K2B_QCAP];
     unsigned short halo[K2B_QCAP];
 };
 
 struct HaloBinArgs {
-    HaloArgs h;
-    const unsigned int* bin_start;    /* [K2_NBINS + 1] */
-    const unsigned short* bin_items;  /* halo index inside the launch */
+    HaloArgs h;                       /* h.pre holds {chi, clo, slo, shi} here (prefilter.h uc2_bounds_cells) */
+    const unsigned int* cell_start;   /* [K2_GRID*K2_GRID + 1] */
+    const unsigned short* cell_items; /* halo index inside the launch */
     unsigned int* ovf_particle;       /* overflow pairs: particle index inside the chunk */
     unsigned short* ovf_halo;
     unsigned long long ovf_cap;
@@ -587,16 +599,14 @@ struct HaloBinArgs {
 };
 
 template <bool VEC>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo_binned(const HaloBinArgs b) {
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo_cells(const HaloBinArgs b) {
     __shared__ float4 s_pre[K2_MAX_HALOS];
-    __shared__ unsigned int s_bin[K2_NBINS + 1];
     __shared__ K2BWarpQueue s_q[SCAN_WARPS];
     __shared__ unsigned int s_qcount[SCAN_WARPS];
     const HaloArgs& a = b.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     K2BWarpQueue& q = s_q[warp];
     for (int h = threadIdx.x; h < a.nhalos; h += SCAN_THREADS) s_pre[h] = a.pre[h];
-    for (int i = threadIdx.x; i <= K2_NBINS; i += SCAN_THREADS) s_bin[i] = b.bin_start[i];
     if (lane == 0) s_qcount[warp] = 0;
     __syncthreads();
     const unsigned int total_warps = gridDim.x * SCAN_WARPS;
@@ -606,51 +616,65 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo_binned(const H
         const long long base = (long long)tile * SCAN_TILE;
         float px[8], py[8], pz[8];
         const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+        float pc[8], ps[8];
+        unsigned int k0[8], k1[8], insane = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (!(valid & (1u << j))) continue;
-            const float r2 = fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j]));
-            const bool insane = !((fabsf(px[j]) >= CC_SANE_LO) & (r2 <= 1.2089258e24f));
-            const float c = pz[j] * rsqrt_fast(r2);
-            const float t = py[j] * rcp_fast(px[j]);
-            const unsigned int g = (unsigned int)(base + tile_local(lane, j));
-            unsigned int k0, k1;
-            if (insane) { /* the exact path decides, against every halo of the launch */
-                k0 = 0; k1 = (unsigned int)a.nhalos;
-            } else {
-                int bin = (int)((c + 1.0f) * (0.5f * K2_NBINS));
-                bin = max(0, min(K2_NBINS - 1, bin));
-                k0 = s_bin[bin]; k1 = s_bin[bin + 1];
-            }
-            for (unsigned int k = k0; k < k1; ++k) {
-                const unsigned int h = insane ? k : (unsigned int)b.bin_items[k];
-                const float4 P = s_pre[h];
-                if (insane | ((c <= P.x) & (c >= P.y) & (t >= P.z) & (t <= P.w))) {
-                    const unsigned int pos = atomicAdd(&s_qcount[warp], 1u);
-                    if (pos < K2B_QCAP) {
-                        q.particle[pos] = g;
-                        q.halo[pos] = (unsigned short)h;
-                    } else {
-                        const unsigned long long o = atomicAdd(b.ovf_count, 1ull);
-                        if (o < b.ovf_cap) {
-                            b.ovf_particle[o] = g;
-                            b.ovf_halo[o] = (unsigned short)h;
+        for (int j = 0; j < 8; ++j) { /* all eight table look-ups are issued before any is used */
+            const float rxy2 = fmaf(py[j], py[j], px[j] * px[j]);
+            const float r2 = fmaf(pz[j], pz[j], rxy2);
+            /* |x| in range keeps x^2+y^2 away from underflow; r^2 <= 2^80 keeps everything finite */
+            if (!((fabsf(px[j]) >= CC_SANE_LO) & (r2 <= 1.2089258e24f))) insane |= 1u << j;
+            pc[j] = pz[j] * rsqrt_fast(r2);
+            /* sin(phi_u) with phi_u = atan(y/x): y / sqrt(x^2+y^2), negated when x < 0 */
+            ps[j] = __int_as_float(__float_as_int(py[j] * rsqrt_fast(rxy2)) ^ (__float_as_int(px[j]) & 0x80000000));
+            int ic = (int)((pc[j] + 1.0f) * (0.5f * K2_GRID)), is = (int)((ps[j] + 1.0f) * (0.5f * K2_GRID));
+            ic = max(0, min(K2_GRID - 1, ic));
+            is = max(0, min(K2_GRID - 1, is));
+            const unsigned int cell = (unsigned int)ic * K2_GRID + (unsigned int)is;
+            k0[j] = __ldg(b.cell_start + cell);
+            k1[j] = __ldg(b.cell_start + cell + 1);
+        }
+        insane &= valid;
+        bool mine = insane != 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine |= ((valid >> j) & 1u) && (k1[j] > k0[j]);
+        if (__any_sync(0xffffffffu, mine)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (!((valid >> j) & 1u)) continue;
+                const bool bad = (insane >> j) & 1u; /* the exact path decides, against every halo of the launch */
+                const unsigned int ka = bad ? 0u : k0[j], kb = bad ? (unsigned int)a.nhalos : k1[j];
+                const unsigned int g = (unsigned int)(base + tile_local(lane, j));
+                for (unsigned int k = ka; k < kb; ++k) {
+                    const unsigned int h = bad ? k : (unsigned int)b.cell_items[k];
+                    const float4 P = s_pre[h];
+                    if (bad | ((pc[j] <= P.x) & (pc[j] >= P.y) & (ps[j] >= P.z) & (ps[j] <= P.w))) {
+                        const unsigned int pos = atomicAdd(&s_qcount[warp], 1u);
+                        if (pos < K2B_QCAP) {
+                            q.particle[pos] = g;
+                            q.halo[pos] = (unsigned short)h;
+                        } else {
+                            const unsigned long long o = atomicAdd(b.ovf_count, 1ull);
+                            if (o < b.ovf_cap) {
+                                b.ovf_particle[o] = g;
+                                b.ovf_halo[o] = (unsigned short)h;
+                            }
                         }
                     }
                 }
             }
-        }
-        __syncwarp();
-        const unsigned int cnt = min(s_qcount[warp], (unsigned int)K2B_QCAP);
-        if (cnt) { /* warp-uniform */
-            for (unsigned int jq = lane; jq < cnt; jq += 32) {
-                const unsigned int gq = q.particle[jq];
-                k2_exact(a, q.halo[jq], a.x[gq], a.y[gq], a.z[gq], (unsigned int)(a.local_base + gq));
+            __syncwarp();
+            const unsigned int cnt = min(s_qcount[warp], (unsigned int)K2B_QCAP);
+            if (cnt) { /* warp-uniform */
+                for (unsigned int jq = lane; jq < cnt; jq += 32) {
+                    const unsigned int gq = q.particle[jq];
+                    k2_exact(a, q.halo[jq], a.x[gq], a.y[gq], a.z[gq], (unsigned int)(a.local_base + gq));
+                }
+                n_cand += cnt;
+                __syncwarp();
+                if (lane == 0) s_qcount[warp] = 0;
+                __syncwarp();
             }
-            __syncwarp();
-            n_cand += cnt;
-            if (lane == 0) s_qcount[warp] = 0;
-            __syncwarp();
         }
     }
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);

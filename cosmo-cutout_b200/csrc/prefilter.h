@@ -97,4 +97,26 @@ static inline void uc2_bounds(const float th[2], const float ph[2], float out4[4
     out4[3] = round_up(th_);
 }
 
+/* cell-index variant (k2_cutout_halo_cells): the azimuth is tested as s = sin(phi) = y*sign(x)/sqrt(x^2+y^2), which
+ * is monotone in phi = atan(y/x) on (-90, 90) deg and bounded, so it can index a uniform grid.  The kernel's s~ and c~
+ * (one rsqrt.approx + two multiplies each) are within 4e-7 ABSOLUTE of the true values (|s|,|c| <= 1), so after the
+ * relative widening of the angles both intervals get an absolute 2e-6 on top. */
+static inline void uc2_bounds_cells(const float th[2], const float ph[2], float out4[4]) {
+    double clo, chi, tl, th_;
+    cos_bounds(th[0], th[1], &clo, &chi);
+    tan_bounds(ph[0], ph[1], &tl, &th_);
+    const double abs_slack = 2e-6;
+    double slo, shi;
+    if (isinf(tl)) slo = tl; else slo = tl / sqrt(1.0 + tl * tl) - abs_slack;
+    if (isinf(th_)) shi = th_; else shi = th_ / sqrt(1.0 + th_ * th_) + abs_slack;
+    if (shi >= 1.0) shi = INFINITY;   /* sin can reach 1 (x == 0 is handled by the range flag, but stay safe) */
+    if (slo <= -1.0) slo = -INFINITY;
+    if (!isinf(chi)) chi += abs_slack;
+    if (!isinf(clo)) clo -= abs_slack;
+    out4[0] = round_up(chi);
+    out4[1] = round_down(clo);
+    out4[2] = round_down(slo);
+    out4[3] = round_up(shi);
+}
+
 }  // namespace ccpf
