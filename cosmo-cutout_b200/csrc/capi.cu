@@ -260,7 +260,8 @@ k1_scan_fn k1_scan_variant(const cc_ctx* c, bool vec) {
 int k1_grid_limit(cc_ctx* c, bool vec, unsigned int* out) {
     int& occ = c->k1_occupancy[vec ? 1 : 0];
     if (occ == 0) {
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k1_scan_variant(c, vec), cck::SCAN_THREADS, 0));
+        CU(cudaFuncSetAttribute((const void*)k1_scan_variant(c, vec), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K1_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k1_scan_variant(c, vec), cck::SCAN_THREADS, cck::K1_SMEM_BYTES));
         if (occ < 1) return fail(CC_ERR_CUDA, "k1_scan cannot be resident on this device");
     }
     *out = (unsigned int)(c->sm_count * occ);
@@ -308,7 +309,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         a.tile_info = (unsigned long long*)(sp + off_info);
         a.result = result;
         a.ntiles = ntiles;
-        k1_scan_variant(c, vec)<<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+        k1_scan_variant(c, vec)<<<grid, cck::SCAN_THREADS, cck::K1_SMEM_BYTES, c->stream>>>(a);
         CU(cudaGetLastError());
         if (ch.last) CU(cudaEventRecord(c->ev_scan1, c->stream));
 

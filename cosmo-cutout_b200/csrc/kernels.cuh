@@ -155,44 +155,120 @@ __device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const Sc
     return (mn > 0.0f) & (window | insane);                         /* octant test, processLC.cpp:279 */
 }
 
-struct K1WarpQueue { /* one per warp: candidates of the current tile */
-    float x[SCAN_TILE], y[SCAN_TILE], z[SCAN_TILE], th[SCAN_TILE], ph[SCAN_TILE];
-    unsigned char idx[SCAN_TILE];
+/* Per-warp candidate queue, kept ACROSS tiles: the exact path costs ~1000 warp instructions whether 1 or 32 lanes
+ * are active, and a narrow window leaves 0-2 candidates per tile, so candidates are batched until at least a warp's
+ * worth is queued and only then run through the exact arithmetic (whole tiles only, so that every tile's records
+ * stay contiguous in the temp region). */
+constexpr int K1_QCAP = SCAN_TILE + 32;     /* drained as soon as 32 are queued, so at most 31 + one whole tile */
+constexpr int K1_QTILES = 34;               /* tiles per batch: each contributes >= 1 of the < 32 queued, + 1 tile */
+struct K1WarpQueue {
+    float x[K1_QCAP], y[K1_QCAP], z[K1_QCAP], th[K1_QCAP], ph[K1_QCAP];
+    unsigned short where[K1_QCAP];          /* (slot of the tile in tile_id[] << 8) | index inside the tile */
+    unsigned int tile_id[K1_QTILES];        /* tiles of the batch, in processing order */
+    unsigned short tile_q[K1_QTILES];       /* queue offset of each tile's first candidate */
 };
+constexpr size_t K1_SMEM_BYTES = sizeof(K1WarpQueue) * SCAN_WARPS + 16;
+
+/* warp-collective: exact test of the queued candidates, survivors -> CTA temp region, (position,count) per tile */
+__device__ __forceinline__ void k1_drain(const ScanArgs& a, K1WarpQueue& q, unsigned int nent, unsigned int ntile_b,
+                                         unsigned int* s_cursor, unsigned long long region0, int lane) {
+    __syncwarp();
+    const unsigned int lane_lt = (1u << lane) - 1u;
+    constexpr int NW = (K1_QCAP + 31) / 32;
+    unsigned int bits[NW];
+    unsigned int K = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        bits[w] = 0;
+        if ((unsigned)(w * 32) < nent) { /* warp-uniform */
+            const unsigned int j = w * 32 + lane;
+            bool pass = false;
+            if (j < nent) {
+                const float x = q.x[j], y = q.y[j], z = q.z[j];
+                if (x > 0.0f && y > 0.0f && z > 0.0f) { /* processLC.cpp:279 */
+                    const float th = ccref::theta_arcsec(x, y, z);
+                    const float ph = ccref::phi_arcsec_plain(x, y);
+                    pass = th > a.th_lo && th < a.th_hi && ph > a.ph_lo && ph < a.ph_hi; /* :287-288 */
+                    q.th[j] = th;
+                    q.ph[j] = ph;
+                }
+            }
+            bits[w] = __ballot_sync(0xffffffffu, pass);
+            K += __popc(bits[w]);
+        }
+    }
+    unsigned int pos0 = 0;
+    if (K) { /* one reservation for the whole batch: records of all its tiles are contiguous and in input order */
+        if (lane == 0) pos0 = atomicAdd(s_cursor, K);
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        unsigned int before = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            if ((unsigned)(w * 32) < nent) {
+                const unsigned int b = bits[w];
+                if ((b >> lane) & 1u) {
+                    const unsigned int j = w * 32 + lane;
+                    const unsigned long long slot = (unsigned long long)pos0 + before + __popc(b & lane_lt);
+                    if (slot < a.region_cap) {
+                        const unsigned int wh = q.where[j];
+                        a.t_idx[region0 + slot] = q.tile_id[wh >> 8] * SCAN_TILE + (wh & 0xffu);
+                        a.t_th[region0 + slot] = q.th[j];
+                        a.t_ph[region0 + slot] = q.ph[j];
+                        a.t_x[region0 + slot] = q.x[j];
+                        a.t_y[region0 + slot] = q.y[j];
+                        a.t_z[region0 + slot] = q.z[j];
+                    }
+                }
+                before += __popc(b);
+            }
+        }
+    }
+    /* survivors in front of queue position p */
+    auto rank = [&](unsigned int p) {
+        unsigned int r = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const unsigned int lo = w * 32;
+            if (p >= lo + 32) r += __popc(bits[w]);
+            else if (p > lo) r += __popc(bits[w] & ((1u << (p - lo)) - 1u));
+        }
+        return r;
+    };
+    for (unsigned int t = lane; t < ntile_b; t += 32) {
+        const unsigned int qs = q.tile_q[t], qe = (t + 1 < ntile_b) ? (unsigned int)q.tile_q[t + 1] : nent;
+        const unsigned int rs = rank(qs), re = rank(qe);
+        a.tile_info[q.tile_id[t]] = ((region0 + pos0 + rs) << 32) | (unsigned long long)(re - rs);
+    }
+    __syncwarp();
+}
 
 template <bool VEC, int MINB>
 __global__ void __launch_bounds__(SCAN_THREADS, MINB) k1_scan(const ScanArgs a) {
-    __shared__ K1WarpQueue s_q[SCAN_WARPS];
-    __shared__ unsigned int s_cursor;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    K1WarpQueue* s_q = reinterpret_cast<K1WarpQueue*>(s_raw);
+    unsigned int* s_cursor = reinterpret_cast<unsigned int*>(s_raw + sizeof(K1WarpQueue) * SCAN_WARPS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     K1WarpQueue& q = s_q[warp];
     const unsigned int total_warps = gridDim.x * SCAN_WARPS;
-    const unsigned int lane_lt = (1u << lane) - 1u;
     const unsigned long long region0 = (unsigned long long)blockIdx.x * a.region_cap;
     unsigned long long n_cand = 0;
-    if (threadIdx.x == 0) s_cursor = 0;
+    unsigned int qcount = 0, ntile_b = 0; /* warp-uniform */
+    if (threadIdx.x == 0) *s_cursor = 0;
     __syncthreads();
 
-    /* software pipeline: the next tile's six LDG.128 are in flight while this tile is processed, so a warp that
-     * drops into the (long, latency-bound) exact path still keeps HBM busy */
-    unsigned int tile = blockIdx.x * SCAN_WARPS + warp;
-    float nx[8], ny[8], nz[8];
-    unsigned int nvalid = 0;
-    if (tile < a.ntiles) nvalid = load_tile<VEC>(a.x, a.y, a.z, (long long)tile * SCAN_TILE, a.n, lane, nx, ny, nz);
-    for (; tile < a.ntiles; tile += total_warps) {
+    for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
+        if (qcount >= 32) { /* a warp's worth of candidates is queued: run them through the exact path */
+            k1_drain(a, q, qcount, ntile_b, s_cursor, region0, lane);
+            qcount = 0; ntile_b = 0;
+        }
         const long long base = (long long)tile * SCAN_TILE;
         float px[8], py[8], pz[8];
-        const unsigned int valid = nvalid;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { px[j] = nx[j]; py[j] = ny[j]; pz[j] = nz[j]; }
-        if (tile + total_warps < a.ntiles)
-            nvalid = load_tile<VEC>(a.x, a.y, a.z, (long long)(tile + total_warps) * SCAN_TILE, a.n, lane, nx, ny, nz);
+        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
         /* ---- pre-filter ---- */
         unsigned int m = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) m |= (unsigned)k1_prefilter(px[j], py[j], pz[j], a) << j;
         m &= valid;
-        unsigned long long info = 0;
         if (__any_sync(0xffffffffu, m != 0)) {
             /* ---- ordered candidate compaction into the warp's queue (chunk, lane, element = input order) ---- */
             const unsigned int cnt = __popc(m & 0xfu) | (__popc(m >> 4) << 16);
@@ -204,76 +280,29 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) k1_scan(const ScanArgs a) 
             }
             const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
             const unsigned int totalA = total & 0xffffu, C = totalA + (total >> 16);
+            if (lane == 0) { q.tile_id[ntile_b] = tile; q.tile_q[ntile_b] = (unsigned short)qcount; }
             const unsigned int ex = inc - cnt;
-            unsigned int posA = ex & 0xffffu, posB = totalA + (ex >> 16);
+            unsigned int posA = qcount + (ex & 0xffffu), posB = qcount + totalA + (ex >> 16);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (m & (1u << j)) {
                     unsigned int& pos = (j < 4) ? posA : posB;
                     q.x[pos] = px[j]; q.y[pos] = py[j]; q.z[pos] = pz[j];
-                    q.idx[pos] = (unsigned char)tile_local(lane, j);
+                    q.where[pos] = (unsigned short)((ntile_b << 8) | tile_local(lane, j));
                     ++pos;
                 }
-            __syncwarp();
+            ++ntile_b;
+            qcount += C; /* <= 31 + SCAN_TILE < K1_QCAP */
             n_cand += C;
-            /* ---- exact path on the densely packed candidates: the reference's arithmetic ---- */
-            unsigned int K = 0;
-            unsigned int bits[SCAN_TILE / 32];
-#pragma unroll
-            for (int w = 0; w < SCAN_TILE / 32; ++w) {
-                bits[w] = 0;
-                if ((unsigned)(w * 32) < C) { /* warp-uniform */
-                    const unsigned int j = w * 32 + lane;
-                    bool pass = false;
-                    if (j < C) {
-                        const float x = q.x[j], y = q.y[j], z = q.z[j];
-                        if (x > 0.0f && y > 0.0f && z > 0.0f) { /* processLC.cpp:279 */
-                            const float th = ccref::theta_arcsec(x, y, z);
-                            const float ph = ccref::phi_arcsec_plain(x, y);
-                            pass = th > a.th_lo && th < a.th_hi && ph > a.ph_lo && ph < a.ph_hi; /* :287-288 */
-                            q.th[j] = th;
-                            q.ph[j] = ph;
-                        }
-                    }
-                    bits[w] = __ballot_sync(0xffffffffu, pass);
-                    K += __popc(bits[w]);
-                }
-            }
-            /* ---- survivors, in input order, to the CTA's region of the temp buffer ---- */
-            unsigned int pos0 = 0;
-            if (K) { /* warp-uniform */
-                if (lane == 0) pos0 = atomicAdd(&s_cursor, K);
-                pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-                unsigned int before = 0;
-#pragma unroll
-                for (int w = 0; w < SCAN_TILE / 32; ++w) {
-                    if ((unsigned)(w * 32) < C) {
-                        const unsigned int b = bits[w];
-                        if ((b >> lane) & 1u) {
-                            const unsigned int j = w * 32 + lane;
-                            const unsigned long long slot = (unsigned long long)pos0 + before + __popc(b & lane_lt);
-                            if (slot < a.region_cap) {
-                                a.t_idx[region0 + slot] = (unsigned int)(base + q.idx[j]);
-                                a.t_th[region0 + slot] = q.th[j];
-                                a.t_ph[region0 + slot] = q.ph[j];
-                                a.t_x[region0 + slot] = q.x[j];
-                                a.t_y[region0 + slot] = q.y[j];
-                                a.t_z[region0 + slot] = q.z[j];
-                            }
-                        }
-                        before += __popc(b);
-                    }
-                }
-            }
-            info = ((region0 + pos0) << 32) | K;
-            __syncwarp(); /* the queue is rewritten by the next tile */
+        } else if (lane == 0) {
+            a.tile_info[tile] = 0ull;
         }
-        if (lane == 0) a.tile_info[tile] = info;
     }
+    if (ntile_b) k1_drain(a, q, qcount, ntile_b, s_cursor, region0, lane);
     __syncthreads();
     if (threadIdx.x == 0) {
-        a.cta_used[blockIdx.x] = s_cursor;
-        atomicMax(a.result + 3, (unsigned long long)s_cursor);
+        a.cta_used[blockIdx.x] = *s_cursor;
+        atomicMax(a.result + 3, (unsigned long long)*s_cursor);
     }
     if (lane == 0 && n_cand) atomicAdd(a.result + 1, n_cand);
 }
