@@ -128,7 +128,7 @@ struct cc_ctx {
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr, ev_total1 = nullptr;
     int64_t launches = 0;
     int k1_occupancy[2] = {0, 0};
-    int k1_minb = 4; /* CTAs per SM the scan kernel is compiled for (CC_K1_MINB=3: more registers, no spill) */
+    int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
     unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
     DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z, t_row;
@@ -252,16 +252,12 @@ struct Chunk {
 const size_t K1_HDR = 64;
 
 typedef void (*k1_scan_fn)(const cck::ScanArgs);
-k1_scan_fn k1_scan_variant(const cc_ctx* c, bool vec) {
-    if (c->k1_minb == 3) return vec ? cck::k1_scan<true, 3> : cck::k1_scan<false, 3>;
-    return vec ? cck::k1_scan<true, 4> : cck::k1_scan<false, 4>;
-}
+k1_scan_fn k1_scan_variant(bool vec) { return vec ? cck::k1_scan<true> : cck::k1_scan<false>; }
 
 int k1_grid_limit(cc_ctx* c, bool vec, unsigned int* out) {
     int& occ = c->k1_occupancy[vec ? 1 : 0];
     if (occ == 0) {
-        CU(cudaFuncSetAttribute((const void*)k1_scan_variant(c, vec), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K1_SMEM_BYTES));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k1_scan_variant(c, vec), cck::SCAN_THREADS, cck::K1_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k1_scan_variant(vec), cck::SCAN_THREADS, 0));
         if (occ < 1) return fail(CC_ERR_CUDA, "k1_scan cannot be resident on this device");
     }
     *out = (unsigned int)(c->sm_count * occ);
@@ -309,7 +305,8 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         a.tile_info = (unsigned long long*)(sp + off_info);
         a.result = result;
         a.ntiles = ntiles;
-        k1_scan_variant(c, vec)<<<grid, cck::SCAN_THREADS, cck::K1_SMEM_BYTES, c->stream>>>(a);
+        a.drain_at = (unsigned int)c->k1_drain_at;
+        k1_scan_variant(vec)<<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
         CU(cudaGetLastError());
         if (ch.last) CU(cudaEventRecord(c->ev_scan1, c->stream));
 
@@ -493,10 +490,11 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         a.n_cand = n_cand;
         a.total_halos = H;
         a.ntiles = (unsigned int)((n_scan + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
+        const size_t pre_bytes = (size_t)a.nhalos * sizeof(float4);
         int& occ = c->k2_occupancy[vec ? 1 : 0];
         if (occ == 0) {
             const void* fn = vec ? (const void*)cck::k2_cutout_halo<true> : (const void*)cck::k2_cutout_halo<false>;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cck::SCAN_THREADS, 0));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cck::SCAN_THREADS, (size_t)cck::K2_MAX_HALOS * sizeof(float4)));
             if (occ < 1) occ = 1;
         }
         const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
@@ -510,16 +508,16 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             b.ovf_halo = (unsigned short*)c->ovf_halo_buf.p;
             b.ovf_cap = (unsigned long long)c->ovf_cap;
             b.ovf_count = rec_count + 2;
-            if (vec) cck::k2_cutout_halo_cells<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
-            else cck::k2_cutout_halo_cells<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(b);
+            if (vec) cck::k2_cutout_halo_cells<true><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(b);
+            else cck::k2_cutout_halo_cells<false><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(b);
             CU(cudaGetLastError());
             cck::k2_overflow<<<c->sm_count * 4, 256, 0, c->stream>>>(b);
             CU(cudaGetLastError());
             CU(cudaMemsetAsync(rec_count + 2, 0, 8, c->stream)); /* the overflow queue is per launch */
             c->launches += 2;
         } else {
-            if (vec) cck::k2_cutout_halo<true><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
-            else cck::k2_cutout_halo<false><<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+            if (vec) cck::k2_cutout_halo<true><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(a);
+            else cck::k2_cutout_halo<false><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(a);
             CU(cudaGetLastError());
             c->launches += 1;
         }
@@ -681,7 +679,7 @@ int cc_create(int device, cc_ctx** out) {
         cudaGetLastError();
     }
     cc_ctx* c = new cc_ctx();
-    if (const char* e = getenv("CC_K1_MINB")) c->k1_minb = atoi(e) == 3 ? 3 : 4;
+    if (const char* e = getenv("CC_K1_DRAIN")) c->k1_drain_at = std::max(1, std::min(32, atoi(e)));
     c->device = device;
     c->sm_count = sms;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -139,6 +139,7 @@ struct ScanArgs {
     unsigned long long* tile_info;    /* [ntiles] (temp position << 32) | survivors of the tile */
     unsigned long long* result;       /* [1] += pre-filter candidates, [3] = max records any CTA wanted */
     unsigned int ntiles;
+    unsigned int drain_at;            /* queued candidates that trigger the exact path (32 = a full warp) */
 };
 
 /* branch-free on purpose: eight of these run back to back per lane and divergent early-outs cost more than the
@@ -156,10 +157,14 @@ __device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const Sc
 }
 
 /* Per-warp candidate queue, kept ACROSS tiles: the exact path costs ~1000 warp instructions whether 1 or 32 lanes
- * are active, and a narrow window leaves 0-2 candidates per tile, so candidates are batched until at least a warp's
- * worth is queued and only then run through the exact arithmetic (whole tiles only, so that every tile's records
- * stay contiguous in the temp region). */
-constexpr int K1_QCAP = SCAN_TILE + 32;     /* drained as soon as 32 are queued, so at most 31 + one whole tile */
+ * are active, and a narrow window leaves 0-2 candidates per tile, so candidates are batched until a warp's worth is
+ * queued and only then run through the exact arithmetic (whole tiles only, so that every tile's records stay
+ * contiguous in the temp region).  The queue is deliberately small: shared memory is carved out of the same 228 KB
+ * as the L1 that buffers the in-flight streaming loads, and the scan slows down measurably when the L1 share
+ * shrinks (profiles/r01: 40 -> 52 KB of shared memory per CTA cost 9 % of the bandwidth).  Tiles with more
+ * candidates than the queue can take go through k1_dense_tile instead. */
+constexpr int K1_QCAP = 160;                /* drained once 32 are queued: at most 31 + K1_QMAX_TILE */
+constexpr int K1_QMAX_TILE = K1_QCAP - 32;  /* candidates one tile may queue */
 constexpr int K1_QTILES = 34;               /* tiles per batch: each contributes >= 1 of the < 32 queued, + 1 tile */
 struct K1WarpQueue {
     float x[K1_QCAP], y[K1_QCAP], z[K1_QCAP], th[K1_QCAP], ph[K1_QCAP];
@@ -167,14 +172,25 @@ struct K1WarpQueue {
     unsigned int tile_id[K1_QTILES];        /* tiles of the batch, in processing order */
     unsigned short tile_q[K1_QTILES];       /* queue offset of each tile's first candidate */
 };
-constexpr size_t K1_SMEM_BYTES = sizeof(K1WarpQueue) * SCAN_WARPS + 16;
 
-/* warp-collective: exact test of the queued candidates, survivors -> CTA temp region, (position,count) per tile */
-__device__ __forceinline__ void k1_drain(const ScanArgs& a, K1WarpQueue& q, unsigned int nent, unsigned int ntile_b,
-                                         unsigned int* s_cursor, unsigned long long region0, int lane) {
+/* use case 1 membership + angles of one particle: the reference's arithmetic (processLC.cpp:279-288) */
+__device__ __forceinline__ bool k1_exact(const ScanArgs& a, float x, float y, float z, float& th, float& ph) {
+    if (!(x > 0.0f && y > 0.0f && z > 0.0f)) return false; /* :279 */
+    th = ccref::theta_arcsec(x, y, z);                       /* :282-283 */
+    ph = ccref::phi_arcsec_plain(x, y);                      /* :284 */
+    return th > a.th_lo && th < a.th_hi && ph > a.ph_lo && ph < a.ph_hi; /* :287-288 */
+}
+
+/* warp-collective: exact test of the queued candidates, survivors -> CTA temp region, (position,count) per tile.
+ * noinline: called from one hot and one cold site; `a` points at the __grid_constant__ kernel parameter */
+__device__ __noinline__ void k1_drain(const ScanArgs* __restrict__ ap, K1WarpQueue* __restrict__ qp, unsigned int nent,
+                                      unsigned int ntile_b, unsigned int* s_cursor, unsigned long long region0) {
+    const ScanArgs& a = *ap;
+    K1WarpQueue& q = *qp;
+    const int lane = threadIdx.x & 31;
     __syncwarp();
     const unsigned int lane_lt = (1u << lane) - 1u;
-    constexpr int NW = (K1_QCAP + 31) / 32;
+    constexpr int NW = K1_QCAP / 32;
     unsigned int bits[NW];
     unsigned int K = 0;
 #pragma unroll
@@ -184,14 +200,9 @@ __device__ __forceinline__ void k1_drain(const ScanArgs& a, K1WarpQueue& q, unsi
             const unsigned int j = w * 32 + lane;
             bool pass = false;
             if (j < nent) {
-                const float x = q.x[j], y = q.y[j], z = q.z[j];
-                if (x > 0.0f && y > 0.0f && z > 0.0f) { /* processLC.cpp:279 */
-                    const float th = ccref::theta_arcsec(x, y, z);
-                    const float ph = ccref::phi_arcsec_plain(x, y);
-                    pass = th > a.th_lo && th < a.th_hi && ph > a.ph_lo && ph < a.ph_hi; /* :287-288 */
-                    q.th[j] = th;
-                    q.ph[j] = ph;
-                }
+                float th, ph;
+                pass = k1_exact(a, q.x[j], q.y[j], q.z[j], th, ph);
+                if (pass) { q.th[j] = th; q.ph[j] = ph; }
             }
             bits[w] = __ballot_sync(0xffffffffu, pass);
             K += __popc(bits[w]);
@@ -242,23 +253,68 @@ __device__ __forceinline__ void k1_drain(const ScanArgs& a, K1WarpQueue& q, unsi
     __syncwarp();
 }
 
-template <bool VEC, int MINB>
-__global__ void __launch_bounds__(SCAN_THREADS, MINB) k1_scan(const ScanArgs a) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    K1WarpQueue* s_q = reinterpret_cast<K1WarpQueue*>(s_raw);
-    unsigned int* s_cursor = reinterpret_cast<unsigned int*>(s_raw + sizeof(K1WarpQueue) * SCAN_WARPS);
+/* warp-collective, cold: a tile with more candidates than the queue takes (a window covering a third of the octant
+ * or more).  No staging: the tile is re-read (it is still in L2), every particle takes the exact test, once to count
+ * and once to write -- survivors of a tile must be contiguous, and nothing is kept between the two rounds. */
+__device__ __noinline__ void k1_dense_tile(const ScanArgs* __restrict__ ap, unsigned int tile, unsigned int* s_cursor,
+                                           unsigned long long region0) {
+    const ScanArgs& a = *ap;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lane_lt = (1u << lane) - 1u;
+    const long long base = (long long)tile * SCAN_TILE;
+    unsigned int K = 0, pos0 = 0, before = 0;
+    for (int round = 0; round < 2; ++round) {
+        for (int w = 0; w < SCAN_TILE / 32; ++w) {
+            const long long g = base + w * 32 + lane;
+            bool pass = false;
+            float x = 0.0f, y = 0.0f, z = 0.0f, th = 0.0f, ph = 0.0f;
+            if (g < a.n) {
+                x = a.x[g]; y = a.y[g]; z = a.z[g];
+                pass = k1_exact(a, x, y, z, th, ph);
+            }
+            const unsigned int b = __ballot_sync(0xffffffffu, pass);
+            if (round == 0) {
+                K += __popc(b);
+            } else {
+                if (pass) {
+                    const unsigned long long slot = (unsigned long long)pos0 + before + __popc(b & lane_lt);
+                    if (slot < a.region_cap) {
+                        a.t_idx[region0 + slot] = (unsigned int)g;
+                        a.t_th[region0 + slot] = th;
+                        a.t_ph[region0 + slot] = ph;
+                        a.t_x[region0 + slot] = x;
+                        a.t_y[region0 + slot] = y;
+                        a.t_z[region0 + slot] = z;
+                    }
+                }
+                before += __popc(b);
+            }
+        }
+        if (round == 0) {
+            if (K == 0) break;
+            if (lane == 0) pos0 = atomicAdd(s_cursor, K);
+            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        }
+    }
+    if (lane == 0) a.tile_info[tile] = ((region0 + pos0) << 32) | (unsigned long long)K;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k1_scan(const __grid_constant__ ScanArgs a) {
+    __shared__ K1WarpQueue s_q[SCAN_WARPS];
+    __shared__ unsigned int s_cursor;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     K1WarpQueue& q = s_q[warp];
     const unsigned int total_warps = gridDim.x * SCAN_WARPS;
     const unsigned long long region0 = (unsigned long long)blockIdx.x * a.region_cap;
     unsigned long long n_cand = 0;
     unsigned int qcount = 0, ntile_b = 0; /* warp-uniform */
-    if (threadIdx.x == 0) *s_cursor = 0;
+    if (threadIdx.x == 0) s_cursor = 0;
     __syncthreads();
 
     for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
-        if (qcount >= 32) { /* a warp's worth of candidates is queued: run them through the exact path */
-            k1_drain(a, q, qcount, ntile_b, s_cursor, region0, lane);
+        if (qcount >= a.drain_at) { /* a warp's worth of candidates is queued: run them through the exact path */
+            k1_drain(&a, &q, qcount, ntile_b, &s_cursor, region0);
             qcount = 0; ntile_b = 0;
         }
         const long long base = (long long)tile * SCAN_TILE;
@@ -280,6 +336,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) k1_scan(const ScanArgs a) 
             }
             const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
             const unsigned int totalA = total & 0xffffu, C = totalA + (total >> 16);
+            n_cand += C;
+            if (C > K1_QMAX_TILE) { /* cold */
+                k1_dense_tile(&a, tile, &s_cursor, region0);
+                continue;
+            }
             if (lane == 0) { q.tile_id[ntile_b] = tile; q.tile_q[ntile_b] = (unsigned short)qcount; }
             const unsigned int ex = inc - cnt;
             unsigned int posA = qcount + (ex & 0xffffu), posB = qcount + totalA + (ex >> 16);
@@ -292,17 +353,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) k1_scan(const ScanArgs a) 
                     ++pos;
                 }
             ++ntile_b;
-            qcount += C; /* <= 31 + SCAN_TILE < K1_QCAP */
-            n_cand += C;
+            qcount += C; /* <= 31 + K1_QMAX_TILE < K1_QCAP */
         } else if (lane == 0) {
             a.tile_info[tile] = 0ull;
         }
     }
-    if (ntile_b) k1_drain(a, q, qcount, ntile_b, s_cursor, region0, lane);
+    if (ntile_b) k1_drain(&a, &q, qcount, ntile_b, &s_cursor, region0);
     __syncthreads();
     if (threadIdx.x == 0) {
-        a.cta_used[blockIdx.x] = *s_cursor;
-        atomicMax(a.result + 3, (unsigned long long)*s_cursor);
+        a.cta_used[blockIdx.x] = s_cursor;
+        atomicMax(a.result + 3, (unsigned long long)s_cursor);
     }
     if (lane == 0 && n_cand) atomicAdd(a.result + 1, n_cand);
 }
@@ -453,7 +513,9 @@ __global__ void __launch_bounds__(256) k1_gather(const GatherConstArgs a) {
  * survivor record (order is restored by k3_*).
  * ================================================================================================ */
 constexpr int K2_MAX_HALOS = 1024; /* halos per launch (pre-filter parameters live in shared memory) */
-constexpr int K2_QCAP = 512;       /* queued (particle, halo) pairs per warp (>= 2 tiles) */
+constexpr int K2_QCAP = SCAN_TILE + 32; /* queued (particle, halo) pairs per warp: drained once more than 32 are
+                                           queued, and one halo iteration can add a whole tile (small on purpose:
+                                           shared memory competes with the L1 that buffers the streaming loads) */
 
 struct HaloDev { /* exact parameters of one halo */
     float R[9];
@@ -532,7 +594,7 @@ __device__ __forceinline__ void k2_drain(const HaloArgs& a, const K2WarpQueue& q
 
 template <bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs a) {
-    __shared__ float4 s_pre[K2_MAX_HALOS];
+    extern __shared__ float4 s_pre[]; /* [nhalos] */
     __shared__ K2WarpQueue s_q[SCAN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     K2WarpQueue& q = s_q[warp];
@@ -629,7 +691,7 @@ struct HaloBinArgs {
 
 template <bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo_cells(const HaloBinArgs b) {
-    __shared__ float4 s_pre[K2_MAX_HALOS];
+    extern __shared__ float4 s_pre[]; /* [nhalos] */
     __shared__ K2BWarpQueue s_q[SCAN_WARPS];
     __shared__ unsigned int s_qcount[SCAN_WARPS];
     const HaloArgs& a = b.h;
