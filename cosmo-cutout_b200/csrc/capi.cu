@@ -138,6 +138,8 @@ struct cc_ctx {
     int64_t n = 0, index_base = 0;
     const void* col[N_IN_COLS] = {};
     DevBuf col_buf[N_IN_COLS];
+    DevBuf payload;          /* interleaved gather columns (kernels.cuh Payload), built when a step becomes resident */
+    bool payload_valid = false;
 
     /* survivors */
     DevBuf out_buf[N_OUT_COLS];
@@ -152,6 +154,8 @@ struct cc_ctx {
     int64_t ovf_cap = 0;
     bool use_bins = false;
     std::vector<cc_halo> index_key; /* halos the resident cell index was built for */
+    std::vector<cc_halo> params_key; /* halos whose device parameters are resident */
+    bool params_bins = false;
     int64_t rec_cap = 0;
 
     /* pinned host mirror for small read-backs */
@@ -332,6 +336,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         g.t_idx = a.t_idx; g.t_row = t.t_row; g.t_th = a.t_th; g.t_ph = a.t_ph;
         g.t_x = a.t_x; g.t_y = a.t_y; g.t_z = a.t_z;
         g.cta_used = a.cta_used;
+        g.payload = (c->streamed || !c->payload_valid) ? nullptr : (const cck::Payload*)c->payload.p + ch.start;
         g.result = result;
         g.region_cap = c->region_cap;
         g.cap = c->out_cap;
@@ -457,9 +462,16 @@ int prepare_halo(cc_ctx* c) {
         if ((rc = c->ovf_particle_buf.ensure((size_t)c->ovf_cap * 4))) return rc;
         if ((rc = c->ovf_halo_buf.ensure((size_t)c->ovf_cap * 2))) return rc;
     }
-    /* pageable -> device copies are staged by the runtime before returning, so the vectors may die */
-    CU(cudaMemcpyAsync(c->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->halo_buf.p, hd.data(), (size_t)H * sizeof(cck::HaloDev), cudaMemcpyHostToDevice, c->stream));
+    /* pageable -> device copies are staged by the runtime before returning, so the vectors may die; repeated
+     * cutouts with the same halos (and the same kernel variant) skip the upload */
+    const bool same_params = c->params_bins == c->use_bins && c->params_key.size() == c->p_halos.size() &&
+                             memcmp(c->params_key.data(), c->p_halos.data(), c->p_halos.size() * sizeof(cc_halo)) == 0;
+    if (!same_params) {
+        CU(cudaMemcpyAsync(c->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->halo_buf.p, hd.data(), (size_t)H * sizeof(cck::HaloDev), cudaMemcpyHostToDevice, c->stream));
+        c->params_key = c->p_halos;
+        c->params_bins = c->use_bins;
+    }
     CU(cudaMemsetAsync(c->counts_buf.p, 0, (size_t)(2 * H) * 8, c->stream));
     CU(cudaMemsetAsync(c->cursor_buf.p, 0, (size_t)H * 8, c->stream));
     CU(cudaMemsetAsync(c->misc_buf.p, 0, 64, c->stream));
@@ -524,10 +536,48 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
     }
     if (ch.last) {
         CU(cudaEventRecord(c->ev_scan1, c->stream));
+        /* ordering + gather, sized on the device: the whole pass is one enqueue, one host synchronisation */
         cck::k3_scan_counts<<<1, 256, 0, c->stream>>>((const unsigned long long*)c->counts_buf.p,
                                                       (unsigned long long*)c->seg_buf.p, H);
         CU(cudaGetLastError());
-        c->launches += 1;
+        const unsigned int g1 = (unsigned int)c->sm_count * 4;
+        cck::BucketArgs b;
+        b.recs = (const cck::Rec*)c->rec_a.p;
+        b.rec_count = rec_count;
+        b.rec_cap = (unsigned long long)c->rec_cap;
+        b.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        b.cursor = (unsigned long long*)c->cursor_buf.p;
+        b.out = (cck::Rec*)c->rec_b.p;
+        cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
+        CU(cudaGetLastError());
+        cck::RankArgs r;
+        r.recs = (const cck::Rec*)c->rec_b.p;
+        r.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        r.rec_cap = (unsigned long long)c->rec_cap;
+        r.rank = (unsigned int*)c->rank_buf.p;
+        r.H = H;
+        /* few halos: many column blocks per halo; many halos: one or two, the y dimension provides the parallelism */
+        const unsigned int gy = (unsigned int)std::min(H, 8192);
+        const unsigned int gx = (unsigned int)std::max(1, std::min(64, (c->sm_count * 8) / (int)gy));
+        cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, 0, c->stream>>>(r);
+        CU(cudaGetLastError());
+        cck::GatherArgs g;
+        g.recs = (const cck::Rec*)c->rec_b.p;
+        g.rank = (const unsigned int*)c->rank_buf.p;
+        g.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        g.rec_count = rec_count;
+        g.rec_cap = (unsigned long long)c->rec_cap;
+        g.out_cap = c->out_cap;
+        g.in = c->gcols;
+        g.payload = (c->streamed || !c->payload_valid) ? nullptr : (const cck::Payload*)c->payload.p;
+        g.out = cols_out_of(c);
+        g.index_base = c->index_base;
+        g.pos_only = c->p_pos_only;
+        cck::k3_gather_halo<<<g1, 256, 0, c->stream>>>(g);
+        CU(cudaGetLastError());
+        c->launches += 4;
+        CU(cudaEventRecord(c->ev_total1, c->stream));
+        c->have_times = true;
         CU(cudaMemcpyAsync(c->h_small, c->misc_buf.p, 32, cudaMemcpyDeviceToHost, c->stream)); /* rec_count, n_cand, -, ovf_max */
         CU(cudaMemcpyAsync(c->h_small + 8, c->counts_buf.p, (size_t)(2 * H) * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(c->h_small + 8 + 2 * H, c->seg_buf.p, (size_t)(H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -588,51 +638,28 @@ int run_streamed(cc_ctx* c) {
 
 int run_pending(cc_ctx* c) { return c->streamed ? run_streamed(c) : run_resident(c); }
 
-/* second half of use case 2, once the record count is known on the host */
-int finish_halo(cc_ctx* c, unsigned long long nrec) {
-    const int H = (int)c->p_halos.size();
-    if (nrec > 0) {
-        cck::BucketArgs b;
-        b.recs = (const cck::Rec*)c->rec_a.p;
-        b.nrec = nrec;
-        b.seg_begin = (const unsigned long long*)c->seg_buf.p;
-        b.cursor = (unsigned long long*)c->cursor_buf.p;
-        b.out = (cck::Rec*)c->rec_b.p;
-        const unsigned int g1 = (unsigned int)std::min<unsigned long long>((nrec + 255) / 256, (unsigned long long)c->sm_count * 8);
-        cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
-        CU(cudaGetLastError());
-        cck::RankArgs r;
-        r.recs = (const cck::Rec*)c->rec_b.p;
-        r.seg_begin = (const unsigned long long*)c->seg_buf.p;
-        r.rank = (unsigned int*)c->rank_buf.p;
-        r.H = H;
-        unsigned long long max_seg = 0;
-        for (int h = 0; h < H; ++h) max_seg = std::max<unsigned long long>(max_seg, (unsigned long long)c->counts[h]);
-        const unsigned int gx = (unsigned int)std::max<unsigned long long>(1, std::min<unsigned long long>((max_seg + cck::K3_THREADS - 1) / cck::K3_THREADS, 1024));
-        for (int h0 = 0; h0 < H; h0 += 32768) {
-            cck::RankArgs rr = r;
-            rr.seg_begin = r.seg_begin + h0;
-            rr.H = std::min(32768, H - h0);
-            /* rank[] is indexed by absolute record position, seg_begin values are absolute: only the halo base shifts */
-            cck::k3_rank<<<dim3(gx, (unsigned int)rr.H), cck::K3_THREADS, 0, c->stream>>>(rr);
-            CU(cudaGetLastError());
-            c->launches += 1;
+/* interleave the seven gather-only columns of the resident step (kernels.cuh, "gather payload") */
+int build_payload(cc_ctx* c) {
+    c->payload_valid = false;
+    if (getenv("CC_NO_PAYLOAD") || c->n == 0) return CC_OK;
+    cudaError_t e = cudaSuccess;
+    if (c->payload.bytes < (size_t)c->n * sizeof(cck::Payload)) {
+        c->payload.release();
+        e = cudaMalloc(&c->payload.p, (size_t)c->n * sizeof(cck::Payload));
+        if (e != cudaSuccess) { /* not enough HBM for the extra 32 B/particle: gather from the columns instead */
+            cudaGetLastError();
+            c->payload.p = nullptr;
+            return CC_OK;
         }
-        cck::GatherArgs g;
-        g.recs = (const cck::Rec*)c->rec_b.p;
-        g.rank = (const unsigned int*)c->rank_buf.p;
-        g.seg_begin = (const unsigned long long*)c->seg_buf.p;
-        g.nrec = nrec;
-        g.in = c->gcols;
-        g.out = cols_out_of(c);
-        g.index_base = c->index_base;
-        g.pos_only = c->p_pos_only;
-        cck::k3_gather_halo<<<g1, 256, 0, c->stream>>>(g);
-        CU(cudaGetLastError());
-        c->launches += 2;
+        c->payload.bytes = (size_t)c->n * sizeof(cck::Payload);
     }
-    CU(cudaEventRecord(c->ev_total1, c->stream));
-    c->have_times = true;
+    const cck::ColsIn ci = cols_in_of(c);
+    const int with_vel = (ci.vx && ci.vy && ci.vz && ci.rot && ci.rep) ? 1 : 0;
+    cck::k_build_payload<<<c->sm_count * 8, 256, 0, c->stream>>>(ci, (cck::Payload*)c->payload.p, c->n, with_vel);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches += 1;
+    c->payload_valid = true;
     return CC_OK;
 }
 
@@ -700,6 +727,7 @@ void cc_destroy(cc_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto& b : c->col_buf) b.release();
+    c->payload.release();
     for (auto& b : c->out_buf) b.release();
     DevBuf* rest[] = {&c->scratch, &c->pre_buf, &c->halo_buf, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
                       &c->seg_buf, &c->cursor_buf, &c->misc_buf, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row,
@@ -736,6 +764,8 @@ int cc_step_release(cc_ctx* c) {
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     for (auto& b : c->col_buf) b.release();
+    c->payload.release();
+    c->payload_valid = false;
     for (auto& p : c->col) p = nullptr;
     c->step_valid = false;
     c->step_owned = false;
@@ -761,7 +791,7 @@ int cc_step_upload(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_b
     c->step_valid = true;
     c->step_owned = true;
     c->pending = P_NONE;
-    return CC_OK;
+    return build_payload(c);
 }
 
 int cc_step_attach(cc_ctx* c, int64_t n, const cc_cols_in* dev, int64_t index_base) {
@@ -774,7 +804,9 @@ int cc_step_attach(cc_ctx* c, int64_t n, const cc_cols_in* dev, int64_t index_ba
     c->step_valid = true;
     c->step_owned = false;
     c->pending = P_NONE;
-    return CC_OK;
+    int rc = use_device(c);
+    if (rc) return rc;
+    return build_payload(c);
 }
 
 int cc_step_synth(cc_ctx* c, int64_t n, uint64_t seed, int64_t index_base, int kind, float box) {
@@ -797,7 +829,7 @@ int cc_step_synth(cc_ctx* c, int64_t n, uint64_t seed, int64_t index_base, int k
     c->step_valid = true;
     c->step_owned = true;
     c->pending = P_NONE;
-    return CC_OK;
+    return build_payload(c);
 }
 
 int cc_synth_host(int64_t n, uint64_t seed, int64_t index_base, int kind, float box, float* x, float* y, float* z,
@@ -918,8 +950,6 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             for (int h = 0; h <= H; ++h) c->seg_begin[h] = (int64_t)c->h_small[8 + 2 * H + h];
             if (tot != nrec) return fail(CC_ERR_CUDA, "internal: record count %lld != sum of halo counts %lld", (long long)nrec, (long long)tot);
             c->stats[0] = halo_scan_limit(c); c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = tot; c->stats[3] = tot_rough;
-            if ((rc = finish_halo(c, (unsigned long long)nrec))) return rc;
-            CU(cudaStreamSynchronize(c->stream));
         }
         c->synced = true;
     }

@@ -61,6 +61,36 @@ __device__ __forceinline__ float a_to_z_dev(float a) {
     return ccref::a_to_z(a);
 }
 
+/* ---- gather payload -------------------------------------------------------------------------------------------
+ * x,y,z are the only columns the scan streams; the other seven are only ever read for survivors, one 4- or 8-byte
+ * element at a time, and every such read costs a 64-128 B DRAM burst (profiles/r01: ~110 B of DRAM traffic per
+ * gathered element).  A resident step therefore also keeps those seven columns interleaved, 32 B per particle, so a
+ * survivor costs one sector instead of seven bursts.  Built once per step by k_build_payload (one extra pass over
+ * 32 B/particle at residency time, amortised over every cutout on the resident step). */
+struct __align__(16) Payload {
+    float vx, vy, vz, a;
+    long long id;
+    int rot, rep;
+};
+__global__ void k_build_payload(ColsIn in, Payload* __restrict__ out, long long n, int with_vel) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Payload p;
+        p.a = in.a[i];
+        p.id = in.id[i];
+        if (with_vel) { p.vx = in.vx[i]; p.vy = in.vy[i]; p.vz = in.vz[i]; p.rot = in.rot[i]; p.rep = in.rep[i]; }
+        else { p.vx = p.vy = p.vz = 0.0f; p.rot = p.rep = 0; }
+        out[i] = p;
+    }
+}
+__device__ __forceinline__ Payload load_payload(const Payload* p) {
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    Payload r;
+    r.vx = __uint_as_float(lo.x); r.vy = __uint_as_float(lo.y); r.vz = __uint_as_float(lo.z); r.a = __uint_as_float(lo.w);
+    r.id = (long long)(((unsigned long long)hi.y << 32) | hi.x);
+    r.rot = (int)hi.z; r.rep = (int)hi.w;
+    return r;
+}
+
 /* approximate reciprocal / reciprocal square root for the pre-filter only (arguments are range-checked, so
  * flushing subnormals is harmless and the slow-path fix-up code of the non-ftz forms is avoided) */
 __device__ __forceinline__ float rcp_fast(float x) {
@@ -470,6 +500,7 @@ struct GatherConstArgs {
     const float *t_th, *t_ph, *t_x, *t_y, *t_z;
     const unsigned int* cta_used;     /* [nregions] */
     const unsigned long long* result; /* [2] = carry: rows written by earlier chunks of a streamed step */
+    const Payload* payload;           /* interleaved gather columns of a resident step, or NULL (streamed step) */
     unsigned int region_cap;
     long long cap;                    /* rows available in `out` */
     long long index_base;             /* global index of the chunk's first particle */
@@ -492,13 +523,20 @@ __global__ void __launch_bounds__(256) k1_gather(const GatherConstArgs a) {
         a.out.x[r] = a.t_x[slot];
         a.out.y[r] = a.t_y[slot];
         a.out.z[r] = a.t_z[slot];
-        a.out.vx[r] = a.in.vx[g];
-        a.out.vy[r] = a.in.vy[g];
-        a.out.vz[r] = a.in.vz[g];
-        a.out.redshift[r] = a_to_z_dev(a.in.a[g]);
-        a.out.id[r] = a.in.id[g];
-        a.out.rot[r] = a.in.rot[g];
-        a.out.rep[r] = a.in.rep[g];
+        if (a.payload) {
+            const Payload p = load_payload(a.payload + g);
+            a.out.vx[r] = p.vx; a.out.vy[r] = p.vy; a.out.vz[r] = p.vz;
+            a.out.redshift[r] = a_to_z_dev(p.a);
+            a.out.id[r] = p.id; a.out.rot[r] = p.rot; a.out.rep[r] = p.rep;
+        } else {
+            a.out.vx[r] = a.in.vx[g];
+            a.out.vy[r] = a.in.vy[g];
+            a.out.vz[r] = a.in.vz[g];
+            a.out.redshift[r] = a_to_z_dev(a.in.a[g]);
+            a.out.id[r] = a.in.id[g];
+            a.out.rot[r] = a.in.rot[g];
+            a.out.rep[r] = a.in.rep[g];
+        }
         if (a.out.index) a.out.index[r] = a.index_base + g;
     }
 }
@@ -523,11 +561,11 @@ struct HaloDev { /* exact parameters of one halo */
     float rth_lo, rth_hi, rph_lo, rph_hi; /* rough: lo <= theta_u < hi (:1334-1337), lo < phi_u < hi (:1400) */
     float pad[3];
 };
-struct Rec {                /* one survivor */
+struct __align__(16) Rec {  /* one survivor, 32 B */
     unsigned long long key; /* (bits of theta_u) << 32 | particle index in the step: the reference's sort order */
     unsigned int halo;
     float th, ph;           /* rotated, halo-centric angles (processLC.cpp:1446-1447) */
-    unsigned int pad;
+    float x, y, z;          /* the position (in registers when the record is made: saves three gathers later) */
 };
 struct HaloArgs {
     const float *x, *y, *z;
@@ -571,7 +609,7 @@ __device__ __forceinline__ void k2_exact(const HaloArgs& a, int h, float x, floa
             r.halo = hg;
             r.th = th;
             r.ph = ph;
-            r.pad = 0;
+            r.x = x; r.y = y; r.z = z;
             a.recs[slot] = r;
         }
     }
@@ -789,20 +827,24 @@ __global__ void __launch_bounds__(256) k2_overflow(const HaloBinArgs b) {
 /* ================================================================================================
  * K3  survivor ordering + gather (use case 2)
  * ================================================================================================ */
+/* All K3 kernels run with fixed grids and read the record count on the device (min(*rec_count, rec_cap)), so the
+ * whole use-case-2 pass is one enqueue with a single host synchronisation at the end. */
 /* scatter records into per-halo segments (unordered inside a segment) */
 struct BucketArgs {
     const Rec* recs;
-    unsigned long long nrec;
+    const unsigned long long* rec_count;
+    unsigned long long rec_cap;
     const unsigned long long* seg_begin; /* [H] exclusive scan of counts */
     unsigned long long* cursor;          /* [H] zeroed */
     Rec* out;
 };
 __global__ void k3_bucket(const BucketArgs a) {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nrec;
+    const unsigned long long nrec = min(*a.rec_count, a.rec_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const Rec r = a.recs[i];
         const unsigned long long p = a.seg_begin[r.halo] + atomicAdd(a.cursor + r.halo, 1ull);
-        a.out[p] = r;
+        if (p < a.rec_cap) a.out[p] = r;
     }
 }
 
@@ -826,33 +868,37 @@ __global__ void k3_scan_counts(const unsigned long long* counts, unsigned long l
 }
 
 /* rank of every record inside its halo segment by counting smaller keys (keys are unique: the low 32 bits
- * are the particle index).  One CTA column per segment chunk; the segment streams through shared memory. */
+ * are the particle index).  grid = (column blocks, halos); the segment streams through shared memory. */
 constexpr int K3_THREADS = 256;
 struct RankArgs {
     const Rec* recs;                     /* bucketed */
     const unsigned long long* seg_begin; /* [H+1] */
+    unsigned long long rec_cap;
     unsigned int* rank;                  /* [nrec] rank inside the segment */
     int H;
 };
 __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
     __shared__ unsigned long long s_key[K3_THREADS];
-    const int h = blockIdx.y;
-    const unsigned long long b = a.seg_begin[h], e = a.seg_begin[h + 1];
-    const unsigned long long len = e - b;
-    for (unsigned long long i0 = (unsigned long long)blockIdx.x * K3_THREADS; i0 < len;
-         i0 += (unsigned long long)gridDim.x * K3_THREADS) {
-        const unsigned long long i = i0 + threadIdx.x;
-        const unsigned long long mykey = (i < len) ? a.recs[b + i].key : 0ull;
-        unsigned int r = 0;
-        for (unsigned long long j0 = 0; j0 < len; j0 += K3_THREADS) {
-            const unsigned long long j = j0 + threadIdx.x;
-            __syncthreads();
-            s_key[threadIdx.x] = (j < len) ? a.recs[b + j].key : ~0ull;
-            __syncthreads();
-            const int lim = (int)min((unsigned long long)K3_THREADS, len - j0);
-            for (int k = 0; k < lim; ++k) r += (s_key[k] < mykey);
+    for (int h = blockIdx.y; h < a.H; h += gridDim.y) {
+        const unsigned long long b = a.seg_begin[h], e = min(a.seg_begin[h + 1], a.rec_cap);
+        if (e <= b) continue;
+        const unsigned long long len = e - b;
+        for (unsigned long long i0 = (unsigned long long)blockIdx.x * K3_THREADS; i0 < len;
+             i0 += (unsigned long long)gridDim.x * K3_THREADS) {
+            const unsigned long long i = i0 + threadIdx.x;
+            const unsigned long long mykey = (i < len) ? a.recs[b + i].key : 0ull;
+            unsigned int r = 0;
+            for (unsigned long long j0 = 0; j0 < len; j0 += K3_THREADS) {
+                const unsigned long long j = j0 + threadIdx.x;
+                __syncthreads();
+                s_key[threadIdx.x] = (j < len) ? a.recs[b + j].key : ~0ull;
+                __syncthreads();
+                const int lim = (int)min((unsigned long long)K3_THREADS, len - j0);
+                for (int k = 0; k < lim; ++k) r += (s_key[k] < mykey);
+            }
+            if (i < len) a.rank[b + i] = r;
         }
-        if (i < len) a.rank[b + i] = r;
+        __syncthreads();
     }
 }
 
@@ -860,31 +906,43 @@ struct GatherArgs {
     const Rec* recs;
     const unsigned int* rank;
     const unsigned long long* seg_begin;
-    unsigned long long nrec;
+    const unsigned long long* rec_count;
+    unsigned long long rec_cap;
+    long long out_cap;
     ColsIn in;
+    const Payload* payload; /* interleaved gather columns of a resident step, or NULL */
     ColsOut out;
     long long index_base;
     int pos_only;
 };
 __global__ void k3_gather_halo(const GatherArgs a) {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nrec;
+    const unsigned long long nrec = min(*a.rec_count, a.rec_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const Rec r = a.recs[i];
         const unsigned long long o = a.seg_begin[r.halo] + a.rank[i];
+        if ((long long)o >= a.out_cap) continue;
         const long long g = (long long)(r.key & 0xffffffffull);
         a.out.theta[o] = r.th;                        /* processLC.cpp:1446-1447 */
         a.out.phi[o] = r.ph;
-        a.out.redshift[o] = a_to_z_dev(a.in.a[g]);    /* :1450 */
-        a.out.x[o] = a.in.x[g];
-        a.out.y[o] = a.in.y[g];
-        a.out.z[o] = a.in.z[g];
-        a.out.id[o] = a.in.id[g];
-        if (!a.pos_only) {                            /* :1455-1461 */
-            a.out.vx[o] = a.in.vx[g];
-            a.out.vy[o] = a.in.vy[g];
-            a.out.vz[o] = a.in.vz[g];
-            a.out.rot[o] = a.in.rot[g];
-            a.out.rep[o] = a.in.rep[g];
+        a.out.x[o] = r.x;
+        a.out.y[o] = r.y;
+        a.out.z[o] = r.z;
+        if (a.payload) {
+            const Payload p = load_payload(a.payload + g);
+            a.out.redshift[o] = a_to_z_dev(p.a);      /* :1450 */
+            a.out.id[o] = p.id;
+            if (!a.pos_only) { a.out.vx[o] = p.vx; a.out.vy[o] = p.vy; a.out.vz[o] = p.vz; a.out.rot[o] = p.rot; a.out.rep[o] = p.rep; }
+        } else {
+            a.out.redshift[o] = a_to_z_dev(a.in.a[g]);
+            a.out.id[o] = a.in.id[g];
+            if (!a.pos_only) {                        /* :1455-1461 */
+                a.out.vx[o] = a.in.vx[g];
+                a.out.vy[o] = a.in.vy[g];
+                a.out.vz[o] = a.in.vz[g];
+                a.out.rot[o] = a.in.rot[g];
+                a.out.rep[o] = a.in.rep[g];
+            }
         }
         a.out.theta_u[o] = __int_as_float((int)(r.key >> 32));
         a.out.index[o] = a.index_base + g;
