@@ -558,7 +558,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         r.H = H;
         /* few halos: many column blocks per halo; many halos: one or two, the y dimension provides the parallelism */
         const unsigned int gy = (unsigned int)std::min(H, 8192);
-        const unsigned int gx = (unsigned int)std::max(1, std::min(64, (c->sm_count * 8) / (int)gy));
+        const unsigned int gx = (unsigned int)std::max(4, std::min(64, (c->sm_count * 8) / (int)gy));
         cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, 0, c->stream>>>(r);
         CU(cudaGetLastError());
         cck::GatherArgs g;
