@@ -111,8 +111,10 @@ def test_step_selection_equals_reference(lc_dirs, tmp_path):
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @needs_ref_bin
-@pytest.mark.parametrize("ngpus", [1])
+@pytest.mark.parametrize("ngpus", [1, 2])
 def test_cli_const_equals_reference(lc_dirs, tmp_path, ngpus):
+    if ngpus > cc.lib().cc_device_count():
+        pytest.skip(f"{ngpus} GPUs needed")
     o1, o2 = tmp_path / "ours", tmp_path / "ref"
     o1.mkdir(); o2.mkdir()
     args = [487, 470, "--theta", 80, 8, "--phi", 40, 10]
@@ -128,14 +130,18 @@ def test_cli_const_equals_reference(lc_dirs, tmp_path, ngpus):
 @pytest.mark.gpu
 @needs_ref_bin
 @pytest.mark.parametrize("pos_only", [False, True])
-def test_cli_halo_equals_reference(lc_dirs, tmp_path, pos_only):
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_cli_halo_equals_reference(lc_dirs, tmp_path, pos_only, ngpus):
+    if ngpus > cc.lib().cc_device_count():
+        pytest.skip(f"{ngpus} GPUs needed")
+    gpu_env = {"CC_NGPUS": str(ngpus)}
     hf = tmp_path / "halos.txt"
     _halo_file(str(hf), [("1001", (150, 20, 12)), ("1002", (30, 170, 100)), ("77", (100, 100, 100)),
                          ("5", (10, 10, 250)), ("6", (120, -60, 40))])
     o1, o2 = tmp_path / "ours", tmp_path / "ref"
     o1.mkdir(); o2.mkdir()
     args = [0.0, 0.06, "-f", hf, "-b", 120] + (["--posOnly"] if pos_only else [])
-    a = _run(cc.CLI_PATH, [lc_dirs, o1] + args + ["--timeit"])
+    a = _run(cc.CLI_PATH, [lc_dirs, o1] + args + ["--timeit"], env=gpu_env)
     _run(REF_BIN, [lc_dirs, o2] + args)
     files = _same_tree(str(o1), str(o2))
     assert len(files) == 5 * (1 + 2 * (7 if pos_only else 12))
@@ -143,10 +149,10 @@ def test_cli_halo_equals_reference(lc_dirs, tmp_path, pos_only):
     sizes = [os.path.getsize(os.path.join(str(o1), "halo_1001", "lcCutout487", "id.487.bin"))]
     assert sizes[0] > 0
     # re-run without --overwrite: every halo is skipped and nothing changes; with --overwrite: identical again
-    b = _run(cc.CLI_PATH, [lc_dirs, o1] + args)
+    b = _run(cc.CLI_PATH, [lc_dirs, o1] + args, env=gpu_env)
     assert "skipping halo" in b.stdout
     _same_tree(str(o1), str(o2))
-    _run(cc.CLI_PATH, [lc_dirs, o1] + args + ["--overwrite"])
+    _run(cc.CLI_PATH, [lc_dirs, o1] + args + ["--overwrite"], env=gpu_env)
     _same_tree(str(o1), str(o2))
 
 
