@@ -355,7 +355,11 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
     return CC_OK;
 }
 
+/* pinned read-back area: [0,32+3H) the cutout's own results, then the exchanged counts of all ranks + offsets */
+size_t small_elems(int H, int R) { return 32 + 3 * (size_t)H + (size_t)R * 2 * H + H + 16; }
+
 int prepare_const(cc_ctx* c) {
+    { int rc0 = ensure_small(c, small_elems(1, c->nranks)); if (rc0) return rc0; }
     if (c->out_cap == 0) {
         /* first guess: 1/16 of the step; cc_cutout_sync grows it to the exact count and re-runs on overflow */
         int rc = ensure_out_cap(c, std::max<int64_t>(c->n / 16, 1 << 16));
@@ -386,7 +390,7 @@ int prepare_halo(cc_ctx* c) {
     if ((rc = c->rec_b.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
     if ((rc = c->rank_buf.ensure((size_t)c->rec_cap * 4))) return rc;
     if ((rc = ensure_out_cap(c, c->rec_cap))) return rc;
-    if ((rc = ensure_small(c, 24 + 3 * (size_t)H + 1))) return rc;
+    if ((rc = ensure_small(c, small_elems(H, c->nranks)))) return rc;
 
     /* host: exact + pre-filter parameters */
     std::vector<float4> pre(H);
@@ -1131,19 +1135,28 @@ int cc_comm_size(cc_ctx* c) { return c ? c->nranks : -1; }
 
 int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64_t* offsets) {
     if (!c) return fail(CC_ERR_ARG, "ctx is NULL");
-    int rc = cc_cutout_sync(c, nullptr, nullptr);
+    if (c->pending == P_NONE) return fail(CC_ERR_STATE, "cc_exchange_counts: no cutout pending");
+    int rc = use_device(c);
     if (rc) return rc;
     const int H = c->nhalos, R = c->nranks;
-    if (H == 0) return CC_OK;
+    if (H == 0) return cc_cutout_sync(c, nullptr, nullptr);
     if ((rc = c->counts_buf.ensure((size_t)2 * H * 8))) return rc;
     if ((rc = c->gather_buf.ensure((size_t)R * 2 * H * 8))) return rc;
     if ((rc = c->offsets_buf.ensure((size_t)H * 8))) return rc;
-    if ((rc = ensure_small(c, 16 + (size_t)R * 2 * H + H))) return rc;
-    /* device-resident send buffer: {counts[H], rough[H]} (use case 2 already has it; use case 1 fills it here) */
-    if (c->pending == P_CONST) {
-        c->h_small[8] = (unsigned long long)c->counts[0];
-        c->h_small[9] = 0;
-        CU(cudaMemcpyAsync(c->counts_buf.p, c->h_small + 8, 16, cudaMemcpyHostToDevice, c->stream));
+    const size_t hg_off = 32 + 3 * (size_t)H; /* behind the cutout's own read-back area */
+    if (c->h_small_elems < small_elems(H, R)) { /* communicator created after the cutout was enqueued */
+        CU(cudaStreamSynchronize(c->stream));
+        std::vector<unsigned long long> keep(c->h_small, c->h_small + c->h_small_elems);
+        if ((rc = ensure_small(c, small_elems(H, R)))) return rc;
+        memcpy(c->h_small, keep.data(), keep.size() * sizeof(unsigned long long));
+    }
+    /* The collective is enqueued BEHIND the cutout kernels on the same stream: no host round trip between the
+     * scan and the exchange.  Survivor counts are exact even when a survivor buffer overflowed (only the stored
+     * rows are clipped), so a local re-run after the synchronisation never needs a second collective -- every rank
+     * issues exactly one all-gather per call. */
+    if (c->pending == P_CONST) { /* device-resident send buffer {count, 0}; use case 2 already has {counts, rough} */
+        CU(cudaMemcpyAsync(c->counts_buf.p, c->scratch.p, 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, c->stream));
     }
     if (c->comm) {
         NC(g_nccl.AllGather(c->counts_buf.p, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, c->stream));
@@ -1154,10 +1167,11 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
                                                           (unsigned long long*)c->offsets_buf.p, H, c->rank);
     CU(cudaGetLastError());
     c->launches += 1;
-    unsigned long long* hg = c->h_small + 16;
+    unsigned long long* hg = c->h_small + hg_off;
     CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if (c->synced) CU(cudaStreamSynchronize(c->stream));
+    else if ((rc = cc_cutout_sync(c, nullptr, nullptr))) return rc; /* one synchronisation for cutout + exchange */
     for (int r = 0; r < R; ++r)
         for (int h = 0; h < H; ++h) {
             if (all_counts) all_counts[(size_t)r * H + h] = (int64_t)hg[(size_t)r * 2 * H + h];

@@ -250,6 +250,28 @@ def test_halo_empty_inputs(ctx):
     assert counts.shape[0] == 0
 
 
+def test_exchange_counts_single_rank(ctx):
+    """count exchange enqueued behind the cutout (no communicator = one rank): counts and zero offsets, for both
+    use cases, whether or not cc_cutout_sync ran first"""
+    cols = H.shell_fixture(500_000, seed=17)
+    theta_cut, phi_cut = cc.cli_bounds(60, 10), cc.cli_bounds(30, 10)
+    want = H.oracle_cutout_const(cols, theta_cut, phi_cut)["id"].shape[0]
+    ctx.upload(cols)
+    ctx.cutout_const(theta_cut, phi_cut)
+    allc, allr, off = ctx.exchange_counts()
+    assert allc.shape == (1, 1) and int(allc[0, 0]) == want and int(off[0]) == 0 and int(allr[0, 0]) == 0
+    assert int(ctx.sync()[0][0]) == want
+    infos = [cc.halo_setup(p, b) for p, b in HALOS[:4]]
+    ctx.cutout_halo([i.halo for i in infos])
+    counts, rough = ctx.sync()
+    allc, allr, off = ctx.exchange_counts()
+    assert np.array_equal(allc[0], counts) and np.array_equal(allr[0], rough) and not off.any()
+    ctx.cutout_halo([i.halo for i in infos])
+    allc2, allr2, _ = ctx.exchange_counts()
+    assert np.array_equal(allc2, allc) and np.array_equal(allr2, allr)
+    H.assert_cols_equal(ctx.fetch(1), H.oracle_cutout_halo(cols, H.oracle_halo_setup(*HALOS[1]))[0])
+
+
 # ------------------------------------------------------------------------------------------------ streamed
 def _pinned(cols):
     out, addrs = {}, []
