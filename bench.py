@@ -364,7 +364,8 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     cores = len(os.sched_getaffinity(0))
-    per = int(args.cpu_sample) if args.cpu_sample else (2_000_000 if wl["uc"] == 2 else 20_000_000)
+    # the reference's own decomposition of this workload on this box: one MPI rank per core, each reading its block
+    per = int(args.cpu_sample) if args.cpu_sample else min(wl["n"] // cores, 8_000_000 if wl["uc"] == 2 else 25_000_000)
     ctx = mp.get_context("spawn")
     tasks = [(args.workload, i * per, per, 20261019, 1) for i in range(cores)]
     with ctx.Pool(cores) as pool:
