@@ -341,7 +341,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         g.region_cap = c->region_cap;
         g.cap = c->out_cap;
         g.index_base = c->index_base + ch.start;
-        cck::k1_gather<<<dim3(4, grid), 256, 0, c->stream>>>(g);
+        cck::k1_gather<<<dim3(16, grid), 256, 0, c->stream>>>(g);
         CU(cudaGetLastError());
         c->launches += 3;
     } else if (ch.last) {

@@ -424,10 +424,12 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
     __syncthreads();
     const unsigned int blk = s_block;
     const unsigned int first = blk * TSCAN_BLOCK + tid * TSCAN_ITEMS;
-    unsigned int c[TSCAN_ITEMS], sum = 0;
+    unsigned int c[TSCAN_ITEMS], p0[TSCAN_ITEMS], sum = 0;
 #pragma unroll
     for (int i = 0; i < TSCAN_ITEMS; ++i) {
-        c[i] = (first + i < a.ntiles) ? (unsigned int)(a.tile_info[first + i] & 0xffffffffull) : 0u;
+        const unsigned long long info = (first + i < a.ntiles) ? a.tile_info[first + i] : 0ull;
+        c[i] = (unsigned int)(info & 0xffffffffull);
+        p0[i] = (unsigned int)(info >> 32);
         sum += c[i];
     }
     unsigned int inc = sum;
@@ -480,13 +482,20 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
         }
     }
     __syncthreads();
+    /* rows of every tile's records (consecutive, in input order), written by the whole warp per non-empty tile so
+     * the stores coalesce even when a tile holds many survivors */
     unsigned int run = (unsigned int)s_excl + before + inc - sum;
 #pragma unroll
     for (int i = 0; i < TSCAN_ITEMS; ++i) {
-        if (c[i]) { /* rows of this tile's records: consecutive, in input order */
-            const unsigned long long pos0 = a.tile_info[first + i] >> 32;
-            for (unsigned int k = 0; k < c[i]; ++k)
-                if (pos0 + k < a.temp_cap) a.t_row[pos0 + k] = run + k;
+        unsigned int nz = __ballot_sync(0xffffffffu, c[i] != 0);
+        while (nz) {
+            const int src = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned int cnt = __shfl_sync(0xffffffffu, c[i], src);
+            const unsigned long long pos = __shfl_sync(0xffffffffu, p0[i], src);
+            const unsigned int r0 = __shfl_sync(0xffffffffu, run, src);
+            for (unsigned int k = lane; k < cnt; k += 32)
+                if (pos + k < a.temp_cap) a.t_row[pos + k] = r0 + k;
         }
         run += c[i];
     }
