@@ -130,6 +130,7 @@ struct cc_ctx {
     int k1_occupancy[2] = {0, 0};
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
+    bool k3_smem_set = false;
     unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
     DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z, t_row;
 
@@ -148,7 +149,8 @@ struct cc_ctx {
     /* scan scratch: [tile_state ... | ticket | result(2) ] */
     DevBuf scratch;
     /* use case 2 scratch */
-    DevBuf pre_buf, halo_buf, rec_a, rec_b, rank_buf, counts_buf, seg_buf, cursor_buf, misc_buf;
+    DevBuf pre_buf, halo_buf, rec_a, rec_b, rank_buf, counts_buf;
+    DevBuf hstate; /* use case 2 device state, one memset / one read-back: [misc 8 | counts 2H | seg H+1 | cursor H] u64 */
     DevBuf bin_start_buf, bin_items_buf, ovf_particle_buf, ovf_halo_buf;
     std::vector<size_t> bin_items_off; /* per launch batch: first item */
     int64_t ovf_cap = 0;
@@ -369,6 +371,12 @@ int prepare_const(cc_ctx* c) {
 }
 
 /* ---------------------------------------------------------------- use case 2 launch */
+size_t hstate_elems(int H) { return 8 + 2 * (size_t)H + ((size_t)H + 1) + (size_t)H; }
+unsigned long long* hs_misc(const cc_ctx* c) { return (unsigned long long*)c->hstate.p; }
+unsigned long long* hs_counts(const cc_ctx* c) { return hs_misc(c) + 8; }
+unsigned long long* hs_seg(const cc_ctx* c, int H) { return hs_counts(c) + 2 * (size_t)H; }
+unsigned long long* hs_cursor(const cc_ctx* c, int H) { return hs_seg(c, H) + (size_t)H + 1; }
+
 int64_t halo_scan_limit(const cc_ctx* c) {
     int64_t n_scan = c->n;
     if (c->p_n_limit >= 0) n_scan = std::max<int64_t>(0, std::min<int64_t>(c->n, c->p_n_limit - c->index_base));
@@ -381,10 +389,7 @@ int prepare_halo(cc_ctx* c) {
     int rc;
     if ((rc = c->pre_buf.ensure((size_t)H * sizeof(float4)))) return rc;
     if ((rc = c->halo_buf.ensure((size_t)H * sizeof(cck::HaloDev)))) return rc;
-    if ((rc = c->counts_buf.ensure((size_t)(2 * H) * 8))) return rc;
-    if ((rc = c->seg_buf.ensure((size_t)(H + 1) * 8))) return rc;
-    if ((rc = c->cursor_buf.ensure((size_t)H * 8))) return rc;
-    if ((rc = c->misc_buf.ensure(64))) return rc;
+    if ((rc = c->hstate.ensure(hstate_elems(H) * 8))) return rc;
     if (c->rec_cap == 0) c->rec_cap = 1 << 20;
     if ((rc = c->rec_a.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
     if ((rc = c->rec_b.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
@@ -476,15 +481,13 @@ int prepare_halo(cc_ctx* c) {
         c->params_key = c->p_halos;
         c->params_bins = c->use_bins;
     }
-    CU(cudaMemsetAsync(c->counts_buf.p, 0, (size_t)(2 * H) * 8, c->stream));
-    CU(cudaMemsetAsync(c->cursor_buf.p, 0, (size_t)H * 8, c->stream));
-    CU(cudaMemsetAsync(c->misc_buf.p, 0, 64, c->stream));
+    CU(cudaMemsetAsync(c->hstate.p, 0, hstate_elems(H) * 8, c->stream));
     return CC_OK;
 }
 
 int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
     const int H = (int)c->p_halos.size();
-    unsigned long long* rec_count = (unsigned long long*)c->misc_buf.p;
+    unsigned long long* rec_count = hs_misc(c);
     unsigned long long* n_cand = rec_count + 1;
     if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
     /* the n_limit clamp (tail drop of the reference's load balancer) applies to step-local indices */
@@ -502,7 +505,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         a.recs = (cck::Rec*)c->rec_a.p;
         a.rec_cap = (unsigned long long)c->rec_cap;
         a.rec_count = rec_count;
-        a.counts = (unsigned long long*)c->counts_buf.p;
+        a.counts = hs_counts(c);
         a.n_cand = n_cand;
         a.total_halos = H;
         a.ntiles = (unsigned int)((n_scan + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
@@ -541,34 +544,37 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
     if (ch.last) {
         CU(cudaEventRecord(c->ev_scan1, c->stream));
         /* ordering + gather, sized on the device: the whole pass is one enqueue, one host synchronisation */
-        cck::k3_scan_counts<<<1, 256, 0, c->stream>>>((const unsigned long long*)c->counts_buf.p,
-                                                      (unsigned long long*)c->seg_buf.p, H);
+        cck::k3_scan_counts<<<1, 256, 0, c->stream>>>(hs_counts(c), hs_seg(c, H), H);
         CU(cudaGetLastError());
         const unsigned int g1 = (unsigned int)c->sm_count * 4;
         cck::BucketArgs b;
         b.recs = (const cck::Rec*)c->rec_a.p;
         b.rec_count = rec_count;
         b.rec_cap = (unsigned long long)c->rec_cap;
-        b.seg_begin = (const unsigned long long*)c->seg_buf.p;
-        b.cursor = (unsigned long long*)c->cursor_buf.p;
+        b.seg_begin = hs_seg(c, H);
+        b.cursor = hs_cursor(c, H);
         b.out = (cck::Rec*)c->rec_b.p;
         cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
         CU(cudaGetLastError());
         cck::RankArgs r;
         r.recs = (const cck::Rec*)c->rec_b.p;
-        r.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        r.seg_begin = hs_seg(c, H);
         r.rec_cap = (unsigned long long)c->rec_cap;
         r.rank = (unsigned int*)c->rank_buf.p;
         r.H = H;
         /* few halos: many column blocks per halo; many halos: one or two, the y dimension provides the parallelism */
         const unsigned int gy = (unsigned int)std::min(H, 8192);
         const unsigned int gx = (unsigned int)std::max(4, std::min(64, (c->sm_count * 8) / (int)gy));
-        cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, 0, c->stream>>>(r);
+        if (!c->k3_smem_set) {
+            CU(cudaFuncSetAttribute((const void*)cck::k3_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K3_SMEM_BYTES));
+            c->k3_smem_set = true;
+        }
+        cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, cck::K3_SMEM_BYTES, c->stream>>>(r);
         CU(cudaGetLastError());
         cck::GatherArgs g;
         g.recs = (const cck::Rec*)c->rec_b.p;
         g.rank = (const unsigned int*)c->rank_buf.p;
-        g.seg_begin = (const unsigned long long*)c->seg_buf.p;
+        g.seg_begin = hs_seg(c, H);
         g.rec_count = rec_count;
         g.rec_cap = (unsigned long long)c->rec_cap;
         g.out_cap = c->out_cap;
@@ -582,9 +588,8 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         c->launches += 4;
         CU(cudaEventRecord(c->ev_total1, c->stream));
         c->have_times = true;
-        CU(cudaMemcpyAsync(c->h_small, c->misc_buf.p, 32, cudaMemcpyDeviceToHost, c->stream)); /* rec_count, n_cand, -, ovf_max */
-        CU(cudaMemcpyAsync(c->h_small + 8, c->counts_buf.p, (size_t)(2 * H) * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(c->h_small + 8 + 2 * H, c->seg_buf.p, (size_t)(H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        /* misc {rec_count, n_cand, -, ovf_max}, counts, rough counts, segment starts: one read-back */
+        CU(cudaMemcpyAsync(c->h_small, c->hstate.p, (8 + 3 * (size_t)H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     }
     return CC_OK;
 }
@@ -734,7 +739,7 @@ void cc_destroy(cc_ctx* c) {
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
     DevBuf* rest[] = {&c->scratch, &c->pre_buf, &c->halo_buf, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
-                      &c->seg_buf, &c->cursor_buf, &c->misc_buf, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row,
+                      &c->hstate, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row,
                       &c->bin_start_buf, &c->bin_items_buf, &c->ovf_particle_buf, &c->ovf_halo_buf};
     for (DevBuf* b : rest) b->release();
     for (auto& sl : c->stage) for (auto& b : sl) b.release();
@@ -1140,7 +1145,7 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
     if (rc) return rc;
     const int H = c->nhalos, R = c->nranks;
     if (H == 0) return cc_cutout_sync(c, nullptr, nullptr);
-    if ((rc = c->counts_buf.ensure((size_t)2 * H * 8))) return rc;
+    if ((rc = c->counts_buf.ensure(16))) return rc;
     if ((rc = c->gather_buf.ensure((size_t)R * 2 * H * 8))) return rc;
     if ((rc = c->offsets_buf.ensure((size_t)H * 8))) return rc;
     const size_t hg_off = 32 + 3 * (size_t)H; /* behind the cutout's own read-back area */
@@ -1158,10 +1163,11 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         CU(cudaMemcpyAsync(c->counts_buf.p, c->scratch.p, 8, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, c->stream));
     }
+    const void* send = (c->pending == P_CONST) ? c->counts_buf.p : (const void*)hs_counts(c);
     if (c->comm) {
-        NC(g_nccl.AllGather(c->counts_buf.p, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, c->stream));
+        NC(g_nccl.AllGather(send, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, c->stream));
     } else {
-        CU(cudaMemcpyAsync(c->gather_buf.p, c->counts_buf.p, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->gather_buf.p, send, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
     cck::k4_offsets<<<(H + 255) / 256, 256, 0, c->stream>>>((const unsigned long long*)c->gather_buf.p,
                                                           (unsigned long long*)c->offsets_buf.p, H, c->rank);

@@ -876,9 +876,14 @@ __global__ void k3_scan_counts(const unsigned long long* counts, unsigned long l
     if (tid == 255) seg_begin[H] = run;
 }
 
-/* rank of every record inside its halo segment by counting smaller keys (keys are unique: the low 32 bits
- * are the particle index).  grid = (column blocks, halos); the segment streams through shared memory. */
+/* rank of every record inside its halo segment = its position in (theta_u, index) order, the order of the
+ * reference's stable arg-sort (processLC.cpp:1214-1221).  Keys are unique (the low 32 bits are the particle index).
+ * Segments of up to K3_SORT_MAX records -- every cluster-sized cutout -- are sorted by ONE CTA with a bitonic
+ * network in shared memory; larger segments fall back to counting smaller keys (all column blocks of the halo,
+ * the segment streamed through shared memory).  grid = (column blocks, halos). */
 constexpr int K3_THREADS = 256;
+constexpr int K3_SORT_MAX = 8192;
+constexpr size_t K3_SMEM_BYTES = (size_t)K3_SORT_MAX * (sizeof(unsigned long long) + sizeof(unsigned short));
 struct RankArgs {
     const Rec* recs;                     /* bucketed */
     const unsigned long long* seg_begin; /* [H+1] */
@@ -887,27 +892,57 @@ struct RankArgs {
     int H;
 };
 __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
-    __shared__ unsigned long long s_key[K3_THREADS];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw);
+    unsigned short* s_idx = reinterpret_cast<unsigned short*>(s_raw + (size_t)K3_SORT_MAX * sizeof(unsigned long long));
+    const unsigned int tid = threadIdx.x;
     for (int h = blockIdx.y; h < a.H; h += gridDim.y) {
         const unsigned long long b = a.seg_begin[h], e = min(a.seg_begin[h + 1], a.rec_cap);
         if (e <= b) continue;
         const unsigned long long len = e - b;
-        for (unsigned long long i0 = (unsigned long long)blockIdx.x * K3_THREADS; i0 < len;
-             i0 += (unsigned long long)gridDim.x * K3_THREADS) {
-            const unsigned long long i = i0 + threadIdx.x;
-            const unsigned long long mykey = (i < len) ? a.recs[b + i].key : 0ull;
-            unsigned int r = 0;
-            for (unsigned long long j0 = 0; j0 < len; j0 += K3_THREADS) {
-                const unsigned long long j = j0 + threadIdx.x;
-                __syncthreads();
-                s_key[threadIdx.x] = (j < len) ? a.recs[b + j].key : ~0ull;
-                __syncthreads();
-                const int lim = (int)min((unsigned long long)K3_THREADS, len - j0);
-                for (int k = 0; k < lim; ++k) r += (s_key[k] < mykey);
+        if (len <= K3_SORT_MAX) {
+            if (blockIdx.x != 0) continue;
+            unsigned int n = 32;
+            while (n < len) n <<= 1;
+            for (unsigned int i = tid; i < n; i += K3_THREADS) {
+                s_key[i] = (i < len) ? a.recs[b + i].key : ~0ull;
+                s_idx[i] = (unsigned short)i;
             }
-            if (i < len) a.rank[b + i] = r;
+            __syncthreads();
+            for (unsigned int k = 2; k <= n; k <<= 1) {
+                for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+                    for (unsigned int t = tid; t < (n >> 1); t += K3_THREADS) {
+                        const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                        const unsigned long long ki = s_key[i], kl = s_key[l];
+                        const bool up = (i & k) == 0;
+                        if ((ki > kl) == up) {
+                            s_key[i] = kl; s_key[l] = ki;
+                            const unsigned short t2 = s_idx[i]; s_idx[i] = s_idx[l]; s_idx[l] = t2;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (unsigned int i = tid; i < len; i += K3_THREADS) a.rank[b + s_idx[i]] = i;
+            __syncthreads();
+        } else {
+            for (unsigned long long i0 = (unsigned long long)blockIdx.x * K3_THREADS; i0 < len;
+                 i0 += (unsigned long long)gridDim.x * K3_THREADS) {
+                const unsigned long long i = i0 + tid;
+                const unsigned long long mykey = (i < len) ? a.recs[b + i].key : 0ull;
+                unsigned int r = 0;
+                for (unsigned long long j0 = 0; j0 < len; j0 += K3_THREADS) {
+                    const unsigned long long j = j0 + tid;
+                    __syncthreads();
+                    s_key[tid] = (j < len) ? a.recs[b + j].key : ~0ull;
+                    __syncthreads();
+                    const int lim = (int)min((unsigned long long)K3_THREADS, len - j0);
+                    for (int k = 0; k < lim; ++k) r += (s_key[k] < mykey);
+                }
+                if (i < len) a.rank[b + i] = r;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 

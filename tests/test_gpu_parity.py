@@ -238,6 +238,21 @@ def test_halo_many_halos_one_pass(ctx):
         H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {h}: ")
 
 
+def test_halo_large_segment(ctx):
+    """a 10-degree box: tens of thousands of survivors in one halo -- beyond the shared-memory sort (K3_SORT_MAX =
+    8192), so the counting fallback orders the segment; a second, small halo in the same pass takes the sort"""
+    cols = H.shell_fixture(2_000_000, seed=77)
+    specs = [((150, 120, 90), 600.0), ((150, 20, 12), 30.0)]
+    ctx.upload(cols)
+    ctx.cutout_halo([cc.halo_setup(p, b).halo for p, b in specs])
+    counts, rough = ctx.sync()
+    assert int(counts[0]) > 8192 > int(counts[1]) > 0
+    for h, (p, b) in enumerate(specs):
+        want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, b))
+        assert int(rough[h]) == want_rough
+        H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {p} {b}: ")
+
+
 def test_halo_empty_inputs(ctx):
     info = cc.halo_setup((150, 20, 12), 10.0)
     ctx.upload(H.slice_cols(H.shell_fixture(10, seed=1), 0, 0))
