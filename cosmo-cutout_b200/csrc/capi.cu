@@ -128,6 +128,7 @@ struct cc_ctx {
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr, ev_total1 = nullptr;
     int64_t launches = 0;
     int k1_occupancy[2] = {0, 0};
+    int64_t last_const_count = -1;
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
     bool k3_smem_set = false;
@@ -343,7 +344,11 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         g.region_cap = c->region_cap;
         g.cap = c->out_cap;
         g.index_base = c->index_base + ch.start;
-        cck::k1_gather<<<dim3(16, grid), 256, 0, c->stream>>>(g);
+        /* blocks per region: sized for the survivors the last cutout on this context produced (or the output
+         * capacity on a first run); the kernel loops, so this only trades launch width against iterations */
+        const int64_t expect = c->last_const_count >= 0 ? c->last_const_count + c->last_const_count / 4 : c->out_cap;
+        const unsigned int gxg = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(16, (expect / grid + 255) / 256));
+        cck::k1_gather<<<dim3(gxg, grid), 256, 0, c->stream>>>(g);
         CU(cudaGetLastError());
         c->launches += 3;
     } else if (ch.last) {
@@ -933,6 +938,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
                 if ((rc = run_pending(c))) return rc;
             }
             c->counts.assign(1, (int64_t)c->h_small[0]);
+            c->last_const_count = c->counts[0];
             c->rough.assign(1, 0);
             c->seg_begin.assign(2, 0);
             c->seg_begin[1] = c->counts[0];

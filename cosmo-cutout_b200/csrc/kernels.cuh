@@ -482,13 +482,17 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
         }
     }
     __syncthreads();
-    /* rows of every tile's records (consecutive, in input order), written by the whole warp per non-empty tile so
-     * the stores coalesce even when a tile holds many survivors */
+    /* rows of every tile's records: consecutive, in input order */
     unsigned int run = (unsigned int)s_excl + before + inc - sum;
 #pragma unroll
     for (int i = 0; i < TSCAN_ITEMS; ++i) {
-        unsigned int nz = __ballot_sync(0xffffffffu, c[i] != 0);
-        while (nz) {
+        const bool big = c[i] > 8;
+        if (!big) { /* the usual case of a narrow window: a handful of rows, written by the owning thread */
+            for (unsigned int k = 0; k < c[i]; ++k)
+                if ((unsigned long long)p0[i] + k < a.temp_cap) a.t_row[p0[i] + k] = run + k;
+        }
+        unsigned int nz = __ballot_sync(0xffffffffu, big);
+        while (nz) { /* dense tiles: the whole warp writes one tile's rows, coalesced */
             const int src = __ffs(nz) - 1;
             nz &= nz - 1;
             const unsigned int cnt = __shfl_sync(0xffffffffu, c[i], src);
