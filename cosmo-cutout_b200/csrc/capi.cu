@@ -304,7 +304,12 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         a.x = ch.x; a.y = ch.y; a.z = ch.z;
         a.n = ch.n;
         a.th_lo = c->p_th[0]; a.th_hi = c->p_th[1]; a.ph_lo = c->p_ph[0]; a.ph_hi = c->p_ph[1];
-        ccpf::uc1_bounds(c->p_th, c->p_ph, &a.chi2, &a.clo2, &a.tlo, &a.thi);
+        {
+            float clo2, tlo;
+            ccpf::uc1_bounds(c->p_th, c->p_ph, &a.chi2, &clo2, &tlo, &a.thi);
+            a.nclo2 = -clo2;
+            a.ntlo = -tlo;
+        }
         a.t_idx = (unsigned int*)c->t_idx.p; a.t_th = (float*)c->t_th.p; a.t_ph = (float*)c->t_ph.p;
         a.t_x = (float*)c->t_x.p; a.t_y = (float*)c->t_y.p; a.t_z = (float*)c->t_z.p;
         a.region_cap = c->region_cap;

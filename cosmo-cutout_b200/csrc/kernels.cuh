@@ -159,7 +159,7 @@ struct ScanArgs {
     const float *x, *y, *z;
     long long n;                      /* particles in this chunk */
     float th_lo, th_hi, ph_lo, ph_hi; /* exact, strict (processLC.cpp:287-288) */
-    float chi2, clo2, tlo, thi;       /* pre-filter (prefilter.h) */
+    float chi2, nclo2, ntlo, thi;     /* pre-filter (prefilter.h): chi2, -clo2, -tlo, thi */
     unsigned int* t_idx;              /* temp records: particle index inside the chunk */
     float *t_th, *t_ph;               /*               theta, phi (arcsec) */
     float *t_x, *t_y, *t_z;           /*               the position (already in registers here: saves three
@@ -172,18 +172,24 @@ struct ScanArgs {
     unsigned int drain_at;            /* queued candidates that trigger the exact path (32 = a full warp) */
 };
 
-/* branch-free on purpose: eight of these run back to back per lane and divergent early-outs cost more than the
- * arithmetic they skip.  NaN coordinates fail `mn > 0` only if all three are NaN; a NaN in one coordinate makes
- * either the window compares false (rejected, like the reference: x>0 && y>0 && z>0 is false for a NaN) or the
- * particle a candidate, and the exact path rejects it. */
+/* Branch-free on purpose: eight of these run back to back per lane and divergent early-outs cost more than the
+ * arithmetic they skip.  Each window condition is turned into a difference by ONE fma -- fma(a,b,-c) has exactly the
+ * sign of a*b - c, so `d > 0` is the exact comparison a*b > c -- and the four differences are reduced with min, so the
+ * whole window is one compare instead of four compare+select pairs (the compiler has 7 predicate registers for 8
+ * particles x 7 conditions).  A NaN difference is dropped by min, which can only ADD candidates; the exact path
+ * rejects them (the reference's x>0 && y>0 && z>0 is false for a NaN). */
 __device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const ScanArgs& a) {
     const float mn = fminf(x, fminf(y, z));
-    const float mx = fmaxf(x, fmaxf(y, z));
     const float r2 = fmaf(z, z, fmaf(y, y, x * x));
     const float z2 = z * z;
-    const bool window = (z2 < a.chi2 * r2) & (z2 > a.clo2 * r2) & (y > a.tlo * x) & (y < a.thi * x);
-    const bool insane = !((mn >= CC_SANE_LO) & (mx <= CC_SANE_HI)); /* let the exact path decide */
-    return (mn > 0.0f) & (window | insane);                         /* octant test, processLC.cpp:279 */
+    const float d1 = fmaf(a.chi2, r2, -z2);  /* > 0  <=>  z^2 < chi2 r^2 */
+    const float d2 = fmaf(a.nclo2, r2, z2);  /* > 0  <=>  z^2 > clo2 r^2   (nclo2 = -clo2) */
+    const float d3 = fmaf(a.ntlo, x, y);     /* > 0  <=>  y > tlo x        (ntlo = -tlo)   */
+    const float d4 = fmaf(a.thi, x, -y);     /* > 0  <=>  y < thi x */
+    const float score = fminf(fminf(d1, d2), fminf(d3, d4));
+    /* inside [2^-30, 2^40] nothing above can overflow or lose relative precision; outside, the exact path decides */
+    const bool sane = (mn >= CC_SANE_LO) & (r2 <= 1.2089258e24f);
+    return sane ? (score > 0.0f) : (mn > 0.0f); /* mn > 0 is the octant test, processLC.cpp:279 */
 }
 
 /* Per-warp candidate queue, kept ACROSS tiles: the exact path costs ~1000 warp instructions whether 1 or 32 lanes
