@@ -133,6 +133,61 @@ def test_const_everything_survives_and_capacity_regrows(ctx):
     H.assert_cols_equal(ctx.fetch(0), want)
 
 
+def test_const_special_values_and_global_index(ctx):
+    """NaN / Inf / zero / subnormal scale factors (redshift = 1/a - 1 must carry the host's bits, including the
+    quieted NaN payload), NaN and Inf coordinates (rejected like the reference), and a shard whose global index
+    base is beyond 2^32"""
+    cols = H.shell_fixture(400_000, seed=33)
+    rng = np.random.default_rng(9)
+    a = cols["a"]
+    pick = rng.choice(400_000, 40_000, replace=False)
+    specials = np.array([np.nan, -np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-45, 1e-39, 3.4e38, 1.0, -1.0, 0.5],
+                        dtype=np.float32)
+    a[pick] = specials[rng.integers(0, len(specials), pick.shape[0])]
+    a[pick[:1000]] = np.array([0x7fa00001, 0xffa12345, 0x7f800001], dtype=np.uint32).view(np.float32)[rng.integers(0, 3, 1000)]
+    bad = rng.choice(400_000, 3_000, replace=False)
+    for k, col in enumerate(("x", "y", "z")):
+        cols[col][bad[k::3]] = np.array([np.nan, np.inf, -np.inf, 0.0], dtype=np.float32)[rng.integers(0, 4, bad[k::3].shape[0])]
+    theta_cut, phi_cut = cc.cli_bounds(60, 29), cc.cli_bounds(45, 44)
+    base = 5_000_000_000
+    ctx.upload(cols, index_base=base)
+    ctx.cutout_const(theta_cut, phi_cut)
+    counts, _ = ctx.sync()
+    got = ctx.fetch(0, names=cc.OUT_COLS + ("index",))
+    want = H.oracle_cutout_const(cols, theta_cut, phi_cut)
+    assert int(counts[0]) == want["id"].shape[0] > 100_000
+    H.assert_cols_equal(got, want, what="special values: ")
+    assert np.isnan(got["redshift"]).any() and np.isinf(got["redshift"]).any()
+    assert np.array_equal(got["index"] - base, got["id"]) and got["index"].min() >= base
+
+
+def test_const_tiny_temp_regions_regrow(ctx):
+    """all survivors sit in a narrow index range, so a handful of CTA temp regions overflow their first-guess
+    capacity: the cutout must notice, grow and re-run"""
+    n = 3_000_000
+    cols = H.shell_fixture(n, seed=34)
+    theta_cut, phi_cut = cc.cli_bounds(87, 2), cc.cli_bounds(2, 2)
+    # park everything outside the window, then drop 150k in-window particles into one contiguous block
+    th, ph = H.oracle_theta_phi(cols["x"], cols["y"], cols["z"], guards=False)
+    inside = (th > theta_cut[0]) & (th < theta_cut[1]) & (ph > phi_cut[0]) & (ph < phi_cut[1])
+    for c in ("x", "y", "z"):
+        cols[c][inside] = -cols[c][inside]
+    rng = np.random.default_rng(35)
+    k = 150_000
+    t = np.deg2rad(rng.uniform(85.2, 88.8, k)); p = np.deg2rad(rng.uniform(0.2, 3.8, k)); r = rng.uniform(100, 300, k)
+    blk = dict(x=r * np.sin(t) * np.cos(p), y=r * np.sin(t) * np.sin(p), z=r * np.cos(t))
+    lo = 1_234_567
+    for c in ("x", "y", "z"):
+        cols[c][lo:lo + k] = blk[c].astype(np.float32)
+    with cc.Context(0) as fresh:  # first-guess capacities
+        fresh.upload(cols)
+        fresh.cutout_const(theta_cut, phi_cut)
+        counts, _ = fresh.sync()
+        want = H.oracle_cutout_const(cols, theta_cut, phi_cut)
+        assert int(counts[0]) == want["id"].shape[0] == k
+        H.assert_cols_equal(fresh.fetch(0), want, what="regrow: ")
+
+
 def test_const_unaligned_device_columns(ctx):
     """attach columns whose device addresses are not 16-byte aligned: the scalar-load kernel variant"""
     import torch
