@@ -131,7 +131,9 @@ struct cc_ctx {
     int64_t last_const_count = -1;
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
-    bool k3_smem_set = false;
+    bool k3_smem_set = false, k3s_smem_set = false;
+    int64_t last_nrec = -1;       /* survivors of the previous use-case-2 cutout on this context */
+    bool force_general = false, used_small = false;
     unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
     DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z, t_row;
 
@@ -554,35 +556,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
     if (ch.last) {
         CU(cudaEventRecord(c->ev_scan1, c->stream));
         /* ordering + gather, sized on the device: the whole pass is one enqueue, one host synchronisation */
-        cck::k3_scan_counts<<<1, 256, 0, c->stream>>>(hs_counts(c), hs_seg(c, H), H);
-        CU(cudaGetLastError());
-        const unsigned int g1 = (unsigned int)c->sm_count * 4;
-        cck::BucketArgs b;
-        b.recs = (const cck::Rec*)c->rec_a.p;
-        b.rec_count = rec_count;
-        b.rec_cap = (unsigned long long)c->rec_cap;
-        b.seg_begin = hs_seg(c, H);
-        b.cursor = hs_cursor(c, H);
-        b.out = (cck::Rec*)c->rec_b.p;
-        cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
-        CU(cudaGetLastError());
-        cck::RankArgs r;
-        r.recs = (const cck::Rec*)c->rec_b.p;
-        r.seg_begin = hs_seg(c, H);
-        r.rec_cap = (unsigned long long)c->rec_cap;
-        r.rank = (unsigned int*)c->rank_buf.p;
-        r.H = H;
-        /* few halos: many column blocks per halo; many halos: one or two, the y dimension provides the parallelism */
-        const unsigned int gy = (unsigned int)std::min(H, 8192);
-        const unsigned int gx = (unsigned int)std::max(4, std::min(64, (c->sm_count * 8) / (int)gy));
-        if (!c->k3_smem_set) {
-            CU(cudaFuncSetAttribute((const void*)cck::k3_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K3_SMEM_BYTES));
-            c->k3_smem_set = true;
-        }
-        cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, cck::K3_SMEM_BYTES, c->stream>>>(r);
-        CU(cudaGetLastError());
         cck::GatherArgs g;
-        g.recs = (const cck::Rec*)c->rec_b.p;
         g.rank = (const unsigned int*)c->rank_buf.p;
         g.seg_begin = hs_seg(c, H);
         g.rec_count = rec_count;
@@ -593,9 +567,57 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         g.out = cols_out_of(c);
         g.index_base = c->index_base;
         g.pos_only = c->p_pos_only;
-        cck::k3_gather_halo<<<g1, 256, 0, c->stream>>>(g);
-        CU(cudaGetLastError());
-        c->launches += 4;
+        /* few survivors last time: speculate that one single-CTA kernel can order and gather everything */
+        const bool small = !c->force_general && c->last_nrec >= 0 && c->last_nrec <= cck::K3_SORT_MAX * 3 / 4 && H <= 65535;
+        c->used_small = small;
+        if (small) {
+            if (!c->k3s_smem_set) {
+                CU(cudaFuncSetAttribute((const void*)cck::k3_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K3S_SMEM_BYTES));
+                c->k3s_smem_set = true;
+            }
+            cck::SmallArgs sa;
+            sa.g = g;
+            sa.g.recs = (const cck::Rec*)c->rec_a.p;
+            sa.counts = hs_counts(c);
+            sa.seg_begin = hs_seg(c, H);
+            sa.misc = hs_misc(c);
+            sa.H = H;
+            cck::k3_small<<<1, cck::K3S_THREADS, cck::K3S_SMEM_BYTES, c->stream>>>(sa);
+            CU(cudaGetLastError());
+            c->launches += 1;
+        } else {
+            cck::k3_scan_counts<<<1, 256, 0, c->stream>>>(hs_counts(c), hs_seg(c, H), H);
+            CU(cudaGetLastError());
+            const unsigned int g1 = (unsigned int)c->sm_count * 4;
+            cck::BucketArgs b;
+            b.recs = (const cck::Rec*)c->rec_a.p;
+            b.rec_count = rec_count;
+            b.rec_cap = (unsigned long long)c->rec_cap;
+            b.seg_begin = hs_seg(c, H);
+            b.cursor = hs_cursor(c, H);
+            b.out = (cck::Rec*)c->rec_b.p;
+            cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
+            CU(cudaGetLastError());
+            cck::RankArgs r;
+            r.recs = (const cck::Rec*)c->rec_b.p;
+            r.seg_begin = hs_seg(c, H);
+            r.rec_cap = (unsigned long long)c->rec_cap;
+            r.rank = (unsigned int*)c->rank_buf.p;
+            r.H = H;
+            /* few halos: many column blocks per halo; many halos: a few, the y dimension provides the parallelism */
+            const unsigned int gy = (unsigned int)std::min(H, 8192);
+            const unsigned int gx = (unsigned int)std::max(4, std::min(64, (c->sm_count * 8) / (int)gy));
+            if (!c->k3_smem_set) {
+                CU(cudaFuncSetAttribute((const void*)cck::k3_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K3_SMEM_BYTES));
+                c->k3_smem_set = true;
+            }
+            cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, cck::K3_SMEM_BYTES, c->stream>>>(r);
+            CU(cudaGetLastError());
+            g.recs = (const cck::Rec*)c->rec_b.p;
+            cck::k3_gather_halo<<<g1, 256, 0, c->stream>>>(g);
+            CU(cudaGetLastError());
+            c->launches += 4;
+        }
         CU(cudaEventRecord(c->ev_total1, c->stream));
         c->have_times = true;
         /* misc {rec_count, n_cand, -, ovf_max}, counts, rough counts, segment starts: one read-back */
@@ -953,13 +975,17 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             for (int attempt = 0; attempt < 4; ++attempt) {
                 CU(cudaStreamSynchronize(c->stream));
                 const int64_t nrec = (int64_t)c->h_small[0], ovf_max = (int64_t)c->h_small[3];
-                if (nrec <= c->rec_cap && ovf_max <= c->ovf_cap) break;
+                const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
+                c->force_general = refused;
+                if (nrec <= c->rec_cap && ovf_max <= c->ovf_cap && !refused) break;
                 if (attempt == 3) return fail(CC_ERR_CUDA, "internal: halo survivor buffers still too small after regrowth");
                 if (nrec > c->rec_cap) c->rec_cap = nrec + nrec / 64;
                 if (ovf_max > c->ovf_cap) c->ovf_cap = ovf_max + ovf_max / 8;
                 if ((rc = run_pending(c))) return rc;
             }
             const int64_t nrec = (int64_t)c->h_small[0];
+            c->last_nrec = nrec;
+            c->force_general = false;
             c->counts.resize(H); c->rough.resize(H); c->seg_begin.resize(H + 1);
             int64_t tot = 0, tot_rough = 0;
             for (int h = 0; h < H; ++h) {

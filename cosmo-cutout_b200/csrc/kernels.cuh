@@ -1003,6 +1003,107 @@ __global__ void k3_gather_halo(const GatherArgs a) {
     }
 }
 
+/* ---- small cutouts: the four kernels above as ONE single-CTA launch -------------------------------------------
+ * A cluster-sized cutout leaves a few hundred survivors; k3_scan_counts + k3_bucket + k3_rank + k3_gather_halo are
+ * then four launch-latency-bound kernels (~20 us of a 250 us step).  When the previous cutout on the context left at
+ * most K3_SORT_MAX survivors the host speculatively enqueues this kernel instead: one CTA scans the halo counts,
+ * sorts ALL records by (halo, theta_u, index) with a bitonic network in shared memory -- the sorted position IS the
+ * output row -- and gathers.  If the record count turns out larger it sets misc[4] and does nothing; the host then
+ * re-runs the cutout through the general kernels. */
+constexpr int K3S_THREADS = 512;
+constexpr size_t K3S_SMEM_BYTES = (size_t)K3_SORT_MAX * (sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
+                                  (size_t)K3S_THREADS * sizeof(unsigned long long);
+struct SmallArgs {
+    GatherArgs g;                        /* recs = the UNbucketed records (rec_a) */
+    const unsigned long long* counts;    /* [H] survivors per halo */
+    unsigned long long* seg_begin;       /* [H+1] out */
+    unsigned long long* misc;            /* [4] = 1 when the record count does not fit */
+    int H;
+};
+__global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw);
+    unsigned short* s_halo = reinterpret_cast<unsigned short*>(s_raw + (size_t)K3_SORT_MAX * 8);
+    unsigned short* s_idx = s_halo + K3_SORT_MAX;
+    unsigned long long* s_part = reinterpret_cast<unsigned long long*>(s_raw + (size_t)K3_SORT_MAX * 12);
+    const unsigned int tid = threadIdx.x;
+    const unsigned long long nrec = *a.g.rec_count;
+    if (nrec > K3_SORT_MAX || nrec > a.g.rec_cap) {
+        if (tid == 0) a.misc[4] = 1ull;
+        return;
+    }
+    /* exclusive scan of the halo counts -> seg_begin (read back by the host) */
+    {
+        const int per = (a.H + K3S_THREADS - 1) / K3S_THREADS;
+        unsigned long long sum = 0;
+        for (int i = tid * per; i < min(a.H, (int)(tid + 1) * per); ++i) sum += a.counts[i];
+        s_part[tid] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long run = 0;
+            for (int i = 0; i < K3S_THREADS; ++i) { const unsigned long long t = s_part[i]; s_part[i] = run; run += t; }
+        }
+        __syncthreads();
+        unsigned long long run = s_part[tid];
+        for (int i = tid * per; i < min(a.H, (int)(tid + 1) * per); ++i) { a.seg_begin[i] = run; run += a.counts[i]; }
+        if (tid == K3S_THREADS - 1) a.seg_begin[a.H] = run;
+    }
+    unsigned int n = 32;
+    while (n < nrec) n <<= 1;
+    for (unsigned int i = tid; i < n; i += K3S_THREADS) {
+        if (i < nrec) { s_key[i] = a.g.recs[i].key; s_halo[i] = (unsigned short)a.g.recs[i].halo; }
+        else { s_key[i] = ~0ull; s_halo[i] = 0xffffu; }
+        s_idx[i] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (unsigned int k = 2; k <= n; k <<= 1) {
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int t = tid; t < (n >> 1); t += K3S_THREADS) {
+                const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const unsigned long long ki = s_key[i], kl = s_key[l];
+                const unsigned short hi = s_halo[i], hl = s_halo[l];
+                const bool greater = (hi != hl) ? (hi > hl) : (ki > kl);
+                const bool up = (i & k) == 0;
+                if (greater == up) {
+                    s_key[i] = kl; s_key[l] = ki;
+                    s_halo[i] = hl; s_halo[l] = hi;
+                    const unsigned short t2 = s_idx[i]; s_idx[i] = s_idx[l]; s_idx[l] = t2;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    /* sorted position = output row (segments are contiguous in halo order) */
+    for (unsigned int o = tid; o < nrec; o += K3S_THREADS) {
+        if ((long long)o >= a.g.out_cap) continue;
+        const Rec r = a.g.recs[s_idx[o]];
+        const long long g = (long long)(r.key & 0xffffffffull);
+        a.g.out.theta[o] = r.th;
+        a.g.out.phi[o] = r.ph;
+        a.g.out.x[o] = r.x;
+        a.g.out.y[o] = r.y;
+        a.g.out.z[o] = r.z;
+        if (a.g.payload) {
+            const Payload p = load_payload(a.g.payload + g);
+            a.g.out.redshift[o] = a_to_z_dev(p.a);
+            a.g.out.id[o] = p.id;
+            if (!a.g.pos_only) { a.g.out.vx[o] = p.vx; a.g.out.vy[o] = p.vy; a.g.out.vz[o] = p.vz; a.g.out.rot[o] = p.rot; a.g.out.rep[o] = p.rep; }
+        } else {
+            a.g.out.redshift[o] = a_to_z_dev(a.g.in.a[g]);
+            a.g.out.id[o] = a.g.in.id[g];
+            if (!a.g.pos_only) {
+                a.g.out.vx[o] = a.g.in.vx[g];
+                a.g.out.vy[o] = a.g.in.vy[g];
+                a.g.out.vz[o] = a.g.in.vz[g];
+                a.g.out.rot[o] = a.g.in.rot[g];
+                a.g.out.rep[o] = a.g.in.rep[g];
+            }
+        }
+        a.g.out.theta_u[o] = __int_as_float((int)(r.key >> 32));
+        a.g.out.index[o] = a.g.index_base + g;
+    }
+}
+
 /* ================================================================================================
  * K4  offsets from the all-gathered counts: offsets[h] = sum_{r < rank} counts[r][h]
  *     gathered layout: [rank][2*H] (counts then rough counts)
