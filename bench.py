@@ -148,6 +148,11 @@ def run_ours(args):
         ident = [cc.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
         ctx.comm_init(world, rank, ident[0])
+        if not args.no_peer:  # count exchange by NVLink peer stores (mailboxes shared through CUDA IPC)
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.comm_peer_handle(world, rank))
+            ctx.comm_peer_attach(handles)
+            dist.barrier()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
     ctx.synth(n, seed=20261019, index_base=rank * n, kind=wl["kind"], box=wl["box"])
@@ -178,20 +183,25 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
+    # per-kernel times (the roofline numerator's denominator) are read from the library's own CUDA events in a
+    # separate untimed pass: reading them costs two synchronising calls per step that do not belong in the timed loop
+    scan_ms, pass_ms = [], []
+    for _ in range(max(3, min(args.steps, 10))):
+        step()
+        scan_ms.append(ctx.last_scan_ms())
+        pass_ms.append(ctx.last_total_ms())
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         time.sleep(0.25)
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms, pass_ms, survivors, scanned = [], [], 0, 0
+    survivors, scanned = 0, 0
     barrier()
     t0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
-        scan_ms.append(ctx.last_scan_ms())
-        pass_ms.append(ctx.last_total_ms())
     ev1.record(stream)
     barrier()
     t1 = time.time()
@@ -285,7 +295,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": wl["desc"], "particles_per_gpu": n, "particles_total": n_total,
                        "survivors_total": survivors_all, "l2": "inputs (12 B x particles per GPU) exceed the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the cutout stream around all timed steps, max over ranks"},
+                       "timing": "CUDA events on the cutout stream around all timed steps, max over ranks",
+                       "count_exchange": ("none (1 GPU)" if world == 1 else
+                                          ("NCCL all-gather" if args.no_peer else "NVLink peer stores (k4_exchange_peer)"))},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "k2_cutout_halo" if wl["uc"] == 2 else "k1_scan",
@@ -406,6 +418,7 @@ def main():
     ap.add_argument("--cpu-sample", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-peer", action="store_true", help="count exchange through NCCL instead of NVLink peer stores")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

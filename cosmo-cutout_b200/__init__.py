@@ -58,6 +58,7 @@ SYMBOLS = (
     "cc_cutout_const_streamed", "cc_cutout_halo_streamed", "cc_host_alloc", "cc_host_free", "cc_host_register",
     "cc_host_unregister",
     "cc_comm_unique_id", "cc_comm_init", "cc_comm_init_all", "cc_exchange_counts", "cc_comm_rank", "cc_comm_size",
+    "cc_comm_peer_handle", "cc_comm_peer_attach",
     "cc_shard_range", "cc_merge_order",
     "cc_last_scan_ms", "cc_last_total_ms", "cc_launch_count", "cc_last_stats",
     "cc_debug_eval", "cc_debug_eval_host",
@@ -108,6 +109,8 @@ def lib():
         L.cc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.cc_comm_init_all.argtypes = [C.c_void_p, C.c_int]
         L.cc_exchange_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cc_comm_peer_handle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.cc_comm_peer_attach.argtypes = [C.c_void_p, C.c_void_p]
         L.cc_comm_rank.argtypes = [C.c_void_p]
         L.cc_comm_size.argtypes = [C.c_void_p]
         L.cc_shard_range.restype = None
@@ -328,6 +331,18 @@ class Context:
     def comm_init(self, nranks, rank, id_bytes):
         buf = C.create_string_buffer(bytes(id_bytes), 128)
         _check(lib().cc_comm_init(self._h, int(nranks), int(rank), buf))
+
+    def comm_peer_handle(self, nranks, rank):
+        """allocate this GPU's count-exchange mailbox and return its 64-byte IPC handle"""
+        buf = C.create_string_buffer(64)
+        _check(lib().cc_comm_peer_handle(self._h, int(nranks), int(rank), buf))
+        return bytes(buf.raw)
+
+    def comm_peer_attach(self, handles):
+        """handles: the 64-byte handles of all ranks, in rank order"""
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(lib().cc_comm_peer_attach(self._h, buf))
 
     def comm_rank(self):
         return int(lib().cc_comm_rank(self._h))

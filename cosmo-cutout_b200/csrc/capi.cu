@@ -192,6 +192,12 @@ struct cc_ctx {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     DevBuf gather_buf, offsets_buf;
+    /* peer-store exchange (kernels.cuh k4_exchange_peer) */
+    DevBuf mailbox;
+    unsigned long long* peer_mb[cck::XCHG_MAX_RANKS] = {};
+    bool peer_opened[cck::XCHG_MAX_RANKS] = {};
+    bool peers_ready = false;
+    unsigned long long xchg_epoch = 0;
 };
 
 namespace {
@@ -370,7 +376,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
 }
 
 /* pinned read-back area: [0,32+3H) the cutout's own results, then the exchanged counts of all ranks + offsets */
-size_t small_elems(int H, int R) { return 32 + 3 * (size_t)H + (size_t)R * 2 * H + H + 16; }
+size_t small_elems(int H, int R) { return 32 + 3 * (size_t)H + (size_t)R * 2 * H + H + 24; }
 
 int prepare_const(cc_ctx* c) {
     { int rc0 = ensure_small(c, small_elems(1, c->nranks)); if (rc0) return rc0; }
@@ -767,6 +773,9 @@ void cc_destroy(cc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int r = 0; r < cck::XCHG_MAX_RANKS; ++r)
+        if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_mb[r]);
+    c->mailbox.release();
     for (auto& b : c->col_buf) b.release();
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
@@ -1169,6 +1178,32 @@ int cc_comm_init_all(cc_ctx** ctxs, int n) {
     for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
     NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
     for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[i]; ctxs[i]->nranks = n; ctxs[i]->rank = i; }
+    /* same process: mailboxes are reachable through plain peer access, no IPC handles needed */
+    if (n <= cck::XCHG_MAX_RANKS) {
+        bool ok = true;
+        for (int i = 0; i < n && ok; ++i)
+            for (int j = 0; j < n && ok; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess || !can) { ok = false; break; }
+                cudaSetDevice(devs[i]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                cudaGetLastError();
+            }
+        const size_t bytes = (size_t)2 * n * cck::XCHG_SLOT * 8;
+        for (int i = 0; i < n && ok; ++i) {
+            cudaSetDevice(devs[i]);
+            ctxs[i]->mailbox.release();
+            if (ctxs[i]->mailbox.ensure(bytes) != CC_OK || cudaMemset(ctxs[i]->mailbox.p, 0, bytes) != cudaSuccess) ok = false;
+            cudaDeviceSynchronize();
+        }
+        for (int i = 0; i < n && ok; ++i) {
+            for (int j = 0; j < n; ++j) ctxs[i]->peer_mb[j] = (unsigned long long*)ctxs[j]->mailbox.p;
+            ctxs[i]->peers_ready = true;
+            ctxs[i]->xchg_epoch = 0;
+        }
+    }
     return CC_OK;
 }
 
@@ -1183,7 +1218,7 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
     const int H = c->nhalos, R = c->nranks;
     if (H == 0) return cc_cutout_sync(c, nullptr, nullptr);
     if ((rc = c->counts_buf.ensure(16))) return rc;
-    if ((rc = c->gather_buf.ensure((size_t)R * 2 * H * 8))) return rc;
+    if ((rc = c->gather_buf.ensure((size_t)R * 2 * H * 8 + 64))) return rc;
     if ((rc = c->offsets_buf.ensure((size_t)H * 8))) return rc;
     const size_t hg_off = 32 + 3 * (size_t)H; /* behind the cutout's own read-back area */
     if (c->h_small_elems < small_elems(H, R)) { /* communicator created after the cutout was enqueued */
@@ -1201,18 +1236,38 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, c->stream));
     }
     const void* send = (c->pending == P_CONST) ? c->counts_buf.p : (const void*)hs_counts(c);
-    if (c->comm) {
-        NC(g_nccl.AllGather(send, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, c->stream));
-    } else {
-        CU(cudaMemcpyAsync(c->gather_buf.p, send, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    cck::k4_offsets<<<(H + 255) / 256, 256, 0, c->stream>>>((const unsigned long long*)c->gather_buf.p,
-                                                          (unsigned long long*)c->offsets_buf.p, H, c->rank);
-    CU(cudaGetLastError());
-    c->launches += 1;
+    const bool peer_path = c->peers_ready && R > 1 && 2 * H <= cck::XCHG_PAYLOAD && !getenv("CC_NO_PEER_XCHG");
     unsigned long long* hg = c->h_small + hg_off;
-    CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long* d_status = (unsigned long long*)((char*)c->gather_buf.p + (size_t)R * 2 * H * 8);
+    CU(cudaMemsetAsync(d_status, 0, 8, c->stream));
+    if (peer_path) { /* NVLink peer stores: one single-CTA kernel, no collective launch */
+        cck::XchgArgs x;
+        memset(&x, 0, sizeof(x));
+        x.send = (const unsigned long long*)send;
+        for (int r = 0; r < R; ++r) x.peer[r] = c->peer_mb[r];
+        x.gathered = (unsigned long long*)c->gather_buf.p;
+        x.offsets = (unsigned long long*)c->offsets_buf.p;
+        x.status = d_status;
+        x.epoch = ++c->xchg_epoch;
+        const char* to = getenv("CC_PEER_TIMEOUT_MS");
+        x.timeout_ns = (unsigned long long)(to ? atoll(to) : 10000) * 1000000ull;
+        x.n = 2 * H; x.H = H; x.R = R; x.rank = c->rank;
+        cck::k4_exchange_peer<<<1, 256, 0, c->stream>>>(x);
+        CU(cudaGetLastError());
+    } else {
+        if (c->comm) {
+            NC(g_nccl.AllGather(send, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, c->stream));
+        } else {
+            if (R > 1) return fail(CC_ERR_STATE, "cc_exchange_counts: %d ranks but neither an NCCL communicator nor peer mailboxes for %d halos", R, H);
+            CU(cudaMemcpyAsync(c->gather_buf.p, send, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        cck::k4_offsets<<<(H + 255) / 256, 256, 0, c->stream>>>((const unsigned long long*)c->gather_buf.p,
+                                                              (unsigned long long*)c->offsets_buf.p, H, c->rank);
+        CU(cudaGetLastError());
+    }
+    c->launches += 1;
+    CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8 + 8, cudaMemcpyDeviceToHost, c->stream)); /* + status */
+    CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H + 1, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, c->stream));
     if (c->synced) CU(cudaStreamSynchronize(c->stream));
     else if ((rc = cc_cutout_sync(c, nullptr, nullptr))) return rc; /* one synchronisation for cutout + exchange */
     for (int r = 0; r < R; ++r)
@@ -1220,8 +1275,54 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
             if (all_counts) all_counts[(size_t)r * H + h] = (int64_t)hg[(size_t)r * 2 * H + h];
             if (all_rough) all_rough[(size_t)r * H + h] = (int64_t)hg[(size_t)r * 2 * H + H + h];
         }
+    if (hg[(size_t)R * 2 * H] != 0)
+        return fail(CC_ERR_NCCL, "cc_exchange_counts: peer exchange timed out (a rank did not enter the exchange)");
     if (offsets)
-        for (int h = 0; h < H; ++h) offsets[h] = (int64_t)hg[(size_t)R * 2 * H + h];
+        for (int h = 0; h < H; ++h) offsets[h] = (int64_t)hg[(size_t)R * 2 * H + 1 + h];
+    return CC_OK;
+}
+
+int cc_comm_peer_handle(cc_ctx* c, int nranks, int rank, void* handle64) {
+    if (!c || !handle64 || nranks < 1 || nranks > cck::XCHG_MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(CC_ERR_ARG, "cc_comm_peer_handle: bad argument (at most %d ranks)", cck::XCHG_MAX_RANKS);
+    if (c->comm && (c->nranks != nranks || c->rank != rank)) return fail(CC_ERR_ARG, "cc_comm_peer_handle: rank/size differ from the NCCL communicator");
+    int rc = use_device(c);
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == CC_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    const size_t bytes = (size_t)2 * nranks * cck::XCHG_SLOT * 8;
+    c->mailbox.release();
+    if ((rc = c->mailbox.ensure(bytes))) return rc;
+    CU(cudaMemset(c->mailbox.p, 0, bytes));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->mailbox.p));
+    memcpy(handle64, &h, sizeof(h));
+    c->nranks = nranks;
+    c->rank = rank;
+    c->peers_ready = false;
+    c->xchg_epoch = 0;
+    return CC_OK;
+}
+
+int cc_comm_peer_attach(cc_ctx* c, const void* handles) {
+    if (!c || !handles) return fail(CC_ERR_ARG, "cc_comm_peer_attach: bad argument");
+    if (!c->mailbox.p) return fail(CC_ERR_STATE, "cc_comm_peer_attach: call cc_comm_peer_handle first");
+    int rc = use_device(c);
+    if (rc) return rc;
+    for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) { c->peer_mb[r] = (unsigned long long*)c->mailbox.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * CC_PEER_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CC_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        c->peer_mb[r] = (unsigned long long*)p;
+        c->peer_opened[r] = true;
+    }
+    c->peers_ready = true;
     return CC_OK;
 }
 

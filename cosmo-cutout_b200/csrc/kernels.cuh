@@ -1116,6 +1116,92 @@ __global__ void k4_offsets(const unsigned long long* gathered, unsigned long lon
     }
 }
 
+/* ---- count exchange by peer stores (NVLink / NVSwitch), no library launch ---------------------------------------
+ * Every GPU owns a mailbox in its own HBM: [2 parities][R ranks][1 epoch word + XCHG_PAYLOAD counters].  To exchange,
+ * a GPU STORES its {counts, rough counts} into slot [parity][its rank] of every peer's mailbox (the peers' mailboxes
+ * are mapped through CUDA IPC or peer access, so these are plain st.global over NVLink), fences, publishes the epoch
+ * with a release store, then waits until all R slots of its OWN mailbox carry the epoch, and computes its row offsets
+ * = sum of the counts of lower ranks.  One single-CTA kernel enqueued behind the cutout kernels: the exchange costs
+ * one NVLink store round instead of a collective launch (~3 us instead of ~40 us of a 250 us step).
+ * Parity double-buffering is enough: a rank can only start exchange e+1 after every peer has posted e, and a peer
+ * posts e+1 only after it finished reading e. */
+constexpr int XCHG_PAYLOAD = 4096;              /* u64 counters per slot: 2 x halos */
+constexpr int XCHG_SLOT = XCHG_PAYLOAD + 8;     /* epoch word (+ padding to keep the payload 64-byte aligned) */
+constexpr int XCHG_MAX_RANKS = 32;
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct XchgArgs {
+    const unsigned long long* send;      /* [n] this GPU's {counts[H], rough[H]} */
+    unsigned long long* peer[XCHG_MAX_RANKS]; /* every rank's mailbox as seen from this GPU (peer[rank] = own) */
+    unsigned long long* gathered;        /* [R][n] out */
+    unsigned long long* offsets;         /* [H] out: sum of counts of lower ranks */
+    unsigned long long* status;          /* [0] set to 1 on time-out */
+    unsigned long long epoch;
+    unsigned long long timeout_ns;
+    int n, H, R, rank;
+};
+
+__global__ void __launch_bounds__(256) k4_exchange_peer(const XchgArgs a) {
+    const int tid = threadIdx.x;
+    const unsigned long long parity = a.epoch & 1ull;
+    const size_t my_slot = ((size_t)parity * a.R + a.rank) * XCHG_SLOT;
+    /* post: my counters into my slot of every mailbox */
+    for (int p = 0; p < a.R; ++p) {
+        unsigned long long* dst = a.peer[p] + my_slot + 8;
+        for (int i = tid; i < a.n; i += blockDim.x) st_relaxed_sys_u64(dst + i, a.send[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < a.R) st_release_sys_u64(a.peer[tid] + my_slot, a.epoch);
+    /* wait: all ranks' slots of MY mailbox */
+    __shared__ int s_timeout;
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    unsigned long long* mine = a.peer[a.rank];
+    if (tid < a.R) {
+        const unsigned long long* flag = mine + ((size_t)parity * a.R + tid) * XCHG_SLOT;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys_u64(flag) != a.epoch) {
+            if (global_timer_ns() - t0 > a.timeout_ns) { s_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (s_timeout) {
+        if (tid == 0) *a.status = 1ull;
+        return;
+    }
+    for (int r = 0; r < a.R; ++r) {
+        const unsigned long long* src = mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8;
+        for (int i = tid; i < a.n; i += blockDim.x) a.gathered[(size_t)r * a.n + i] = ld_relaxed_sys_u64(src + i);
+    }
+    for (int h = tid; h < a.H; h += blockDim.x) {
+        unsigned long long run = 0;
+        for (int r = 0; r < a.rank; ++r) run += ld_relaxed_sys_u64(mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8 + h);
+        a.offsets[h] = run;
+    }
+}
+
 /* ================================================================================================
  * synthetic lightcone generator (counter-based; cc_synth_host in capi.cu computes the same bits)
  * ================================================================================================ */

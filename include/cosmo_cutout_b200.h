@@ -162,6 +162,14 @@ int cc_comm_init_all(cc_ctx** ctxs, int n);
 int cc_exchange_counts(cc_ctx* ctx, int64_t* all_counts, int64_t* all_rough, int64_t* offsets);
 int cc_comm_rank(cc_ctx* ctx);
 int cc_comm_size(cc_ctx* ctx);
+/* Optional fast path for the count exchange: peer stores over NVLink instead of a collective launch.  Every rank
+ * allocates a mailbox and exports it (cc_comm_peer_handle, a cudaIpcMemHandle_t); the handles of all ranks, in rank
+ * order, are handed to cc_comm_peer_attach.  cc_exchange_counts then uses one single-CTA kernel that stores this
+ * GPU's counters into every peer's mailbox and waits for theirs (up to 2048 halos per cutout; more falls back to
+ * NCCL).  cc_comm_init_all sets this up by itself when the GPUs of the process have peer access. */
+#define CC_PEER_HANDLE_BYTES 64
+int cc_comm_peer_handle(cc_ctx* ctx, int nranks, int rank, void* handle64);
+int cc_comm_peer_attach(cc_ctx* ctx, const void* handles);
 
 /* ------------------------------------------------------------------ multi-GPU: host-side plan (no GPU needed)
  * Contiguous index shard of rank r out of nranks over n particles: [lo, hi).  Replaces the reference's
