@@ -111,3 +111,23 @@ def test_synth_host_is_deterministic_and_sliceable():
     assert (c["x"] < 0).any() and (np.abs(c["x"]) < 300).all()
     assert np.array_equal(a["id"], np.arange(10_000))
     assert a["rotation"].min() >= 0 and a["rotation"].max() <= 5 and a["replication"].max() < 2 ** 20
+
+
+def test_entry_points_reject_bad_arguments_without_touching_a_gpu():
+    """error conventions of the C ABI: negative codes + a message, no crash, nothing thrown"""
+    L = cc.lib()
+    null = C.c_void_p()
+    two = (C.c_float * 2)(1.0, 2.0)
+    for call in (lambda: L.cc_cutout_const(null, two, two),
+                 lambda: L.cc_cutout_halo(null, 1, null, 0, -1),
+                 lambda: L.cc_cutout_sync(null, null, null),
+                 lambda: L.cc_step_upload(null, 10, null, 0),
+                 lambda: L.cc_exchange_counts(null, null, null, null),
+                 lambda: L.cc_cutout_fetch(null, 0, 0, 0, null),
+                 lambda: L.cc_comm_peer_attach(null, null),
+                 lambda: L.cc_halo_setup(null, C.c_float(10.0), null)):
+        assert call() < 0
+    assert L.cc_last_error() is not None
+    assert L.cc_step_size(null) == -1 and L.cc_launch_count(null) == 0
+    out = C.c_void_p()
+    assert L.cc_create(-1, C.byref(out)) < 0 and not out.value
