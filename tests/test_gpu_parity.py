@@ -409,3 +409,28 @@ def test_large_resident_const_100m(ctx):
     want, want_rough = H.oracle_cutout_halo(sub, H.oracle_halo_setup((150, 20, 12), 10.0))
     assert int(rough[0]) == want_rough
     H.assert_cols_equal({k: got[k] for k in cc.OUT_COLS}, want, what="100M halo: ")
+
+
+def test_device_cols_and_attach_with_torch(ctx):
+    """the device-pointer side of the C ABI: attach torch-owned device columns, read the survivor columns straight
+    from HBM (cc_cutout_device_cols) -- no host copies made by the library"""
+    import ctypes as C
+    import torch
+    cols = H.shell_fixture(400_000, seed=55)
+    keep = {k: torch.from_numpy(cols[k]).cuda() for k in cc.IN_COLS}
+    torch.cuda.synchronize()
+    ctx.attach(400_000, {k: t.data_ptr() for k, t in keep.items()})
+    theta_cut, phi_cut = cc.cli_bounds(60, 10), cc.cli_bounds(30, 10)
+    ctx.cutout_const(theta_cut, phi_cut)
+    counts, _ = ctx.sync()
+    want = H.oracle_cutout_const(cols, theta_cut, phi_cut)
+    dev = cc.ColsOut()
+    row0, cnt = C.c_int64(-1), C.c_int64(-1)
+    cc._check(cc.lib().cc_cutout_device_cols(ctx._h, 0, C.byref(dev), C.byref(row0), C.byref(cnt)))
+    assert cnt.value == int(counts[0]) == want["id"].shape[0] and row0.value == 0
+    for name, dt in (("theta", torch.float32), ("id", torch.int64), ("replication", torch.int32)):
+        host = torch.empty(cnt.value, dtype=dt)
+        nbytes = cnt.value * host.element_size()
+        rc = torch.cuda.cudart().cudaMemcpy(host.data_ptr(), getattr(dev, name), nbytes, 2)  # device to host
+        assert int(rc) == 0
+        assert host.numpy().tobytes() == want[name].tobytes(), name
