@@ -132,6 +132,8 @@ struct cc_ctx {
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
     bool k3_smem_set = false, k3s_smem_set = false;
+    bool k2_tma = false, k2t_ready = false;
+    int k2t_occ = 0;
     int64_t last_nrec = -1;       /* survivors of the previous use-case-2 cutout on this context */
     bool force_general = false, used_small = false;
     unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
@@ -552,6 +554,20 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             CU(cudaGetLastError());
             CU(cudaMemsetAsync(rec_count + 2, 0, 8, c->stream)); /* the overflow queue is per launch */
             c->launches += 2;
+        } else if (c->k2_tma && vec) { /* bulk-copy fed variant (CC_K2_TMA=1) */
+            const size_t smem = cck::K2T_SMEM_BASE + pre_bytes;
+            if (!c->k2t_ready) {
+                CU(cudaFuncSetAttribute((const void*)cck::k2_cutout_halo_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(cck::K2T_SMEM_BASE + cck::K2_MAX_HALOS * sizeof(float4))));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->k2t_occ, (const void*)cck::k2_cutout_halo_tma, cck::SCAN_THREADS,
+                                                                  cck::K2T_SMEM_BASE + 64 * sizeof(float4)));
+                if (c->k2t_occ < 1) c->k2t_occ = 1;
+                c->k2t_ready = true;
+            }
+            const unsigned int gridt = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * c->k2t_occ)));
+            cck::k2_cutout_halo_tma<<<gridt, cck::SCAN_THREADS, smem, c->stream>>>(a);
+            CU(cudaGetLastError());
+            c->launches += 1;
         } else {
             if (vec) cck::k2_cutout_halo<true><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(a);
             else cck::k2_cutout_halo<false><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(a);
@@ -753,6 +769,7 @@ int cc_create(int device, cc_ctx** out) {
         cudaGetLastError();
     }
     cc_ctx* c = new cc_ctx();
+    if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("CC_K1_DRAIN")) c->k1_drain_at = std::max(1, std::min(32, atoi(e)));
     c->device = device;
     c->sm_count = sms;

@@ -720,6 +720,153 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
 }
 
+/* ---- TMA-fed variant of the halo scan -------------------------------------------------------------------------
+ * Same arithmetic and queueing as k2_cutout_halo, but a tile's x,y,z reach the SM through the bulk-copy engine
+ * (cp.async.bulk global -> shared, completion on an mbarrier) instead of LDG.128 into registers: every warp owns a ring
+ * of K2T_STAGES tile buffers and keeps K2T_STAGES-1 tiles in flight at all times, without spending registers or L1
+ * lines on them.  Selected with CC_K2_TMA=1 (profiles/r01 has the A/B numbers). */
+constexpr int K2T_STAGES = 3;
+constexpr int K2T_TILE_BYTES = SCAN_TILE * 4; /* one column of one tile */
+struct __align__(128) K2TWarpRing {
+    float buf[K2T_STAGES][3][SCAN_TILE];
+    unsigned long long bar[K2T_STAGES];
+};
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS, 2) k2_cutout_halo_tma(const HaloArgs a) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    K2TWarpRing* s_ring = reinterpret_cast<K2TWarpRing*>(s_dyn);
+    float4* s_pre = reinterpret_cast<float4*>(s_dyn + sizeof(K2TWarpRing) * SCAN_WARPS);
+    __shared__ K2WarpQueue s_q[SCAN_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    K2WarpQueue& q = s_q[warp];
+    K2TWarpRing& ring = s_ring[warp];
+    for (int h = threadIdx.x; h < a.nhalos; h += SCAN_THREADS) s_pre[h] = a.pre[h];
+    if (lane == 0)
+        for (int s = 0; s < K2T_STAGES; ++s) mbar_init(&ring.bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const unsigned int total_warps = gridDim.x * SCAN_WARPS;
+    const unsigned int first = blockIdx.x * SCAN_WARPS + warp;
+    const unsigned int full_tiles = (unsigned int)(a.n / SCAN_TILE); /* tiles the bulk engine can take whole */
+    unsigned long long n_cand = 0;
+    unsigned int qcount = 0; /* warp-uniform */
+
+    auto issue = [&](unsigned int tile, int stage) { /* lane 0 only */
+        const size_t off = (size_t)tile * SCAN_TILE;
+        mbar_expect_tx(&ring.bar[stage], 3 * K2T_TILE_BYTES);
+        bulk_g2s(ring.buf[stage][0], a.x + off, K2T_TILE_BYTES, &ring.bar[stage]);
+        bulk_g2s(ring.buf[stage][1], a.y + off, K2T_TILE_BYTES, &ring.bar[stage]);
+        bulk_g2s(ring.buf[stage][2], a.z + off, K2T_TILE_BYTES, &ring.bar[stage]);
+    };
+    if (lane == 0)
+        for (int s = 0; s < K2T_STAGES; ++s) {
+            const unsigned long long t = (unsigned long long)first + (unsigned long long)s * total_warps;
+            if (t < full_tiles) issue((unsigned int)t, s);
+        }
+
+    unsigned int k = 0;
+    for (unsigned int tile = first; tile < a.ntiles; tile += total_warps, ++k) {
+        const long long base = (long long)tile * SCAN_TILE;
+        float px[8], py[8], pz[8];
+        unsigned int valid;
+        if (tile < full_tiles) {
+            const int stage = (int)(k % K2T_STAGES);
+            mbar_wait(&ring.bar[stage], (k / K2T_STAGES) & 1u);
+            const float4 xa = *reinterpret_cast<const float4*>(&ring.buf[stage][0][4 * lane]);
+            const float4 xb = *reinterpret_cast<const float4*>(&ring.buf[stage][0][128 + 4 * lane]);
+            const float4 ya = *reinterpret_cast<const float4*>(&ring.buf[stage][1][4 * lane]);
+            const float4 yb = *reinterpret_cast<const float4*>(&ring.buf[stage][1][128 + 4 * lane]);
+            const float4 za = *reinterpret_cast<const float4*>(&ring.buf[stage][2][4 * lane]);
+            const float4 zb = *reinterpret_cast<const float4*>(&ring.buf[stage][2][128 + 4 * lane]);
+            px[0] = xa.x; px[1] = xa.y; px[2] = xa.z; px[3] = xa.w; px[4] = xb.x; px[5] = xb.y; px[6] = xb.z; px[7] = xb.w;
+            py[0] = ya.x; py[1] = ya.y; py[2] = ya.z; py[3] = ya.w; py[4] = yb.x; py[5] = yb.y; py[6] = yb.z; py[7] = yb.w;
+            pz[0] = za.x; pz[1] = za.y; pz[2] = za.z; pz[3] = za.w; pz[4] = zb.x; pz[5] = zb.y; pz[6] = zb.z; pz[7] = zb.w;
+            valid = 0xffu;
+            __syncwarp(); /* every lane has read the stage: refill it with the tile K2T_STAGES ahead */
+            const unsigned long long nxt = (unsigned long long)tile + (unsigned long long)K2T_STAGES * total_warps;
+            if (lane == 0 && nxt < full_tiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue((unsigned int)nxt, stage);
+            }
+        } else { /* the ragged last tile of the step */
+            valid = load_tile<false>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+        }
+        float pc[8], pt[8];
+        unsigned int insane = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float r2 = fmaf(pz[j], pz[j], fmaf(py[j], py[j], px[j] * px[j]));
+            if (!((fabsf(px[j]) >= CC_SANE_LO) & (r2 <= 1.2089258e24f))) insane |= 1u << j;
+            pc[j] = pz[j] * rsqrt_fast(r2);
+            pt[j] = py[j] * rcp_fast(px[j]);
+        }
+        insane &= valid;
+        for (int h = 0; h < a.nhalos; ++h) {
+            const float4 P = s_pre[h];
+            bool mine = insane != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                mine |= (pc[j] <= P.x) & (pc[j] >= P.y) & (pt[j] >= P.z) & (pt[j] <= P.w);
+            if (__any_sync(0xffffffffu, mine)) {
+                unsigned int m = insane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    m |= (unsigned)((pc[j] <= P.x) & (pc[j] >= P.y) & (pt[j] >= P.z) & (pt[j] <= P.w)) << j;
+                m &= valid;
+                const unsigned int c = __popc(m);
+                unsigned int inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                unsigned int pos = qcount + inc - c;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (m & (1u << j)) {
+                        q.particle[pos] = (unsigned int)(base + tile_local(lane, j));
+                        q.halo[pos] = (unsigned short)h;
+                        ++pos;
+                    }
+                qcount += __shfl_sync(0xffffffffu, inc, 31);
+                if (qcount > K2_QCAP - SCAN_TILE) {
+                    k2_drain(a, q, qcount, lane);
+                    n_cand += qcount;
+                    qcount = 0;
+                }
+            }
+        }
+    }
+    if (qcount) {
+        k2_drain(a, q, qcount, lane);
+        n_cand += qcount;
+    }
+    if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
+}
+constexpr size_t K2T_SMEM_BASE = sizeof(K2TWarpRing) * SCAN_WARPS;
+
 /* ---- many halos: a (cos theta_u, sin phi_u) cell index over the halos of the launch ----------------------------
  * With hundreds of halos per pass the loop "every particle x every halo" is compute-bound (and a 1-D theta index
  * still leaves ~1 % of the halos per particle: profiles/r01).  The host rasterises each halo's widened rough
