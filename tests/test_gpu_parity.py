@@ -428,9 +428,12 @@ def test_device_cols_and_attach_with_torch(ctx):
     row0, cnt = C.c_int64(-1), C.c_int64(-1)
     cc._check(cc.lib().cc_cutout_device_cols(ctx._h, 0, C.byref(dev), C.byref(row0), C.byref(cnt)))
     assert cnt.value == int(counts[0]) == want["id"].shape[0] and row0.value == 0
-    for name, dt in (("theta", torch.float32), ("id", torch.int64), ("replication", torch.int32)):
-        host = torch.empty(cnt.value, dtype=dt)
-        nbytes = cnt.value * host.element_size()
-        rc = torch.cuda.cudart().cudaMemcpy(host.data_ptr(), getattr(dev, name), nbytes, 2)  # device to host
-        assert int(rc) == 0
-        assert host.numpy().tobytes() == want[name].tobytes(), name
+    try:
+        from cuda import cudart  # cuda-python: a plain cudaMemcpy on the raw device pointers
+    except Exception:
+        pytest.skip("cuda-python not importable")
+    for name, dt in (("theta", np.float32), ("id", np.int64), ("replication", np.int32)):
+        host = np.empty(cnt.value, dtype=dt)
+        (err,) = cudart.cudaMemcpy(host.ctypes.data, getattr(dev, name), host.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        assert int(err) == 0
+        assert host.tobytes() == want[name].tobytes(), name
