@@ -263,7 +263,7 @@ struct Chunk {
 
 /* scratch layout of use case 1:
  *   [ result: 4 x u64 | ticket u32 (+pad to 64 B) | block_state: nblocks x u64 | tile_info: ntiles x u64 |
- *     tile_base: ntiles x u32 | cta_used: grid x u32 ]
+ *     cta_used: grid x u32 ]
  * result[0] survivors so far (carried across the chunks of a streamed step), [1] pre-filter candidates,
  * [2] carry seen by the current chunk's gather, [3] max records any CTA wanted (temp-region overflow check) */
 const size_t K1_HDR = 64;
@@ -294,8 +294,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
     /* scratch */
     const size_t off_state = K1_HDR;
     const size_t off_info = off_state + ((size_t)nblocks + 8) * 8;
-    const size_t off_base = off_info + ((size_t)ntiles + 8) * 8;
-    const size_t off_used = off_base + (((size_t)ntiles + 8) * 4 + 7) / 8 * 8;
+    const size_t off_used = off_info + ((size_t)ntiles + 8) * 8;
     const size_t bytes = off_used + ((size_t)grid_max + 8) * 4;
     if ((rc = c->scratch.ensure(bytes))) return rc;
     /* temp records: one private region per CTA */
@@ -764,10 +763,6 @@ int cc_create(int device, cc_ctx** out) {
     int rc = check_sm100(device, &sms);
     if (rc) return rc;
     CU(cudaSetDevice(device));
-    if (const char* e = getenv("CC_L2_FETCH")) { /* experiment knob: 32 / 64 / 128 bytes */
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
-        cudaGetLastError();
-    }
     cc_ctx* c = new cc_ctx();
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("CC_K1_DRAIN")) c->k1_drain_at = std::max(1, std::min(32, atoi(e)));

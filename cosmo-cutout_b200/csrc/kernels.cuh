@@ -1,17 +1,22 @@
 /*
  * kernels.cuh -- sm_100a kernels of the lightcone cutout path.
  *
- *   k1_cutout_const   use case 1: fused octant test -> pre-filter -> exact (theta,phi) -> window test ->
- *                     order-preserving single-pass compaction (warp ballot/popc + decoupled look-back over
- *                     tiles) -> 12-column gather.            replaces processLC.cpp:276-310
- *   k2_cutout_halo    use case 2: one pass over x,y,z for a batch of halos: pre-filter -> exact un-rotated
+ *   k1_scan / k1_tile_scan / k1_gather
+ *                     use case 1: octant test -> pre-filter -> exact (theta,phi) -> strict window test ->
+ *                     ballot/popc compaction into per-CTA temp regions; exclusive scan of the tile counts by
+ *                     decoupled look-back; order-preserving 12-column gather.   replaces processLC.cpp:276-310
+ *   k2_cutout_halo (+ _cells, _tma, k2_overflow)
+ *                     use case 2: one pass over x,y,z for a batch of halos: pre-filter -> exact un-rotated
  *                     (theta_u,phi_u) -> rough test -> R.v -> exact rotated angles -> fine test -> survivor
  *                     records.                               replaces processLC.cpp:897-909, :1334-1340, :1383-1481
- *   k3_*              survivor ordering by (theta_u, input index) per halo
- *                                                            replaces processLC.cpp:1214-1221 (restricted to survivors)
- *   k3_gather_halo    column gather of the ordered survivors replaces processLC.cpp:1446-1461
- *   k4_offsets        exclusive scan over ranks of the all-gathered counts
- *                                                            replaces processLC.cpp:331-337, :1569-1583
+ *   k3_scan_counts / k3_bucket / k3_rank / k3_gather_halo, k3_small
+ *                     survivor ordering by (theta_u, input index) per halo and column gather
+ *                                                            replaces processLC.cpp:1214-1221 (restricted to
+ *                                                            survivors) and :1446-1461
+ *   k4_offsets / k4_exchange_peer
+ *                     exclusive scan over ranks of the exchanged counts (after an NCCL all-gather, or with the
+ *                     exchange itself done by NVLink peer stores)   replaces processLC.cpp:331-337, :1569-1583
+ *   k_build_payload, k_synth, k_debug_eval                   residency helper, synthetic data, test hook
  *
  * Exactness: whatever reaches an output column or decides membership is computed by ccref:: functions
  * (ref_math.cuh) -- the reference's operation sequence.  The pre-filter is the only approximate code; it may
@@ -149,7 +154,7 @@ __device__ __forceinline__ unsigned int tile_local(int lane, int j) { return (un
  *                 atomics) + one 8-byte (position, count) word per tile.  No block barrier, no inter-tile wait:
  *                 a warp stalled in the fp64 divide chain never holds up the loads of the other 31 warps of its SM.
  *   k1_tile_scan  exclusive scan of the per-tile counts: single pass, decoupled look-back across blocks.
- *   k1_gather     one thread per survivor record: row = carry + tile_base[tile] + rank -> 12-column gather,
+ *   k1_gather     one thread per survivor record: row = carry + the row k1_tile_scan wrote -> 12-column gather,
  *                 survivors stay in input order (processLC.cpp:291-307).
  *
  * (A first version chained the look-back through the particle tiles themselves; with 3 KB tiles the chain can
