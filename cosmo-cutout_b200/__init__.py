@@ -227,6 +227,8 @@ class Context:
         self.nhalos = 0
         self.pos_only = False
         self.kind = None
+        self._halo_cache = None
+        self._count_bufs = None
 
     def close(self):
         if self._h:
@@ -279,8 +281,15 @@ class Context:
         _check(lib().cc_cutout_const(self._h, _ptr(tc), _ptr(pc)))
         self.nhalos, self.pos_only, self.kind = 1, False, "const"
 
+    def _halo_array(self, halos):
+        """ctypes array of the halo structs; the same list object passed again reuses the marshalled array (the
+        structs are copied on marshalling: mutate-and-reuse callers must pass a new list)"""
+        if self._halo_cache is None or self._halo_cache[0] is not halos or len(halos) != self._halo_cache[2]:
+            self._halo_cache = (halos, (Halo * len(halos))(*halos), len(halos))
+        return self._halo_cache[1]
+
     def cutout_halo(self, halos, pos_only=False, n_limit_global=-1):
-        arr = (Halo * len(halos))(*halos)
+        arr = self._halo_array(halos)
         _check(lib().cc_cutout_halo(self._h, len(halos), arr, int(bool(pos_only)), int(n_limit_global)))
         self.nhalos, self.pos_only, self.kind = len(halos), bool(pos_only), "halo"
 
@@ -294,7 +303,7 @@ class Context:
         self.nhalos, self.pos_only, self.kind = 1, False, "const"
 
     def cutout_halo_streamed(self, cols, halos, pos_only=False, n_limit_global=-1, index_base=0):
-        arr = (Halo * len(halos))(*halos)
+        arr = self._halo_array(halos)
         s = _cols_in_struct(cols)
         self._keep = cols
         _check(lib().cc_cutout_halo_streamed(self._h, int(cols["x"].shape[0]), C.byref(s), int(index_base),
@@ -302,10 +311,13 @@ class Context:
         self.nhalos, self.pos_only, self.kind = len(halos), bool(pos_only), "halo"
 
     def sync(self):
-        counts = np.zeros(max(self.nhalos, 1), dtype=np.int64)
-        rough = np.zeros(max(self.nhalos, 1), dtype=np.int64)
-        _check(lib().cc_cutout_sync(self._h, _ptr(counts), _ptr(rough)))
-        return counts[:self.nhalos], rough[:self.nhalos]
+        n = max(self.nhalos, 1)
+        if self._count_bufs is None or self._count_bufs[0].shape[0] != n:
+            c, r = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+            self._count_bufs = (c, r, _ptr(c), _ptr(r))
+        c, r, pc, pr = self._count_bufs
+        _check(lib().cc_cutout_sync(self._h, pc, pr))
+        return c[:self.nhalos].copy(), r[:self.nhalos].copy()
 
     def fetch(self, halo=0, names=None, count=None):
         if names is None:
