@@ -298,7 +298,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
     const size_t bytes = off_used + ((size_t)grid_max + 8) * 4;
     if ((rc = c->scratch.ensure(bytes))) return rc;
     /* temp records: one private region per CTA */
-    if (c->region_cap == 0) c->region_cap = (unsigned int)std::min<int64_t>(0x7fffffff, c->out_cap + c->out_cap / 4) / grid_max + 256;
+    c->region_cap = std::max(c->region_cap, (unsigned int)(std::min<int64_t>(0x7fffffff, c->out_cap + c->out_cap / 4) / grid_max + 256));
     const size_t temp_elems = (size_t)grid_max * c->region_cap;
     DevBuf* temps[] = {&c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row};
     for (DevBuf* t : temps)
@@ -381,8 +381,8 @@ size_t small_elems(int H, int R) { return 32 + 3 * (size_t)H + (size_t)R * 2 * H
 
 int prepare_const(cc_ctx* c) {
     { int rc0 = ensure_small(c, small_elems(1, c->nranks)); if (rc0) return rc0; }
-    if (c->out_cap == 0) {
-        /* first guess: 1/16 of the step; cc_cutout_sync grows it to the exact count and re-runs on overflow */
+    /* first guess: 1/16 of the step; cc_cutout_sync grows it to the exact count and re-runs on overflow */
+    {
         int rc = ensure_out_cap(c, std::max<int64_t>(c->n / 16, 1 << 16));
         if (rc) return rc;
     }

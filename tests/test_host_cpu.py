@@ -131,3 +131,11 @@ def test_entry_points_reject_bad_arguments_without_touching_a_gpu():
     assert L.cc_step_size(null) == -1 and L.cc_launch_count(null) == 0
     out = C.c_void_p()
     assert L.cc_create(-1, C.byref(out)) < 0 and not out.value
+
+
+def test_binding_fails_loudly_when_the_library_is_missing(monkeypatch):
+    import importlib
+    monkeypatch.setattr(cc, "_lib", None)
+    monkeypatch.setattr(cc, "LIB_PATH", os.path.join(REPO, "cosmo-cutout_b200", "lib", "does_not_exist.so"))
+    with pytest.raises(cc.CutoutError, match="missing"):
+        cc.lib()
