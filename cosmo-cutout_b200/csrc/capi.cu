@@ -129,6 +129,7 @@ struct cc_ctx {
     int64_t launches = 0;
     int k1_occupancy[2] = {0, 0};
     int64_t last_const_count = -1;
+    int gather_gx_cap = 256; /* CC_GATHER_GX */
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
     bool k3_smem_set = false, k3s_smem_set = false;
@@ -361,7 +362,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         /* blocks per region: sized for the survivors the last cutout on this context produced (or the output
          * capacity on a first run); the kernel loops, so this only trades launch width against iterations */
         const int64_t expect = c->last_const_count >= 0 ? c->last_const_count + c->last_const_count / 4 : c->out_cap;
-        const unsigned int gxg = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(16, (expect / grid + 255) / 256));
+        const unsigned int gxg = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(c->gather_gx_cap, (expect / grid + 255) / 256));
         cck::k1_gather<<<dim3(gxg, grid), 256, 0, c->stream>>>(g);
         CU(cudaGetLastError());
         c->launches += 3;
@@ -765,6 +766,7 @@ int cc_create(int device, cc_ctx** out) {
     CU(cudaSetDevice(device));
     cc_ctx* c = new cc_ctx();
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
+    if (const char* e = getenv("CC_GATHER_GX")) c->gather_gx_cap = std::max(1, std::min(1024, atoi(e)));
     if (const char* e = getenv("CC_K1_DRAIN")) c->k1_drain_at = std::max(1, std::min(32, atoi(e)));
     c->device = device;
     c->sm_count = sms;
