@@ -1367,7 +1367,7 @@ int cc_last_stats(cc_ctx* c, int64_t out[4]) {
 
 /* ------------------------------------------------------------------ test hooks */
 int cc_debug_eval(cc_ctx* c, int op, int64_t n, const float* in0, const float* in1, const float* in2, float* out0) {
-    if (!c || n < 0 || !in0 || !out0 || op < 0 || op > 5) return fail(CC_ERR_ARG, "cc_debug_eval: bad argument");
+    if (!c || n < 0 || !in0 || !out0 || op < 0 || op > 6) return fail(CC_ERR_ARG, "cc_debug_eval: bad argument");
     if ((op == 2 && (!in1 || !in2)) || ((op == 3 || op == 4) && !in1)) return fail(CC_ERR_ARG, "cc_debug_eval: missing input");
     int rc = use_device(c);
     if (rc) return rc;
@@ -1393,7 +1393,7 @@ int cc_debug_eval(cc_ctx* c, int op, int64_t n, const float* in0, const float* i
 }
 
 int cc_debug_eval_host(int op, int64_t n, const float* in0, const float* in1, const float* in2, float* out0) {
-    if (n < 0 || !in0 || !out0 || op < 0 || op > 5) return fail(CC_ERR_ARG, "cc_debug_eval_host: bad argument");
+    if (n < 0 || !in0 || !out0 || op < 0 || op > 6) return fail(CC_ERR_ARG, "cc_debug_eval_host: bad argument");
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         float r;
@@ -1403,7 +1403,8 @@ int cc_debug_eval_host(int op, int64_t n, const float* in0, const float* in1, co
             case 2: r = ccref::theta_arcsec(in0[i], in1[i], in2[i]); break;
             case 3: r = ccref::phi_arcsec_plain(in0[i], in1[i]); break;
             case 4: r = ccref::phi_arcsec_guarded(in0[i], in1[i]); break;
-            default: r = ccref::a_to_z(in0[i]); break;
+            case 5: r = ccref::a_to_z(in0[i]); break;
+            default: r = ccref::to_arcsec(in0[i]); break; /* 6: specification form (true fp64 division) */
         }
         out0[i] = r;
     }

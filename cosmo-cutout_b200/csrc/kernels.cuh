@@ -1418,7 +1418,8 @@ __global__ void k_debug_eval(int op, long long n, const float* in0, const float*
             case 2: r = ccref::theta_arcsec(in0[i], in1[i], in2[i]); break;
             case 3: r = ccref::phi_arcsec_plain(in0[i], in1[i]); break;
             case 4: r = ccref::phi_arcsec_guarded(in0[i], in1[i]); break;
-            default: r = a_to_z_dev(in0[i]); break;
+            case 5: r = a_to_z_dev(in0[i]); break;
+            default: r = ccref::to_arcsec_fast(in0[i]); break; /* 6: the device's division-free arcsecond scaling */
         }
         out[i] = r;
     }

@@ -196,7 +196,8 @@ int cc_last_stats(cc_ctx* ctx, int64_t out[4]);
 /* ------------------------------------------------------------------ test hooks (device arithmetic)
  * Evaluate the device restatement of the reference arithmetic element-wise on HOST arrays (copied to the
  * GPU and back): op 0 = acosf, 1 = atanf (in0 only); 2 = theta(x,y,z) -> out0, 3 = use-case-1 phi(x,y),
- * 4 = use-case-2 phi(x,y) with the x==0 guards; 5 = aToZ(in0). */
+ * 4 = use-case-2 phi(x,y) with the x==0 guards; 5 = aToZ(in0); 6 = radians -> arcsec scaling of in0 (the device
+ * evaluates its division-free form, cc_debug_eval_host the specification form with a true fp64 division). */
 int cc_debug_eval(cc_ctx* ctx, int op, int64_t n, const float* in0, const float* in1, const float* in2,
                   float* out0);
 /* host build of the same restatement (ref_math.cuh compiled for the CPU), same ops */

@@ -36,6 +36,15 @@ def test_device_libm_equals_host_restatement_on_all_floats(ctx):
             assert _same_float_bits(d, h), (op, c0)
 
 
+def test_device_arcsec_scaling_equals_specification_on_all_floats(ctx):
+    """op 6: the device's division-free radians->arcsec scaling vs the specification form (true fp64 division, host)
+    on all 2^32 float bit patterns"""
+    chunk = 1 << 26
+    for c0 in range(0, 1 << 32, chunk):
+        x = np.arange(c0, c0 + chunk, dtype=np.uint64).astype(np.uint32).view(np.float32)
+        assert _same_float_bits(ctx.debug_eval(6, x), cc.debug_eval_host(6, x)), c0
+
+
 def test_device_libm_equals_glibc_sample(ctx):
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.uniform(-1.0, 1.0, 2_000_000), rng.normal(0, 50, 2_000_000),

@@ -83,6 +83,16 @@ def test_restated_libm_equals_glibc_everywhere(tmp_path):
     assert "acosf mismatches=0 atanf mismatches=0 checked=4294967296" in out, out
 
 
+def test_division_free_arcsec_scaling_is_exact_everywhere(tmp_path):
+    """the device replaces `/ PI` by reciprocal-multiply + one fma correction: proven equal to the true fp64 division
+    for every finite non-zero float (all 2^32 bit patterns, ~3 s)"""
+    exe = str(tmp_path / "check_arcsec")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-ffp-contract=off", "-fopenmp", "-mfma",
+                           os.path.join(REPO, "tests", "native", "check_arcsec_fast.cpp"), "-o", exe, "-lm"])
+    out = subprocess.check_output([exe]).decode()
+    assert "quotient_mismatches=0 float_mismatches=0" in out and "checked=4278190078" in out, out
+
+
 def test_host_build_of_device_arithmetic_equals_oracle():
     cols = H.concat_cols(H.shell_fixture(200_000, seed=3), H.shell_fixture(200_000, seed=4, octant=False),
                          H.edge_fixture((306000, 320400), (0, 14400)))
