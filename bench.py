@@ -14,6 +14,8 @@ Printed JSON (one line, rank 0):
   value      whole-job Gparticles/s with the step resident in HBM (CUDA events on the cutout stream, max over ranks)
   e2e        same metric through the C ABI with HOST (pinned) columns: x,y,z streamed H2D double-buffered inside
              the timed region, survivors copied back to host inside the timed region
+  dtype      "f32": the path computes in the reference's own arithmetic (fp32 products/libm, one fp64 scaling per
+             angle), bit-exact -- not a reduced-precision variant
   roofline   dominant kernel (the scan): algorithmic bytes (12 B per particle scanned + 84 B per survivor;
              44 B with posOnly) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the real reference (oracle/_ref, single rank = 1 core, as shipped it has no threading) on a
@@ -296,7 +298,7 @@ def run_ours(args):
             "metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 reference arithmetic + f64 arcsec scaling (bit-exact); u64 compaction",
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["desc"], "particles_per_gpu": n, "particles_total": n_total,
                        "survivors_total": survivors_all, "l2": "inputs (12 B x particles per GPU) exceed the 126 MB L2; no flush needed",
@@ -419,7 +421,7 @@ def run_cfg3(args):
         out = {"metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": world,
                "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None,
-               "dtype": "f32 reference arithmetic + f64 arcsec scaling (bit-exact); u64 compaction", "data": "synthetic",
+               "dtype": "f32", "data": "synthetic",
                "config": {"workload": "BASELINE cfg3: full-depth halo cutout, 30 lightcone steps, 1B particles total, every "
                                       "step streamed from pinned host (x,y,z H2D double-buffered, other columns read in "
                                       "place for survivors)", "particles_total": m_step * lc_steps,
@@ -512,7 +514,7 @@ def run_reference(args):
     v = cores * per / slowest / 1e9
     out = {"impl": "reference", "metric": "Gparticles/s filtered", "value": round(v, 6), "unit": "Gparticles/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(slowest * 1e3, 3),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 libm + f64 scaling (CPU)",
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": wl["desc"], "sample_particles_per_step": cores * per},
            "cpu_baseline": {"value": round(v, 6), "unit": "Gparticles/s", "cores": cores, "kind": kind,
