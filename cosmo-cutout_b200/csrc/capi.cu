@@ -132,6 +132,7 @@ struct cc_ctx {
     int gather_gx_cap = 256; /* CC_GATHER_GX */
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
+    bool k2c_ready = false;
     bool k3_smem_set = false, k3s_smem_set = false;
     bool k2_tma = false, k2t_ready = false;
     int k2t_occ = 0;
@@ -157,9 +158,8 @@ struct cc_ctx {
     /* use case 2 scratch */
     DevBuf pre_buf, halo_buf, rec_a, rec_b, rank_buf, counts_buf;
     DevBuf hstate; /* use case 2 device state, one memset / one read-back: [misc 8 | counts 2H | seg H+1 | cursor H] u64 */
-    DevBuf bin_start_buf, bin_items_buf, ovf_particle_buf, ovf_halo_buf;
+    DevBuf bin_start_buf, bin_bits_buf, bin_items_buf; /* cell index: {first,end} per cell, occupancy bitmap, halo lists */
     std::vector<size_t> bin_items_off; /* per launch batch: first item */
-    int64_t ovf_cap = 0;
     bool use_bins = false;
     std::vector<cc_halo> index_key; /* halos the resident cell index was built for */
     std::vector<cc_halo> params_key; /* halos whose device parameters are resident */
@@ -447,12 +447,15 @@ int prepare_halo(cc_ctx* c) {
         if (!same) { /* rasterise every halo's window, then a counting sort into CSR lists */
             struct Box { int c0, c1, s0, s1; };
             auto cell_of = [G](double v) { return std::floor((v + 1.0) * (0.5 * G)); };
-            std::vector<unsigned int> starts((size_t)nbatch * (ncell + 1));
+            std::vector<unsigned int> starts(ncell + 1);
+            std::vector<uint2> ranges((size_t)nbatch * ncell);
+            std::vector<unsigned int> bits((size_t)nbatch * cck::K2_BITWORDS, 0u);
             std::vector<unsigned short> items;
             c->bin_items_off.assign((size_t)nbatch, 0);
             for (int bi = 0; bi < nbatch; ++bi) {
                 const int h0 = bi * cck::K2_MAX_HALOS, hn = std::min(cck::K2_MAX_HALOS, H - h0);
-                unsigned int* st = starts.data() + (size_t)bi * (ncell + 1);
+                unsigned int* st = starts.data();
+                std::fill(starts.begin(), starts.end(), 0u);
                 std::vector<Box> boxes((size_t)hn);
                 for (int h = 0; h < hn; ++h) {
                     const float4 P = pre[h0 + h];
@@ -478,18 +481,28 @@ int prepare_halo(cc_ctx* c) {
                     for (int ic = bx.c0; ic <= bx.c1; ++ic)
                         for (int is = bx.s0; is <= bx.s1; ++is) items[base_item + fill[(size_t)ic * G + is]++] = (unsigned short)h;
                 }
+                uint2* rg = ranges.data() + (size_t)bi * ncell;
+                unsigned int* bw = bits.data() + (size_t)bi * cck::K2_BITWORDS;
+                for (int ic = 0; ic < G; ++ic)
+                    for (int is = 0; is < G; ++is) {
+                        const size_t cell = (size_t)ic * G + is;
+                        rg[cell] = make_uint2(st[cell], st[cell + 1]);
+                        if (st[cell + 1] > st[cell]) {
+                            const unsigned int bit = (unsigned int)(ic >> 1) * cck::K2_COARSE + (unsigned int)(is >> 1);
+                            bw[bit >> 5] |= 1u << (bit & 31u);
+                        }
+                    }
             }
-            if ((rc = c->bin_start_buf.ensure(starts.size() * 4))) return rc;
+            if ((rc = c->bin_start_buf.ensure(ranges.size() * sizeof(uint2)))) return rc;
+            if ((rc = c->bin_bits_buf.ensure(bits.size() * 4))) return rc;
             if ((rc = c->bin_items_buf.ensure(std::max<size_t>(items.size(), 8) * 2))) return rc;
-            CU(cudaMemcpyAsync(c->bin_start_buf.p, starts.data(), starts.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->bin_start_buf.p, ranges.data(), ranges.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->bin_bits_buf.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, c->stream));
             if (!items.empty())
                 CU(cudaMemcpyAsync(c->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
-            CU(cudaStreamSynchronize(c->stream)); /* `starts`/`items` are pageable and die here */
+            CU(cudaStreamSynchronize(c->stream)); /* `ranges`/`bits`/`items` are pageable and die here */
             c->index_key = c->p_halos;
         }
-        if (c->ovf_cap == 0) c->ovf_cap = 1 << 22;
-        if ((rc = c->ovf_particle_buf.ensure((size_t)c->ovf_cap * 4))) return rc;
-        if ((rc = c->ovf_halo_buf.ensure((size_t)c->ovf_cap * 2))) return rc;
     }
     /* pageable -> device copies are staged by the runtime before returning, so the vectors may die; repeated
      * cutouts with the same halos (and the same kernel variant) skip the upload */
@@ -537,23 +550,23 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             if (occ < 1) occ = 1;
         }
         const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
-        if (c->use_bins) {
+        if (c->use_bins) { /* one 32-warp CTA per SM: bitmap + windows + pair buffers take 128 KB of its shared memory */
             cck::HaloBinArgs b;
             b.h = a;
             const int bi = h0 / cck::K2_MAX_HALOS;
-            b.cell_start = (const unsigned int*)c->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID + 1);
+            b.cell_range = (const uint2*)c->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID);
+            b.cell_bits = (const unsigned int*)c->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
             b.cell_items = (const unsigned short*)c->bin_items_buf.p + c->bin_items_off[(size_t)bi];
-            b.ovf_particle = (unsigned int*)c->ovf_particle_buf.p;
-            b.ovf_halo = (unsigned short*)c->ovf_halo_buf.p;
-            b.ovf_cap = (unsigned long long)c->ovf_cap;
-            b.ovf_count = rec_count + 2;
-            if (vec) cck::k2_cutout_halo_cells<true><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(b);
-            else cck::k2_cutout_halo_cells<false><<<grid, cck::SCAN_THREADS, pre_bytes, c->stream>>>(b);
+            if (!c->k2c_ready) {
+                CU(cudaFuncSetAttribute((const void*)cck::k2_cutout_halo_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K2C_SMEM));
+                CU(cudaFuncSetAttribute((const void*)cck::k2_cutout_halo_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K2C_SMEM));
+                c->k2c_ready = true;
+            }
+            const unsigned int cgrid = std::max(1u, std::min((a.ntiles + cck::K2C_WARPS - 1) / cck::K2C_WARPS, (unsigned int)c->sm_count));
+            if (vec) cck::k2_cutout_halo_cells<true><<<cgrid, cck::K2C_THREADS, cck::K2C_SMEM, c->stream>>>(b);
+            else cck::k2_cutout_halo_cells<false><<<cgrid, cck::K2C_THREADS, cck::K2C_SMEM, c->stream>>>(b);
             CU(cudaGetLastError());
-            cck::k2_overflow<<<c->sm_count * 4, 256, 0, c->stream>>>(b);
-            CU(cudaGetLastError());
-            CU(cudaMemsetAsync(rec_count + 2, 0, 8, c->stream)); /* the overflow queue is per launch */
-            c->launches += 2;
+            c->launches += 1;
         } else if (c->k2_tma && vec) { /* bulk-copy fed variant (CC_K2_TMA=1) */
             const size_t smem = cck::K2T_SMEM_BASE + pre_bytes;
             if (!c->k2t_ready) {
@@ -642,7 +655,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         }
         CU(cudaEventRecord(c->ev_total1, c->stream));
         c->have_times = true;
-        /* misc {rec_count, n_cand, -, ovf_max}, counts, rough counts, segment starts: one read-back */
+        /* misc {rec_count, n_cand, ...}, counts, rough counts, segment starts: one read-back */
         CU(cudaMemcpyAsync(c->h_small, c->hstate.p, (8 + 3 * (size_t)H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     }
     return CC_OK;
@@ -795,7 +808,7 @@ void cc_destroy(cc_ctx* c) {
     for (auto& b : c->out_buf) b.release();
     DevBuf* rest[] = {&c->scratch, &c->pre_buf, &c->halo_buf, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
                       &c->hstate, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row,
-                      &c->bin_start_buf, &c->bin_items_buf, &c->ovf_particle_buf, &c->ovf_halo_buf};
+                      &c->bin_start_buf, &c->bin_bits_buf, &c->bin_items_buf};
     for (DevBuf* b : rest) b->release();
     for (auto& sl : c->stage) for (auto& b : sl) b.release();
     for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
@@ -997,13 +1010,12 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             const int H = c->nhalos;
             for (int attempt = 0; attempt < 4; ++attempt) {
                 CU(cudaStreamSynchronize(c->stream));
-                const int64_t nrec = (int64_t)c->h_small[0], ovf_max = (int64_t)c->h_small[3];
+                const int64_t nrec = (int64_t)c->h_small[0];
                 const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
                 c->force_general = refused;
-                if (nrec <= c->rec_cap && ovf_max <= c->ovf_cap && !refused) break;
+                if (nrec <= c->rec_cap && !refused) break;
                 if (attempt == 3) return fail(CC_ERR_CUDA, "internal: halo survivor buffers still too small after regrowth");
                 if (nrec > c->rec_cap) c->rec_cap = nrec + nrec / 64;
-                if (ovf_max > c->ovf_cap) c->ovf_cap = ovf_max + ovf_max / 8;
                 if ((rc = run_pending(c))) return rc;
             }
             const int64_t nrec = (int64_t)c->h_small[0];

@@ -5,7 +5,7 @@
  *                     use case 1: octant test -> pre-filter -> exact (theta,phi) -> strict window test ->
  *                     ballot/popc compaction into per-CTA temp regions; exclusive scan of the tile counts by
  *                     decoupled look-back; order-preserving 12-column gather.   replaces processLC.cpp:276-310
- *   k2_cutout_halo (+ _cells, _tma, k2_overflow)
+ *   k2_cutout_halo (+ _cells, _tma)
  *                     use case 2: one pass over x,y,z for a batch of halos: pre-filter -> exact un-rotated
  *                     (theta_u,phi_u) -> rough test -> R.v -> exact rotated angles -> fine test -> survivor
  *                     records.                               replaces processLC.cpp:897-909, :1334-1340, :1383-1481
@@ -639,6 +639,49 @@ __device__ __forceinline__ void k2_exact(const HaloArgs& a, int h, float x, floa
     }
 }
 
+/* the same exact path for up to 32 pairs at once, one per live lane (the cell-index kernel, where a third of the
+ * instructions are spent here); EVERY lane of the warp must call.  The
+ * halo's parameters come in as five 16-byte loads issued together (one L2 round trip instead of three dependent
+ * ones), and the survivors of the warp claim their record slots with one atomic. */
+__device__ __forceinline__ void k2_exact_warp(const HaloArgs& a, bool live, int h, float x, float y, float z,
+                                              unsigned int local_n, int lane) {
+    static_assert(sizeof(HaloDev) == 80, "five float4 loads below");
+    const float4* __restrict__ Hq = reinterpret_cast<const float4*>(a.halos + (live ? h : 0));
+    const float4 q0 = __ldg(Hq), q1 = __ldg(Hq + 1), q2 = __ldg(Hq + 2), q3 = __ldg(Hq + 3), q4 = __ldg(Hq + 4);
+    const float th_lo = q2.y, th_hi = q2.z, ph_lo = q2.w, ph_hi = q3.x; /* fine, strict (processLC.cpp:1439-1440) */
+    const float rth_lo = q3.y, rth_hi = q3.z, rph_lo = q3.w, rph_hi = q4.x;
+    const unsigned int hg = (unsigned int)(a.halo0 + h);
+    const float thu = ccref::theta_arcsec(x, y, z);       /* processLC.cpp:899-900 */
+    const float phu = ccref::phi_arcsec_guarded(x, y);    /* :903-908 */
+    const bool rough = live && (thu >= rth_lo && thu < rth_hi) /* :1334-1340 (two lower_bounds) */
+                            && (phu > rph_lo && phu < rph_hi); /* :1400 */
+    if (!__any_sync(0xffffffffu, rough)) return;
+    if (rough) atomicAdd(a.counts + a.total_halos + hg, 1ull); /* rough_cutout_size, :1436 */
+    const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+    float rx, ry, rz;
+    ccref::mat_vec(R, x, y, z, rx, ry, rz);               /* :1419-1422 */
+    const float th = ccref::theta_arcsec(rx, ry, rz);     /* :1425-1426 */
+    const float ph = ccref::phi_arcsec_guarded(rx, ry);   /* :1430-1435 */
+    const bool fine = rough && th > th_lo && th < th_hi && ph > ph_lo && ph < ph_hi; /* :1439-1440 */
+    const unsigned int m = __ballot_sync(0xffffffffu, fine);
+    if (m == 0) return;
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(a.rec_count, (unsigned long long)__popc(m));
+    slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+    if (fine) {
+        atomicAdd(a.counts + hg, 1ull);
+        if (slot < a.rec_cap) {
+            Rec r;
+            r.key = ((unsigned long long)(unsigned int)__float_as_int(thu) << 32) | local_n;
+            r.halo = hg;
+            r.th = th;
+            r.ph = ph;
+            r.x = x; r.y = y; r.z = z;
+            a.recs[slot] = r;
+        }
+    }
+}
+
 struct K2WarpQueue {
     unsigned int particle[K2_QCAP]; /* index inside the chunk */
     unsigned short halo[K2_QCAP];
@@ -877,122 +920,244 @@ constexpr size_t K2T_SMEM_BASE = sizeof(K2TWarpRing) * SCAN_WARPS;
  * still leaves ~1 % of the halos per particle: profiles/r01).  The host rasterises each halo's widened rough
  * window [clo,chi] x [slo,shi] into a K2_GRID x K2_GRID grid over (c, s) in [-1,1]^2 (+-1 cell of slack) and builds
  * a CSR list of halos per cell.  A particle computes c = z/r and s = sin(phi_u) = y*sign(x)/sqrt(x^2+y^2), looks up
- * its cell (one 8-byte read from an L2-resident table) and tests only the halos listed there -- for cluster-sized
+ * its cell (one 8-byte read from an L2-resident table) and owes one test per halo listed there -- for cluster-sized
  * boxes most cells are empty.  This plays the role of the reference's theta-sorted index (processLC.cpp:1214-1221,
- * :1334-1340) without sorting or re-reading 12 B/particle data.  Pairs that pass go to the warp queue; pairs that
- * do not fit go to a global overflow queue drained by k2_overflow. */
+ * :1334-1340) without sorting or re-reading 12 B/particle data.
+ *
+ * Lists differ in length from lane to lane, so the warp never walks them in place.  One CTA of 32 warps per SM
+ * keeps a 512 x 512 occupancy bitmap of the grid (one bit per 2 x 2 cells) in shared memory: most particles are
+ * ruled out by one shared-memory read, the rest fetch their cell's {first, end} from the L2-resident table.  Every
+ * lane then expands its (particle, list item) pairs -- position included, it is in registers -- into the warp's
+ * shared-memory buffer, and the warp works through the buffer 32 pairs at a time with all lanes busy: halo id from
+ * the list, four compares against the halo's window, in-place compaction of what passes to the front of the
+ * buffer, and the exact path (k2_exact_warp) for every 32 tested pairs.  Untested and tested remainders (< 32
+ * each) stay in the buffer for the next tile; a tile that owes more pairs than fit is taken in several passes.
+ * Tiles are 128 particles (4 per lane) so that the positions stay in registers next to the pair bookkeeping. */
 constexpr int K2_GRID = 1024;
-constexpr int K2B_QCAP = 256; /* warp queue of the cell kernel (the rest goes to the global overflow queue) */
-struct K2BWarpQueue {
-    unsigned int particle[K2B_QCAP];
-    unsigned short halo[K2B_QCAP];
+constexpr int K2_COARSE = K2_GRID / 2;                       /* occupancy bitmap: one bit per 2 x 2 cells */
+constexpr int K2_BITWORDS = K2_COARSE * K2_COARSE / 32;      /* 32 KB, resident in shared memory */
+constexpr int K2C_THREADS = 1024, K2C_WARPS = K2C_THREADS / 32; /* one CTA per SM shares the bitmap */
+constexpr int K2C_TILE = 128; /* particles per warp tile */
+constexpr int K2C_PCAP = 128; /* pairs per warp buffer: 20 B each */
+struct K2CPairs {
+    unsigned int k[K2C_PCAP]; /* index into cell_items; once tested: the halo */
+    unsigned int g[K2C_PCAP]; /* particle index inside the chunk */
+    float x[K2C_PCAP], y[K2C_PCAP], z[K2C_PCAP];
 };
+constexpr size_t K2C_SMEM = (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4) + sizeof(K2CPairs) * K2C_WARPS;
 
 struct HaloBinArgs {
     HaloArgs h;                       /* h.pre holds {chi, clo, slo, shi} here (prefilter.h uc2_bounds_cells) */
-    const unsigned int* cell_start;   /* [K2_GRID*K2_GRID + 1] */
+    const unsigned int* cell_bits;    /* [K2_BITWORDS]: bit set when any of the 2 x 2 cells lists a halo */
+    const uint2* cell_range;          /* [K2_GRID*K2_GRID] {first, end} into cell_items */
     const unsigned short* cell_items; /* halo index inside the launch */
-    unsigned int* ovf_particle;       /* overflow pairs: particle index inside the chunk */
-    unsigned short* ovf_halo;
-    unsigned long long ovf_cap;
-    unsigned long long* ovf_count;    /* may exceed ovf_cap: detected on the host */
 };
 
+/* (c, s) of the cell index */
+__device__ __forceinline__ void k2c_coords(float x, float y, float z, float& c, float& s, bool& sane) {
+    const float rxy2 = fmaf(y, y, x * x);
+    const float r2 = fmaf(z, z, rxy2);
+    /* |x| in range keeps x^2+y^2 away from underflow; r^2 <= 2^80 keeps everything finite */
+    sane = (fabsf(x) >= CC_SANE_LO) & (r2 <= 1.2089258e24f);
+    c = z * rsqrt_fast(r2);
+    /* sin(phi_u) with phi_u = atan(y/x): y / sqrt(x^2+y^2), negated when x < 0 */
+    s = __int_as_float(__float_as_int(y * rsqrt_fast(rxy2)) ^ (__float_as_int(x) & 0x80000000));
+}
+
+/* one out-of-range position against every halo of the launch (rare) */
+__device__ __noinline__ void k2c_exact_all(const HaloArgs& a, float x, float y, float z, unsigned int local_n, int lane) {
+    for (int h0 = 0; h0 < a.nhalos; h0 += 32) {
+        const int h = h0 + lane;
+        k2_exact_warp(a, h < a.nhalos, h < a.nhalos ? h : 0, x, y, z, local_n, lane);
+    }
+}
+
 template <bool VEC>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo_cells(const HaloBinArgs b) {
-    extern __shared__ float4 s_pre[]; /* [nhalos] */
-    __shared__ K2BWarpQueue s_q[SCAN_WARPS];
-    __shared__ unsigned int s_qcount[SCAN_WARPS];
+__global__ void __launch_bounds__(K2C_THREADS, 1) k2_cutout_halo_cells(const __grid_constant__ HaloBinArgs b) {
+    extern __shared__ __align__(16) unsigned char s_cells[];
+    unsigned int* s_bits = reinterpret_cast<unsigned int*>(s_cells);
+    float4* s_pre = reinterpret_cast<float4*>(s_cells + (size_t)K2_BITWORDS * 4);
+    K2CPairs* s_p = reinterpret_cast<K2CPairs*>(s_cells + (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4));
     const HaloArgs& a = b.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    K2BWarpQueue& q = s_q[warp];
-    for (int h = threadIdx.x; h < a.nhalos; h += SCAN_THREADS) s_pre[h] = a.pre[h];
-    if (lane == 0) s_qcount[warp] = 0;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    K2CPairs& P = s_p[warp];
+    for (int i = threadIdx.x; i < K2_BITWORDS / 4; i += K2C_THREADS)
+        reinterpret_cast<uint4*>(s_bits)[i] = __ldg(reinterpret_cast<const uint4*>(b.cell_bits) + i);
+    for (int h = threadIdx.x; h < a.nhalos; h += K2C_THREADS) s_pre[h] = a.pre[h];
     __syncthreads();
-    const unsigned int total_warps = gridDim.x * SCAN_WARPS;
+    const unsigned int total_warps = gridDim.x * K2C_WARPS;
+    const unsigned int ntiles = (unsigned int)((a.n + K2C_TILE - 1) / K2C_TILE);
     unsigned long long n_cand = 0;
+    /* warp-uniform buffer state: [0, nc) tested pairs waiting for the exact path, [nc, nc + nu) untested pairs */
+    unsigned int nc = 0, nu = 0;
+    bool flush = false;
 
-    for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
-        const long long base = (long long)tile * SCAN_TILE;
-        float px[8], py[8], pz[8];
-        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
-        float pc[8], ps[8];
-        unsigned int k0[8], k1[8], insane = 0;
+    for (unsigned int tile = blockIdx.x * K2C_WARPS + warp; !flush; tile += total_warps) {
+        float px[4], py[4], pz[4];
+        unsigned int k0[4], cnt[4], mine = 0, off = 0, total = 0;
+        const long long base = (long long)tile * K2C_TILE;
+        if (tile < ntiles) {
+            unsigned int valid = 0;
+            if (VEC && base + K2C_TILE <= a.n) {
+                const float4 vx = ldg_stream4(a.x + base + 4 * lane), vy = ldg_stream4(a.y + base + 4 * lane),
+                             vz = ldg_stream4(a.z + base + 4 * lane);
+                px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+                py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+                pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+                valid = 0xfu;
+            } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { /* all eight table look-ups are issued before any is used */
-            const float rxy2 = fmaf(py[j], py[j], px[j] * px[j]);
-            const float r2 = fmaf(pz[j], pz[j], rxy2);
-            /* |x| in range keeps x^2+y^2 away from underflow; r^2 <= 2^80 keeps everything finite */
-            if (!((fabsf(px[j]) >= CC_SANE_LO) & (r2 <= 1.2089258e24f))) insane |= 1u << j;
-            pc[j] = pz[j] * rsqrt_fast(r2);
-            /* sin(phi_u) with phi_u = atan(y/x): y / sqrt(x^2+y^2), negated when x < 0 */
-            ps[j] = __int_as_float(__float_as_int(py[j] * rsqrt_fast(rxy2)) ^ (__float_as_int(px[j]) & 0x80000000));
-            int ic = (int)((pc[j] + 1.0f) * (0.5f * K2_GRID)), is = (int)((ps[j] + 1.0f) * (0.5f * K2_GRID));
-            ic = max(0, min(K2_GRID - 1, ic));
-            is = max(0, min(K2_GRID - 1, is));
-            const unsigned int cell = (unsigned int)ic * K2_GRID + (unsigned int)is;
-            k0[j] = __ldg(b.cell_start + cell);
-            k1[j] = __ldg(b.cell_start + cell + 1);
-        }
-        insane &= valid;
-        bool mine = insane != 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mine |= ((valid >> j) & 1u) && (k1[j] > k0[j]);
-        if (__any_sync(0xffffffffu, mine)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (!((valid >> j) & 1u)) continue;
-                const bool bad = (insane >> j) & 1u; /* the exact path decides, against every halo of the launch */
-                const unsigned int ka = bad ? 0u : k0[j], kb = bad ? (unsigned int)a.nhalos : k1[j];
-                const unsigned int g = (unsigned int)(base + tile_local(lane, j));
-                for (unsigned int k = ka; k < kb; ++k) {
-                    const unsigned int h = bad ? k : (unsigned int)b.cell_items[k];
-                    const float4 P = s_pre[h];
-                    if (bad | ((pc[j] <= P.x) & (pc[j] >= P.y) & (ps[j] >= P.z) & (ps[j] <= P.w))) {
-                        const unsigned int pos = atomicAdd(&s_qcount[warp], 1u);
-                        if (pos < K2B_QCAP) {
-                            q.particle[pos] = g;
-                            q.halo[pos] = (unsigned short)h;
-                        } else {
-                            const unsigned long long o = atomicAdd(b.ovf_count, 1ull);
-                            if (o < b.ovf_cap) {
-                                b.ovf_particle[o] = g;
-                                b.ovf_halo[o] = (unsigned short)h;
-                            }
-                        }
+                for (int j = 0; j < 4; ++j) {
+                    const long long g = base + 4 * lane + j;
+                    px[j] = py[j] = pz[j] = 1.0f;
+                    if (g < a.n) {
+                        px[j] = __ldcs(a.x + g); py[j] = __ldcs(a.y + g); pz[j] = __ldcs(a.z + g);
+                        valid |= 1u << j;
                     }
                 }
             }
-            __syncwarp();
-            const unsigned int cnt = min(s_qcount[warp], (unsigned int)K2B_QCAP);
-            if (cnt) { /* warp-uniform */
-                for (unsigned int jq = lane; jq < cnt; jq += 32) {
-                    const unsigned int gq = q.particle[jq];
-                    k2_exact(a, q.halo[jq], a.x[gq], a.y[gq], a.z[gq], (unsigned int)(a.local_base + gq));
+            unsigned int insane = 0, hit = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { /* cell of every particle; most are ruled out by the shared-memory bitmap */
+                float pc, ps;
+                bool sane;
+                k2c_coords(px[j], py[j], pz[j], pc, ps, sane);
+                if (!sane) insane |= 1u << j;
+                int ic = (int)((pc + 1.0f) * (0.5f * K2_GRID)), is = (int)((ps + 1.0f) * (0.5f * K2_GRID));
+                ic = max(0, min(K2_GRID - 1, ic));
+                is = max(0, min(K2_GRID - 1, is));
+                k0[j] = (unsigned int)ic * K2_GRID + (unsigned int)is;
+                const unsigned int bit = (unsigned int)(ic >> 1) * K2_COARSE + (unsigned int)(is >> 1);
+                hit |= ((s_bits[bit >> 5] >> (bit & 31u)) & 1u) << j;
+            }
+            insane &= valid;
+            hit &= valid & ~insane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { /* the look-ups that remain are issued together */
+                uint2 r = make_uint2(0u, 0u);
+                if ((hit >> j) & 1u) r = __ldg(b.cell_range + k0[j]);
+                k0[j] = r.x;
+                cnt[j] = r.y - r.x;
+                mine += cnt[j];
+            }
+            /* out-of-range positions: the exact path decides, against every halo of the launch, warp-cooperatively */
+            if (__any_sync(0xffffffffu, insane != 0)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    unsigned int m = __ballot_sync(0xffffffffu, (insane >> j) & 1u);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float x = __shfl_sync(0xffffffffu, px[j], src), y = __shfl_sync(0xffffffffu, py[j], src),
+                                    z = __shfl_sync(0xffffffffu, pz[j], src);
+                        k2c_exact_all(a, x, y, z, (unsigned int)(a.local_base + base + 4 * src + j), lane);
+                        n_cand += (unsigned int)a.nhalos;
+                    }
                 }
-                n_cand += cnt;
-                __syncwarp();
-                if (lane == 0) s_qcount[warp] = 0;
+            }
+            /* position of this lane's pairs in the tile's pair sequence */
+            unsigned int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            total = __shfl_sync(0xffffffffu, inc, 31);
+            off = inc - mine;
+            if (total == 0) continue;
+        } else {
+            flush = true; /* past this warp's last tile: one more trip to empty the buffer */
+        }
+        unsigned int w0 = 0;
+        do {
+            if (total) { /* expand the pairs [w0, w1) of the tile behind what the buffer holds */
+                const unsigned int fill = nc + nu;
+                const unsigned int w1 = min(total, w0 + (K2C_PCAP - fill));
+                if (w0 == 0 && w1 == total) { /* the usual case: everything fits */
+                    unsigned int e = fill + off;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        for (unsigned int t = 0; t < cnt[j]; ++t, ++e) {
+                            P.k[e] = k0[j] + t;
+                            P.g[e] = (unsigned int)(base + 4 * lane + j);
+                            P.x[e] = px[j]; P.y[e] = py[j]; P.z[e] = pz[j];
+                        }
+                } else if (off < w1 && off + mine > w0) {
+                    unsigned int pos = off;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned int lo = pos < w0 ? w0 - pos : 0u;
+                        const unsigned int hi = w1 > pos ? min(cnt[j], w1 - pos) : 0u;
+                        for (unsigned int t = lo; t < hi; ++t) {
+                            const unsigned int e = fill + (pos + t - w0);
+                            P.k[e] = k0[j] + t;
+                            P.g[e] = (unsigned int)(base + 4 * lane + j);
+                            P.x[e] = px[j]; P.y[e] = py[j]; P.z[e] = pz[j];
+                        }
+                        pos += cnt[j];
+                    }
+                }
+                nu += w1 - w0;
+                w0 = w1;
                 __syncwarp();
             }
-        }
+            /* test rounds: full ones only, unless the buffer is being emptied */
+            unsigned int i0 = nc;
+            while (nu >= 32u || (flush && nu > 0u)) {
+                const unsigned int m = min(nu, 32u);
+                const unsigned int i = i0 + lane;
+                bool pass = false;
+                unsigned int h = 0, g = 0;
+                float x = 0.0f, y = 0.0f, z = 0.0f;
+                if ((unsigned int)lane < m) {
+                    h = __ldg(b.cell_items + P.k[i]);
+                    g = P.g[i];
+                    x = P.x[i]; y = P.y[i]; z = P.z[i];
+                    const float4 W = s_pre[h];
+                    float pc, ps;
+                    bool sane;
+                    k2c_coords(x, y, z, pc, ps, sane);
+                    pass = (pc <= W.x) & (pc >= W.y) & (ps >= W.z) & (ps <= W.w);
+                }
+                const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+                __syncwarp(); /* every lane holds its pair in registers: the compaction below may overwrite it */
+                if (pass) {
+                    const unsigned int e = nc + __popc(pm & lt_mask);
+                    P.k[e] = h;
+                    P.g[e] = g;
+                    P.x[e] = x; P.y[e] = y; P.z[e] = z;
+                }
+                nc += __popc(pm);
+                nu -= m;
+                i0 += m;
+                __syncwarp();
+            }
+            /* exact path: full rounds of tested pairs (the newest 32 each time) */
+            while (nc >= 32u || (flush && nc > 0u)) {
+                const unsigned int m = min(nc, 32u);
+                nc -= m;
+                const unsigned int e = nc + lane;
+                const bool live = (unsigned int)lane < m;
+                unsigned int h = 0, g = 0;
+                float x = 1.0f, y = 1.0f, z = 1.0f;
+                if (live) { h = P.k[e]; g = P.g[e]; x = P.x[e]; y = P.y[e]; z = P.z[e]; }
+                k2_exact_warp(a, live, (int)h, x, y, z, (unsigned int)(a.local_base + g), lane);
+                n_cand += m;
+            }
+            /* close the gap between the tested and the untested remainder */
+            if (nu && i0 != nc) {
+                unsigned int k = 0, g = 0;
+                float x = 0.0f, y = 0.0f, z = 0.0f;
+                __syncwarp();
+                if ((unsigned int)lane < nu) { k = P.k[i0 + lane]; g = P.g[i0 + lane]; x = P.x[i0 + lane]; y = P.y[i0 + lane]; z = P.z[i0 + lane]; }
+                __syncwarp();
+                if ((unsigned int)lane < nu) { P.k[nc + lane] = k; P.g[nc + lane] = g; P.x[nc + lane] = x; P.y[nc + lane] = y; P.z[nc + lane] = z; }
+            }
+            __syncwarp();
+        } while (w0 < total);
     }
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
-}
-
-/* pairs that did not fit a warp queue */
-__global__ void __launch_bounds__(256) k2_overflow(const HaloBinArgs b) {
-    const unsigned long long wanted = *b.ovf_count;
-    const unsigned long long n = min(wanted, b.ovf_cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && wanted) atomicMax(b.ovf_count + 1, wanted); /* host: overflow check */
-    unsigned long long mine = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned int g = b.ovf_particle[i];
-        k2_exact(b.h, b.ovf_halo[i], b.h.x[g], b.h.y[g], b.h.z[g], (unsigned int)(b.h.local_base + g));
-        ++mine;
-    }
-    if (mine) atomicAdd(b.h.n_cand, mine);
 }
 
 /* ================================================================================================

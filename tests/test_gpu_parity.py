@@ -302,6 +302,36 @@ def test_halo_many_halos_one_pass(ctx):
         H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {h}: ")
 
 
+def test_halo_cell_index_overlapping_halos_and_special_positions(ctx):
+    """the cell-index kernel (>= 8 halos): 48 halos whose windows all overlap, so a 256-particle tile owes far more
+    (particle, halo) pairs than the warp's pair buffer holds (several passes per tile), plus positions the
+    pre-filter cannot judge (zero / tiny / huge / Inf coordinates, all octants) that take the every-halo path"""
+    rng = np.random.default_rng(17)
+    cols = H.concat_cols(H.shell_fixture(300_000, seed=51), H.shell_fixture(100_000, seed=52, octant=False))
+    n = cols["x"].shape[0]
+    bad = rng.choice(n, 1_500, replace=False)
+    # one special coordinate per particle, none that makes theta_u NaN: the reference orders theta_u with
+    # std::stable_sort / lower_bound (processLC.cpp:1214-1221, :1334-1337), which is unspecified once a NaN is in
+    # the array (DESIGN.md "NaN theta"), so there is nothing to be equal to
+    vals = np.array([np.inf, -np.inf, 0.0, -0.0, 1e-12, -1e-12, 1e-40, 3e38], dtype=np.float32)
+    for k, col in enumerate(("x", "y", "z")):
+        v = vals if col != "z" else vals[2:]
+        cols[col][bad[k::3]] = v[rng.integers(0, len(v), bad[k::3].shape[0])]
+    cols["x"][bad[:200]] = np.float32(1e-12)  # tiny x next to ordinary y, z: phi_u close to 90 degrees
+    centre = np.array([120.0, 90.0, 100.0])
+    pos = (centre + rng.uniform(-4, 4, (48, 3))).astype(np.float32)
+    boxes = rng.uniform(40.0, 90.0, 48)
+    infos = [cc.halo_setup(p, b) for p, b in zip(pos, boxes)]
+    ctx.upload(cols)
+    ctx.cutout_halo([i.halo for i in infos])
+    counts, rough = ctx.sync()
+    assert ctx.stats()["candidates"] > 20 * int(counts.max())  # many pairs per particle went through the exact path
+    for h in range(0, 48, 5):
+        want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(pos[h], boxes[h]))
+        assert int(counts[h]) == want["id"].shape[0] > 20 and int(rough[h]) == want_rough
+        H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {h}: ")
+
+
 def test_halo_large_segment(ctx):
     """a 10-degree box: tens of thousands of survivors in one halo -- beyond the shared-memory sort (K3_SORT_MAX =
     8192), so the counting fallback orders the segment; a second, small halo in the same pass takes the sort"""
