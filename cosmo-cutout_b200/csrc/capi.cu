@@ -133,6 +133,7 @@ struct cc_ctx {
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
     bool k2c_ready = false;
+    int k2c_warps = 24; /* 24 warps per CTA at 80 registers (CC_K2C_WARPS=32: 32 warps at 64, measured slower: spills) */
     bool k3_smem_set = false, k3s_smem_set = false;
     bool k2_tma = false, k2t_ready = false;
     int k2t_occ = 0;
@@ -157,7 +158,7 @@ struct cc_ctx {
     DevBuf scratch;
     /* use case 2 scratch */
     DevBuf pre_buf, halo_buf, rec_a, rec_b, rank_buf, counts_buf;
-    DevBuf hstate; /* use case 2 device state, one memset / one read-back: [misc 8 | counts 2H | seg H+1 | cursor H] u64 */
+    DevBuf hstate; /* use case 2 device state, one memset / one read-back: [misc 8 | counts 2H | seg H+1 | cursor 16H] u64 */
     DevBuf bin_start_buf, bin_bits_buf, bin_items_buf; /* cell index: {first,end} per cell, occupancy bitmap, halo lists */
     std::vector<size_t> bin_items_off; /* per launch batch: first item */
     bool use_bins = false;
@@ -391,7 +392,7 @@ int prepare_const(cc_ctx* c) {
 }
 
 /* ---------------------------------------------------------------- use case 2 launch */
-size_t hstate_elems(int H) { return 8 + 2 * (size_t)H + ((size_t)H + 1) + (size_t)H; }
+size_t hstate_elems(int H) { return 8 + 2 * (size_t)H + ((size_t)H + 1) + (size_t)cck::K3_CURSOR_STRIDE * (size_t)H; }
 unsigned long long* hs_misc(const cc_ctx* c) { return (unsigned long long*)c->hstate.p; }
 unsigned long long* hs_counts(const cc_ctx* c) { return hs_misc(c) + 8; }
 unsigned long long* hs_seg(const cc_ctx* c, int H) { return hs_counts(c) + 2 * (size_t)H; }
@@ -558,13 +559,25 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             b.cell_bits = (const unsigned int*)c->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
             b.cell_items = (const unsigned short*)c->bin_items_buf.p + c->bin_items_off[(size_t)bi];
             if (!c->k2c_ready) {
-                CU(cudaFuncSetAttribute((const void*)cck::k2_cutout_halo_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K2C_SMEM));
-                CU(cudaFuncSetAttribute((const void*)cck::k2_cutout_halo_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K2C_SMEM));
+                const void* fns[4] = {(const void*)cck::k2_cutout_halo_cells<true, 32>, (const void*)cck::k2_cutout_halo_cells<false, 32>,
+                                      (const void*)cck::k2_cutout_halo_cells<true, 24>, (const void*)cck::k2_cutout_halo_cells<false, 24>};
+                for (int i = 0; i < 4; ++i)
+                    CU(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::k2c_smem(i < 2 ? 32 : 24)));
+                const char* e = getenv("CC_K2C_WARPS");
+                c->k2c_warps = (e && atoi(e) == 32) ? 32 : 24;
                 c->k2c_ready = true;
             }
-            const unsigned int cgrid = std::max(1u, std::min((a.ntiles + cck::K2C_WARPS - 1) / cck::K2C_WARPS, (unsigned int)c->sm_count));
-            if (vec) cck::k2_cutout_halo_cells<true><<<cgrid, cck::K2C_THREADS, cck::K2C_SMEM, c->stream>>>(b);
-            else cck::k2_cutout_halo_cells<false><<<cgrid, cck::K2C_THREADS, cck::K2C_SMEM, c->stream>>>(b);
+            const unsigned int cw = (unsigned int)c->k2c_warps;
+            const unsigned int ctiles = (unsigned int)((n_scan + cck::K2C_TILE - 1) / cck::K2C_TILE);
+            const unsigned int cgrid = std::max(1u, std::min((ctiles + cw - 1) / cw, (unsigned int)c->sm_count));
+            const size_t csmem = cck::k2c_smem((int)cw);
+            if (cw == 32) {
+                if (vec) cck::k2_cutout_halo_cells<true, 32><<<cgrid, 1024, csmem, c->stream>>>(b);
+                else cck::k2_cutout_halo_cells<false, 32><<<cgrid, 1024, csmem, c->stream>>>(b);
+            } else {
+                if (vec) cck::k2_cutout_halo_cells<true, 24><<<cgrid, 768, csmem, c->stream>>>(b);
+                else cck::k2_cutout_halo_cells<false, 24><<<cgrid, 768, csmem, c->stream>>>(b);
+            }
             CU(cudaGetLastError());
             c->launches += 1;
         } else if (c->k2_tma && vec) { /* bulk-copy fed variant (CC_K2_TMA=1) */
@@ -593,6 +606,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         /* ordering + gather, sized on the device: the whole pass is one enqueue, one host synchronisation */
         cck::GatherArgs g;
         g.rank = (const unsigned int*)c->rank_buf.p;
+        g.sorted = nullptr;
         g.seg_begin = hs_seg(c, H);
         g.rec_count = rec_count;
         g.rec_cap = (unsigned long long)c->rec_cap;
@@ -623,7 +637,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         } else {
             cck::k3_scan_counts<<<1, 256, 0, c->stream>>>(hs_counts(c), hs_seg(c, H), H);
             CU(cudaGetLastError());
-            const unsigned int g1 = (unsigned int)c->sm_count * 4;
+            const unsigned int g1 = (unsigned int)c->sm_count * 8; /* 2048 threads per SM: every record is a chain of dependent L2 round trips */
             cck::BucketArgs b;
             b.recs = (const cck::Rec*)c->rec_a.p;
             b.rec_count = rec_count;
@@ -638,10 +652,11 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             r.seg_begin = hs_seg(c, H);
             r.rec_cap = (unsigned long long)c->rec_cap;
             r.rank = (unsigned int*)c->rank_buf.p;
+            r.sorted = (unsigned long long*)c->rec_a.p; /* the unbucketed records are dead once k3_bucket ran */
             r.H = H;
-            /* few halos: many column blocks per halo; many halos: a few, the y dimension provides the parallelism */
+            /* few halos: many chunk slots per halo; many halos: a few, the y dimension provides the parallelism */
             const unsigned int gy = (unsigned int)std::min(H, 8192);
-            const unsigned int gx = (unsigned int)std::max(4, std::min(64, (c->sm_count * 8) / (int)gy));
+            const unsigned int gx = (unsigned int)std::max(8, std::min(64, (c->sm_count * 8) / (int)gy));
             if (!c->k3_smem_set) {
                 CU(cudaFuncSetAttribute((const void*)cck::k3_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K3_SMEM_BYTES));
                 c->k3_smem_set = true;
@@ -649,6 +664,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, cck::K3_SMEM_BYTES, c->stream>>>(r);
             CU(cudaGetLastError());
             g.recs = (const cck::Rec*)c->rec_b.p;
+            g.sorted = (const unsigned long long*)c->rec_a.p;
             cck::k3_gather_halo<<<g1, 256, 0, c->stream>>>(g);
             CU(cudaGetLastError());
             c->launches += 4;

@@ -924,27 +924,32 @@ constexpr size_t K2T_SMEM_BASE = sizeof(K2TWarpRing) * SCAN_WARPS;
  * boxes most cells are empty.  This plays the role of the reference's theta-sorted index (processLC.cpp:1214-1221,
  * :1334-1340) without sorting or re-reading 12 B/particle data.
  *
- * Lists differ in length from lane to lane, so the warp never walks them in place.  One CTA of 32 warps per SM
- * keeps a 512 x 512 occupancy bitmap of the grid (one bit per 2 x 2 cells) in shared memory: most particles are
- * ruled out by one shared-memory read, the rest fetch their cell's {first, end} from the L2-resident table.  Every
- * lane then expands its (particle, list item) pairs -- position included, it is in registers -- into the warp's
- * shared-memory buffer, and the warp works through the buffer 32 pairs at a time with all lanes busy: halo id from
- * the list, four compares against the halo's window, in-place compaction of what passes to the front of the
- * buffer, and the exact path (k2_exact_warp) for every 32 tested pairs.  Untested and tested remainders (< 32
- * each) stay in the buffer for the next tile; a tile that owes more pairs than fit is taken in several passes.
- * Tiles are 128 particles (4 per lane) so that the positions stay in registers next to the pair bookkeeping. */
+ * One CTA of 32 warps per SM keeps a 512 x 512 occupancy bitmap of the grid (one bit per 2 x 2 cells) in shared
+ * memory: most particles are ruled out by one shared-memory read, the rest ("hits") fetch their cell's
+ * {first, end} from the L2-resident table.  Hits are few and scattered over the lanes, so the warp never works on
+ * them in place: every lane pushes its hits -- position included, it is in registers -- onto the warp's
+ * shared-memory stack, and whenever 32 are stacked the warp pops them, one per lane: (c, s), the next halo of the
+ * cell's list, four compares against that halo's window; a pair that passes goes onto a second stack of tested
+ * pairs, and a hit whose list has more halos is pushed back with the list advanced by one (lists differ in length,
+ * this keeps every round full).  Whenever 32 tested pairs are stacked they take the exact path (k2_exact_warp) with
+ * all lanes busy.  Remainders (< 32 each) stay stacked for the next tile.  Tiles are 128 particles (4 per lane) to
+ * keep registers for the bookkeeping. */
 constexpr int K2_GRID = 1024;
 constexpr int K2_COARSE = K2_GRID / 2;                       /* occupancy bitmap: one bit per 2 x 2 cells */
 constexpr int K2_BITWORDS = K2_COARSE * K2_COARSE / 32;      /* 32 KB, resident in shared memory */
-constexpr int K2C_THREADS = 1024, K2C_WARPS = K2C_THREADS / 32; /* one CTA per SM shares the bitmap */
+/* one CTA per SM shares the bitmap: 32 warps at 64 registers, or 24 warps at 80 (template parameter WARPS) */
 constexpr int K2C_TILE = 128; /* particles per warp tile */
-constexpr int K2C_PCAP = 128; /* pairs per warp buffer: 20 B each */
-struct K2CPairs {
-    unsigned int k[K2C_PCAP]; /* index into cell_items; once tested: the halo */
-    unsigned int g[K2C_PCAP]; /* particle index inside the chunk */
-    float x[K2C_PCAP], y[K2C_PCAP], z[K2C_PCAP];
+constexpr int K2C_HCAP = 96;  /* stacked hits per warp (a tile with more is taken in several passes) */
+constexpr int K2C_CCAP = 64;  /* stacked tested pairs per warp: < 32 waiting + <= 32 from one round */
+struct __align__(16) K2CStacks {
+    float4 hp[K2C_HCAP];         /* hit: x, y, z, particle index inside the chunk (bits) */
+    uint2 hl[K2C_HCAP];          /*      {next item of the cell's list, items left} */
+    float4 cp[K2C_CCAP];         /* tested pair: x, y, z, particle index (bits) */
+    unsigned int ch[K2C_CCAP];   /*              halo inside the launch */
 };
-constexpr size_t K2C_SMEM = (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4) + sizeof(K2CPairs) * K2C_WARPS;
+constexpr size_t k2c_smem(int warps) {
+    return (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4) + sizeof(K2CStacks) * (size_t)warps;
+}
 
 struct HaloBinArgs {
     HaloArgs h;                       /* h.pre holds {chi, clo, slo, shi} here (prefilter.h uc2_bounds_cells) */
@@ -972,16 +977,17 @@ __device__ __noinline__ void k2c_exact_all(const HaloArgs& a, float x, float y, 
     }
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(K2C_THREADS, 1) k2_cutout_halo_cells(const __grid_constant__ HaloBinArgs b) {
+template <bool VEC, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __grid_constant__ HaloBinArgs b) {
+    constexpr int K2C_THREADS = WARPS * 32, K2C_WARPS = WARPS;
     extern __shared__ __align__(16) unsigned char s_cells[];
     unsigned int* s_bits = reinterpret_cast<unsigned int*>(s_cells);
     float4* s_pre = reinterpret_cast<float4*>(s_cells + (size_t)K2_BITWORDS * 4);
-    K2CPairs* s_p = reinterpret_cast<K2CPairs*>(s_cells + (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4));
+    K2CStacks* s_st = reinterpret_cast<K2CStacks*>(s_cells + (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4));
     const HaloArgs& a = b.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    K2CPairs& P = s_p[warp];
+    K2CStacks& S = s_st[warp];
     for (int i = threadIdx.x; i < K2_BITWORDS / 4; i += K2C_THREADS)
         reinterpret_cast<uint4*>(s_bits)[i] = __ldg(reinterpret_cast<const uint4*>(b.cell_bits) + i);
     for (int h = threadIdx.x; h < a.nhalos; h += K2C_THREADS) s_pre[h] = a.pre[h];
@@ -989,15 +995,16 @@ __global__ void __launch_bounds__(K2C_THREADS, 1) k2_cutout_halo_cells(const __g
     const unsigned int total_warps = gridDim.x * K2C_WARPS;
     const unsigned int ntiles = (unsigned int)((a.n + K2C_TILE - 1) / K2C_TILE);
     unsigned long long n_cand = 0;
-    /* warp-uniform buffer state: [0, nc) tested pairs waiting for the exact path, [nc, nc + nu) untested pairs */
-    unsigned int nc = 0, nu = 0;
+    unsigned int nh = 0, nc = 0; /* warp-uniform stack heights: hits, tested pairs */
+    unsigned int w0 = 0;         /* hits of the current tile already pushed (non-zero: the tile is being re-read) */
     bool flush = false;
 
-    for (unsigned int tile = blockIdx.x * K2C_WARPS + warp; !flush; tile += total_warps) {
-        float px[4], py[4], pz[4];
-        unsigned int k0[4], cnt[4], mine = 0, off = 0, total = 0;
-        const long long base = (long long)tile * K2C_TILE;
+    for (unsigned int tile = blockIdx.x * K2C_WARPS + warp; !flush;) {
         if (tile < ntiles) {
+            /* nothing of the tile stays in registers across the rounds below: a tile with more hits than the
+             * stack has room for is simply read again for its next pass (rare) */
+            const long long base = (long long)tile * K2C_TILE;
+            float px[4], py[4], pz[4];
             unsigned int valid = 0;
             if (VEC && base + K2C_TILE <= a.n) {
                 const float4 vx = ldg_stream4(a.x + base + 4 * lane), vy = ldg_stream4(a.y + base + 4 * lane),
@@ -1017,32 +1024,33 @@ __global__ void __launch_bounds__(K2C_THREADS, 1) k2_cutout_halo_cells(const __g
                     }
                 }
             }
-            unsigned int insane = 0, hit = 0;
+            unsigned int cell[4], insane = 0, hit = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) { /* cell of every particle; most are ruled out by the shared-memory bitmap */
                 float pc, ps;
                 bool sane;
                 k2c_coords(px[j], py[j], pz[j], pc, ps, sane);
                 if (!sane) insane |= 1u << j;
-                int ic = (int)((pc + 1.0f) * (0.5f * K2_GRID)), is = (int)((ps + 1.0f) * (0.5f * K2_GRID));
-                ic = max(0, min(K2_GRID - 1, ic));
-                is = max(0, min(K2_GRID - 1, is));
-                k0[j] = (unsigned int)ic * K2_GRID + (unsigned int)is;
-                const unsigned int bit = (unsigned int)(ic >> 1) * K2_COARSE + (unsigned int)(is >> 1);
+                /* NaN -> 0, anything large -> 2^32-1 -> G-1: always a valid cell */
+                const unsigned int ic = min(__float2uint_rz(fmaf(pc, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+                const unsigned int is = min(__float2uint_rz(fmaf(ps, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+                cell[j] = ic * K2_GRID + is;
+                const unsigned int bit = (ic >> 1) * K2_COARSE + (is >> 1);
                 hit |= ((s_bits[bit >> 5] >> (bit & 31u)) & 1u) << j;
             }
             insane &= valid;
             hit &= valid & ~insane;
+            uint2 rg[4];
+            unsigned int mine = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) { /* the look-ups that remain are issued together */
-                uint2 r = make_uint2(0u, 0u);
-                if ((hit >> j) & 1u) r = __ldg(b.cell_range + k0[j]);
-                k0[j] = r.x;
-                cnt[j] = r.y - r.x;
-                mine += cnt[j];
+                rg[j] = make_uint2(0u, 0u);
+                if ((hit >> j) & 1u) rg[j] = __ldg(b.cell_range + cell[j]);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mine += rg[j].y != rg[j].x ? 1u : 0u;
             /* out-of-range positions: the exact path decides, against every halo of the launch, warp-cooperatively */
-            if (__any_sync(0xffffffffu, insane != 0)) {
+            if (w0 == 0 && __any_sync(0xffffffffu, insane != 0)) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     unsigned int m = __ballot_sync(0xffffffffu, (insane >> j) & 1u);
@@ -1056,106 +1064,84 @@ __global__ void __launch_bounds__(K2C_THREADS, 1) k2_cutout_halo_cells(const __g
                     }
                 }
             }
-            /* position of this lane's pairs in the tile's pair sequence */
+            /* position of this lane's hits among the tile's hits */
             unsigned int inc = mine;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += t;
             }
-            total = __shfl_sync(0xffffffffu, inc, 31);
-            off = inc - mine;
-            if (total == 0) continue;
-        } else {
-            flush = true; /* past this warp's last tile: one more trip to empty the buffer */
-        }
-        unsigned int w0 = 0;
-        do {
-            if (total) { /* expand the pairs [w0, w1) of the tile behind what the buffer holds */
-                const unsigned int fill = nc + nu;
-                const unsigned int w1 = min(total, w0 + (K2C_PCAP - fill));
-                if (w0 == 0 && w1 == total) { /* the usual case: everything fits */
-                    unsigned int e = fill + off;
+            const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
+            const unsigned int w1 = min(total, w0 + (K2C_HCAP - nh));
+            unsigned int pos = inc - mine;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        for (unsigned int t = 0; t < cnt[j]; ++t, ++e) {
-                            P.k[e] = k0[j] + t;
-                            P.g[e] = (unsigned int)(base + 4 * lane + j);
-                            P.x[e] = px[j]; P.y[e] = py[j]; P.z[e] = pz[j];
-                        }
-                } else if (off < w1 && off + mine > w0) {
-                    unsigned int pos = off;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const unsigned int lo = pos < w0 ? w0 - pos : 0u;
-                        const unsigned int hi = w1 > pos ? min(cnt[j], w1 - pos) : 0u;
-                        for (unsigned int t = lo; t < hi; ++t) {
-                            const unsigned int e = fill + (pos + t - w0);
-                            P.k[e] = k0[j] + t;
-                            P.g[e] = (unsigned int)(base + 4 * lane + j);
-                            P.x[e] = px[j]; P.y[e] = py[j]; P.z[e] = pz[j];
-                        }
-                        pos += cnt[j];
+            for (int j = 0; j < 4; ++j)
+                if (rg[j].y != rg[j].x) {
+                    if (pos >= w0 && pos < w1) {
+                        const unsigned int e = nh + (pos - w0);
+                        S.hp[e] = make_float4(px[j], py[j], pz[j], __uint_as_float((unsigned int)(base + 4 * lane + j)));
+                        S.hl[e] = make_uint2(rg[j].x, rg[j].y - rg[j].x);
                     }
+                    ++pos;
                 }
-                nu += w1 - w0;
-                w0 = w1;
-                __syncwarp();
-            }
-            /* test rounds: full ones only, unless the buffer is being emptied */
-            unsigned int i0 = nc;
-            while (nu >= 32u || (flush && nu > 0u)) {
-                const unsigned int m = min(nu, 32u);
-                const unsigned int i = i0 + lane;
-                bool pass = false;
-                unsigned int h = 0, g = 0;
-                float x = 0.0f, y = 0.0f, z = 0.0f;
-                if ((unsigned int)lane < m) {
-                    h = __ldg(b.cell_items + P.k[i]);
-                    g = P.g[i];
-                    x = P.x[i]; y = P.y[i]; z = P.z[i];
-                    const float4 W = s_pre[h];
-                    float pc, ps;
-                    bool sane;
-                    k2c_coords(x, y, z, pc, ps, sane);
-                    pass = (pc <= W.x) & (pc >= W.y) & (ps >= W.z) & (ps <= W.w);
-                }
-                const unsigned int pm = __ballot_sync(0xffffffffu, pass);
-                __syncwarp(); /* every lane holds its pair in registers: the compaction below may overwrite it */
-                if (pass) {
-                    const unsigned int e = nc + __popc(pm & lt_mask);
-                    P.k[e] = h;
-                    P.g[e] = g;
-                    P.x[e] = x; P.y[e] = y; P.z[e] = z;
-                }
-                nc += __popc(pm);
-                nu -= m;
-                i0 += m;
-                __syncwarp();
-            }
-            /* exact path: full rounds of tested pairs (the newest 32 each time) */
-            while (nc >= 32u || (flush && nc > 0u)) {
-                const unsigned int m = min(nc, 32u);
-                nc -= m;
-                const unsigned int e = nc + lane;
-                const bool live = (unsigned int)lane < m;
-                unsigned int h = 0, g = 0;
-                float x = 1.0f, y = 1.0f, z = 1.0f;
-                if (live) { h = P.k[e]; g = P.g[e]; x = P.x[e]; y = P.y[e]; z = P.z[e]; }
-                k2_exact_warp(a, live, (int)h, x, y, z, (unsigned int)(a.local_base + g), lane);
-                n_cand += m;
-            }
-            /* close the gap between the tested and the untested remainder */
-            if (nu && i0 != nc) {
-                unsigned int k = 0, g = 0;
-                float x = 0.0f, y = 0.0f, z = 0.0f;
-                __syncwarp();
-                if ((unsigned int)lane < nu) { k = P.k[i0 + lane]; g = P.g[i0 + lane]; x = P.x[i0 + lane]; y = P.y[i0 + lane]; z = P.z[i0 + lane]; }
-                __syncwarp();
-                if ((unsigned int)lane < nu) { P.k[nc + lane] = k; P.g[nc + lane] = g; P.x[nc + lane] = x; P.y[nc + lane] = y; P.z[nc + lane] = z; }
+            nh += w1 - w0;
+            if (w1 < total) {
+                w0 = w1; /* same tile again after the rounds */
+            } else {
+                w0 = 0;
+                tile += total_warps;
             }
             __syncwarp();
-        } while (w0 < total);
+        } else {
+            flush = true; /* past this warp's last tile: empty the stacks */
+        }
+        /* pop 32 hits (whatever is left when the stacks are being emptied), test ONE list item of each, and push
+         * the hits with a longer list back: every round tests with all lanes busy */
+        while (nh >= 32u || (flush && (nh | nc) != 0u)) {
+            const unsigned int m = min(nh, 32u);
+            nh -= m;
+            float4 q = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            uint2 l = make_uint2(0u, 0u);
+            unsigned int h = 0;
+            bool pass = false;
+            if ((unsigned int)lane < m) {
+                q = S.hp[nh + lane];
+                l = S.hl[nh + lane];
+                h = __ldg(b.cell_items + l.x);
+                float pc, ps;
+                bool sane;
+                k2c_coords(q.x, q.y, q.z, pc, ps, sane);
+                const float4 W = s_pre[h];
+                pass = (pc <= W.x) & (pc >= W.y) & (ps >= W.z) & (ps <= W.w);
+            }
+            const unsigned int mm = __ballot_sync(0xffffffffu, l.y > 1u);
+            const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+            __syncwarp(); /* every lane holds its hit in registers: the pushes below may overwrite it */
+            if (l.y > 1u) {
+                const unsigned int e = nh + __popc(mm & lt_mask);
+                S.hp[e] = q;
+                S.hl[e] = make_uint2(l.x + 1u, l.y - 1u);
+            }
+            nh += __popc(mm);
+            if (pass) {
+                const unsigned int e = nc + __popc(pm & lt_mask);
+                S.cp[e] = q;
+                S.ch[e] = h;
+            }
+            nc += __popc(pm);
+            __syncwarp();
+            /* a full round of the exact path (newest 32); at the very end, whatever is left */
+            if (nc >= 32u || (flush && nh == 0u && nc != 0u)) {
+                const unsigned int mc = min(nc, 32u);
+                nc -= mc;
+                const bool lv = (unsigned int)lane < mc;
+                const unsigned int e = lv ? nc + lane : 0u;
+                const float4 c4 = S.cp[e];
+                k2_exact_warp(a, lv, (int)S.ch[e], c4.x, c4.y, c4.z, (unsigned int)a.local_base + __float_as_uint(c4.w), lane);
+                n_cand += mc;
+                __syncwarp();
+            }
+        }
     }
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
 }
@@ -1166,21 +1152,37 @@ __global__ void __launch_bounds__(K2C_THREADS, 1) k2_cutout_halo_cells(const __g
 /* All K3 kernels run with fixed grids and read the record count on the device (min(*rec_count, rec_cap)), so the
  * whole use-case-2 pass is one enqueue with a single host synchronisation at the end. */
 /* scatter records into per-halo segments (unordered inside a segment) */
+constexpr int K3_CURSOR_STRIDE = 16;
 struct BucketArgs {
     const Rec* recs;
     const unsigned long long* rec_count;
     unsigned long long rec_cap;
     const unsigned long long* seg_begin; /* [H] exclusive scan of counts */
-    unsigned long long* cursor;          /* [H] zeroed */
+    unsigned long long* cursor;          /* [H * K3_CURSOR_STRIDE] zeroed: one 128-byte line per halo (atomics on
+                                            one line queue up in the L2) */
     Rec* out;
 };
 __global__ void k3_bucket(const BucketArgs a) {
     const unsigned long long nrec = min(*a.rec_count, a.rec_cap);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const Rec r = a.recs[i];
-        const unsigned long long p = a.seg_begin[r.halo] + atomicAdd(a.cursor + r.halo, 1ull);
-        if (p < a.rec_cap) a.out[p] = r;
+    const unsigned int lane = threadIdx.x & 31u;
+    /* warp-uniform trip count; lanes holding records of the same halo claim their slots with one atomic (the
+     * records of a large cutout would otherwise queue up on its one cursor) */
+    for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < nrec;
+         i0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = i0 + lane;
+        const bool live = i < nrec;
+        Rec r;
+        r.halo = 0xffffffffu;
+        if (live) r = a.recs[i];
+        const unsigned int peers = __match_any_sync(0xffffffffu, r.halo);
+        const int leader = __ffs(peers) - 1;
+        unsigned long long first = 0;
+        if (live && (int)lane == leader) first = atomicAdd(a.cursor + (size_t)r.halo * K3_CURSOR_STRIDE, (unsigned long long)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (live) {
+            const unsigned long long p = a.seg_begin[r.halo] + first + __popc(peers & ((1u << lane) - 1u));
+            if (p < a.rec_cap) a.out[p] = r;
+        }
     }
 }
 
@@ -1205,68 +1207,109 @@ __global__ void k3_scan_counts(const unsigned long long* counts, unsigned long l
 
 /* rank of every record inside its halo segment = its position in (theta_u, index) order, the order of the
  * reference's stable arg-sort (processLC.cpp:1214-1221).  Keys are unique (the low 32 bits are the particle index).
- * Segments of up to K3_SORT_MAX records -- every cluster-sized cutout -- are sorted by ONE CTA with a bitonic
- * network in shared memory; larger segments fall back to counting smaller keys (all column blocks of the halo,
- * the segment streamed through shared memory).  grid = (column blocks, halos). */
-constexpr int K3_THREADS = 256;
-constexpr int K3_SORT_MAX = 8192;
-constexpr size_t K3_SMEM_BYTES = (size_t)K3_SORT_MAX * (sizeof(unsigned long long) + sizeof(unsigned short));
+ * A segment is cut into chunks of K3_CHUNK records; ONE CTA orders a chunk in shared memory: theta_u of a cutout is
+ * spread evenly over a narrow window, so the keys are first dealt into up to K3_NB buckets by the leading bits of
+ * (theta_u - min) -- a monotonic map, ~8 keys per bucket -- with a counting sort, and each key then counts the
+ * smaller keys of its own bucket.  (A bitonic network over the chunk did 10x the shared-memory traffic.)
+ * Cluster-sized cutouts are a single chunk: the CTA stores, per OUTPUT row, which record goes there, so that
+ * k3_gather_halo writes its rows coalesced.  For a longer segment it stores the record's rank inside its chunk and
+ * the chunk's sorted keys, and k3_gather_halo adds, per record, the number of smaller keys in the OTHER chunks of
+ * the segment (one binary search per chunk) and scatters.  grid = (chunk slots, halos). */
+constexpr int K3_THREADS = 512;
+constexpr int K3_SORT_MAX = 8192; /* k3_small: records one CTA sorts */
+constexpr int K3_CHUNK = 4096;
+constexpr int K3_NB = 512;        /* buckets per chunk */
+static_assert(K3_NB == K3_THREADS, "k3_rank scans one bucket count per thread");
+constexpr size_t K3_SMEM_BYTES = (size_t)K3_CHUNK * (2 * sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
+                                 (size_t)(K3_NB + 1) * sizeof(unsigned int);
 struct RankArgs {
     const Rec* recs;                     /* bucketed */
     const unsigned long long* seg_begin; /* [H+1] */
     unsigned long long rec_cap;
-    unsigned int* rank;                  /* [nrec] rank inside the segment */
+    unsigned int* rank;                  /* [nrec] single-chunk segment: record of row i; else: rank inside the chunk */
+    unsigned long long* sorted;          /* [nrec] sorted keys of every chunk of a multi-chunk segment */
     int H;
 };
 __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw);
-    unsigned short* s_idx = reinterpret_cast<unsigned short*>(s_raw + (size_t)K3_SORT_MAX * sizeof(unsigned long long));
-    const unsigned int tid = threadIdx.x;
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw);          /* as loaded */
+    unsigned long long* s_grp = s_key + K3_CHUNK;                                       /* grouped by bucket */
+    unsigned short* s_src = reinterpret_cast<unsigned short*>(s_grp + K3_CHUNK);        /* grouped: position as loaded */
+    unsigned short* s_slot = s_src + K3_CHUNK;                                          /* as loaded: slot inside the bucket */
+    unsigned int* s_start = reinterpret_cast<unsigned int*>(s_slot + K3_CHUNK);         /* [K3_NB + 1] */
+    __shared__ unsigned int s_min, s_max, s_warp[K3_THREADS / 32];
+    const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (int h = blockIdx.y; h < a.H; h += gridDim.y) {
         const unsigned long long b = a.seg_begin[h], e = min(a.seg_begin[h + 1], a.rec_cap);
         if (e <= b) continue;
         const unsigned long long len = e - b;
-        if (len <= K3_SORT_MAX) {
-            if (blockIdx.x != 0) continue;
-            unsigned int n = 32;
-            while (n < len) n <<= 1;
-            for (unsigned int i = tid; i < n; i += K3_THREADS) {
-                s_key[i] = (i < len) ? a.recs[b + i].key : ~0ull;
-                s_idx[i] = (unsigned short)i;
+        for (unsigned long long c0 = (unsigned long long)blockIdx.x * K3_CHUNK; c0 < len; c0 += (unsigned long long)gridDim.x * K3_CHUNK) {
+            const unsigned int m = (unsigned int)min((unsigned long long)K3_CHUNK, len - c0);
+            if (tid == 0) { s_min = 0xffffffffu; s_max = 0u; }
+            for (unsigned int i = tid; i <= K3_NB; i += K3_THREADS) s_start[i] = 0u;
+            __syncthreads();
+            unsigned int lo = 0xffffffffu, hi = 0u;
+            for (unsigned int i = tid; i < m; i += K3_THREADS) {
+                const unsigned long long k = a.recs[b + c0 + i].key;
+                s_key[i] = k;
+                lo = min(lo, (unsigned int)(k >> 32));
+                hi = max(hi, (unsigned int)(k >> 32));
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); }
+            __syncthreads();
+            const unsigned int kmin = s_min;
+            unsigned int shift = 0; /* bucket = (theta bits - min) >> shift, < K3_NB */
+            while (((s_max - kmin) >> shift) >= (unsigned int)K3_NB) ++shift;
+            for (unsigned int i = tid; i < m; i += K3_THREADS) {
+                const unsigned int bk = ((unsigned int)(s_key[i] >> 32) - kmin) >> shift;
+                s_slot[i] = (unsigned short)atomicAdd(&s_start[bk + 1], 1u); /* counts land one to the right */
             }
             __syncthreads();
-            for (unsigned int k = 2; k <= n; k <<= 1) {
-                for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-                    for (unsigned int t = tid; t < (n >> 1); t += K3_THREADS) {
-                        const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                        const unsigned long long ki = s_key[i], kl = s_key[l];
-                        const bool up = (i & k) == 0;
-                        if ((ki > kl) == up) {
-                            s_key[i] = kl; s_key[l] = ki;
-                            const unsigned short t2 = s_idx[i]; s_idx[i] = s_idx[l]; s_idx[l] = t2;
-                        }
+            /* inclusive scan of the counts: s_start[bk] = first position of bucket bk (one entry per thread,
+             * K3_NB == K3_THREADS) */
+            {
+                unsigned int v = s_start[tid + 1];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, v, d);
+                    if (lane >= (unsigned int)d) v += t;
+                }
+                if (lane == 31) s_warp[warp] = v;
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned int w = lane < K3_THREADS / 32 ? s_warp[lane] : 0u;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned int t = __shfl_up_sync(0xffffffffu, w, d);
+                        if (lane >= (unsigned int)d) w += t;
                     }
-                    __syncthreads();
+                    if (lane < K3_THREADS / 32) s_warp[lane] = w;
                 }
+                __syncthreads();
+                s_start[tid + 1] = v + (warp ? s_warp[warp - 1] : 0u);
             }
-            for (unsigned int i = tid; i < len; i += K3_THREADS) a.rank[b + s_idx[i]] = i;
             __syncthreads();
-        } else {
-            for (unsigned long long i0 = (unsigned long long)blockIdx.x * K3_THREADS; i0 < len;
-                 i0 += (unsigned long long)gridDim.x * K3_THREADS) {
-                const unsigned long long i = i0 + tid;
-                const unsigned long long mykey = (i < len) ? a.recs[b + i].key : 0ull;
-                unsigned int r = 0;
-                for (unsigned long long j0 = 0; j0 < len; j0 += K3_THREADS) {
-                    const unsigned long long j = j0 + tid;
-                    __syncthreads();
-                    s_key[tid] = (j < len) ? a.recs[b + j].key : ~0ull;
-                    __syncthreads();
-                    const int lim = (int)min((unsigned long long)K3_THREADS, len - j0);
-                    for (int k = 0; k < lim; ++k) r += (s_key[k] < mykey);
+            for (unsigned int i = tid; i < m; i += K3_THREADS) {
+                const unsigned long long k = s_key[i];
+                const unsigned int p = s_start[((unsigned int)(k >> 32) - kmin) >> shift] + s_slot[i];
+                s_grp[p] = k;
+                s_src[p] = (unsigned short)i;
+            }
+            __syncthreads();
+            for (unsigned int p = tid; p < m; p += K3_THREADS) {
+                const unsigned long long k = s_grp[p];
+                const unsigned int bk = ((unsigned int)(k >> 32) - kmin) >> shift;
+                const unsigned int q0 = s_start[bk], q1 = s_start[bk + 1];
+                unsigned int r = q0;
+                for (unsigned int q = q0; q < q1; ++q) r += s_grp[q] < k;
+                if (len <= K3_CHUNK) {
+                    a.rank[b + r] = s_src[p];
+                } else {
+                    a.rank[b + c0 + s_src[p]] = r;
+                    a.sorted[b + c0 + r] = k;
                 }
-                if (i < len) a.rank[b + i] = r;
             }
             __syncthreads();
         }
@@ -1276,6 +1319,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
 struct GatherArgs {
     const Rec* recs;
     const unsigned int* rank;
+    const unsigned long long* sorted; /* k3_rank's sorted chunk keys (multi-chunk segments) */
     const unsigned long long* seg_begin;
     const unsigned long long* rec_count;
     unsigned long long rec_cap;
@@ -1290,8 +1334,27 @@ __global__ void k3_gather_halo(const GatherArgs a) {
     const unsigned long long nrec = min(*a.rec_count, a.rec_cap);
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        const Rec r = a.recs[i];
-        const unsigned long long o = a.seg_begin[r.halo] + a.rank[i];
+        Rec r = a.recs[i]; /* every record of a segment names the segment's halo */
+        const unsigned long long sb = a.seg_begin[r.halo];
+        const unsigned long long len = min(a.seg_begin[r.halo + 1], a.rec_cap) - sb;
+        unsigned long long o;
+        if (len <= K3_CHUNK) { /* thread = output row: rows are written coalesced */
+            o = i;
+            r = a.recs[sb + a.rank[i]];
+        } else { /* thread = record: rank inside its chunk + smaller keys in the other chunks of the segment */
+            o = sb + a.rank[i];
+            const unsigned long long mine = (i - sb) / K3_CHUNK;
+            for (unsigned long long c = 0; c * K3_CHUNK < len; ++c) {
+                if (c == mine) continue;
+                const unsigned long long* ck = a.sorted + sb + c * K3_CHUNK;
+                unsigned int lo = 0, hi = (unsigned int)min((unsigned long long)K3_CHUNK, len - c * K3_CHUNK);
+                while (lo < hi) {
+                    const unsigned int mid = (lo + hi) >> 1;
+                    if (ck[mid] < r.key) lo = mid + 1; else hi = mid;
+                }
+                o += lo;
+            }
+        }
         if ((long long)o >= a.out_cap) continue;
         const long long g = (long long)(r.key & 0xffffffffull);
         a.out.theta[o] = r.th;                        /* processLC.cpp:1446-1447 */
