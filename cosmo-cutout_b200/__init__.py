@@ -54,7 +54,7 @@ SYMBOLS = (
     "cc_halo_setup", "cc_cli_bounds", "cc_ref_scatter_kept",
     "cc_step_upload", "cc_step_attach", "cc_step_synth", "cc_synth_host", "cc_step_download", "cc_step_size",
     "cc_step_release",
-    "cc_cutout_const", "cc_cutout_halo", "cc_cutout_sync", "cc_cutout_fetch", "cc_cutout_device_cols",
+    "cc_cutout_const", "cc_cutout_halo", "cc_cutout_sync", "cc_cutout_fetch", "cc_cutout_fetch_all", "cc_cutout_device_cols",
     "cc_cutout_const_streamed", "cc_cutout_halo_streamed", "cc_host_alloc", "cc_host_free", "cc_host_register",
     "cc_host_unregister",
     "cc_comm_unique_id", "cc_comm_init", "cc_comm_init_all", "cc_exchange_counts", "cc_comm_rank", "cc_comm_size",
@@ -97,6 +97,7 @@ def lib():
         L.cc_cutout_halo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64]
         L.cc_cutout_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cc_cutout_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+        L.cc_cutout_fetch_all.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.cc_cutout_device_cols.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cc_cutout_const_streamed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.cc_cutout_halo_streamed.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
@@ -330,6 +331,22 @@ class Context:
             setattr(s, k, _ptr(out.get(k)))
         _check(lib().cc_cutout_fetch(self._h, int(halo), 0, int(count), C.byref(s)))
         return out
+
+    def fetch_all(self, counts, names=None, out=None):
+        """all halos with one copy per column: returns (columns, row offsets [H+1]); halo h = rows off[h]:off[h+1].
+        `out` may hold preallocated (e.g. pinned) arrays of at least sum(counts) rows per column"""
+        if names is None:
+            names = OUT_COLS_POSONLY if self.pos_only else OUT_COLS
+        off = np.zeros(len(counts) + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        total = int(off[-1])
+        if out is None:
+            out = {k: np.empty(total, dtype=COL_DTYPES[k]) for k in names}
+        s = ColsOut()
+        for k in OUT_COLS_ALL:
+            setattr(s, k, _ptr(out.get(k)) if k in names else None)
+        _check(lib().cc_cutout_fetch_all(self._h, total, C.byref(s)))
+        return {k: out[k][:total] for k in names}, off
 
     def exchange_counts(self):
         n, r = self.comm_size(), max(self.nhalos, 1)

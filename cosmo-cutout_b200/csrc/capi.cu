@@ -185,6 +185,9 @@ struct cc_ctx {
 
     /* streamed step (pinned host -> HBM double buffering) */
     bool streamed = false;
+    bool host_gather = false;    /* streamed step: vx..replication of the survivors are picked from the host columns by
+                                    the host when they are fetched, not read across PCIe 4 bytes at a time by the GPU */
+    std::vector<int64_t> fetch_index; /* scratch of fetch_rows */
     cc_cols_in host_cols = {};
     cck::ColsIn gcols = {};      /* where survivor columns are gathered from */
     cudaStream_t copy_stream = nullptr;
@@ -350,6 +353,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         /* survivor columns other than x,y,z are indexed by the chunk-local particle index */
         g.in.vx += ch.start; g.in.vy += ch.start; g.in.vz += ch.start; g.in.a += ch.start; g.in.id += ch.start;
         g.in.rot += ch.start; g.in.rep += ch.start;
+        if (c->streamed && c->host_gather) g.in = cck::ColsIn{}; /* the host picks these columns itself (fetch_rows) */
         g.out = cols_out_of(c);
         g.out.theta_u = nullptr;
         g.t_idx = a.t_idx; g.t_row = t.t_row; g.t_th = a.t_th; g.t_ph = a.t_ph;
@@ -612,6 +616,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         g.rec_cap = (unsigned long long)c->rec_cap;
         g.out_cap = c->out_cap;
         g.in = c->gcols;
+        if (c->streamed && c->host_gather) g.in = cck::ColsIn{}; /* the host picks these columns itself (fetch_rows) */
         g.payload = (c->streamed || !c->payload_valid) ? nullptr : (const cck::Payload*)c->payload.p;
         g.out = cols_out_of(c);
         g.index_base = c->index_base;
@@ -1057,27 +1062,68 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
     return CC_OK;
 }
 
+namespace {
+int fetch_rows(cc_ctx* c, int64_t row0, int64_t count, const cc_cols_out* host, const char* who) {
+    int rc = use_device(c);
+    if (rc) return rc;
+    void* dst[N_OUT_COLS] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->redshift, host->theta, host->phi,
+                             host->id, host->rotation, host->replication, host->theta_u, host->index};
+    const bool pos_only = (c->pending == P_HALO) && c->p_pos_only;
+    /* streamed step: the device gathered x,y,z,theta,phi(,theta_u),index; the other columns are picked here from
+     * the caller's host columns by survivor index */
+    const bool by_host = c->streamed && c->host_gather;
+    auto host_picked = [](int i) { return i == OC_VX || i == OC_VY || i == OC_VZ || i == OC_RED || i == OC_ID || i == OC_ROT || i == OC_REP; };
+    bool need_index = false;
+    for (int i = 0; i < N_OUT_COLS; ++i) {
+        if (!dst[i] || count == 0) continue;
+        if (pos_only && (i == OC_VX || i == OC_VY || i == OC_VZ || i == OC_ROT || i == OC_REP))
+            return fail(CC_ERR_ARG, "%s: velocity/rotation/replication were not gathered (pos_only)", who);
+        if (c->pending == P_CONST && i == OC_THU) return fail(CC_ERR_ARG, "%s: theta_u exists only for halo cutouts", who);
+        if (by_host && host_picked(i)) { need_index = true; continue; }
+        CU(cudaMemcpyAsync(dst[i], (const char*)c->out_buf[i].p + (size_t)row0 * OUT_COL_SIZE[i], (size_t)count * OUT_COL_SIZE[i],
+                           cudaMemcpyDeviceToHost, c->stream));
+    }
+    const int64_t* index = host->index;
+    if (need_index && !index) {
+        c->fetch_index.resize((size_t)count);
+        index = c->fetch_index.data();
+        CU(cudaMemcpyAsync(c->fetch_index.data(), (const char*)c->out_buf[OC_IDX].p + (size_t)row0 * 8, (size_t)count * 8,
+                           cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (need_index) {
+        const cc_cols_in& in = c->host_cols;
+        const int64_t base = c->index_base;
+#pragma omp parallel for schedule(static) if (count > 65536)
+        for (int64_t r = 0; r < count; ++r) {
+            const int64_t g = index[r] - base;
+            if (host->vx) host->vx[r] = in.vx[g];
+            if (host->vy) host->vy[r] = in.vy[g];
+            if (host->vz) host->vz[r] = in.vz[g];
+            if (host->redshift) host->redshift[r] = ccref::a_to_z(in.a[g]); /* processLC.cpp:305 / :1450 */
+            if (host->id) host->id[r] = in.id[g];
+            if (host->rotation) host->rotation[r] = in.rotation[g];
+            if (host->replication) host->replication[r] = in.replication[g];
+        }
+    }
+    return CC_OK;
+}
+}  // namespace
+
 int cc_cutout_fetch(cc_ctx* c, int halo, int64_t first, int64_t count, const cc_cols_out* host) {
     if (!c || !host) return fail(CC_ERR_ARG, "cc_cutout_fetch: bad argument");
     if (c->pending == P_NONE || !c->synced) return fail(CC_ERR_STATE, "cc_cutout_fetch: call cc_cutout_sync first");
     if (halo < 0 || halo >= c->nhalos) return fail(CC_ERR_ARG, "cc_cutout_fetch: halo %d out of range", halo);
     if (first < 0 || count < 0 || first + count > c->counts[halo]) return fail(CC_ERR_ARG, "cc_cutout_fetch: rows out of range");
-    int rc = use_device(c);
-    if (rc) return rc;
-    const int64_t row0 = c->seg_begin[halo] + first;
-    void* dst[N_OUT_COLS] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->redshift, host->theta, host->phi,
-                             host->id, host->rotation, host->replication, host->theta_u, host->index};
-    const bool pos_only = (c->pending == P_HALO) && c->p_pos_only;
-    for (int i = 0; i < N_OUT_COLS; ++i) {
-        if (!dst[i] || count == 0) continue;
-        if (pos_only && (i == OC_VX || i == OC_VY || i == OC_VZ || i == OC_ROT || i == OC_REP))
-            return fail(CC_ERR_ARG, "cc_cutout_fetch: velocity/rotation/replication were not gathered (pos_only)");
-        if (c->pending == P_CONST && i == OC_THU) return fail(CC_ERR_ARG, "cc_cutout_fetch: theta_u exists only for halo cutouts");
-        CU(cudaMemcpyAsync(dst[i], (const char*)c->out_buf[i].p + (size_t)row0 * OUT_COL_SIZE[i], (size_t)count * OUT_COL_SIZE[i],
-                           cudaMemcpyDeviceToHost, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
-    return CC_OK;
+    return fetch_rows(c, c->seg_begin[halo] + first, count, host, "cc_cutout_fetch");
+}
+
+int cc_cutout_fetch_all(cc_ctx* c, int64_t total, const cc_cols_out* host) {
+    if (!c || !host) return fail(CC_ERR_ARG, "cc_cutout_fetch_all: bad argument");
+    if (c->pending == P_NONE || !c->synced) return fail(CC_ERR_STATE, "cc_cutout_fetch_all: call cc_cutout_sync first");
+    const int64_t have = c->nhalos > 0 ? c->seg_begin[(size_t)c->nhalos] : 0;
+    if (total != have) return fail(CC_ERR_ARG, "cc_cutout_fetch_all: total %lld is not the survivor count %lld", (long long)total, (long long)have);
+    return fetch_rows(c, 0, total, host, "cc_cutout_fetch_all");
 }
 
 int cc_cutout_device_cols(cc_ctx* c, int halo, cc_cols_out* dev, int64_t* row0, int64_t* count) {
@@ -1088,6 +1134,8 @@ int cc_cutout_device_cols(cc_ctx* c, int halo, cc_cols_out* dev, int64_t* row0, 
     dev->x = o.x; dev->y = o.y; dev->z = o.z; dev->vx = o.vx; dev->vy = o.vy; dev->vz = o.vz;
     dev->redshift = o.redshift; dev->theta = o.theta; dev->phi = o.phi; dev->id = (int64_t*)o.id;
     dev->rotation = o.rot; dev->replication = o.rep; dev->theta_u = o.theta_u; dev->index = (int64_t*)o.index;
+    if (c->streamed && c->host_gather) /* never gathered on the device: see cc_cutout_*_streamed */
+        dev->vx = dev->vy = dev->vz = dev->redshift = nullptr, dev->id = nullptr, dev->rotation = dev->replication = nullptr;
     if (row0) *row0 = c->seg_begin[halo];
     if (count) *count = c->counts[halo];
     return CC_OK;
@@ -1096,13 +1144,14 @@ int cc_cutout_device_cols(cc_ctx* c, int halo, cc_cols_out* dev, int64_t* row0, 
 /* ------------------------------------------------------------------ streamed step */
 namespace {
 /* a streamed step needs host columns the GPU can address: pinned (cudaHostAlloc / cudaHostRegister) memory */
-int map_host_col(const void* h, const char* name, bool required, const void** dev) {
+int map_host_col(const void* h, const char* name, bool required, const void** dev, bool* on_host) {
     *dev = nullptr;
+    *on_host = true;
     if (!h) return required ? fail(CC_ERR_ARG, "streamed cutout: column %s is required", name) : CC_OK;
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, h);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(CC_ERR_ARG, "streamed cutout: cannot query column %s", name); }
-    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { *dev = h; return CC_OK; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { *dev = h; *on_host = false; return CC_OK; }
     if (at.type != cudaMemoryTypeHost)
         return fail(CC_ERR_ARG, "streamed cutout: column %s is pageable host memory; allocate it with cc_host_alloc or pin it "
                     "with cc_host_register (or use cc_step_upload for pageable data)", name);
@@ -1122,10 +1171,14 @@ int begin_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_b
     const void* h[N_IN_COLS] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->a, host->id, host->rotation, host->replication};
     const char* names[N_IN_COLS] = {"x", "y", "z", "vx", "vy", "vz", "a", "id", "rotation", "replication"};
     const void* d[N_IN_COLS];
+    bool all_host = true;
     for (int i = 0; i < N_IN_COLS; ++i) {
         const bool vel = (i == COL_VX || i == COL_VY || i == COL_VZ || i == COL_ROT || i == COL_REP);
-        if ((rc = map_host_col(h[i], names[i], vel ? need_vel : true, &d[i]))) return rc;
+        bool on_host = true;
+        if ((rc = map_host_col(h[i], names[i], vel ? need_vel : true, &d[i], &on_host))) return rc;
+        if (i != COL_X && i != COL_Y && i != COL_Z) all_host = all_host && on_host;
     }
+    c->host_gather = all_host && !getenv("CC_DEVICE_GATHER");
     c->host_cols = *host;
     c->gcols.x = (const float*)d[COL_X]; c->gcols.y = (const float*)d[COL_Y]; c->gcols.z = (const float*)d[COL_Z];
     c->gcols.vx = (const float*)d[COL_VX]; c->gcols.vy = (const float*)d[COL_VY]; c->gcols.vz = (const float*)d[COL_VZ];

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) k1_gather(const GatherConstArgs a) {
             a.out.vx[r] = p.vx; a.out.vy[r] = p.vy; a.out.vz[r] = p.vz;
             a.out.redshift[r] = a_to_z_dev(p.a);
             a.out.id[r] = p.id; a.out.rot[r] = p.rot; a.out.rep[r] = p.rep;
-        } else {
+        } else if (a.in.a) { /* NULL: a streamed step whose other columns the host gathers itself (capi.cu fetch_rows) */
             a.out.vx[r] = a.in.vx[g];
             a.out.vy[r] = a.in.vy[g];
             a.out.vz[r] = a.in.vz[g];
@@ -1367,7 +1367,7 @@ __global__ void k3_gather_halo(const GatherArgs a) {
             a.out.redshift[o] = a_to_z_dev(p.a);      /* :1450 */
             a.out.id[o] = p.id;
             if (!a.pos_only) { a.out.vx[o] = p.vx; a.out.vy[o] = p.vy; a.out.vz[o] = p.vz; a.out.rot[o] = p.rot; a.out.rep[o] = p.rep; }
-        } else {
+        } else if (a.in.a) {
             a.out.redshift[o] = a_to_z_dev(a.in.a[g]);
             a.out.id[o] = a.in.id[g];
             if (!a.pos_only) {                        /* :1455-1461 */
@@ -1468,7 +1468,7 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
             a.g.out.redshift[o] = a_to_z_dev(p.a);
             a.g.out.id[o] = p.id;
             if (!a.g.pos_only) { a.g.out.vx[o] = p.vx; a.g.out.vy[o] = p.vy; a.g.out.vz[o] = p.vz; a.g.out.rot[o] = p.rot; a.g.out.rep[o] = p.rep; }
-        } else {
+        } else if (a.g.in.a) {
             a.g.out.redshift[o] = a_to_z_dev(a.g.in.a[g]);
             a.g.out.id[o] = a.g.in.id[g];
             if (!a.g.pos_only) {

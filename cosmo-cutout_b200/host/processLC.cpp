@@ -97,6 +97,14 @@ struct Survivors {
         if (vel) { vx.resize(k); vy.resize(k); vz.resize(k); rotation.resize(k); replication.resize(k); }
         if (keys) { theta_u.resize(k); index.resize(k); }
     }
+    /* rows [row, row+k) of src */
+    void slice_of(const Survivors& src, size_t row, size_t k, bool vel, bool keys) {
+        n = k;
+        auto cp = [row, k](auto& dst, const auto& from) { dst.assign(from.begin() + (ptrdiff_t)row, from.begin() + (ptrdiff_t)(row + k)); };
+        cp(x, src.x); cp(y, src.y); cp(z, src.z); cp(redshift, src.redshift); cp(theta, src.theta); cp(phi, src.phi); cp(id, src.id);
+        if (vel) { cp(vx, src.vx); cp(vy, src.vy); cp(vz, src.vz); cp(rotation, src.rotation); cp(replication, src.replication); }
+        if (keys) { cp(theta_u, src.theta_u); cp(index, src.index); }
+    }
     cc_cols_out view(bool vel, bool keys) {
         cc_cols_out o;
         memset(&o, 0, sizeof(o));
@@ -406,6 +414,20 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
         duration = wall_seconds() - start;
         if (timeit) cout << "cutout computation time (all halos of the step): " << duration << " s" << endl;
 
+        /* the survivors of ALL halos of the step, one transfer per column and GPU (a --haloFile run has hundreds of
+         * halos per step); halo ai of GPU r sits at rows [row_of[r][ai], +count) */
+        vector<Survivors> fetched((size_t)numranks);
+        vector<vector<size_t>> row_of((size_t)numranks, vector<size_t>((size_t)A + 1, 0));
+        for (int r = 0; r < numranks; ++r)
+            for (int ai = 0; ai < A; ++ai)
+                row_of[(size_t)r][(size_t)ai + 1] = row_of[(size_t)r][(size_t)ai] + (size_t)all_counts[(size_t)r * (size_t)A + (size_t)ai];
+        for_each_gpu(numranks, [&](int r) {
+            const size_t k = row_of[(size_t)r][(size_t)A];
+            fetched[(size_t)r].resize(k, !positionOnly, true);
+            const cc_cols_out o = fetched[(size_t)r].view(!positionOnly, true);
+            check(cc_cutout_fetch_all(g_pool.ctx[r], (int64_t)k, &o));
+        });
+
         for (int ai = 0; ai < A; ++ai) {
             const int h = active[(size_t)ai];
             const bool printHalo = (numHalos < 20) || (h % 100 == 0);
@@ -431,12 +453,8 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
             /* every GPU's survivors arrive ordered by (theta_u, index); a single-rank reference run orders the whole
              * step that way (:1214-1221), so merge the per-GPU lists on those keys */
             vector<Survivors> parts((size_t)numranks);
-            for (int r = 0; r < numranks; ++r) {
-                const size_t k = (size_t)np_count[(size_t)r];
-                parts[(size_t)r].resize(k, !positionOnly, true);
-                const cc_cols_out o = parts[(size_t)r].view(!positionOnly, true);
-                if (k) check(cc_cutout_fetch(g_pool.ctx[r], ai, 0, (int64_t)k, &o));
-            }
+            for (int r = 0; r < numranks; ++r)
+                parts[(size_t)r].slice_of(fetched[(size_t)r], row_of[(size_t)r][(size_t)ai], (size_t)np_count[(size_t)r], !positionOnly, true);
             CutoutFiles files(subdirs_of[(size_t)h], step, !positionOnly);
             if (numranks == 1) {
                 files.write_block(parts[0], parts[0].n, 0);

@@ -128,14 +128,22 @@ int cc_cutout_halo(cc_ctx* ctx, int nhalos, const cc_halo* halos, int pos_only, 
 int cc_cutout_sync(cc_ctx* ctx, int64_t* counts, int64_t* rough_counts);
 /* Copy halo h's survivors (h = 0 for use case 1) to host columns, rows [first, first+count). */
 int cc_cutout_fetch(cc_ctx* ctx, int halo, int64_t first, int64_t count, const cc_cols_out* host);
+/* Copy the survivors of ALL halos of the last cutout with one transfer per column: rows are packed halo after halo,
+ * halo h at rows [sum(counts[0..h)), +counts[h]) (counts from cc_cutout_sync); `total` must be sum(counts).  With
+ * hundreds of halos per pass (--haloFile) this replaces thousands of small copies. */
+int cc_cutout_fetch_all(cc_ctx* ctx, int64_t total, const cc_cols_out* host);
 /* Device pointers to the packed survivor columns of the last cutout (valid until the next cutout call):
  * halo h occupies rows [row0, row0+count). */
 int cc_cutout_device_cols(cc_ctx* ctx, int halo, cc_cols_out* dev, int64_t* row0, int64_t* count);
 
 /* ------------------------------------------------------------------ streamed step (replaces the GenericIO
  * read path for steps that are not resident: pinned host -> HBM double-buffered, processLC.cpp:102-139).
- * One call = upload x,y,z in tiles on a copy stream overlapped with the cutout kernel on the previous tile;
- * the remaining columns of the survivors are gathered straight from the (pinned, mapped) host columns.
+ * One call = upload x,y,z in tiles on a copy stream overlapped with the cutout kernel on the previous tile.
+ * The other columns never cross the bus as a whole: cc_cutout_fetch / cc_cutout_fetch_all pick vx..replication of
+ * the survivors from the caller's host columns by survivor index (reading them from the GPU 4 bytes at a time
+ * over PCIe costs ~10 ns per value: 90 ms for 1.5 M survivors), so the host columns must stay valid and unchanged
+ * until the survivors have been fetched, and cc_cutout_device_cols returns NULL for those columns.  Host columns
+ * that are really device or managed memory, or CC_DEVICE_GATHER=1, keep the gather on the GPU.
  * Results are fetched with cc_cutout_sync / cc_cutout_fetch as usual. */
 int cc_cutout_const_streamed(cc_ctx* ctx, int64_t n, const cc_cols_in* host, int64_t index_base,
                              const float theta_cut[2], const float phi_cut[2]);

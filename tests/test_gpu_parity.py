@@ -1,6 +1,8 @@
 """GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against the oracle
 (oracle/liboracle.so, pinned to the real reference by tests/test_oracle_vs_ref.py) on the same seeded inputs.
 Bar: byte-exact for every column, the survivor set and its order."""
+import os
+
 import numpy as np
 import pytest
 
@@ -296,10 +298,15 @@ def test_halo_many_halos_one_pass(ctx):
     ctx.upload(cols)
     ctx.cutout_halo([i.halo for i in infos])
     counts, rough = ctx.sync()
+    everything, off = ctx.fetch_all(counts)  # one copy per column; halo h = rows off[h]:off[h+1]
+    assert int(off[-1]) == int(counts.sum()) == everything["id"].shape[0]
     for h in list(range(0, 1100, 97)) + [1023, 1024, 1099]:
         want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(pos[h], 30.0))
         assert int(counts[h]) == want["id"].shape[0] and int(rough[h]) == want_rough
         H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {h}: ")
+        H.assert_cols_equal({k: v[off[h]:off[h + 1]] for k, v in everything.items()}, want, what=f"halo {h} (fetch_all): ")
+    with pytest.raises(Exception):
+        ctx.fetch_all(counts[:-1])  # wrong total
 
 
 def test_halo_cell_index_overlapping_halos_and_special_positions(ctx):
@@ -409,6 +416,31 @@ def test_streamed_equals_oracle(ctx):
         want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup((150, 20, 12), 60.0))
         assert int(rough[0]) == want_rough
         H.assert_cols_equal(ctx.fetch(0), want, what="streamed halo: ")
+        # a dozen halos (cell-index kernel) over the first 3M particles, a global index base, everything fetched at
+        # once; the survivors' vx..replication are picked on the host from the pinned columns -- and, as a
+        # cross-check, by the GPU (CC_DEVICE_GATHER=1)
+        n2 = 3_000_000
+        sub, pin2 = H.slice_cols(cols, 0, n2), {k: v[:n2] for k, v in pin.items()}
+        rng = np.random.default_rng(3)
+        pos = rng.uniform(40, 250, (12, 3)).astype(np.float32)
+        halos = [cc.halo_setup(p, 90.0).halo for p in pos]
+        wants = [H.oracle_cutout_halo(sub, H.oracle_halo_setup(p, 90.0)) for p in pos]
+        base = 7_000_000_000
+        for device_gather in (False, True):
+            if device_gather:
+                os.environ["CC_DEVICE_GATHER"] = "1"
+            try:
+                ctx.cutout_halo_streamed(pin2, halos, n_limit_global=base + cc.ref_scatter_kept(n2, 1), index_base=base)
+                counts, rough = ctx.sync()
+                everything, off = ctx.fetch_all(counts, names=cc.OUT_COLS + ("index",))
+            finally:
+                os.environ.pop("CC_DEVICE_GATHER", None)
+            assert int(counts.sum()) > 1000
+            for h, (want, want_rough) in enumerate(wants):
+                got = {k: v[off[h]:off[h + 1]] for k, v in everything.items()}
+                assert int(rough[h]) == want_rough
+                H.assert_cols_equal(got, want, what=f"streamed halo {h} (device_gather={device_gather}): ")
+                assert np.array_equal(got["index"] - base, got["id"])
     finally:
         del pin
         for a in addrs:
