@@ -435,6 +435,10 @@ int prepare_halo(cc_ctx* c) {
         for (int i = 0; i < 9; ++i) d.R[i] = s.R[i];
         d.th_lo = s.theta_cut[0]; d.th_hi = s.theta_cut[1]; d.ph_lo = s.phi_cut[0]; d.ph_hi = s.phi_cut[1];
         d.rth_lo = s.theta_rough[0]; d.rth_hi = s.theta_rough[1]; d.rph_lo = s.phi_rough[0]; d.rph_hi = s.phi_rough[1];
+        ccpf::uc2_bounds_cells_inner(s.theta_rough, s.phi_rough, p4); /* second filter of the cell-index kernel */
+        d.in_chi = p4[0]; d.in_clo = p4[1]; d.in_slo = p4[2]; d.in_shi = p4[3];
+        ccpf::uc2_bounds(s.theta_cut, s.phi_cut, p4);
+        d.f_chi = p4[0]; d.f_clo = p4[1]; d.f_tlo = p4[2]; d.f_thi = p4[3];
     }
     /* many halos: (cos theta, sin phi) cell index per launch batch (kernels.cuh, k2_cutout_halo_cells) */
     c->use_bins = H >= 8 && !getenv("CC_NO_BINS");

@@ -584,6 +584,9 @@ struct HaloDev { /* exact parameters of one halo */
     float th_lo, th_hi, ph_lo, ph_hi;     /* fine, strict (processLC.cpp:1439-1440) */
     float rth_lo, rth_hi, rph_lo, rph_hi; /* rough: lo <= theta_u < hi (:1334-1337), lo < phi_u < hi (:1400) */
     float pad[3];
+    /* cell-index kernel, second filter (prefilter.h): */
+    float in_chi, in_clo, in_slo, in_shi; /* inside this (cos theta_u, sin phi_u) window the rough test is certain to pass */
+    float f_chi, f_clo, f_tlo, f_thi;     /* outside this (cos theta, tan phi) window of the ROTATED position the fine test is certain to fail */
 };
 struct __align__(16) Rec {  /* one survivor, 32 B */
     unsigned long long key; /* (bits of theta_u) << 32 | particle index in the step: the reference's sort order */
@@ -645,7 +648,7 @@ __device__ __forceinline__ void k2_exact(const HaloArgs& a, int h, float x, floa
  * ones), and the survivors of the warp claim their record slots with one atomic. */
 __device__ __forceinline__ void k2_exact_warp(const HaloArgs& a, bool live, int h, float x, float y, float z,
                                               unsigned int local_n, int lane) {
-    static_assert(sizeof(HaloDev) == 80, "five float4 loads below");
+    static_assert(sizeof(HaloDev) == 112 && offsetof(HaloDev, rph_hi) == 64, "five float4 loads below");
     const float4* __restrict__ Hq = reinterpret_cast<const float4*>(a.halos + (live ? h : 0));
     const float4 q0 = __ldg(Hq), q1 = __ldg(Hq + 1), q2 = __ldg(Hq + 2), q3 = __ldg(Hq + 3), q4 = __ldg(Hq + 4);
     const float th_lo = q2.y, th_hi = q2.z, ph_lo = q2.w, ph_hi = q3.x; /* fine, strict (processLC.cpp:1439-1440) */
@@ -946,6 +949,8 @@ struct __align__(16) K2CStacks {
     uint2 hl[K2C_HCAP];          /*      {next item of the cell's list, items left} */
     float4 cp[K2C_CCAP];         /* tested pair: x, y, z, particle index (bits) */
     unsigned int ch[K2C_CCAP];   /*              halo inside the launch */
+    float4 xp[K2C_CCAP];         /* pair that needs the exact arithmetic */
+    unsigned int xh[K2C_CCAP];
 };
 constexpr size_t k2c_smem(int warps) {
     return (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4) + sizeof(K2CStacks) * (size_t)warps;
@@ -995,7 +1000,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
     const unsigned int total_warps = gridDim.x * K2C_WARPS;
     const unsigned int ntiles = (unsigned int)((a.n + K2C_TILE - 1) / K2C_TILE);
     unsigned long long n_cand = 0;
-    unsigned int nh = 0, nc = 0; /* warp-uniform stack heights: hits, tested pairs */
+    unsigned int nh = 0, nc = 0, nx = 0; /* warp-uniform stack heights: hits, tested pairs, pairs for the exact path */
     unsigned int w0 = 0;         /* hits of the current tile already pushed (non-zero: the tile is being re-read) */
     bool flush = false;
 
@@ -1097,7 +1102,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
         }
         /* pop 32 hits (whatever is left when the stacks are being emptied), test ONE list item of each, and push
          * the hits with a longer list back: every round tests with all lanes busy */
-        while (nh >= 32u || (flush && (nh | nc) != 0u)) {
+        while (nh >= 32u || (flush && (nh | nc | nx) != 0u)) {
             const unsigned int m = min(nh, 32u);
             nh -= m;
             float4 q = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
@@ -1130,16 +1135,58 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
             }
             nc += __popc(pm);
             __syncwarp();
-            /* a full round of the exact path (newest 32); at the very end, whatever is left */
-            if (nc >= 32u || (flush && nh == 0u && nc != 0u)) {
-                const unsigned int mc = min(nc, 32u);
-                nc -= mc;
-                const bool lv = (unsigned int)lane < mc;
-                const unsigned int e = lv ? nc + lane : 0u;
-                const float4 c4 = S.cp[e];
-                k2_exact_warp(a, lv, (int)S.ch[e], c4.x, c4.y, c4.z, (unsigned int)a.local_base + __float_as_uint(c4.w), lane);
-                n_cand += mc;
-                __syncwarp();
+            /* tested pairs, 32 at a time (at the very end, whatever is left): the second filter, then the exact
+             * path for what it cannot decide */
+            const bool last = flush && nh == 0u;
+            for (;;) {
+                if (nx >= 32u || (last && nc == 0u && nx != 0u)) { /* exact arithmetic, newest 32 */
+                    const unsigned int mx = min(nx, 32u);
+                    nx -= mx;
+                    const bool lv = (unsigned int)lane < mx;
+                    const unsigned int e = lv ? nx + lane : 0u;
+                    const float4 c4 = S.xp[e];
+                    k2_exact_warp(a, lv, (int)S.xh[e], c4.x, c4.y, c4.z, (unsigned int)a.local_base + __float_as_uint(c4.w), lane);
+                    n_cand += mx;
+                    __syncwarp();
+                    continue;
+                }
+                if (nc >= 32u || (last && nc != 0u)) {
+                    /* A pair that is certainly inside the rough window (inner (c, s) window) AND certainly outside
+                     * the fine window (rotated position against the widened fine window) only counts as a rough
+                     * survivor: 5 of 6 pairs of a cluster-sized cutout.  The rest takes the exact path. */
+                    const unsigned int mc = min(nc, 32u);
+                    nc -= mc;
+                    const bool lv = (unsigned int)lane < mc;
+                    const unsigned int e = lv ? nc + lane : 0u;
+                    const float4 c4 = S.cp[e];
+                    const unsigned int h = lv ? S.ch[e] : 0u;
+                    const float4* __restrict__ Hq = reinterpret_cast<const float4*>(a.halos + h);
+                    const float4 q0 = __ldg(Hq), q1 = __ldg(Hq + 1), q2 = __ldg(Hq + 2), q5 = __ldg(Hq + 5), q6 = __ldg(Hq + 6);
+                    float pc, ps;
+                    bool sane;
+                    k2c_coords(c4.x, c4.y, c4.z, pc, ps, sane);
+                    const bool sure_rough = (pc <= q5.x) & (pc >= q5.y) & (ps >= q5.z) & (ps <= q5.w);
+                    const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+                    float rx, ry, rz;
+                    ccref::mat_vec(R, c4.x, c4.y, c4.z, rx, ry, rz); /* the exact path's own rotated position */
+                    const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+                    const bool sane_r = (fabsf(rx) >= CC_SANE_LO) & (r2 <= 1.2089258e24f);
+                    const float cf = rz * rsqrt_fast(r2), tf = ry * rcp_fast(rx);
+                    const bool maybe_fine = !sane_r | ((cf <= q6.x) & (cf >= q6.y) & (tf >= q6.z) & (tf <= q6.w));
+                    const bool counted = lv && sure_rough && !maybe_fine;
+                    if (counted) atomicAdd(a.counts + a.total_halos + (unsigned int)a.halo0 + h, 1ull); /* rough_cutout_size, :1436 */
+                    const bool need = lv && !counted;
+                    const unsigned int xm = __ballot_sync(0xffffffffu, need);
+                    if (need) {
+                        const unsigned int x = nx + __popc(xm & lt_mask);
+                        S.xp[x] = c4;
+                        S.xh[x] = h;
+                    }
+                    nx += __popc(xm);
+                    __syncwarp();
+                    continue;
+                }
+                break;
             }
         }
     }

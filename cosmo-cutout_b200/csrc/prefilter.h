@@ -119,4 +119,45 @@ static inline void uc2_bounds_cells(const float th[2], const float ph[2], float 
     out4[3] = round_up(shi);
 }
 
+/* The same model read the other way: an INNER window in (c, s) space.  A pair whose cheap (c~, s~) lies inside it is
+ * certain to pass the exact rough test (lo <= theta_u < hi, lo < phi_u < hi), so its exact angles need not be
+ * evaluated to count it.  Every step of the outer derivation is monotone and every error term is two-sided: shrink
+ * the angles by the margins instead of widening them, shrink again in cos / tan space, take off the absolute slack,
+ * round inward.  Unbounded sides stay unbounded exactly where the outer window has them (theta_u <= 0 or >= pi,
+ * |phi_u| >= pi/2 cannot occur for an in-range position).  A window narrower than its margins comes out empty
+ * (lo > hi): nothing is certain, everything goes to the exact path. */
+static inline void uc2_bounds_cells_inner(const float th[2], const float ph[2], float out4[4]) {
+    out4[0] = -INFINITY; out4[1] = INFINITY; out4[2] = INFINITY; out4[3] = -INFINITY; /* empty */
+    if (!(th[0] == th[0]) || !(th[1] == th[1]) || !(ph[0] == ph[0]) || !(ph[1] == ph[1])) return;
+    const double abs_slack = 2e-6;
+    const double a_lo = arcsec_to_rad(th[0]), a_hi = arcsec_to_rad(th[1]);
+    const double b_lo = arcsec_to_rad(ph[0]), b_hi = arcsec_to_rad(ph[1]);
+    const double lo = a_lo + CC_PF_MARGIN * fabs(a_lo) + CC_PF_ABS_RAD, hi = a_hi - CC_PF_MARGIN * fabs(a_hi) - CC_PF_ABS_RAD;
+    const double pl = b_lo + CC_PF_MARGIN * fabs(b_lo) + CC_PF_ABS_RAD, pu = b_hi - CC_PF_MARGIN * fabs(b_hi) - CC_PF_ABS_RAD;
+    const double half_pi = M_PI / 2;
+    double chi, clo, slo, shi;
+    if (a_lo < 0.0) chi = INFINITY;               /* theta_u >= 0 > lo always */
+    else if (lo >= M_PI) return;
+    else { const double c = cos(lo); chi = c - CC_PF_MARGIN * fabs(c) - abs_slack; }
+    if (a_hi > M_PI + 1e-3) clo = -INFINITY;      /* theta_u <= pi (+ rounding) < hi always */
+    else if (hi <= 0.0) return;
+    else { const double c = cos(hi < M_PI ? hi : M_PI); clo = c + CC_PF_MARGIN * fabs(c) + abs_slack; }
+    if (b_lo < -half_pi - 1e-3) slo = -INFINITY;  /* |phi_u| <= pi/2 (+ rounding) */
+    else if (pl >= half_pi) return;
+    else {
+        const double t = tan(pl > -half_pi ? pl : -half_pi + 1e-12), tt = t + CC_PF_MARGIN * fabs(t);
+        slo = tt / sqrt(1.0 + tt * tt) + abs_slack;
+    }
+    if (b_hi > half_pi + 1e-3) shi = INFINITY;
+    else if (pu <= -half_pi) return;
+    else {
+        const double t = tan(pu < half_pi ? pu : half_pi - 1e-12), tt = t - CC_PF_MARGIN * fabs(t);
+        shi = tt / sqrt(1.0 + tt * tt) - abs_slack;
+    }
+    out4[0] = isinf(chi) ? (float)chi : round_down(chi);
+    out4[1] = isinf(clo) ? (float)clo : round_up(clo);
+    out4[2] = isinf(slo) ? (float)slo : round_up(slo);
+    out4[3] = isinf(shi) ? (float)shi : round_down(shi);
+}
+
 }  // namespace ccpf

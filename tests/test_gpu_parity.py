@@ -339,6 +339,49 @@ def test_halo_cell_index_overlapping_halos_and_special_positions(ctx):
         H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {h}: ")
 
 
+def test_halo_cell_index_window_edges(ctx):
+    """the cell-index kernel's second filter decides most pairs without the exact arithmetic: "certainly inside the
+    rough window" and "certainly outside the fine window".  Aim particles at every bound of both windows -- the
+    rough one in the un-rotated frame, the fine one in the rotated frame (directions built there and carried back
+    with R^-1, so float rounding scatters them to both sides of the bound) -- for 9 halos in one pass"""
+    rng = np.random.default_rng(23)
+    specs = [((150, 20, 12), 40.0), ((30, 170, 100), 25.0), ((100, 100, 100), 90.0), ((10, 10, 250), 60.0),
+             ((200, 120, 40), 15.0), ((60, 60, 20), 33.0), ((250, 30, 160), 70.0), ((90, 200, 30), 50.0), ((140, 140, 140), 45.0)]
+    infos = [cc.halo_setup(p, b) for p, b in specs]
+    parts = [H.shell_fixture(500_000, seed=61)]
+    conv = 3.14159265 / 180.0 / 3600.0
+    for k, info in enumerate(infos):
+        hal = info.halo
+        parts.append(H.edge_fixture(hal.theta_rough, hal.phi_rough, seed=100 + k, per_bound=48))
+        # fine window: (theta', phi') on each bound +- a few ulps, mid-window in the other angle
+        Rinv = np.array(list(info.R_inv), dtype=np.float64).reshape(3, 3)
+        tc, pc = np.array(hal.theta_cut, dtype=np.float64), np.array(hal.phi_cut, dtype=np.float64)
+        pts = []
+        for which, bound in (("t", tc[0]), ("t", tc[1]), ("p", pc[0]), ("p", pc[1])):
+            for _ in range(48):
+                jit = float(rng.integers(-3, 4)) * float(np.spacing(np.float32(abs(bound) + 1.0)))
+                t = (bound + jit if which == "t" else tc.mean() + rng.uniform(-0.45, 0.45) * (tc[1] - tc[0])) * conv
+                f = (bound + jit if which == "p" else pc.mean() + rng.uniform(-0.45, 0.45) * (pc[1] - pc[0])) * conv
+                r = rng.uniform(60, 400)
+                pts.append(Rinv @ (r * np.array([np.sin(t) * np.cos(f), np.sin(t) * np.sin(f), np.cos(t)])))
+        pts = np.array(pts, dtype=np.float32)
+        e = H.slice_cols(H.shell_fixture(pts.shape[0], seed=200 + k), 0, pts.shape[0])
+        e["x"], e["y"], e["z"] = pts[:, 0].copy(), pts[:, 1].copy(), pts[:, 2].copy()
+        parts.append(e)
+    cols = H.concat_cols(*parts)
+    cols["id"] = np.arange(cols["x"].shape[0], dtype=np.int64)
+    ctx.upload(cols)
+    ctx.cutout_halo([i.halo for i in infos])
+    counts, rough = ctx.sync()
+    near = 0
+    for h, (p, b) in enumerate(specs):
+        want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, b))
+        assert int(counts[h]) == want["id"].shape[0] and int(rough[h]) == want_rough, (h, p, b)
+        H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {p} {b}: ")
+        near += int(np.isin(want["id"], np.arange(500_000, cols["x"].shape[0])).sum())
+    assert near > 200  # edge particles did land inside
+
+
 def test_halo_large_segment(ctx):
     """a 10-degree box: tens of thousands of survivors in one halo -- beyond the shared-memory sort (K3_SORT_MAX =
     8192), so the counting fallback orders the segment; a second, small halo in the same pass takes the sort"""
