@@ -133,7 +133,8 @@ struct cc_ctx {
     int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
     bool k2c_ready = false;
-    int k2c_warps = 24; /* 24 warps per CTA at 80 registers (CC_K2C_WARPS=32: 32 warps at 64, measured slower: spills) */
+    int k2c_warps = 20; /* warps of the one CTA per SM: 20 at 96 registers, no spills, 161 KB of shared memory (24 at 80
+                           registers spill and leave too little L1; 16 hide less latency); CC_K2C_WARPS=24|16 for A/B runs */
     bool k3_smem_set = false, k3s_smem_set = false;
     bool k2_tma = false, k2t_ready = false;
     int k2t_occ = 0;
@@ -567,24 +568,30 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             b.cell_bits = (const unsigned int*)c->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
             b.cell_items = (const unsigned short*)c->bin_items_buf.p + c->bin_items_off[(size_t)bi];
             if (!c->k2c_ready) {
-                const void* fns[4] = {(const void*)cck::k2_cutout_halo_cells<true, 32>, (const void*)cck::k2_cutout_halo_cells<false, 32>,
-                                      (const void*)cck::k2_cutout_halo_cells<true, 24>, (const void*)cck::k2_cutout_halo_cells<false, 24>};
-                for (int i = 0; i < 4; ++i)
-                    CU(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::k2c_smem(i < 2 ? 32 : 24)));
+                const void* fns[6] = {(const void*)cck::k2_cutout_halo_cells<true, 24>, (const void*)cck::k2_cutout_halo_cells<false, 24>,
+                                      (const void*)cck::k2_cutout_halo_cells<true, 20>, (const void*)cck::k2_cutout_halo_cells<false, 20>,
+                                      (const void*)cck::k2_cutout_halo_cells<true, 16>, (const void*)cck::k2_cutout_halo_cells<false, 16>};
+                const int ws[3] = {24, 20, 16};
+                for (int i = 0; i < 6; ++i)
+                    CU(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::k2c_smem(ws[i / 2])));
                 const char* e = getenv("CC_K2C_WARPS");
-                c->k2c_warps = (e && atoi(e) == 32) ? 32 : 24;
+                const int w = e ? atoi(e) : 20;
+                c->k2c_warps = (w == 16 || w == 24) ? w : 20;
                 c->k2c_ready = true;
             }
             const unsigned int cw = (unsigned int)c->k2c_warps;
             const unsigned int ctiles = (unsigned int)((n_scan + cck::K2C_TILE - 1) / cck::K2C_TILE);
             const unsigned int cgrid = std::max(1u, std::min((ctiles + cw - 1) / cw, (unsigned int)c->sm_count));
             const size_t csmem = cck::k2c_smem((int)cw);
-            if (cw == 32) {
-                if (vec) cck::k2_cutout_halo_cells<true, 32><<<cgrid, 1024, csmem, c->stream>>>(b);
-                else cck::k2_cutout_halo_cells<false, 32><<<cgrid, 1024, csmem, c->stream>>>(b);
-            } else {
+            if (cw == 24) {
                 if (vec) cck::k2_cutout_halo_cells<true, 24><<<cgrid, 768, csmem, c->stream>>>(b);
                 else cck::k2_cutout_halo_cells<false, 24><<<cgrid, 768, csmem, c->stream>>>(b);
+            } else if (cw == 20) {
+                if (vec) cck::k2_cutout_halo_cells<true, 20><<<cgrid, 640, csmem, c->stream>>>(b);
+                else cck::k2_cutout_halo_cells<false, 20><<<cgrid, 640, csmem, c->stream>>>(b);
+            } else {
+                if (vec) cck::k2_cutout_halo_cells<true, 16><<<cgrid, 512, csmem, c->stream>>>(b);
+                else cck::k2_cutout_halo_cells<false, 16><<<cgrid, 512, csmem, c->stream>>>(b);
             }
             CU(cudaGetLastError());
             c->launches += 1;

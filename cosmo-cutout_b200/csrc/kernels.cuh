@@ -940,9 +940,9 @@ constexpr size_t K2T_SMEM_BASE = sizeof(K2TWarpRing) * SCAN_WARPS;
 constexpr int K2_GRID = 1024;
 constexpr int K2_COARSE = K2_GRID / 2;                       /* occupancy bitmap: one bit per 2 x 2 cells */
 constexpr int K2_BITWORDS = K2_COARSE * K2_COARSE / 32;      /* 32 KB, resident in shared memory */
-/* one CTA per SM shares the bitmap: 32 warps at 64 registers, or 24 warps at 80 (template parameter WARPS) */
+/* one CTA per SM shares the bitmap: WARPS warps (template parameter; 20 at 96 registers by default) */
 constexpr int K2C_TILE = 128; /* particles per warp tile */
-constexpr int K2C_HCAP = 96;  /* stacked hits per warp (a tile with more is taken in several passes) */
+constexpr int K2C_HCAP = 64;  /* stacked hits per warp (a tile with more is taken in several passes) */
 constexpr int K2C_CCAP = 64;  /* stacked tested pairs per warp: < 32 waiting + <= 32 from one round */
 struct __align__(16) K2CStacks {
     float4 hp[K2C_HCAP];         /* hit: x, y, z, particle index inside the chunk (bits) */
@@ -951,6 +951,7 @@ struct __align__(16) K2CStacks {
     unsigned int ch[K2C_CCAP];   /*              halo inside the launch */
     float4 xp[K2C_CCAP];         /* pair that needs the exact arithmetic */
     unsigned int xh[K2C_CCAP];
+    float4 next[3][32];          /* x, y, z of the warp's NEXT tile, filled by cp.async while this one is worked on */
 };
 constexpr size_t k2c_smem(int warps) {
     return (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4) + sizeof(K2CStacks) * (size_t)warps;
@@ -962,6 +963,12 @@ struct HaloBinArgs {
     const uint2* cell_range;          /* [K2_GRID*K2_GRID] {first, end} into cell_items */
     const unsigned short* cell_items; /* halo index inside the launch */
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 /* (c, s) of the cell index */
 __device__ __forceinline__ void k2c_coords(float x, float y, float z, float& c, float& s, bool& sane) {
@@ -1004,6 +1011,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
     unsigned int w0 = 0;         /* hits of the current tile already pushed (non-zero: the tile is being re-read) */
     bool flush = false;
 
+    /* a whole, 16-byte aligned tile is fetched one trip ahead into shared memory (each lane copies, and later reads
+     * back, its own 3 x 16 bytes): the DRAM latency of tile t+1 hides behind the work on tile t without holding
+     * registers across that work */
+    auto whole = [&](unsigned int t) { return VEC && t < ntiles && (long long)(t + 1) * K2C_TILE <= a.n; };
+    auto prefetch = [&](unsigned int t) {
+        const long long o = (long long)t * K2C_TILE + 4 * lane;
+        cp_async16(&S.next[0][lane], a.x + o);
+        cp_async16(&S.next[1][lane], a.y + o);
+        cp_async16(&S.next[2][lane], a.z + o);
+        cp_async_commit();
+    };
+    {
+        const unsigned int first = blockIdx.x * K2C_WARPS + warp;
+        if (whole(first)) prefetch(first);
+    }
+
     for (unsigned int tile = blockIdx.x * K2C_WARPS + warp; !flush;) {
         if (tile < ntiles) {
             /* nothing of the tile stays in registers across the rounds below: a tile with more hits than the
@@ -1011,7 +1034,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
             const long long base = (long long)tile * K2C_TILE;
             float px[4], py[4], pz[4];
             unsigned int valid = 0;
-            if (VEC && base + K2C_TILE <= a.n) {
+            if (w0 == 0 && whole(tile)) {
+                cp_async_wait_all();
+                const float4 vx = S.next[0][lane], vy = S.next[1][lane], vz = S.next[2][lane];
+                if (whole(tile + total_warps)) prefetch(tile + total_warps);
+                px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+                py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+                pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+                valid = 0xfu;
+            } else if (VEC && base + K2C_TILE <= a.n) { /* another pass over the same tile */
                 const float4 vx = ldg_stream4(a.x + base + 4 * lane), vy = ldg_stream4(a.y + base + 4 * lane),
                              vz = ldg_stream4(a.z + base + 4 * lane);
                 px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;

@@ -1,6 +1,6 @@
 # halo parity tests + cfg5/cfg2 bench + launch list of cfg5
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "halo or golden or exchange" > gpurun_out/pytest_cells4.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/pytest_cells4.log
-for v in 32 24; do
+for v in 24 20 16; do
   CC_K2C_WARPS=$v timeout 400 python bench.py --workload cfg5 --no-cpu-baseline --no-e2e > gpurun_out/q_cfg5_w$v.json 2> gpurun_out/q_cfg5_w$v.err
   python - <<PY
 import json
