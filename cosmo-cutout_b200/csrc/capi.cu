@@ -49,6 +49,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr; /* optional */
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -79,6 +80,7 @@ int nccl_load() {
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
+    *(void**)(&g_nccl.CommInitRankConfig) = dlsym(h, "ncclCommInitRankConfig");
     g_nccl.handle = h;
     return CC_OK;
 }
@@ -1268,6 +1270,25 @@ int cc_comm_unique_id(void* id128) {
     return CC_OK;
 }
 
+namespace {
+/* The exchange moves {count, rough count} per halo -- a few bytes to a few KB -- so the communicator is limited to
+ * ONE CTA.  This is not only thrift: with NCCL 2.28.9 (P2P over cuMem) and its default CTA count, the cell-index
+ * kernel of the next step, which needs every SM free for its one 161 KB-shared-memory CTA per SM, ran 1.65x slower
+ * (1.31 ms instead of 0.79 ms at 2 GPUs; 2.27.3, NCCL_P2P_DISABLE=1, NCCL_CUMEM_ENABLE=0 or NCCL_MAX_CTAS=1 all
+ * remove the effect; profiles/r01/README.md). */
+ncclResult_t comm_init_rank(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank) {
+    if (g_nccl.CommInitRankConfig && !getenv("CC_NCCL_DEFAULT_CTAS")) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = 1;
+        const ncclResult_t r = g_nccl.CommInitRankConfig(comm, nranks, id, rank, &cfg);
+        if (r != ncclInvalidArgument && r != ncclInvalidUsage) return r;
+        /* a library older than the header this was compiled against may refuse the config: plain init */
+    }
+    return g_nccl.CommInitRank(comm, nranks, id, rank);
+}
+}  // namespace
+
 int cc_comm_init(cc_ctx* c, int nranks, int rank, const void* id128) {
     if (!c || nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(CC_ERR_ARG, "cc_comm_init: bad argument");
     int rc = nccl_load();
@@ -1275,7 +1296,7 @@ int cc_comm_init(cc_ctx* c, int nranks, int rank, const void* id128) {
     if ((rc = use_device(c))) return rc;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    NC(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    NC(comm_init_rank(&c->comm, nranks, id, rank));
     c->nranks = nranks;
     c->rank = rank;
     return CC_OK;
@@ -1288,7 +1309,20 @@ int cc_comm_init_all(cc_ctx** ctxs, int n) {
     std::vector<int> devs(n);
     std::vector<ncclComm_t> comms(n);
     for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
-    NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    { /* ncclCommInitAll, spelled out so that the one-CTA configuration applies (comm_init_rank) */
+        ncclUniqueId id;
+        NC(g_nccl.GetUniqueId(&id));
+        NC(g_nccl.GroupStart());
+        ncclResult_t first_err = ncclSuccess;
+        for (int i = 0; i < n; ++i) {
+            if (cudaSetDevice(devs[i]) != cudaSuccess) { cudaGetLastError(); first_err = ncclUnhandledCudaError; break; }
+            const ncclResult_t r = comm_init_rank(&comms[i], n, id, i);
+            if (r != ncclSuccess && first_err == ncclSuccess) first_err = r;
+        }
+        const ncclResult_t ge = g_nccl.GroupEnd();
+        NC(first_err);
+        NC(ge);
+    }
     for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[i]; ctxs[i]->nranks = n; ctxs[i]->rank = i; }
     /* same process: mailboxes are reachable through plain peer access, no IPC handles needed */
     if (n <= cck::XCHG_MAX_RANKS) {
