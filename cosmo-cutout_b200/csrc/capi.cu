@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -1113,7 +1114,13 @@ int fetch_rows(cc_ctx* c, int64_t row0, int64_t count, const cc_cols_out* host, 
     if (need_index) {
         const cc_cols_in& in = c->host_cols;
         const int64_t base = c->index_base;
-#pragma omp parallel for schedule(static) if (count > 65536)
+        /* threads: this rank's share of the host cores (launchers such as torchrun pin OMP_NUM_THREADS to 1, which
+         * would leave a million random reads per column to one core); CC_HOST_THREADS overrides */
+        int nt = std::max(1, (int)std::thread::hardware_concurrency() / std::max(1, c->nranks));
+        nt = std::min(nt, 32);
+        if (const char* e = getenv("CC_HOST_THREADS")) nt = std::max(1, atoi(e));
+        if (count <= 65536) nt = 1;
+#pragma omp parallel for schedule(static) num_threads(nt)
         for (int64_t r = 0; r < count; ++r) {
             const int64_t g = index[r] - base;
             if (host->vx) host->vx[r] = in.vx[g];
