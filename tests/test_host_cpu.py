@@ -93,6 +93,20 @@ def test_division_free_arcsec_scaling_is_exact_everywhere(tmp_path):
     assert "quotient_mismatches=0 float_mismatches=0" in out and "checked=4278190078" in out, out
 
 
+def test_conservative_windows_hold_against_exact_arithmetic(tmp_path):
+    """prefilter.h: the outer windows never reject what the exact test accepts and the inner window of the cell-index
+    kernel's second filter never accepts what the exact rough test rejects -- 4000 windows x 600 points aimed at the
+    bounds, each with the worst-case error of the device's approximations applied both ways"""
+    exe = str(tmp_path / "check_windows")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-ffp-contract=off",
+                           "-I" + os.path.join(REPO, "cosmo-cutout_b200", "csrc"), "-x", "c++",
+                           os.path.join(REPO, "tests", "native", "check_window_filters.cpp"), "-o", exe, "-lm"])
+    out = subprocess.check_output([exe]).decode()
+    assert "violations=0" in out and "windows=4000" in out, out
+    decided = int(out.split("inner_decided=")[1].split()[0])
+    assert decided > 100_000, out  # the inner window is not vacuous
+
+
 def test_host_build_of_device_arithmetic_equals_oracle():
     cols = H.concat_cols(H.shell_fixture(200_000, seed=3), H.shell_fixture(200_000, seed=4, octant=False),
                          H.edge_fixture((306000, 320400), (0, 14400)))
