@@ -1266,19 +1266,21 @@ __global__ void k3_bucket(const BucketArgs a) {
 
 /* exclusive scan of H counts (H is small: one CTA, serial chunks) */
 __global__ void k3_scan_counts(const unsigned long long* counts, unsigned long long* seg_begin, int H) {
-    __shared__ unsigned long long s_part[256];
-    const int tid = threadIdx.x;
+    __shared__ unsigned long long s_part[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5; /* 256 threads */
     const int per = (H + 255) / 256;
     unsigned long long sum = 0;
     for (int i = tid * per; i < min(H, (tid + 1) * per); ++i) sum += counts[i];
-    s_part[tid] = sum;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long run = 0;
-        for (int i = 0; i < 256; ++i) { const unsigned long long t = s_part[i]; s_part[i] = run; run += t; }
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
     }
+    if (lane == 31) s_part[warp] = inc;
     __syncthreads();
-    unsigned long long run = s_part[tid];
+    unsigned long long run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += s_part[w];
     for (int i = tid * per; i < min(H, (tid + 1) * per); ++i) { seg_begin[i] = run; run += counts[i]; }
     if (tid == 255) seg_begin[H] = run;
 }
@@ -1495,14 +1497,28 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
         const int per = (a.H + K3S_THREADS - 1) / K3S_THREADS;
         unsigned long long sum = 0;
         for (int i = tid * per; i < min(a.H, (int)(tid + 1) * per); ++i) sum += a.counts[i];
-        s_part[tid] = sum;
+        /* block-wide exclusive scan of the per-thread sums: shuffles inside the warp, then the 16 warp totals
+         * (a serial loop over 512 shared-memory entries here cost 6 us of a 220 us step) */
+        const unsigned int lane = tid & 31u, warp = tid >> 5;
+        unsigned long long inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (unsigned int)d) inc += t;
+        }
+        if (lane == 31) s_part[warp] = inc;
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long run = 0;
-            for (int i = 0; i < K3S_THREADS; ++i) { const unsigned long long t = s_part[i]; s_part[i] = run; run += t; }
+        if (warp == 0) {
+            unsigned long long w = lane < K3S_THREADS / 32 ? s_part[lane] : 0ull;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= (unsigned int)d) w += t;
+            }
+            if (lane < K3S_THREADS / 32) s_part[lane] = w; /* inclusive warp totals */
         }
         __syncthreads();
-        unsigned long long run = s_part[tid];
+        unsigned long long run = inc - sum + (warp ? s_part[warp - 1] : 0ull);
         for (int i = tid * per; i < min(a.H, (int)(tid + 1) * per); ++i) { a.seg_begin[i] = run; run += a.counts[i]; }
         if (tid == K3S_THREADS - 1) a.seg_begin[a.H] = run;
     }
