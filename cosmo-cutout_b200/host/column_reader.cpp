@@ -6,6 +6,10 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
 #include <thread>
 
 #include "util.h"
@@ -27,13 +31,158 @@ void PinnedBuffer::release() {
     bytes_ = 0;
 }
 
+/* ---------------------------------------------------------------- GenericIO on-disk format (read side)
+ * All integers are u64 and all reals f64 in the FILE's byte order ("HACC01L" little, "HACC01B" big):
+ *   global header   Magic[8] HeaderSize NElems Dims[3] NVars VarsSize VarsStart NRanks RanksSize RanksStart
+ *                   GlobalHeaderSize PhysOrigin[3] PhysScale[3] BlocksSize BlocksStart      (the last two, like any
+ *                   later field, only when GlobalHeaderSize says they are there)
+ *   variable header Name[256] Flags Size [ElementSize]           VarsSize bytes each, NVars of them at VarsStart
+ *   rank header     Coords[3] NElems Start [GlobalRank]          RanksSize bytes each, NRanks of them at RanksStart
+ *   block header    Filters[4][8] Start Size                     BlocksSize bytes each, NRanks x NVars at BlocksStart
+ *   CRC64 (8 bytes) closes the header (HeaderSize includes it) and follows every variable's data of every rank.
+ * Without block headers the variables of a rank follow each other from the rank's Start, each NElems*Size bytes
+ * plus the 8-byte CRC. */
+namespace {
+struct FileBytes {
+    int fd = -1;
+    uint64_t size = 0;
+    explicit FileBytes(const std::string& f) {
+        fd = open(f.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd >= 0 && fstat(fd, &st) == 0) size = (uint64_t)st.st_size;
+    }
+    ~FileBytes() { if (fd >= 0) close(fd); }
+    bool get(uint64_t off, void* dst, size_t n) const {
+        if (fd < 0 || off + n > size) return false;
+        size_t done = 0;
+        while (done < n) {
+            const ssize_t got = pread(fd, (char*)dst + done, n - done, (off_t)(off + done));
+            if (got <= 0) return false;
+            done += (size_t)got;
+        }
+        return true;
+    }
+};
+inline uint64_t bswap64(uint64_t v) { return __builtin_bswap64(v); }
+inline void swap_elems(void* p, size_t n, size_t size) {
+    if (size == 2) { uint16_t* q = (uint16_t*)p; for (size_t i = 0; i < n; ++i) q[i] = __builtin_bswap16(q[i]); }
+    else if (size == 4) { uint32_t* q = (uint32_t*)p; for (size_t i = 0; i < n; ++i) q[i] = __builtin_bswap32(q[i]); }
+    else if (size == 8) { uint64_t* q = (uint64_t*)p; for (size_t i = 0; i < n; ++i) q[i] = __builtin_bswap64(q[i]); }
+}
+bool host_is_little() { const uint16_t one = 1; return *(const unsigned char*)&one == 1; }
+bool is_gio_magic(const char* m, bool* big) {
+    if (memcmp(m, "HACC01L", 8) == 0) { *big = false; return true; }
+    if (memcmp(m, "HACC01B", 8) == 0) { *big = true; return true; }
+    return false;
+}
+}  // namespace
+
+void ColumnReader::parseGio(const std::string& file, bool is_main, std::vector<int32_t>* partitions) {
+    FileBytes fb(file);
+    char magic[8];
+    bool big = false;
+    if (!fb.get(0, magic, 8) || !is_gio_magic(magic, &big)) die("GenericIO reader: " + file + " is not a GenericIO file");
+    const bool swap = big == host_is_little();
+    auto u64_at = [&](uint64_t off) {
+        uint64_t v = 0;
+        if (!fb.get(off, &v, 8)) die("GenericIO reader: truncated header in " + file);
+        return swap ? bswap64(v) : v;
+    };
+    /* field k (0-based, 8 bytes each) after the magic */
+    const uint64_t header_size = u64_at(8 + 8 * 0), nvars = u64_at(8 + 8 * 5), vars_size = u64_at(8 + 8 * 6),
+                   vars_start = u64_at(8 + 8 * 7), nranks = u64_at(8 + 8 * 8), ranks_size = u64_at(8 + 8 * 9),
+                   ranks_start = u64_at(8 + 8 * 10), global_size = u64_at(8 + 8 * 11);
+    /* PhysOrigin[3], PhysScale[3] are fields 12..17; BlocksSize, BlocksStart 18, 19 */
+    uint64_t blocks_size = 0, blocks_start = 0;
+    if (global_size >= 8 + 8 * 20) { blocks_size = u64_at(8 + 8 * 18); blocks_start = u64_at(8 + 8 * 19); }
+    if (header_size > fb.size || vars_size < 256 + 16 || ranks_size < 40 || nvars > 4096 || nranks > (1u << 24) ||
+        vars_start + nvars * vars_size > header_size || ranks_start + nranks * ranks_size > header_size)
+        die("GenericIO reader: implausible header in " + file);
+    std::vector<GioVar> vars((size_t)nvars);
+    for (uint64_t v = 0; v < nvars; ++v) {
+        char name[257];
+        if (!fb.get(vars_start + v * vars_size, name, 256)) die("GenericIO reader: truncated variable table in " + file);
+        name[256] = 0;
+        vars[(size_t)v].name = name;
+        vars[(size_t)v].size = u64_at(vars_start + v * vars_size + 256 + 8);
+    }
+    const bool has_blocks = blocks_size >= 48 && blocks_start != 0;
+    for (uint64_t r = 0; r < nranks; ++r) {
+        const uint64_t o = ranks_start + r * ranks_size;
+        GioBlock b;
+        b.file = file;
+        b.swap = swap;
+        b.nelems = u64_at(o + 24);
+        b.start = u64_at(o + 32);
+        b.global_rank = ranks_size >= 48 ? u64_at(o + 40) : r;
+        b.vars = vars;
+        b.first_elem = 0;
+        if (has_blocks) {
+            for (uint64_t v = 0; v < nvars; ++v) {
+                const uint64_t bo = blocks_start + (r * nvars + v) * blocks_size;
+                char filt[8];
+                if (!fb.get(bo, filt, 8)) die("GenericIO reader: truncated block table in " + file);
+                b.var_filtered.push_back(filt[0] != 0);
+                b.var_start.push_back(u64_at(bo + 32));
+            }
+        }
+        if (is_main && partitions) {
+            /* a partitioned main file holds only the rank map: its own blocks carry "$rank"/"$partition" */
+            bool map_only = false;
+            for (const GioVar& gv : vars) map_only = map_only || gv.name == "$partition";
+            if (map_only) {
+                /* read this block's $partition values */
+                uint64_t off = b.start;
+                for (size_t v = 0; v < vars.size(); ++v) {
+                    const uint64_t at = has_blocks ? b.var_start[v] : off;
+                    if (vars[v].name == "$partition") {
+                        if (vars[v].size != 4) die("GenericIO reader: $partition is not 32-bit in " + file);
+                        std::vector<int32_t> part((size_t)b.nelems);
+                        if (b.nelems && !fb.get(at, part.data(), (size_t)b.nelems * 4)) die("GenericIO reader: truncated rank map in " + file);
+                        if (swap) swap_elems(part.data(), part.size(), 4);
+                        partitions->insert(partitions->end(), part.begin(), part.end());
+                    }
+                    off += b.nelems * vars[v].size + 8;
+                }
+                continue;
+            }
+        }
+        blocks_.push_back(b);
+    }
+}
+
 void ColumnReader::openAndReadHeader() {
-    struct stat st;
-    const std::string xfile = path_ + "#x";
-    if (stat(xfile.c_str(), &st) != 0)
-        die("column reader: no column store for " + xfile +
-            " (expected one raw little-endian file per variable next to the header)");
-    nelems_ = (size_t)st.st_size / 4;
+    blocks_.clear();
+    gio_ = false;
+    {
+        FileBytes fb(path_);
+        char magic[8];
+        bool big;
+        gio_ = fb.get(0, magic, 8) && is_gio_magic(magic, &big);
+    }
+    if (!gio_) {
+        struct stat st;
+        const std::string xfile = path_ + "#x";
+        if (stat(xfile.c_str(), &st) != 0)
+            die("column reader: " + path_ + " is not a GenericIO file and there is no column store " + xfile +
+                " (one raw little-endian file per variable next to the header)");
+        nelems_ = (size_t)st.st_size / 4;
+        return;
+    }
+    std::vector<int32_t> partitions;
+    parseGio(path_, true, &partitions);
+    if (!partitions.empty()) { /* partitioned: the data lives in <header>#<p>, each a complete GenericIO file */
+        std::vector<int32_t> uniq(partitions);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        blocks_.clear();
+        for (int32_t p : uniq) parseGio(path_ + "#" + std::to_string(p), false, nullptr);
+    }
+    /* element order of a single-rank read: writing ranks in global rank order */
+    std::stable_sort(blocks_.begin(), blocks_.end(), [](const GioBlock& a, const GioBlock& b) { return a.global_rank < b.global_rank; });
+    uint64_t total = 0;
+    for (GioBlock& b : blocks_) { b.first_elem = total; total += b.nelems; }
+    nelems_ = (size_t)total;
 }
 
 void ColumnReader::addVariable(const std::string& name, PinnedBuffer* dst, size_t elem_size) {
@@ -52,12 +201,40 @@ static void read_whole(const std::string& file, void* dst, size_t bytes, std::st
     close(fd);
 }
 
+void ColumnReader::readGioVar(const Var& v, std::string* err) const {
+    char* dst = (char*)v.dst->data();
+    for (const GioBlock& b : blocks_) {
+        size_t vi = b.vars.size();
+        uint64_t off = b.start;
+        for (size_t i = 0; i < b.vars.size(); ++i) {
+            if (b.vars[i].name == v.name) { vi = i; break; }
+            off += b.nelems * b.vars[i].size + 8; /* data + CRC64 */
+        }
+        if (vi == b.vars.size()) { *err = "variable " + v.name + " not in " + b.file; return; }
+        if (b.vars[vi].size != v.elem_size) {
+            *err = "variable " + v.name + " has " + std::to_string(b.vars[vi].size) + "-byte elements in " + b.file + ", expected " +
+                   std::to_string(v.elem_size);
+            return;
+        }
+        if (!b.var_start.empty()) {
+            if (b.var_filtered[vi]) { *err = "variable " + v.name + " in " + b.file + " is compressed (filter blocks are not supported)"; return; }
+            off = b.var_start[vi];
+        }
+        if (b.nelems == 0) continue;
+        FileBytes fb(b.file);
+        char* at = dst + b.first_elem * v.elem_size;
+        if (!fb.get(off, at, (size_t)b.nelems * v.elem_size)) { *err = "short read of " + v.name + " in " + b.file; return; }
+        if (b.swap) swap_elems(at, (size_t)b.nelems, v.elem_size);
+    }
+}
+
 void ColumnReader::readData() {
     std::vector<std::string> errs(vars_.size());
     std::vector<std::thread> th;
     for (size_t i = 0; i < vars_.size(); ++i) {
         void* dst = vars_[i].dst->ensure(nelems_ * vars_[i].elem_size);
-        th.emplace_back(read_whole, path_ + "#" + vars_[i].name, dst, nelems_ * vars_[i].elem_size, &errs[i]);
+        if (gio_) th.emplace_back(&ColumnReader::readGioVar, this, std::cref(vars_[i]), &errs[i]);
+        else th.emplace_back(read_whole, path_ + "#" + vars_[i].name, dst, nelems_ * vars_[i].elem_size, &errs[i]);
     }
     for (auto& t : th) t.join();
     for (const auto& e : errs)

@@ -2,13 +2,23 @@
  * host/column_reader.h -- the input side of a lightcone step: named columns -> pinned host buffers.
  *
  * Stands where the reference uses GenericIO (processLC.cpp:94-139, :854-889): open a step's header file, ask for
- * the element count, register the variables wanted, read.  GenericIO itself is an un-vendored, un-pinned external
- * library that is not available here, so the only back-end is the flat column layout
- *     <dir>/<header>            (may be empty)
- *     <dir>/<header>#<var>      raw little-endian array of the variable, one file per variable
- * -- names containing '#' are ignored by header discovery, exactly as GenericIO's own rank files are
- * (util.cpp:289-291).  Buffers are cudaHostAlloc'ed (pinned, mapped) through the C ABI so the GPU can stream
- * x,y,z from them with cudaMemcpyAsync and gather the survivors' other columns in place.
+ * the element count, register the variables wanted, read.  Two back-ends, chosen by the header file's first bytes:
+ *
+ *   flat columns     <dir>/<header>            (empty, or anything that is not a GenericIO file)
+ *                    <dir>/<header>#<var>      raw little-endian array of the variable, one file per variable
+ *   GenericIO file   <dir>/<header> starts with the magic "HACC01L" / "HACC01B": the self-describing HACC format
+ *                    (global header, variable headers, one header per writing rank, optional block headers, CRC64
+ *                    after the header and after every data block), optionally partitioned into <header>#<p>
+ *                    files through the "$rank"/"$partition" map of the main file.  Ranks are read in global rank
+ *                    order, which is the element order a single-rank GenericIO::readData (MismatchRedistribute)
+ *                    produces.  Both byte orders; uncompressed blocks only; CRCs are not verified.
+ *
+ * GenericIO itself is an un-vendored, un-pinned external library that is not available here: the
+ * second back-end is written from the published on-disk format and is exercised against files produced by an
+ * independent writer in tests/harness.py (write_gio_step), NOT against the library -- treat it as unverified on
+ * real HACC output until it has read one.  Names containing '#' are ignored by header discovery, exactly as the
+ * reference ignores GenericIO's partition files (util.cpp:289-291).  Buffers are cudaHostAlloc'ed (pinned, mapped)
+ * through the C ABI so the GPU can stream x,y,z from them with cudaMemcpyAsync.
  */
 #ifndef CC_HOST_COLUMN_READER_H
 #define CC_HOST_COLUMN_READER_H
@@ -40,9 +50,10 @@ private:
 
 class ColumnReader {
 public:
-    explicit ColumnReader(const std::string& header_path) : path_(header_path), nelems_(0) {}
-    /* element count from the size of the x column */
+    explicit ColumnReader(const std::string& header_path) : path_(header_path), nelems_(0), gio_(false) {}
+    /* flat columns: element count from the size of the x column; GenericIO: sum over the rank headers */
     void openAndReadHeader();
+    bool isGenericIO() const { return gio_; }
     size_t readNumElems() const { return nelems_; }
     void addVariable(const std::string& name, PinnedBuffer* dst, size_t elem_size);
     /* reads every registered variable (one thread per variable) */
@@ -50,9 +61,25 @@ public:
 
 private:
     struct Var { std::string name; PinnedBuffer* dst; size_t elem_size; };
+    /* one writing rank's block of one GenericIO (partition) file */
+    struct GioVar { std::string name; uint64_t size; };
+    struct GioBlock {
+        std::string file;
+        bool swap;                      /* file byte order differs from the host's */
+        uint64_t global_rank, nelems, start;
+        std::vector<GioVar> vars;       /* in file order */
+        std::vector<uint64_t> var_start; /* explicit per-variable offsets (block headers) or empty */
+        std::vector<bool> var_filtered;  /* block carries a compression filter */
+        uint64_t first_elem;            /* position of the block's first element in the assembled column */
+    };
+    void parseGio(const std::string& file, bool is_main, std::vector<int32_t>* partitions);
+    void readGioVar(const Var& v, std::string* err) const;
+
     std::string path_;
     size_t nelems_;
+    bool gio_;
     std::vector<Var> vars_;
+    std::vector<GioBlock> blocks_;
 };
 
 /* the ten input columns of a step in pinned memory (util.h:33-47 Buffers_read) */

@@ -126,6 +126,95 @@ def write_flat_step(root, step, cols, prefix="lc", names=IN_COLS):
     return header
 
 
+def write_gio_step(root, step, cols, prefix="lc", names=IN_COLS, nranks=3, big_endian=False, block_headers=False,
+                   partitions=0, old_headers=False, seed=0):
+    """A lightcone step in the GenericIO on-disk format (written here from the format description, independently of
+    the reader under test): global header, variable headers, one rank header per writing rank, optional block
+    headers, 8 CRC bytes after the header and after every data block (not a real CRC: the reader does not verify
+    them).  The particles are cut into `nranks` contiguous pieces of uneven size (one of them empty when nranks > 2).
+    partitions > 0: the main file only carries the "$rank"/"$partition" map and the data goes to '<header>#<p>',
+    ranks dealt round-robin to partitions and stored there in DESCENDING rank order, so a reader has to restore the
+    global rank order.  old_headers: rank headers without GlobalRank, variable headers without ElementSize, global
+    header without the Blocks fields (the format's size fields make such files readable)."""
+    rng = np.random.default_rng(seed)
+    n = cols["x"].shape[0]
+    d = os.path.join(root, f"{prefix}{step}")
+    os.makedirs(d, exist_ok=True)
+    header = os.path.join(d, f"lc_intrp_output.{step}")
+    E = ">" if big_endian else "<"
+    cuts = np.sort(rng.integers(0, n + 1, nranks - 1)) if nranks > 1 else np.array([], dtype=np.int64)
+    if nranks > 2:
+        cuts[1] = cuts[0]  # an empty rank
+    bounds = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+
+    def u64(*v):
+        return np.array(v, dtype=E + "u8").tobytes()
+
+    def f64(*v):
+        return np.array(v, dtype=E + "f8").tobytes()
+
+    def gio_bytes(ranks, variables):
+        """ranks: list of (global_rank, {name: array}); variables: list of (name, numpy dtype string without order)"""
+        nvars = len(variables)
+        vars_size = 256 + 16 + (0 if old_headers else 8)
+        ranks_size = 40 + (0 if old_headers else 8)
+        use_blocks = block_headers and not old_headers
+        global_size = 8 + 8 * (18 if old_headers else 20)
+        blocks_size = 48 if use_blocks else 0
+        vars_start = global_size
+        ranks_start = vars_start + nvars * vars_size
+        blocks_start = ranks_start + len(ranks) * ranks_size if use_blocks else 0
+        header_size = ranks_start + len(ranks) * ranks_size + len(ranks) * nvars * blocks_size + 8
+        # data layout
+        off = header_size
+        rank_start, block_start, payload = [], [], []
+        for (_gr, data) in ranks:
+            rank_start.append(off)
+            for (name, dt) in variables:
+                a = np.ascontiguousarray(data[name]).astype(E + dt)
+                if use_blocks:  # block headers allow (and the writer of the library leaves) gaps: add one
+                    pad = b"\xAB" * 16
+                    payload.append(pad)
+                    off += len(pad)
+                block_start.append((off, a.nbytes))
+                payload.append(a.tobytes())
+                payload.append(b"\xC5" * 8)
+                off += a.nbytes + 8
+        total = sum(data[variables[0][0]].shape[0] for (_gr, data) in ranks)
+        out = [b"HACC01B\0" if big_endian else b"HACC01L\0"]
+        out.append(u64(header_size, total, 1, 1, 1, nvars, vars_size, vars_start, len(ranks), ranks_size, ranks_start, global_size))
+        out.append(f64(0, 0, 0, 256, 256, 256))
+        if not old_headers:
+            out.append(u64(blocks_size, blocks_start))
+        for (name, dt) in variables:
+            size = np.dtype(dt).itemsize
+            flags = (1 if dt[0] == "f" else 0) | (2 if dt[0] in "fi" else 0)
+            out.append(name.encode().ljust(256, b"\0") + u64(flags, size) + (b"" if old_headers else u64(size)))
+        for k, (gr, data) in enumerate(ranks):
+            ne = data[variables[0][0]].shape[0]
+            out.append(u64(gr % 4, gr // 4, 0, ne, rank_start[k]) + (b"" if old_headers else u64(gr)))
+        if use_blocks:
+            for (st, sz) in block_start:
+                out.append(b"\0" * 32 + u64(st, sz))
+        out.append(b"\xC5" * 8)
+        blob = b"".join(out)
+        assert len(blob) == header_size, (len(blob), header_size)
+        return blob + b"".join(payload)
+
+    variables = [(nme, {"id": "i8", "rotation": "i4", "replication": "i4"}.get(nme, "f4")) for nme in names]
+    ranks = [(r, {nme: cols[nme][bounds[r]:bounds[r + 1]] for nme in names}) for r in range(nranks)]
+    if partitions <= 0:
+        open(header, "wb").write(gio_bytes(ranks, variables))
+    else:
+        part_of = np.arange(nranks, dtype=np.int32) % partitions
+        open(header, "wb").write(gio_bytes([(0, {"$rank": np.arange(nranks, dtype=np.int32), "$partition": part_of})],
+                                           [("$rank", "i4"), ("$partition", "i4")]))
+        for p_ in range(partitions):
+            mine = [ranks[r] for r in range(nranks) if part_of[r] == p_][::-1]
+            open(header + f"#{p_}", "wb").write(gio_bytes(mine, variables))
+    return header
+
+
 def read_cutout_dir(d, step, names=OUT_COLS):
     out = {}
     for nme in names:

@@ -165,3 +165,26 @@ def test_cli_single_halo_equals_reference(lc_dirs, tmp_path):
     _run(cc.CLI_PATH, [lc_dirs, o1] + args)
     _run(REF_BIN, [lc_dirs, o2] + args)
     assert len(_same_tree(str(o1), str(o2))) == 1 + 2 * 12
+
+
+@pytest.mark.gpu
+@needs_ref_bin
+def test_cli_reads_genericio_format_input(tmp_path):
+    """the same steps once as flat columns (read by the reference binary through its shimmed reader) and once in the
+    GenericIO on-disk format -- a single file, a partitioned big-endian one, one with block headers -- give the same
+    output trees, for both use cases"""
+    flat, gio = tmp_path / "flat", tmp_path / "gio"
+    flat.mkdir(); gio.mkdir()
+    variants = {499: dict(nranks=4), 475: dict(nranks=6, partitions=3, big_endian=True), 487: dict(nranks=3, block_headers=True)}
+    for step, seed in ((487, 1), (475, 2), (499, 3)):
+        cols = H.concat_cols(H.shell_fixture(120_000, seed=seed), H.shell_fixture(40_000, seed=seed + 10, octant=False))
+        H.write_flat_step(str(flat), step, cols)
+        H.write_gio_step(str(gio), step, cols, seed=seed, **variants[step])
+    for name, args in (("const", [499, 470, "--theta", 80, 8, "--phi", 40, 10]),
+                       ("halo", [499, 470, "--halo", 150, 20, 12, "--boxLength", 90])):
+        o1, o2 = tmp_path / ("ours_" + name), tmp_path / ("ref_" + name)
+        o1.mkdir(); o2.mkdir()
+        _run(cc.CLI_PATH, [str(gio), o1] + args)
+        _run(REF_BIN, [str(flat), o2] + args)
+        files = _same_tree(str(o1), str(o2))
+        assert len(files) >= 2 * 12 and any("475" in f for f in files) and any("487" in f for f in files)

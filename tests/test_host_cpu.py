@@ -107,6 +107,63 @@ def test_conservative_windows_hold_against_exact_arithmetic(tmp_path):
     assert decided > 100_000, out  # the inner window is not vacuous
 
 
+@pytest.fixture(scope="module")
+def gio_dump(tmp_path_factory):
+    """the product's column reader compiled into a stand-alone dump tool (pinned allocation replaced by malloc)"""
+    exe = str(tmp_path_factory.mktemp("gio") / "gio_dump")
+    host = os.path.join(REPO, "cosmo-cutout_b200", "host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + host, "-I" + os.path.join(REPO, "include"),
+                           os.path.join(REPO, "tests", "native", "gio_dump.cpp"), os.path.join(host, "column_reader.cpp"),
+                           "-o", exe, "-lpthread"])
+    return exe
+
+
+GIO_VARIANTS = [dict(nranks=1), dict(nranks=4), dict(nranks=5, block_headers=True), dict(nranks=3, big_endian=True),
+                dict(nranks=6, partitions=3), dict(nranks=7, partitions=2, big_endian=True, block_headers=True),
+                dict(nranks=4, old_headers=True)]
+
+
+@pytest.mark.parametrize("variant", GIO_VARIANTS, ids=lambda v: "-".join(f"{k}{int(x)}" for k, x in v.items()))
+def test_column_reader_reads_genericio_format(gio_dump, tmp_path, variant):
+    """host/column_reader.cpp, GenericIO back-end: files written by an independent writer (harness.write_gio_step)
+    -- one file or partitioned, either byte order, with and without block headers, old header sizes -- come back as
+    the same columns, in global rank order, as the flat column store gives"""
+    cols = H.shell_fixture(20_011, seed=8)
+    header = H.write_gio_step(str(tmp_path), 487, cols, seed=3, **variant)
+    for pos_only in (False, True):
+        out = tmp_path / ("dump_p" if pos_only else "dump")
+        out.mkdir()
+        msg = subprocess.check_output([gio_dump, header, str(out)] + (["posOnly"] if pos_only else [])).decode()
+        assert f"n={cols['x'].shape[0]}" in msg, msg
+        names = ("x", "y", "z", "a", "id") if pos_only else cc.IN_COLS
+        for k in names:
+            got = np.fromfile(str(out / (k + ".bin")), dtype=cols[k].dtype)
+            assert got.tobytes() == np.ascontiguousarray(cols[k]).tobytes(), k
+
+
+def test_column_reader_flat_store_and_errors(gio_dump, tmp_path):
+    cols = H.shell_fixture(1000, seed=9)
+    header = H.write_flat_step(str(tmp_path), 475, cols)
+    out = tmp_path / "dump"
+    out.mkdir()
+    assert "n=1000" in subprocess.check_output([gio_dump, header, str(out)]).decode()
+    assert np.fromfile(str(out / "id.bin"), dtype=np.int64).tobytes() == cols["id"].tobytes()
+    # a GenericIO file with a variable of the wrong width, and a truncated one, are refused with a message
+    bad = dict(cols)
+    bad["id"] = cols["id"].astype(np.int32)
+    h2 = H.write_gio_step(str(tmp_path / "w"), 487, bad, nranks=2)
+    blob = open(h2, "rb").read()
+    # patch the declared size of "id" from 8 to 4 (the harness writes i8 data; declare it 4 bytes wide)
+    at = blob.index(b"id".ljust(256, b"\0")) + 256 + 8
+    open(h2, "wb").write(blob[:at] + np.array([4], dtype="<u8").tobytes() + blob[at + 8:])
+    p = subprocess.run([gio_dump, h2, str(out)], stdout=subprocess.PIPE)
+    assert p.returncode != 0 and b"4-byte elements" in p.stdout
+    h3 = H.write_gio_step(str(tmp_path / "t"), 487, cols, nranks=3)
+    open(h3, "r+b").truncate(os.path.getsize(h3) - 5000)
+    p = subprocess.run([gio_dump, h3, str(out)], stdout=subprocess.PIPE)
+    assert p.returncode != 0 and b"short read" in p.stdout
+
+
 def test_host_build_of_device_arithmetic_equals_oracle():
     cols = H.concat_cols(H.shell_fixture(200_000, seed=3), H.shell_fixture(200_000, seed=4, octant=False),
                          H.edge_fixture((306000, 320400), (0, 14400)))
