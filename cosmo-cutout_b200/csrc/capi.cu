@@ -129,6 +129,10 @@ struct cc_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr, ev_total1 = nullptr;
+    /* the survivor counts are final long before the survivors are ordered and gathered: the count exchange runs on
+     * its own stream from that point on, next to the ordering / gather kernels */
+    cudaEvent_t ev_counts = nullptr, ev_xchg = nullptr;
+    cudaStream_t xchg_stream = nullptr;
     int64_t launches = 0;
     int k1_occupancy[2] = {0, 0};
     int64_t last_const_count = -1;
@@ -351,6 +355,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         t.nblocks = nblocks;
         cck::k1_tile_scan<<<nblocks, cck::TSCAN_THREADS, 0, c->stream>>>(t);
         CU(cudaGetLastError());
+        if (ch.last) CU(cudaEventRecord(c->ev_counts, c->stream));
 
         cck::GatherConstArgs g;
         g.in = c->gcols;
@@ -377,6 +382,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         c->launches += 3;
     } else if (ch.last) {
         CU(cudaEventRecord(c->ev_scan1, c->stream));
+        CU(cudaEventRecord(c->ev_counts, c->stream));
     }
     if (ch.last) {
         CU(cudaEventRecord(c->ev_total1, c->stream));
@@ -627,6 +633,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
     }
     if (ch.last) {
         CU(cudaEventRecord(c->ev_scan1, c->stream));
+        CU(cudaEventRecord(c->ev_counts, c->stream));
         /* ordering + gather, sized on the device: the whole pass is one enqueue, one host synchronisation */
         cck::GatherArgs g;
         g.rank = (const unsigned int*)c->rank_buf.p;
@@ -826,7 +833,10 @@ int cc_create(int device, cc_ctx** out) {
     c->sm_count = sms;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_scan0) != cudaSuccess || cudaEventCreate(&c->ev_scan1) != cudaSuccess ||
-        cudaEventCreate(&c->ev_total1) != cudaSuccess) {
+        cudaEventCreate(&c->ev_total1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_xchg, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->xchg_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return fail(CC_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -857,6 +867,9 @@ void cc_destroy(cc_ctx* c) {
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->ev_scan0) cudaEventDestroy(c->ev_scan0);
     if (c->ev_scan1) cudaEventDestroy(c->ev_scan1);
+    if (c->ev_counts) cudaEventDestroy(c->ev_counts);
+    if (c->ev_xchg) cudaEventDestroy(c->ev_xchg);
+    if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
     if (c->ev_total1) cudaEventDestroy(c->ev_total1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1380,19 +1393,23 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         if ((rc = ensure_small(c, small_elems(H, R)))) return rc;
         memcpy(c->h_small, keep.data(), keep.size() * sizeof(unsigned long long));
     }
-    /* The collective is enqueued BEHIND the cutout kernels on the same stream: no host round trip between the
-     * scan and the exchange.  Survivor counts are exact even when a survivor buffer overflowed (only the stored
-     * rows are clipped), so a local re-run after the synchronisation never needs a second collective -- every rank
-     * issues exactly one all-gather per call. */
+    /* The collective is enqueued on the exchange stream behind the event that marks the counts final (after the scan
+     * kernel of use case 2, after the tile scan of use case 1): no host round trip between the scan and the
+     * exchange, and the exchange runs NEXT TO the ordering / gather kernels instead of after them.  The cutout stream
+     * then waits for the exchange, so stream order (and anything timed on the cutout stream) includes it.  Survivor
+     * counts are exact even when a survivor buffer overflowed (only the stored rows are clipped), so a local re-run
+     * after the synchronisation never needs a second collective -- every rank issues exactly one all-gather per call. */
+    cudaStream_t xs = c->xchg_stream;
+    CU(cudaStreamWaitEvent(xs, c->ev_counts, 0));
     if (c->pending == P_CONST) { /* device-resident send buffer {count, 0}; use case 2 already has {counts, rough} */
-        CU(cudaMemcpyAsync(c->counts_buf.p, c->scratch.p, 8, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, c->stream));
+        CU(cudaMemcpyAsync(c->counts_buf.p, c->scratch.p, 8, cudaMemcpyDeviceToDevice, xs));
+        CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, xs));
     }
     const void* send = (c->pending == P_CONST) ? c->counts_buf.p : (const void*)hs_counts(c);
     const bool peer_path = c->peers_ready && R > 1 && 2 * H <= cck::XCHG_PAYLOAD && !getenv("CC_NO_PEER_XCHG");
     unsigned long long* hg = c->h_small + hg_off;
     unsigned long long* d_status = (unsigned long long*)((char*)c->gather_buf.p + (size_t)R * 2 * H * 8);
-    CU(cudaMemsetAsync(d_status, 0, 8, c->stream));
+    CU(cudaMemsetAsync(d_status, 0, 8, xs));
     if (peer_path) { /* NVLink peer stores: one single-CTA kernel, no collective launch */
         cck::XchgArgs x;
         memset(&x, 0, sizeof(x));
@@ -1405,22 +1422,24 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         const char* to = getenv("CC_PEER_TIMEOUT_MS");
         x.timeout_ns = (unsigned long long)(to ? atoll(to) : 10000) * 1000000ull;
         x.n = 2 * H; x.H = H; x.R = R; x.rank = c->rank;
-        cck::k4_exchange_peer<<<1, 256, 0, c->stream>>>(x);
+        cck::k4_exchange_peer<<<1, 256, 0, xs>>>(x);
         CU(cudaGetLastError());
     } else {
         if (c->comm) {
-            NC(g_nccl.AllGather(send, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, c->stream));
+            NC(g_nccl.AllGather(send, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, xs));
         } else {
             if (R > 1) return fail(CC_ERR_STATE, "cc_exchange_counts: %d ranks but neither an NCCL communicator nor peer mailboxes for %d halos", R, H);
-            CU(cudaMemcpyAsync(c->gather_buf.p, send, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->gather_buf.p, send, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, xs));
         }
-        cck::k4_offsets<<<(H + 255) / 256, 256, 0, c->stream>>>((const unsigned long long*)c->gather_buf.p,
+        cck::k4_offsets<<<(H + 255) / 256, 256, 0, xs>>>((const unsigned long long*)c->gather_buf.p,
                                                               (unsigned long long*)c->offsets_buf.p, H, c->rank);
         CU(cudaGetLastError());
     }
     c->launches += 1;
-    CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8 + 8, cudaMemcpyDeviceToHost, c->stream)); /* + status */
-    CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H + 1, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8 + 8, cudaMemcpyDeviceToHost, xs)); /* + status */
+    CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H + 1, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, xs));
+    CU(cudaEventRecord(c->ev_xchg, xs));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_xchg, 0));
     if (c->synced) CU(cudaStreamSynchronize(c->stream));
     else if ((rc = cc_cutout_sync(c, nullptr, nullptr))) return rc; /* one synchronisation for cutout + exchange */
     for (int r = 0; r < R; ++r)
