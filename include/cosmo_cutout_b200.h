@@ -166,7 +166,10 @@ int cc_comm_init(cc_ctx* ctx, int nranks, int rank, const void* id128);
 int cc_comm_init_all(cc_ctx** ctxs, int n);
 /* After cc_cutout_*: gathers counts of all ranks.  all_counts[r*nhalos+h], all_rough[r*nhalos+h] (host,
  * may be NULL); offsets[h] = sum of counts of ranks < this rank (the file offset, in rows). Implies a
- * cc_cutout_sync.  Without a communicator it degenerates to one rank. */
+ * cc_cutout_sync.  Without a communicator it degenerates to one rank.  The exchange is enqueued on the context's
+ * second stream behind the device event "counts are final", so it runs next to the ordering / gather kernels of
+ * the pending cutout; the cutout stream (cc_stream) waits for it.  Like any collective it must be entered by every
+ * rank.  The communicator is created with one CTA (the payload is a few KB). */
 int cc_exchange_counts(cc_ctx* ctx, int64_t* all_counts, int64_t* all_rough, int64_t* offsets);
 int cc_comm_rank(cc_ctx* ctx);
 int cc_comm_size(cc_ctx* ctx);
