@@ -16,6 +16,7 @@
  */
 #include "processLC.h"
 
+#include <dirent.h>
 #include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
@@ -116,6 +117,68 @@ struct Survivors {
     }
 };
 
+/* ---------------------------------------------------------------- input read-ahead
+ * While step i is being cut out and written, a background thread already reads step i+1 into the second set of
+ * pinned buffers: once a cutout takes milliseconds the file read is the end-to-end bottleneck.
+ * Costs a second set of input buffers in host memory; CC_NO_READAHEAD=1 turns it off. */
+class StepReadAhead {
+public:
+    StepReadAhead() : slot_(0), pending_(false), enabled_(!(getenv("CC_NO_READAHEAD") && string(getenv("CC_NO_READAHEAD")) == "1")) {}
+    ~StepReadAhead() { if (pending_) th_.join(); }
+    /* the columns of `header`: already being read, or read now */
+    StepColumns& take(const string& header, bool positionOnly) {
+        if (pending_) {
+            th_.join();
+            pending_ = false;
+            if (pending_header_ == header && pending_pos_ == positionOnly) { slot_ = 1 - slot_; return buf_[slot_]; }
+        }
+        buf_[slot_].read(header, positionOnly);
+        return buf_[slot_];
+    }
+    /* start reading the step that will be asked for next (into the buffers not handed out last) */
+    void start(const string& header, bool positionOnly) {
+        if (!enabled_ || pending_) return;
+        pending_header_ = header;
+        pending_pos_ = positionOnly;
+        StepColumns* dst = &buf_[1 - slot_];
+        th_ = std::thread([dst, header, positionOnly] { dst->read(header, positionOnly); });
+        pending_ = true;
+    }
+
+private:
+    StepColumns buf_[2];
+    int slot_;
+    bool pending_, enabled_;
+    string pending_header_;
+    bool pending_pos_ = false;
+    std::thread th_;
+};
+
+/* header file of the next step that will be processed after position i (step 499 is skipped), or "" */
+string next_header(const string& dir_name, const string& subdirPrefix, const vector<string>& step_strings, size_t i) {
+    for (size_t j = i + 1; j < step_strings.size(); ++j) {
+        if (atoi(step_strings[j].c_str()) == 499) continue;
+        const string step_dir = dir_name + subdirPrefix + step_strings[j];
+        /* the same selection as getLCFile (util.cpp:286-292), but silent: anything irregular is left to the step's
+         * own turn, where getLCFile reports it exactly as before */
+        DIR* dp = opendir(step_dir.c_str());
+        if (!dp) return "";
+        string file_name;
+        int found = 0;
+        while (struct dirent* e = readdir(dp)) {
+            const string name(e->d_name);
+            if (name.find("lc") != string::npos && name.find("#") == string::npos && name.find("SubInput") == string::npos) {
+                file_name = name;
+                ++found;
+            }
+        }
+        closedir(dp);
+        if (found != 1) return "";
+        return step_dir + "/" + file_name;
+    }
+    return "";
+}
+
 /* ---------------------------------------------------------------- output files (processLC.cpp:226-264 / :1291-1302) */
 struct ColumnFile {
     int fd = -1;
@@ -209,7 +272,7 @@ void processLC(string dir_name, string out_dir, vector<string> step_strings, vec
     g_pool.ensure(numranks);
     const string subdirPrefix = find_prefix(dir_name, true);
 
-    StepColumns cols; /* pinned buffers are reused across steps */
+    StepReadAhead reader; /* two sets of pinned buffers, reused across steps */
     for (size_t i = 0; i < step_strings.size(); ++i) {
         const int step = atoi(step_strings[i].c_str());
         if (step == 499) continue; /* z = 0: zero lightcone volume (processLC.cpp:72-73) */
@@ -219,7 +282,11 @@ void processLC(string dir_name, string out_dir, vector<string> step_strings, vec
         getLCFile(step_dir, file_name);
         const string header = step_dir + "/" + file_name;
         cout << "Opening file: " << header << endl;
-        cols.read(header, false);
+        StepColumns& cols = reader.take(header, false);
+        {
+            const string nxt = next_header(dir_name, subdirPrefix, step_strings, i);
+            if (!nxt.empty()) reader.start(nxt, false);
+        }
         const size_t Np = cols.n;
         cout << "Number of elements in lc step at rank " << myrank << ": " << Np << endl;
 
@@ -352,7 +419,7 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
     g_pool.ensure(numranks);
     const bool keep_tail = getenv("CC_KEEP_TAIL") && string(getenv("CC_KEEP_TAIL")) == "1";
     vector<double> read_times, redist_times, sort_times, cutout_times, write_times;
-    StepColumns cols;
+    StepReadAhead reader;
 
     for (size_t i = 0; i < step_strings.size(); ++i) {
         double start = wall_seconds();
@@ -366,7 +433,11 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
         getLCFile(step_dir, file_name);
         const string header = step_dir + "/" + file_name;
         cout << "Opening file: " << header << endl;
-        cols.read(header, positionOnly);
+        StepColumns& cols = reader.take(header, positionOnly);
+        {
+            const string nxt = next_header(dir_name, subdirPrefix, step_strings, i);
+            if (!nxt.empty()) reader.start(nxt, positionOnly);
+        }
         const size_t Np = cols.n;
         double duration = wall_seconds() - start;
         if (timeit) cout << "Read time: " << duration << " s" << endl;
