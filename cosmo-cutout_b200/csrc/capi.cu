@@ -514,7 +514,7 @@ int prepare_halo(cc_ctx* c) {
                             const size_t cell = (size_t)ic * G + is;
                             rg[cell] = make_uint2(st[cell], st[cell + 1]);
                             if (st[cell + 1] > st[cell]) {
-                                const unsigned int bit = (unsigned int)(ic >> 1) * cck::K2_COARSE + (unsigned int)(is >> 1);
+                                const unsigned int bit = (unsigned int)(ic >> cck::K2_CSHIFT) * cck::K2_COARSE + (unsigned int)(is >> cck::K2_CSHIFT);
                                 bw[bit >> 5] |= 1u << (bit & 31u);
                             }
                         }

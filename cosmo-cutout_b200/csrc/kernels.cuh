@@ -921,13 +921,13 @@ constexpr size_t K2T_SMEM_BASE = sizeof(K2TWarpRing) * SCAN_WARPS;
 /* ---- many halos: a (cos theta_u, sin phi_u) cell index over the halos of the launch ----------------------------
  * With hundreds of halos per pass the loop "every particle x every halo" is compute-bound (and a 1-D theta index
  * still leaves ~1 % of the halos per particle: profiles/r01).  The host rasterises each halo's widened rough
- * window [clo,chi] x [slo,shi] into a K2_GRID x K2_GRID grid over (c, s) in [-1,1]^2 (+-1 cell of slack) and builds
+ * window [clo,chi] x [slo,shi] into a K2_GRID x K2_GRID (2048^2) grid over (c, s) in [-1,1]^2 (+-1 cell of slack) and builds
  * a CSR list of halos per cell.  A particle computes c = z/r and s = sin(phi_u) = y*sign(x)/sqrt(x^2+y^2), looks up
  * its cell (one 8-byte read from an L2-resident table) and owes one test per halo listed there -- for cluster-sized
  * boxes most cells are empty.  This plays the role of the reference's theta-sorted index (processLC.cpp:1214-1221,
  * :1334-1340) without sorting or re-reading 12 B/particle data.
  *
- * One CTA of 32 warps per SM keeps a 512 x 512 occupancy bitmap of the grid (one bit per 2 x 2 cells) in shared
+ * One CTA of 20 warps per SM keeps a 512 x 512 occupancy bitmap of the grid (one bit per 4 x 4 cells) in shared
  * memory: most particles are ruled out by one shared-memory read, the rest ("hits") fetch their cell's
  * {first, end} from the L2-resident table.  Hits are few and scattered over the lanes, so the warp never works on
  * them in place: every lane pushes its hits -- position included, it is in registers -- onto the warp's
@@ -937,8 +937,13 @@ constexpr size_t K2T_SMEM_BASE = sizeof(K2TWarpRing) * SCAN_WARPS;
  * this keeps every round full).  Whenever 32 tested pairs are stacked they take the exact path (k2_exact_warp) with
  * all lanes busy.  Remainders (< 32 each) stay stacked for the next tile.  Tiles are 128 particles (4 per lane) to
  * keep registers for the bookkeeping. */
-constexpr int K2_GRID = 1024;
-constexpr int K2_COARSE = K2_GRID / 2;                       /* occupancy bitmap: one bit per 2 x 2 cells */
+#ifndef CC_K2_GRID
+#define CC_K2_GRID 2048 /* 1024: 12 % slower on 1000 cluster-sized halos (more pairs per hit); the 32 MB table stays L2-resident */
+#endif
+constexpr int K2_GRID = CC_K2_GRID;
+constexpr int K2_CSHIFT = K2_GRID == 2048 ? 2 : 1;
+constexpr int K2_COARSE = K2_GRID >> K2_CSHIFT;              /* occupancy bitmap: 512 x 512 bits, one per 4 x 4 (2 x 2) cells */
+static_assert(K2_COARSE == 512, "the bitmap is sized for 32 KB of shared memory");
 constexpr int K2_BITWORDS = K2_COARSE * K2_COARSE / 32;      /* 32 KB, resident in shared memory */
 /* one CTA per SM shares the bitmap: WARPS warps (template parameter; 20 at 96 registers by default) */
 constexpr int K2C_TILE = 128; /* particles per warp tile */
@@ -1071,7 +1076,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
                 const unsigned int ic = min(__float2uint_rz(fmaf(pc, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
                 const unsigned int is = min(__float2uint_rz(fmaf(ps, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
                 cell[j] = ic * K2_GRID + is;
-                const unsigned int bit = (ic >> 1) * K2_COARSE + (is >> 1);
+                const unsigned int bit = (ic >> K2_CSHIFT) * K2_COARSE + (is >> K2_CSHIFT);
                 hit |= ((s_bits[bit >> 5] >> (bit & 31u)) & 1u) << j;
             }
             insane &= valid;
