@@ -216,6 +216,17 @@ def test_const_unaligned_device_columns(ctx):
     ctx.cutout_const(theta_cut, phi_cut)
     ctx.sync()
     H.assert_cols_equal(ctx.fetch(0), H.oracle_cutout_const(sub, theta_cut, phi_cut))
+    # the halo kernels on the same unaligned columns (n is not a multiple of the tile either): one halo (plain scan)
+    # and nine halos (cell-index scan, which then reads its tiles without the cp.async prefetch)
+    rng = np.random.default_rng(4)
+    pos = np.vstack([[150, 20, 12], rng.uniform(40, 250, (8, 3))]).astype(np.float32)
+    for nh in (1, 9):
+        ctx.cutout_halo([cc.halo_setup(p, 90.0).halo for p in pos[:nh]])
+        counts, rough = ctx.sync()
+        for h in range(nh):
+            want, want_rough = H.oracle_cutout_halo(sub, H.oracle_halo_setup(pos[h], 90.0))
+            assert int(counts[h]) == want["id"].shape[0] and int(rough[h]) == want_rough
+            H.assert_cols_equal(ctx.fetch(h), want, what=f"unaligned, {nh} halos, halo {h}: ")
 
 
 def test_const_shards_concatenate_to_single_rank_order(ctx):
