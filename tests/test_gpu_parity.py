@@ -470,6 +470,16 @@ def test_streamed_equals_oracle(ctx):
         want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup((150, 20, 12), 60.0))
         assert int(rough[0]) == want_rough
         H.assert_cols_equal(ctx.fetch(0), want, what="streamed halo: ")
+        # nine halos over all three chunks: the cell-index kernel with a non-zero chunk offset (two halos checked: the
+        # oracle sorts all 33 M particles per halo)
+        rng = np.random.default_rng(11)
+        pos9 = np.vstack([[150, 20, 12], rng.uniform(40, 250, (8, 3))]).astype(np.float32)
+        ctx.cutout_halo_streamed(pin, [cc.halo_setup(p, 60.0).halo for p in pos9], n_limit_global=limit)
+        counts, rough = ctx.sync()
+        for h in (0, 5):
+            want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(pos9[h], 60.0))
+            assert int(counts[h]) == want["id"].shape[0] and int(rough[h]) == want_rough
+            H.assert_cols_equal(ctx.fetch(h), want, what=f"streamed, 9 halos, halo {h}: ")
         # a dozen halos (cell-index kernel) over the first 3M particles, a global index base, everything fetched at
         # once; the survivors' vx..replication are picked on the host from the pinned columns -- and, as a
         # cross-check, by the GPU (CC_DEVICE_GATHER=1)
