@@ -408,6 +408,23 @@ def test_halo_large_segment(ctx):
         H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {p} {b}: ")
 
 
+def test_halo_huge_segment_regrows_and_merges_hundreds_of_chunks(ctx):
+    """a 60-degree box: more than 2^20 survivors in ONE halo -- beyond the initial record capacity (the pass is re-run
+    at the exact size) and hundreds of 4096-record chunks, each ordered by one CTA and merged by binary searches"""
+    cols = H.shell_fixture(5_000_000, seed=91)
+    p, b = (100, 100, 100), 3600.0
+    fresh = cc.Context(0)  # a context whose buffers still have their initial sizes
+    try:
+        fresh.upload(cols)
+        fresh.cutout_halo([cc.halo_setup(p, b).halo])
+        counts, rough = fresh.sync()
+        want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, b))
+        assert int(counts[0]) == want["id"].shape[0] > (1 << 20) and int(rough[0]) == want_rough
+        H.assert_cols_equal(fresh.fetch(0), want, what="huge segment: ")
+    finally:
+        fresh.close()
+
+
 def test_halo_empty_inputs(ctx):
     info = cc.halo_setup((150, 20, 12), 10.0)
     ctx.upload(H.slice_cols(H.shell_fixture(10, seed=1), 0, 0))
