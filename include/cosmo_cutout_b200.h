@@ -126,11 +126,13 @@ int cc_cutout_halo(cc_ctx* ctx, int nhalos, const cc_halo* halos, int pos_only, 
 /* Wait for the pending cutout; counts[h] = survivors, rough_counts[h] = survivors of the rough cut
  * (processLC.cpp:1436; 0 for use case 1).  Either array may be NULL. */
 int cc_cutout_sync(cc_ctx* ctx, int64_t* counts, int64_t* rough_counts);
-/* Copy halo h's survivors (h = 0 for use case 1) to host columns, rows [first, first+count). */
+/* Copy halo h's survivors (h = 0 for use case 1) to host columns, rows [first, first+count): the contents of the
+ * reference's Buffers_write vectors (util.h:53-70) as filled by processLC.cpp:291-307 / :1446-1461. */
 int cc_cutout_fetch(cc_ctx* ctx, int halo, int64_t first, int64_t count, const cc_cols_out* host);
 /* Copy the survivors of ALL halos of the last cutout with one transfer per column: rows are packed halo after halo,
  * halo h at rows [sum(counts[0..h)), +counts[h]) (counts from cc_cutout_sync); `total` must be sum(counts).  With
- * hundreds of halos per pass (--haloFile) this replaces thousands of small copies. */
+ * hundreds of halos per pass (--haloFile, main.cpp:295-349) this replaces thousands of small copies; the rows are
+ * what the reference hands to its per-halo writes, processLC.cpp:1628-1697. */
 int cc_cutout_fetch_all(cc_ctx* ctx, int64_t total, const cc_cols_out* host);
 /* Device pointers to the packed survivor columns of the last cutout (valid until the next cutout call):
  * halo h occupies rows [row0, row0+count). */
