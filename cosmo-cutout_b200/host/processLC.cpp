@@ -227,10 +227,10 @@ struct CutoutFiles {
 };
 
 template <typename T>
-void print_vec(const char* label, const vector<T>& v) {
-    cout << label << ": [";
-    for (const T& e : v) cout << e << ",";
-    cout << "]" << endl;
+void print_vec(const char* label, const vector<T>& v, std::ostream& os = cout) {
+    os << label << ": [";
+    for (const T& e : v) os << e << ",";
+    os << "]" << endl;
 }
 
 void print_times(const char* name, const vector<double>& v) {
@@ -499,12 +499,14 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
             check(cc_cutout_fetch_all(g_pool.ctx[r], (int64_t)k, &o));
         });
 
-        for (int ai = 0; ai < A; ++ai) {
+        /* per halo: merge the GPUs' lists and write the column files.  A --haloFile step has hundreds of halos and
+         * twelve small files each: halos are written by a few threads at a time, each logging into its own buffer,
+         * and the buffers are printed in halo order */
+        auto write_halo = [&](int ai, std::ostream& log) -> double {
             const int h = active[(size_t)ai];
             const bool printHalo = (numHalos < 20) || (h % 100 == 0);
-            if (printHalo) cout << "\n---------- cutout at halo " << h << "----------" << endl;
-            cutout_times.push_back(duration / A);
-            start = wall_seconds();
+            if (printHalo) log << "\n---------- cutout at halo " << h << "----------" << endl;
+            const double t0 = wall_seconds();
             vector<int64_t> np_count((size_t)numranks), np_rough((size_t)numranks), np_offset((size_t)numranks);
             int64_t tot = 0, tot_rough = 0;
             for (int r = 0; r < numranks; ++r) {
@@ -515,11 +517,11 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
                 tot_rough += np_rough[(size_t)r];
             }
             if (printHalo) {
-                cout << "(" << tot_rough << ") " << tot << " total particles in (rough) cutout" << endl;
-                print_vec("rank object rough counts", np_rough);
-                print_vec("rank object counts", np_count);
-                print_vec("rank offsets", np_offset);
-                cout << "Writing files..." << endl;
+                log << "(" << tot_rough << ") " << tot << " total particles in (rough) cutout" << endl;
+                print_vec("rank object rough counts", np_rough, log);
+                print_vec("rank object counts", np_count, log);
+                print_vec("rank offsets", np_offset, log);
+                log << "Writing files..." << endl;
             }
             /* every GPU's survivors arrive ordered by (theta_u, index); a single-rank reference run orders the whole
              * step that way (:1214-1221), so merge the per-GPU lists on those keys */
@@ -550,10 +552,30 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
                 }
                 files.write_block(m, (size_t)tot, 0);
             }
-            const double wdur = wall_seconds() - start;
-            if (timeit && printHalo) cout << "write time: " << wdur << " s" << endl;
-            write_times.push_back(wdur);
+            const double wdur = wall_seconds() - t0;
+            if (timeit && printHalo) log << "write time: " << wdur << " s" << endl;
+            return wdur;
+        };
+        const int writers = std::max(1, std::min({A, 16, (int)std::thread::hardware_concurrency()}));
+        for (int a0 = 0; a0 < A; a0 += writers) {
+            const int a1 = std::min(A, a0 + writers);
+            vector<std::ostringstream> logs((size_t)(a1 - a0));
+            vector<double> wd((size_t)(a1 - a0), 0.0);
+            if (a1 - a0 == 1) {
+                wd[0] = write_halo(a0, logs[0]);
+            } else {
+                vector<std::thread> th;
+                for (int ai = a0; ai < a1; ++ai)
+                    th.emplace_back([&, ai] { wd[(size_t)(ai - a0)] = write_halo(ai, logs[(size_t)(ai - a0)]); });
+                for (auto& t : th) t.join();
+            }
+            for (int ai = a0; ai < a1; ++ai) {
+                cout << logs[(size_t)(ai - a0)].str();
+                cutout_times.push_back(duration / A);
+                write_times.push_back(wd[(size_t)(ai - a0)]);
+            }
         }
+        cout.flush();
     }
     if (timeit) { /* reference :1718-1756: arrays ready to paste into python */
         cout << endl;
