@@ -26,6 +26,20 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in L.cc_version()
 
 
+def test_header_is_plain_c_and_the_integration_stub_links(tmp_path):
+    """include/cosmo_cutout_b200.h compiles as C11 with -pedantic, and the call sequence of INTEGRATION.md section 3
+    (tests/native/abi_stub.c) links against the product library; without a GPU the stub sees cc_create fail loudly"""
+    exe = str(tmp_path / "abi_stub")
+    libdir = os.path.join(REPO, "cosmo-cutout_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(REPO, "include"),
+                           os.path.join(REPO, "tests", "native", "abi_stub.c"), "-o", exe,
+                           "-L" + libdir, "-lcosmo_cutout_b200", "-Wl,-rpath," + libdir])
+    p = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert p.returncode == 0 and "theta bounds 306000.0 320400.0" in p.stdout, p.stdout
+    if cc.lib().cc_device_count() == 0:
+        assert "cc_create without a GPU: rc=" in p.stdout and "rc=0" not in p.stdout
+
+
 def test_no_cpu_fallback_without_gpu():
     if cc.lib().cc_device_count() > 0:
         pytest.skip("a GPU is present")
