@@ -60,7 +60,7 @@ SYMBOLS = (
     "cc_comm_unique_id", "cc_comm_init", "cc_comm_init_all", "cc_exchange_counts", "cc_comm_rank", "cc_comm_size",
     "cc_comm_peer_handle", "cc_comm_peer_attach",
     "cc_shard_range", "cc_merge_order",
-    "cc_last_scan_ms", "cc_last_total_ms", "cc_launch_count", "cc_last_stats",
+    "cc_last_scan_ms", "cc_last_total_ms", "cc_launch_count", "cc_last_stats", "cc_last_stats_ex", "cc_set_option",
     "cc_debug_eval", "cc_debug_eval_host",
 )
 
@@ -124,6 +124,8 @@ def lib():
         L.cc_launch_count.restype = C.c_int64
         L.cc_launch_count.argtypes = [C.c_void_p]
         L.cc_last_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.cc_last_stats_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.cc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.cc_debug_eval.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 4
         L.cc_debug_eval_host.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 4
         _lib = L
@@ -393,6 +395,17 @@ class Context:
         out = np.zeros(4, dtype=np.int64)
         _check(lib().cc_last_stats(self._h, _ptr(out)))
         return dict(scanned=int(out[0]), candidates=int(out[1]), survivors=int(out[2]), rough=int(out[3]))
+
+    def stats_ex(self):
+        out = np.zeros(8, dtype=np.int64)
+        _check(lib().cc_last_stats_ex(self._h, _ptr(out), 8))
+        return dict(scanned=int(out[0]), candidates=int(out[1]), survivors=int(out[2]), rough=int(out[3]),
+                    nan_theta=int(out[4]), payload_resident=bool(out[5]), payload_build_ms=out[6] / 1000.0,
+                    tail_dropped=int(out[7]))
+
+    def set_option(self, key, value):
+        """cc_set_option: payload=auto|always|never, exchange=auto|nccl|peer, gather=auto|ldst|bulk"""
+        _check(lib().cc_set_option(self._h, key.encode(), value.encode()))
 
     def stream(self):
         return lib().cc_stream(self._h)

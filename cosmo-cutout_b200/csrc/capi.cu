@@ -8,7 +8,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
-#include <nccl.h> /* types and enums only; the library itself is dlopen()ed on first use */
+#include <nccl.h>
+#include <omp.h> /* types and enums only; the library itself is dlopen()ed on first use */
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -134,10 +135,7 @@ struct cc_ctx {
     cudaEvent_t ev_counts = nullptr, ev_xchg = nullptr;
     cudaStream_t xchg_stream = nullptr;
     int64_t launches = 0;
-    int k1_occupancy[2] = {0, 0};
     int64_t last_const_count = -1;
-    int gather_gx_cap = 256; /* CC_GATHER_GX */
-    int k1_drain_at = 32; /* CC_K1_DRAIN: 1 = exact path after every tile with candidates */
     int k2_occupancy[2] = {0, 0};
     bool k2c_ready = false;
     int k2c_warps = 20; /* warps of the one CTA per SM: 20 at 96 registers, no spills, 161 KB of shared memory (24 at 80
@@ -147,16 +145,25 @@ struct cc_ctx {
     int k2t_occ = 0;
     int64_t last_nrec = -1;       /* survivors of the previous use-case-2 cutout on this context */
     bool force_general = false, used_small = false;
-    unsigned int region_cap = 0; /* temp records per CTA region (use case 1) */
-    DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z, t_row;
+    unsigned int region_cap_w = 0; /* temp records per WARP region (use case 1) */
+    int gather_mode = 0;         /* use case 1 gather: 0 auto, 1 k1s_gather (plain stores), 2 k1s_gather_bulk (cp.async.bulk
+                                    stores from shared memory); cc_set_option "gather" / CC_GATHER */
+    bool gather_bulk_ready = false;
+    int k1s_occupancy[2] = {0, 0};
+    DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z;
 
     /* resident step */
     bool step_valid = false, step_owned = false;
     int64_t n = 0, index_base = 0;
     const void* col[N_IN_COLS] = {};
     DevBuf col_buf[N_IN_COLS];
-    DevBuf payload;          /* interleaved gather columns (kernels.cuh Payload), built when a step becomes resident */
+    DevBuf payload;          /* interleaved gather columns (kernels.cuh Payload): built lazily, see maybe_build_payload */
     bool payload_valid = false;
+    int payload_policy = 0;  /* 0 auto (second dense cutout on a resident step), 1 always, 2 never; cc_set_option "payload" */
+    int64_t step_last_survivors = -1; /* survivors of the previous cutout on the resident step (-1: none yet) */
+    cudaEvent_t ev_pay0 = nullptr, ev_pay1 = nullptr;
+    bool payload_timed = false;       /* the pending cutout built the payload: ev_pay0..ev_pay1 is its duration */
+    int xchg_mode = 0;       /* 0 auto (peer mailboxes when attached, else NCCL), 1 NCCL, 2 peer; cc_set_option "exchange" */
 
     /* survivors */
     DevBuf out_buf[N_OUT_COLS];
@@ -165,14 +172,26 @@ struct cc_ctx {
     /* scan scratch: [tile_state ... | ticket | result(2) ] */
     DevBuf scratch;
     /* use case 2 scratch */
-    DevBuf pre_buf, halo_buf, rec_a, rec_b, rank_buf, counts_buf;
+    DevBuf rec_a, rec_b, rank_buf, counts_buf;
     DevBuf hstate; /* use case 2 device state, one memset / one read-back: [misc 8 | counts 2H | seg H+1 | cursor 16H] u64 */
-    DevBuf bin_start_buf, bin_bits_buf, bin_items_buf; /* cell index: {first,end} per cell, occupancy bitmap, halo lists */
-    std::vector<size_t> bin_items_off; /* per launch batch: first item */
+    /* Device-resident parameters (+ cell index) of the halo sets recently cut on this context.  A processLC call cuts
+     * every step with ONE halo set, and a batch job (lc_cutout -f with several box sizes, BASELINE config 5) alternates
+     * between a few: each set is prepared once (1000 halos: ~1 ms of trigonometry + the rasterisation of the cell
+     * index) and found again by comparing the cc_halo arrays.  Least recently used set is replaced. */
+    struct HaloSet {
+        std::vector<cc_halo> key;
+        bool bins = false;
+        DevBuf pre_buf, halo_buf;
+        DevBuf bin_start_buf, bin_bits_buf, bin_items_buf; /* cell index: {first,end} per cell, occupancy bitmap, halo lists */
+        std::vector<size_t> bin_items_off;                 /* per launch batch: first item */
+        uint64_t last_use = 0;
+        void release() { pre_buf.release(); halo_buf.release(); bin_start_buf.release(); bin_bits_buf.release(); bin_items_buf.release(); key.clear(); }
+    };
+    static const int MAX_HALO_SETS = 8;
+    HaloSet halo_sets[MAX_HALO_SETS];
+    HaloSet* hs = nullptr;   /* the set of the pending cutout */
+    uint64_t halo_set_clock = 0;
     bool use_bins = false;
-    std::vector<cc_halo> index_key; /* halos the resident cell index was built for */
-    std::vector<cc_halo> params_key; /* halos whose device parameters are resident */
-    bool params_bins = false;
     int64_t rec_cap = 0;
 
     /* pinned host mirror for small read-backs */
@@ -189,6 +208,7 @@ struct cc_ctx {
     int nhalos = 0; /* of the pending/last cutout (1 for use case 1) */
     std::vector<int64_t> counts, rough, seg_begin;
     int64_t stats[4] = {};
+    int64_t nan_theta = 0;  /* use case 2: scanned particles whose un-rotated theta is NaN (see cc_last_stats_ex) */
     bool have_times = false;
 
     /* streamed step (pinned host -> HBM double buffering) */
@@ -274,55 +294,49 @@ struct Chunk {
     bool first, last;
 };
 
-/* scratch layout of use case 1:
- *   [ result: 4 x u64 | ticket u32 (+pad to 64 B) | block_state: nblocks x u64 | tile_info: ntiles x u64 |
- *     cta_used: grid x u32 ]
- * result[0] survivors so far (carried across the chunks of a streamed step), [1] pre-filter candidates,
- * [2] carry seen by the current chunk's gather, [3] max records any CTA wanted (temp-region overflow check) */
 const size_t K1_HDR = 64;
 
-typedef void (*k1_scan_fn)(const cck::ScanArgs);
-k1_scan_fn k1_scan_variant(bool vec) { return vec ? cck::k1_scan<true> : cck::k1_scan<false>; }
-
-int k1_grid_limit(cc_ctx* c, bool vec, unsigned int* out) {
-    int& occ = c->k1_occupancy[vec ? 1 : 0];
-    if (occ == 0) {
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k1_scan_variant(vec), cck::SCAN_THREADS, 0));
-        if (occ < 1) return fail(CC_ERR_CUDA, "k1_scan cannot be resident on this device");
-    }
-    *out = (unsigned int)(c->sm_count * occ);
-    return CC_OK;
-}
+/* ---- use case 1 (kernels.cuh "K1") ------------------------------------------------------------------------------
+ * scratch: [ result: 4 x u64 | ticket u32 (+pad to 64 B) | block_state: nblocks x u64 | seg_info: nseg x u64 |
+ *            seg_row: nseg x u32 ]
+ * result[0] survivors so far (carried across the chunks of a streamed step), [1] pre-filter candidates,
+ * [2] carry seen by the current chunk's gather, [3] max records any warp wanted (record-region overflow check) */
+typedef void (*k1s_scan_fn)(const cck::SegScanArgs);
+k1s_scan_fn k1s_scan_variant(bool vec) { return vec ? cck::k1s_scan<true> : cck::k1s_scan<false>; }
 
 int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
-    const unsigned long long ntiles64 = (unsigned long long)((ch.n + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
     if (ch.n > 0xfffffff0ll) return fail(CC_ERR_ARG, "chunk too large (%lld particles)", (long long)ch.n);
-    const unsigned int ntiles = (unsigned int)ntiles64;
-    const unsigned int nblocks = (ntiles + cck::TSCAN_BLOCK - 1) / cck::TSCAN_BLOCK;
+    const unsigned int ntiles = (unsigned int)((ch.n + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
+    const unsigned int nseg = (ntiles + cck::K1S_TILES - 1) / cck::K1S_TILES;
+    const unsigned int nblocks = (nseg + cck::TSCAN_BLOCK - 1) / cck::TSCAN_BLOCK;
     const bool vec = aligned16(ch.x) && aligned16(ch.y) && aligned16(ch.z);
-    unsigned int grid_max = 0;
-    int rc = k1_grid_limit(c, vec, &grid_max);
-    if (rc) return rc;
-    const unsigned int grid = std::max(1u, std::min((ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, grid_max));
-    /* scratch */
+    int& occ = c->k1s_occupancy[vec ? 1 : 0];
+    if (occ == 0) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k1s_scan_variant(vec), cck::SCAN_THREADS, 0));
+        if (occ < 1) return fail(CC_ERR_CUDA, "k1s_scan cannot be resident on this device");
+    }
+    const unsigned int grid_max = (unsigned int)(c->sm_count * occ);
+    const unsigned int grid = std::max(1u, std::min((nseg + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, grid_max));
+    const unsigned int warps_max = grid_max * cck::SCAN_WARPS, total_warps = grid * cck::SCAN_WARPS;
+    int rc;
     const size_t off_state = K1_HDR;
     const size_t off_info = off_state + ((size_t)nblocks + 8) * 8;
-    const size_t off_used = off_info + ((size_t)ntiles + 8) * 8;
-    const size_t bytes = off_used + ((size_t)grid_max + 8) * 4;
+    const size_t off_row = off_info + ((size_t)nseg + 8) * 8;
+    const size_t bytes = off_row + ((size_t)nseg + 8) * 4;
     if ((rc = c->scratch.ensure(bytes))) return rc;
-    /* temp records: one private region per CTA */
-    c->region_cap = std::max(c->region_cap, (unsigned int)(std::min<int64_t>(0x7fffffff, c->out_cap + c->out_cap / 4) / grid_max + 256));
-    const size_t temp_elems = (size_t)grid_max * c->region_cap;
-    DevBuf* temps[] = {&c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row};
+    /* records: one private region per warp */
+    c->region_cap_w = std::max(c->region_cap_w, (unsigned int)(std::min<int64_t>(0x7fffffff, c->out_cap + c->out_cap / 4) / warps_max + 256));
+    const size_t temp_elems = (size_t)warps_max * c->region_cap_w;
+    DevBuf* temps[] = {&c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
     for (DevBuf* t : temps)
         if ((rc = t->ensure(temp_elems * 4))) return rc;
     char* sp = (char*)c->scratch.p;
-    if (ch.first) CU(cudaMemsetAsync(sp, 0, off_info, c->stream));                     /* totals + ticket + block states */
-    else CU(cudaMemsetAsync(sp + 32, 0, off_info - 32, c->stream));                    /* keep the running totals */
+    if (ch.first) CU(cudaMemsetAsync(sp, 0, off_info, c->stream));       /* totals + ticket + block states */
+    else CU(cudaMemsetAsync(sp + 32, 0, off_info - 32, c->stream));      /* keep the running totals */
     unsigned long long* result = (unsigned long long*)sp;
     if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
-    if (ntiles > 0) {
-        cck::ScanArgs a;
+    if (nseg > 0) {
+        cck::SegScanArgs a;
         a.x = ch.x; a.y = ch.y; a.z = ch.z;
         a.n = ch.n;
         a.th_lo = c->p_th[0]; a.th_hi = c->p_th[1]; a.ph_lo = c->p_ph[0]; a.ph_hi = c->p_ph[1];
@@ -334,30 +348,28 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         }
         a.t_idx = (unsigned int*)c->t_idx.p; a.t_th = (float*)c->t_th.p; a.t_ph = (float*)c->t_ph.p;
         a.t_x = (float*)c->t_x.p; a.t_y = (float*)c->t_y.p; a.t_z = (float*)c->t_z.p;
-        a.region_cap = c->region_cap;
-        a.cta_used = (unsigned int*)(sp + off_used);
-        a.tile_info = (unsigned long long*)(sp + off_info);
+        a.region_cap = c->region_cap_w;
+        a.seg_info = (unsigned long long*)(sp + off_info);
         a.result = result;
+        a.nseg = nseg;
         a.ntiles = ntiles;
-        a.drain_at = (unsigned int)c->k1_drain_at;
-        k1_scan_variant(vec)<<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
+        k1s_scan_variant(vec)<<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
         CU(cudaGetLastError());
         if (ch.last) CU(cudaEventRecord(c->ev_scan1, c->stream));
 
-        cck::TileScanArgs t;
-        t.tile_info = a.tile_info;
-        t.t_row = (unsigned int*)c->t_row.p;
-        t.temp_cap = (unsigned long long)temp_elems;
+        cck::SegPrefixArgs t;
+        t.seg_info = a.seg_info;
+        t.seg_row = (unsigned int*)(sp + off_row);
         t.block_state = (unsigned long long*)(sp + off_state);
         t.ticket = (unsigned int*)(sp + 32);
         t.result = result;
-        t.ntiles = ntiles;
+        t.nseg = nseg;
         t.nblocks = nblocks;
-        cck::k1_tile_scan<<<nblocks, cck::TSCAN_THREADS, 0, c->stream>>>(t);
+        cck::k1s_seg_scan<<<nblocks, cck::TSCAN_THREADS, 0, c->stream>>>(t);
         CU(cudaGetLastError());
         if (ch.last) CU(cudaEventRecord(c->ev_counts, c->stream));
 
-        cck::GatherConstArgs g;
+        cck::SegGatherArgs g;
         g.in = c->gcols;
         /* survivor columns other than x,y,z are indexed by the chunk-local particle index */
         g.in.vx += ch.start; g.in.vy += ch.start; g.in.vz += ch.start; g.in.a += ch.start; g.in.id += ch.start;
@@ -365,19 +377,30 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         if (c->streamed && c->host_gather) g.in = cck::ColsIn{}; /* the host picks these columns itself (fetch_rows) */
         g.out = cols_out_of(c);
         g.out.theta_u = nullptr;
-        g.t_idx = a.t_idx; g.t_row = t.t_row; g.t_th = a.t_th; g.t_ph = a.t_ph;
-        g.t_x = a.t_x; g.t_y = a.t_y; g.t_z = a.t_z;
-        g.cta_used = a.cta_used;
-        g.payload = (c->streamed || !c->payload_valid) ? nullptr : (const cck::Payload*)c->payload.p + ch.start;
+        g.t_idx = a.t_idx; g.t_th = a.t_th; g.t_ph = a.t_ph; g.t_x = a.t_x; g.t_y = a.t_y; g.t_z = a.t_z;
+        g.seg_info = a.seg_info;
+        g.seg_row = t.seg_row;
         g.result = result;
-        g.region_cap = c->region_cap;
+        g.payload = (c->streamed || !c->payload_valid) ? nullptr : (const cck::Payload*)c->payload.p + ch.start;
+        g.region_cap = c->region_cap_w;
+        g.total_warps = total_warps;
+        g.nseg = nseg;
         g.cap = c->out_cap;
         g.index_base = c->index_base + ch.start;
-        /* blocks per region: sized for the survivors the last cutout on this context produced (or the output
-         * capacity on a first run); the kernel loops, so this only trades launch width against iterations */
-        const int64_t expect = c->last_const_count >= 0 ? c->last_const_count + c->last_const_count / 4 : c->out_cap;
-        const unsigned int gxg = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(c->gather_gx_cap, (expect / grid + 255) / 256));
-        cck::k1_gather<<<dim3(gxg, grid), 256, 0, c->stream>>>(g);
+        const unsigned int ggrid = (nseg + cck::K1G_SEGS - 1) / cck::K1G_SEGS;
+        /* bulk stores pay when a CTA's block of rows fills the staging buffer (measured: 3 % faster gather at 4.5 %
+         * survivors, 2x slower at 0.2 %, profiles/r02): "auto" decides on the survivors of the previous cutout */
+        const int64_t expect = c->last_const_count >= 0 ? c->last_const_count : 0;
+        const bool bulk = c->gather_mode == 2 || (c->gather_mode == 0 && expect / std::max(1u, ggrid) >= cck::K1GB_ROWS);
+        if (bulk) {
+            if (!c->gather_bulk_ready) {
+                CU(cudaFuncSetAttribute((const void*)cck::k1s_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K1GB_SMEM));
+                c->gather_bulk_ready = true;
+            }
+            cck::k1s_gather_bulk<<<ggrid, cck::K1G_THREADS, cck::K1GB_SMEM, c->stream>>>(g);
+        } else {
+            cck::k1s_gather<<<ggrid, cck::K1G_THREADS, 0, c->stream>>>(g);
+        }
         CU(cudaGetLastError());
         c->launches += 3;
     } else if (ch.last) {
@@ -422,8 +445,6 @@ int prepare_halo(cc_ctx* c) {
     const int H = (int)c->p_halos.size();
     if (c->n > 0xffffffffll) return fail(CC_ERR_ARG, "step too large for one shard (%lld particles)", (long long)c->n);
     int rc;
-    if ((rc = c->pre_buf.ensure((size_t)H * sizeof(float4)))) return rc;
-    if ((rc = c->halo_buf.ensure((size_t)H * sizeof(cck::HaloDev)))) return rc;
     if ((rc = c->hstate.ensure(hstate_elems(H) * 8))) return rc;
     if (c->rec_cap == 0) c->rec_cap = 1 << 20;
     if ((rc = c->rec_a.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
@@ -434,14 +455,25 @@ int prepare_halo(cc_ctx* c) {
 
     /* many halos: (cos theta, sin phi) cell index per launch batch (kernels.cuh, k2_cutout_halo_cells) */
     c->use_bins = H >= 8 && !getenv("CC_NO_BINS");
-    /* repeated cutouts with the same halos (and the same kernel variant) reuse the device-resident parameters and
-     * cell index: nothing is recomputed on the host (1000 halos cost ~0.3 ms of trigonometry otherwise) */
+    /* repeated cutouts with a known halo set (and the same kernel variant) reuse its device-resident parameters and
+     * cell index: nothing is recomputed on the host */
     const size_t key_bytes = c->p_halos.size() * sizeof(cc_halo);
-    const bool same_params = c->params_bins == c->use_bins && c->params_key.size() == c->p_halos.size() &&
-                             memcmp(c->params_key.data(), c->p_halos.data(), key_bytes) == 0;
-    const bool same_index = !c->use_bins || (c->index_key.size() == c->p_halos.size() &&
-                                             memcmp(c->index_key.data(), c->p_halos.data(), key_bytes) == 0);
-    if (!(same_params && same_index)) {
+    cc_ctx::HaloSet* hs = nullptr;
+    cc_ctx::HaloSet* lru = &c->halo_sets[0];
+    for (auto& e : c->halo_sets) {
+        if (e.key.size() == c->p_halos.size() && e.bins == c->use_bins && !e.key.empty() &&
+            memcmp(e.key.data(), c->p_halos.data(), key_bytes) == 0) { hs = &e; break; }
+        if (e.last_use < lru->last_use) lru = &e;
+    }
+    const bool known = hs != nullptr;
+    if (!known) hs = lru;
+    hs->last_use = ++c->halo_set_clock;
+    c->hs = hs;
+    if (!known) {
+        CU(cudaStreamSynchronize(c->stream)); /* kernels of an earlier cutout may still read the set being replaced */
+        hs->key.clear();
+        if ((rc = hs->pre_buf.ensure((size_t)H * sizeof(float4)))) return rc;
+        if ((rc = hs->halo_buf.ensure((size_t)H * sizeof(cck::HaloDev)))) return rc;
         /* host: exact + pre-filter parameters */
         std::vector<float4> pre(H);
         std::vector<cck::HaloDev> hd(H);
@@ -460,7 +492,6 @@ int prepare_halo(cc_ctx* c) {
             ccpf::uc2_bounds(s.theta_cut, s.phi_cut, p4);
             d.f_chi = p4[0]; d.f_clo = p4[1]; d.f_tlo = p4[2]; d.f_thi = p4[3];
         }
-        /* many halos: (cos theta, sin phi) cell index per launch batch (kernels.cuh, k2_cutout_halo_cells) */
         if (c->use_bins) {
             const int G = cck::K2_GRID;
             const size_t ncell = (size_t)G * G;
@@ -470,74 +501,68 @@ int prepare_halo(cc_ctx* c) {
                 ccpf::uc2_bounds_cells(c->p_halos[h].theta_rough, c->p_halos[h].phi_rough, p4);
                 pre[h] = make_float4(p4[0], p4[1], p4[2], p4[3]);
             }
-            if (!same_index) { /* rasterise every halo's window, then a counting sort into CSR lists */
-                struct Box { int c0, c1, s0, s1; };
-                auto cell_of = [G](double v) { return std::floor((v + 1.0) * (0.5 * G)); };
-                std::vector<unsigned int> starts(ncell + 1);
-                std::vector<uint2> ranges((size_t)nbatch * ncell);
-                std::vector<unsigned int> bits((size_t)nbatch * cck::K2_BITWORDS, 0u);
-                std::vector<unsigned short> items;
-                c->bin_items_off.assign((size_t)nbatch, 0);
-                for (int bi = 0; bi < nbatch; ++bi) {
-                    const int h0 = bi * cck::K2_MAX_HALOS, hn = std::min(cck::K2_MAX_HALOS, H - h0);
-                    unsigned int* st = starts.data();
-                    std::fill(starts.begin(), starts.end(), 0u);
-                    std::vector<Box> boxes((size_t)hn);
-                    for (int h = 0; h < hn; ++h) {
-                        const float4 P = pre[h0 + h];
-                        Box bx = {0, -1, 0, -1}; /* empty */
-                        if (P.y <= P.x && P.z <= P.w) {
-                            auto clampi = [G](double v) { return (int)std::max(0.0, std::min((double)G - 1, v)); };
-                            bx.c0 = clampi(cell_of(std::max<double>(P.y, -1.0)) - 1.0);
-                            bx.c1 = clampi(cell_of(std::min<double>(P.x, 1.0)) + 1.0);
-                            bx.s0 = clampi(cell_of(std::max<double>(P.z, -1.0)) - 1.0);
-                            bx.s1 = clampi(cell_of(std::min<double>(P.w, 1.0)) + 1.0);
-                        }
-                        boxes[(size_t)h] = bx;
-                        for (int ic = bx.c0; ic <= bx.c1; ++ic)
-                            for (int is = bx.s0; is <= bx.s1; ++is) st[(size_t)ic * G + is + 1] += 1;
+            /* rasterise every halo's window, then a counting sort into CSR lists */
+            struct Box { int c0, c1, s0, s1; };
+            auto cell_of = [G](double v) { return std::floor((v + 1.0) * (0.5 * G)); };
+            std::vector<unsigned int> starts(ncell + 1);
+            std::vector<uint2> ranges((size_t)nbatch * ncell);
+            std::vector<unsigned int> bits((size_t)nbatch * cck::K2_BITWORDS, 0u);
+            std::vector<unsigned short> items;
+            hs->bin_items_off.assign((size_t)nbatch, 0);
+            for (int bi = 0; bi < nbatch; ++bi) {
+                const int h0 = bi * cck::K2_MAX_HALOS, hn = std::min(cck::K2_MAX_HALOS, H - h0);
+                unsigned int* st = starts.data();
+                std::fill(starts.begin(), starts.end(), 0u);
+                std::vector<Box> boxes((size_t)hn);
+                for (int h = 0; h < hn; ++h) {
+                    const float4 P = pre[h0 + h];
+                    Box bx = {0, -1, 0, -1}; /* empty */
+                    if (P.y <= P.x && P.z <= P.w) {
+                        auto clampi = [G](double v) { return (int)std::max(0.0, std::min((double)G - 1, v)); };
+                        bx.c0 = clampi(cell_of(std::max<double>(P.y, -1.0)) - 1.0);
+                        bx.c1 = clampi(cell_of(std::min<double>(P.x, 1.0)) + 1.0);
+                        bx.s0 = clampi(cell_of(std::max<double>(P.z, -1.0)) - 1.0);
+                        bx.s1 = clampi(cell_of(std::min<double>(P.w, 1.0)) + 1.0);
                     }
-                    for (size_t i = 0; i < ncell; ++i) st[i + 1] += st[i]; /* st[i] = first item of cell i */
-                    const size_t base_item = items.size();
-                    c->bin_items_off[(size_t)bi] = base_item;
-                    items.resize(base_item + st[ncell]);
-                    std::vector<unsigned int> fill(st, st + ncell);
-                    for (int h = 0; h < hn; ++h) {
-                        const Box& bx = boxes[(size_t)h];
-                        for (int ic = bx.c0; ic <= bx.c1; ++ic)
-                            for (int is = bx.s0; is <= bx.s1; ++is) items[base_item + fill[(size_t)ic * G + is]++] = (unsigned short)h;
-                    }
-                    uint2* rg = ranges.data() + (size_t)bi * ncell;
-                    unsigned int* bw = bits.data() + (size_t)bi * cck::K2_BITWORDS;
-                    for (int ic = 0; ic < G; ++ic)
-                        for (int is = 0; is < G; ++is) {
-                            const size_t cell = (size_t)ic * G + is;
-                            rg[cell] = make_uint2(st[cell], st[cell + 1]);
-                            if (st[cell + 1] > st[cell]) {
-                                const unsigned int bit = (unsigned int)(ic >> cck::K2_CSHIFT) * cck::K2_COARSE + (unsigned int)(is >> cck::K2_CSHIFT);
-                                bw[bit >> 5] |= 1u << (bit & 31u);
-                            }
-                        }
+                    boxes[(size_t)h] = bx;
+                    for (int ic = bx.c0; ic <= bx.c1; ++ic)
+                        for (int is = bx.s0; is <= bx.s1; ++is) st[(size_t)ic * G + is + 1] += 1;
                 }
-                if ((rc = c->bin_start_buf.ensure(ranges.size() * sizeof(uint2)))) return rc;
-                if ((rc = c->bin_bits_buf.ensure(bits.size() * 4))) return rc;
-                if ((rc = c->bin_items_buf.ensure(std::max<size_t>(items.size(), 8) * 2))) return rc;
-                CU(cudaMemcpyAsync(c->bin_start_buf.p, ranges.data(), ranges.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
-                CU(cudaMemcpyAsync(c->bin_bits_buf.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, c->stream));
-                if (!items.empty())
-                    CU(cudaMemcpyAsync(c->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
-                CU(cudaStreamSynchronize(c->stream)); /* `ranges`/`bits`/`items` are pageable and die here */
-                c->index_key = c->p_halos;
+                for (size_t i = 0; i < ncell; ++i) st[i + 1] += st[i]; /* st[i] = first item of cell i */
+                const size_t base_item = items.size();
+                hs->bin_items_off[(size_t)bi] = base_item;
+                items.resize(base_item + st[ncell]);
+                std::vector<unsigned int> fill(st, st + ncell);
+                for (int h = 0; h < hn; ++h) {
+                    const Box& bx = boxes[(size_t)h];
+                    for (int ic = bx.c0; ic <= bx.c1; ++ic)
+                        for (int is = bx.s0; is <= bx.s1; ++is) items[base_item + fill[(size_t)ic * G + is]++] = (unsigned short)h;
+                }
+                uint2* rg = ranges.data() + (size_t)bi * ncell;
+                unsigned int* bw = bits.data() + (size_t)bi * cck::K2_BITWORDS;
+                for (int ic = 0; ic < G; ++ic)
+                    for (int is = 0; is < G; ++is) {
+                        const size_t cell = (size_t)ic * G + is;
+                        rg[cell] = make_uint2(st[cell], st[cell + 1]);
+                        if (st[cell + 1] > st[cell]) {
+                            const unsigned int bit = (unsigned int)(ic >> cck::K2_CSHIFT) * cck::K2_COARSE + (unsigned int)(is >> cck::K2_CSHIFT);
+                            bw[bit >> 5] |= 1u << (bit & 31u);
+                        }
+                    }
             }
+            if ((rc = hs->bin_start_buf.ensure(ranges.size() * sizeof(uint2)))) return rc;
+            if ((rc = hs->bin_bits_buf.ensure(bits.size() * 4))) return rc;
+            if ((rc = hs->bin_items_buf.ensure(std::max<size_t>(items.size(), 8) * 2))) return rc;
+            CU(cudaMemcpyAsync(hs->bin_start_buf.p, ranges.data(), ranges.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(hs->bin_bits_buf.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            if (!items.empty())
+                CU(cudaMemcpyAsync(hs->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
         }
-        /* pageable -> device copies are staged by the runtime before returning, so the vectors may die; repeated
-         * cutouts with the same halos (and the same kernel variant) skip the upload */
-        if (!same_params) {
-            CU(cudaMemcpyAsync(c->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(c->halo_buf.p, hd.data(), (size_t)H * sizeof(cck::HaloDev), cudaMemcpyHostToDevice, c->stream));
-            c->params_key = c->p_halos;
-            c->params_bins = c->use_bins;
-        }
+        CU(cudaMemcpyAsync(hs->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(hs->halo_buf.p, hd.data(), (size_t)H * sizeof(cck::HaloDev), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream)); /* the host vectors are pageable and die here */
+        hs->key = c->p_halos;
+        hs->bins = c->use_bins;
     }
     CU(cudaMemsetAsync(c->hstate.p, 0, hstate_elems(H) * 8, c->stream));
     return CC_OK;
@@ -558,13 +583,14 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         a.local_base = ch.start;
         a.nhalos = std::min(cck::K2_MAX_HALOS, H - h0);
         a.halo0 = h0;
-        a.pre = (const float4*)c->pre_buf.p + h0;
-        a.halos = (const cck::HaloDev*)c->halo_buf.p + h0;
+        a.pre = (const float4*)c->hs->pre_buf.p + h0;
+        a.halos = (const cck::HaloDev*)c->hs->halo_buf.p + h0;
         a.recs = (cck::Rec*)c->rec_a.p;
         a.rec_cap = (unsigned long long)c->rec_cap;
         a.rec_count = rec_count;
         a.counts = hs_counts(c);
         a.n_cand = n_cand;
+        a.nan_count = rec_count + 5;
         a.total_halos = H;
         a.ntiles = (unsigned int)((n_scan + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
         const size_t pre_bytes = (size_t)a.nhalos * sizeof(float4);
@@ -579,9 +605,9 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             cck::HaloBinArgs b;
             b.h = a;
             const int bi = h0 / cck::K2_MAX_HALOS;
-            b.cell_range = (const uint2*)c->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID);
-            b.cell_bits = (const unsigned int*)c->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
-            b.cell_items = (const unsigned short*)c->bin_items_buf.p + c->bin_items_off[(size_t)bi];
+            b.cell_range = (const uint2*)c->hs->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID);
+            b.cell_bits = (const unsigned int*)c->hs->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
+            b.cell_items = (const unsigned short*)c->hs->bin_items_buf.p + c->hs->bin_items_off[(size_t)bi];
             if (!c->k2c_ready) {
                 const void* fns[6] = {(const void*)cck::k2_cutout_halo_cells<true, 24>, (const void*)cck::k2_cutout_halo_cells<false, 24>,
                                       (const void*)cck::k2_cutout_halo_cells<true, 20>, (const void*)cck::k2_cutout_halo_cells<false, 20>,
@@ -710,9 +736,12 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
 }
 
 /* ---------------------------------------------------------------- whole-step drivers */
+int maybe_build_payload(cc_ctx* c);
+
 int run_resident(cc_ctx* c) {
     int rc = (c->pending == P_CONST) ? prepare_const(c) : prepare_halo(c);
     if (rc) return rc;
+    if ((rc = maybe_build_payload(c))) return rc;
     c->gcols = cols_in_of(c);
     Chunk ch;
     ch.x = c->gcols.x; ch.y = c->gcols.y; ch.z = c->gcols.z;
@@ -762,29 +791,46 @@ int run_streamed(cc_ctx* c) {
 
 int run_pending(cc_ctx* c) { return c->streamed ? run_streamed(c) : run_resident(c); }
 
-/* interleave the seven gather-only columns of the resident step (kernels.cuh, "gather payload") */
-int build_payload(cc_ctx* c) {
-    c->payload_valid = false;
-    if (getenv("CC_NO_PAYLOAD") || c->n == 0) return CC_OK;
-    cudaError_t e = cudaSuccess;
+/* Interleave the seven gather-only columns of the resident step (kernels.cuh, "gather payload").
+ * Costs one pass over 64 B/particle (1.46 ms per 100 M particles) and 32 B/particle of HBM, so it is built LAZILY, inside
+ * the cutout call that first profits from it (its time lands in that cutout): policy "auto" builds it when the previous
+ * cutout on this resident step left at least max(65536, n/512) survivors -- a sparse cutout (a cluster-sized halo: a
+ * few hundred survivors) never pays for it and gathers from the caller's columns instead; "always"/"never" force it
+ * (cc_set_option "payload", or CC_PAYLOAD / CC_NO_PAYLOAD in the environment). */
+int maybe_build_payload(cc_ctx* c) {
+    if (c->payload_valid || c->streamed || c->n == 0 || c->payload_policy == 2) return CC_OK;
+    if (c->payload_policy == 0) {
+        const int64_t need = std::max<int64_t>(65536, c->n / 512);
+        if (c->step_last_survivors < need) return CC_OK;
+    }
     if (c->payload.bytes < (size_t)c->n * sizeof(cck::Payload)) {
         c->payload.release();
-        e = cudaMalloc(&c->payload.p, (size_t)c->n * sizeof(cck::Payload));
+        const cudaError_t e = cudaMalloc(&c->payload.p, (size_t)c->n * sizeof(cck::Payload));
         if (e != cudaSuccess) { /* not enough HBM for the extra 32 B/particle: gather from the columns instead */
             cudaGetLastError();
             c->payload.p = nullptr;
+            c->payload_policy = 2;
             return CC_OK;
         }
         c->payload.bytes = (size_t)c->n * sizeof(cck::Payload);
     }
     const cck::ColsIn ci = cols_in_of(c);
     const int with_vel = (ci.vx && ci.vy && ci.vz && ci.rot && ci.rep) ? 1 : 0;
+    CU(cudaEventRecord(c->ev_pay0, c->stream));
     cck::k_build_payload<<<c->sm_count * 8, 256, 0, c->stream>>>(ci, (cck::Payload*)c->payload.p, c->n, with_vel);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(c->ev_pay1, c->stream));
     c->launches += 1;
     c->payload_valid = true;
+    c->payload_timed = true;
     return CC_OK;
+}
+
+/* a new step became resident */
+void reset_step_state(cc_ctx* c) {
+    c->payload_valid = false;
+    c->step_last_survivors = -1;
+    c->payload_timed = false;
 }
 
 int check_sm100(int device, int* sm_count) {
@@ -827,13 +873,15 @@ int cc_create(int device, cc_ctx** out) {
     CU(cudaSetDevice(device));
     cc_ctx* c = new cc_ctx();
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
-    if (const char* e = getenv("CC_GATHER_GX")) c->gather_gx_cap = std::max(1, std::min(1024, atoi(e)));
-    if (const char* e = getenv("CC_K1_DRAIN")) c->k1_drain_at = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("CC_GATHER")) c->gather_mode = !strcmp(e, "bulk") ? 2 : !strcmp(e, "ldst") ? 1 : 0;
+    if (getenv("CC_NO_PAYLOAD")) c->payload_policy = 2;
+    if (const char* e = getenv("CC_PAYLOAD")) c->payload_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
     c->device = device;
     c->sm_count = sms;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_scan0) != cudaSuccess || cudaEventCreate(&c->ev_scan1) != cudaSuccess ||
         cudaEventCreate(&c->ev_total1) != cudaSuccess ||
+        cudaEventCreate(&c->ev_pay0) != cudaSuccess || cudaEventCreate(&c->ev_pay1) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_xchg, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->xchg_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -857,10 +905,10 @@ void cc_destroy(cc_ctx* c) {
     for (auto& b : c->col_buf) b.release();
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
-    DevBuf* rest[] = {&c->scratch, &c->pre_buf, &c->halo_buf, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
-                      &c->hstate, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z, &c->t_row,
-                      &c->bin_start_buf, &c->bin_bits_buf, &c->bin_items_buf};
+    DevBuf* rest[] = {&c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
+                      &c->hstate, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
     for (DevBuf* b : rest) b->release();
+    for (auto& e : c->halo_sets) e.release();
     for (auto& sl : c->stage) for (auto& b : sl) b.release();
     for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -871,6 +919,8 @@ void cc_destroy(cc_ctx* c) {
     if (c->ev_xchg) cudaEventDestroy(c->ev_xchg);
     if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
     if (c->ev_total1) cudaEventDestroy(c->ev_total1);
+    if (c->ev_pay0) cudaEventDestroy(c->ev_pay0);
+    if (c->ev_pay1) cudaEventDestroy(c->ev_pay1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -896,7 +946,7 @@ int cc_step_release(cc_ctx* c) {
     CU(cudaStreamSynchronize(c->stream));
     for (auto& b : c->col_buf) b.release();
     c->payload.release();
-    c->payload_valid = false;
+    reset_step_state(c);
     for (auto& p : c->col) p = nullptr;
     c->step_valid = false;
     c->step_owned = false;
@@ -922,7 +972,8 @@ int cc_step_upload(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_b
     c->step_valid = true;
     c->step_owned = true;
     c->pending = P_NONE;
-    return build_payload(c);
+    reset_step_state(c);
+    return CC_OK;
 }
 
 int cc_step_attach(cc_ctx* c, int64_t n, const cc_cols_in* dev, int64_t index_base) {
@@ -935,9 +986,8 @@ int cc_step_attach(cc_ctx* c, int64_t n, const cc_cols_in* dev, int64_t index_ba
     c->step_valid = true;
     c->step_owned = false;
     c->pending = P_NONE;
-    int rc = use_device(c);
-    if (rc) return rc;
-    return build_payload(c);
+    reset_step_state(c);
+    return use_device(c);
 }
 
 int cc_step_synth(cc_ctx* c, int64_t n, uint64_t seed, int64_t index_base, int kind, float box) {
@@ -960,13 +1010,18 @@ int cc_step_synth(cc_ctx* c, int64_t n, uint64_t seed, int64_t index_base, int k
     c->step_valid = true;
     c->step_owned = true;
     c->pending = P_NONE;
-    return build_payload(c);
+    reset_step_state(c);
+    return CC_OK;
 }
 
 int cc_synth_host(int64_t n, uint64_t seed, int64_t index_base, int kind, float box, float* x, float* y, float* z,
                   float* vx, float* vy, float* vz, float* a, int64_t* id, int32_t* rotation, int32_t* replication) {
     if (n < 0 || !x || !y || !z) return fail(CC_ERR_ARG, "cc_synth_host: bad argument");
-#pragma omp parallel for schedule(static)
+    /* launchers such as torchrun pin OMP_NUM_THREADS to 1: CC_HOST_THREADS overrides */
+    int nt = 0;
+    if (const char* e = getenv("CC_HOST_THREADS")) nt = std::max(1, atoi(e));
+    if (nt <= 0) nt = std::max(1, omp_get_max_threads());
+#pragma omp parallel for schedule(static) num_threads(nt)
     for (int64_t i = 0; i < n; ++i) {
         float fx, fy, fz, fvx, fvy, fvz, fa;
         long long fid;
@@ -1015,6 +1070,7 @@ int cc_cutout_const(cc_ctx* c, const float theta_cut[2], const float phi_cut[2])
     c->pending = P_CONST;
     c->synced = false;
     c->streamed = false;
+    c->payload_timed = false;
     return run_pending(c);
 }
 
@@ -1032,6 +1088,7 @@ int cc_cutout_halo(cc_ctx* c, int nhalos, const cc_halo* halos, int pos_only, in
     c->pending = P_HALO;
     c->synced = false;
     c->streamed = false;
+    c->payload_timed = false;
     if (nhalos == 0) { c->counts.clear(); c->rough.clear(); c->seg_begin.assign(1, 0); c->synced = true; return CC_OK; }
     return run_pending(c);
 }
@@ -1047,19 +1104,22 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
                 CU(cudaStreamSynchronize(c->stream));
                 const int64_t k = (int64_t)c->h_small[0];
                 const uint64_t max_used = c->h_small[3];
-                if (k <= c->out_cap && max_used <= c->region_cap) break;
+                unsigned int& region_cap = c->region_cap_w;
+                if (k <= c->out_cap && max_used <= region_cap) break;
                 if (attempt == 3) return fail(CC_ERR_CUDA, "internal: survivor buffers still too small after regrowth");
                 /* survivors exceeded the output rows or a CTA's temp region: grow to what was needed, run again */
                 if (k > c->out_cap && (rc = ensure_out_cap(c, k + k / 64))) return rc;
-                if (max_used > c->region_cap) c->region_cap = (unsigned int)std::min<uint64_t>(0xfffffff0u, max_used + max_used / 8 + 256);
+                if (max_used > region_cap) region_cap = (unsigned int)std::min<uint64_t>(0xfffffff0u, max_used + max_used / 8 + 256);
                 if ((rc = run_pending(c))) return rc;
             }
             c->counts.assign(1, (int64_t)c->h_small[0]);
             c->last_const_count = c->counts[0];
+            if (!c->streamed) c->step_last_survivors = c->counts[0];
             c->rough.assign(1, 0);
             c->seg_begin.assign(2, 0);
             c->seg_begin[1] = c->counts[0];
             c->stats[0] = c->n; c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = c->counts[0]; c->stats[3] = 0;
+            c->nan_theta = 0;
         } else {
             const int H = c->nhalos;
             for (int attempt = 0; attempt < 4; ++attempt) {
@@ -1074,6 +1134,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             }
             const int64_t nrec = (int64_t)c->h_small[0];
             c->last_nrec = nrec;
+            if (!c->streamed) c->step_last_survivors = nrec;
             c->force_general = false;
             c->counts.resize(H); c->rough.resize(H); c->seg_begin.resize(H + 1);
             int64_t tot = 0, tot_rough = 0;
@@ -1085,6 +1146,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             for (int h = 0; h <= H; ++h) c->seg_begin[h] = (int64_t)c->h_small[8 + 2 * H + h];
             if (tot != nrec) return fail(CC_ERR_CUDA, "internal: record count %lld != sum of halo counts %lld", (long long)nrec, (long long)tot);
             c->stats[0] = halo_scan_limit(c); c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = tot; c->stats[3] = tot_rough;
+            c->nan_theta = (int64_t)c->h_small[5];
         }
         c->synced = true;
     }
@@ -1229,6 +1291,7 @@ int begin_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_b
     c->index_base = index_base;
     c->streamed = true;
     c->synced = false;
+    c->payload_timed = false;
     return CC_OK;
 }
 }  // namespace
@@ -1406,7 +1469,9 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, xs));
     }
     const void* send = (c->pending == P_CONST) ? c->counts_buf.p : (const void*)hs_counts(c);
-    const bool peer_path = c->peers_ready && R > 1 && 2 * H <= cck::XCHG_PAYLOAD && !getenv("CC_NO_PEER_XCHG");
+    if (c->xchg_mode == 2 && R > 1 && !(c->peers_ready && 2 * H <= cck::XCHG_PAYLOAD))
+        return fail(CC_ERR_STATE, "cc_exchange_counts: exchange=peer but no mailboxes are attached (or more than %d halos)", cck::XCHG_PAYLOAD / 2);
+    const bool peer_path = c->peers_ready && R > 1 && 2 * H <= cck::XCHG_PAYLOAD && c->xchg_mode != 1 && !getenv("CC_NO_PEER_XCHG");
     unsigned long long* hg = c->h_small + hg_off;
     unsigned long long* d_status = (unsigned long long*)((char*)c->gather_buf.p + (size_t)R * 2 * H * 8);
     CU(cudaMemsetAsync(d_status, 0, 8, xs));
@@ -1425,7 +1490,7 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         cck::k4_exchange_peer<<<1, 256, 0, xs>>>(x);
         CU(cudaGetLastError());
     } else {
-        if (c->comm) {
+        if (c->comm && R > 1) {
             NC(g_nccl.AllGather(send, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, xs));
         } else {
             if (R > 1) return fail(CC_ERR_STATE, "cc_exchange_counts: %d ranks but neither an NCCL communicator nor peer mailboxes for %d halos", R, H);
@@ -1520,6 +1585,44 @@ int cc_last_stats(cc_ctx* c, int64_t out[4]) {
     if (!c || !out) return fail(CC_ERR_ARG, "bad argument");
     if (!c->synced) return fail(CC_ERR_STATE, "no synced cutout");
     for (int i = 0; i < 4; ++i) out[i] = c->stats[i];
+    return CC_OK;
+}
+
+int cc_last_stats_ex(cc_ctx* c, int64_t* out, int n) {
+    if (!c || !out || n < 0) return fail(CC_ERR_ARG, "bad argument");
+    if (!c->synced) return fail(CC_ERR_STATE, "no synced cutout");
+    int64_t v[CC_STATS_EX_FIELDS] = {};
+    for (int i = 0; i < 4; ++i) v[i] = c->stats[i];
+    v[4] = c->nan_theta;
+    v[5] = c->payload_valid ? 1 : 0;
+    if (c->payload_timed) {
+        cudaSetDevice(c->device);
+        float ms = 0.0f;
+        if (cudaStreamSynchronize(c->stream) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev_pay0, c->ev_pay1) == cudaSuccess)
+            v[6] = (int64_t)(ms * 1000.0f);
+        else cudaGetLastError();
+    }
+    v[7] = (c->pending == P_HALO) ? c->n - c->stats[0] : 0;
+    for (int i = 0; i < n && i < CC_STATS_EX_FIELDS; ++i) out[i] = v[i];
+    return CC_OK;
+}
+
+int cc_set_option(cc_ctx* c, const char* key, const char* value) {
+    if (!c || !key || !value) return fail(CC_ERR_ARG, "cc_set_option: bad argument");
+    const std::string k = key, v = value;
+    if (k == "payload") {
+        if (v == "auto") c->payload_policy = 0; else if (v == "always") c->payload_policy = 1;
+        else if (v == "never") c->payload_policy = 2; else return fail(CC_ERR_ARG, "cc_set_option: payload = auto|always|never");
+        if (c->payload_policy == 2 && c->pending == P_NONE) c->payload_valid = false;
+    } else if (k == "exchange") {
+        if (v == "auto") c->xchg_mode = 0; else if (v == "nccl") c->xchg_mode = 1; else if (v == "peer") c->xchg_mode = 2;
+        else return fail(CC_ERR_ARG, "cc_set_option: exchange = auto|nccl|peer");
+    } else if (k == "gather") {
+        if (v == "auto") c->gather_mode = 0; else if (v == "ldst") c->gather_mode = 1; else if (v == "bulk") c->gather_mode = 2;
+        else return fail(CC_ERR_ARG, "cc_set_option: gather = auto|ldst|bulk");
+    } else {
+        return fail(CC_ERR_ARG, "cc_set_option: unknown key '%s'", key);
+    }
     return CC_OK;
 }
 

@@ -1,9 +1,9 @@
 /*
  * kernels.cuh -- sm_100a kernels of the lightcone cutout path.
  *
- *   k1_scan / k1_tile_scan / k1_gather
+ *   k1s_scan / k1s_seg_scan / k1s_gather (+ _bulk)
  *                     use case 1: octant test -> pre-filter -> exact (theta,phi) -> strict window test ->
- *                     ballot/popc compaction into per-CTA temp regions; exclusive scan of the tile counts by
+ *                     ballot/popc compaction into per-warp record regions; exclusive scan of the segment counts by
  *                     decoupled look-back; order-preserving 12-column gather.   replaces processLC.cpp:276-310
  *   k2_cutout_halo (+ _cells, _tma)
  *                     use case 2: one pass over x,y,z for a batch of halos: pre-filter -> exact un-rotated
@@ -143,47 +143,14 @@ __device__ __forceinline__ unsigned int load_tile(const float* __restrict__ x, c
 /* index inside the tile of element j of this lane */
 __device__ __forceinline__ unsigned int tile_local(int lane, int j) { return (unsigned)((j >> 2) * 128 + 4 * lane + (j & 3)); }
 
-/* ================================================================================================
- * K1  use case 1, three phases
- *
- *   k1_scan       the bandwidth-bound pass.  Every warp owns tiles of 256 consecutive particles and runs the whole
- *                 chain for a tile by itself: coalesced float4 loads of x,y,z -> pre-filter -> ballot/popc
- *                 compaction of the candidates into the warp's shared-memory queue -> exact reference arithmetic
- *                 on the queued candidates -> ballot/popc compaction of the survivors -> (index, theta, phi)
- *                 records appended to the CTA's private region of a temp buffer (shared-memory cursor, no global
- *                 atomics) + one 8-byte (position, count) word per tile.  No block barrier, no inter-tile wait:
- *                 a warp stalled in the fp64 divide chain never holds up the loads of the other 31 warps of its SM.
- *   k1_tile_scan  exclusive scan of the per-tile counts: single pass, decoupled look-back across blocks.
- *   k1_gather     one thread per survivor record: row = carry + the row k1_tile_scan wrote -> 12-column gather,
- *                 survivors stay in input order (processLC.cpp:291-307).
- *
- * (A first version chained the look-back through the particle tiles themselves; with 3 KB tiles the chain can
- *  only advance ~32 tiles per L2 round trip and capped the pass at ~14 % of HBM bandwidth -- profiles/r01.)
- * ================================================================================================ */
-struct ScanArgs {
-    const float *x, *y, *z;
-    long long n;                      /* particles in this chunk */
-    float th_lo, th_hi, ph_lo, ph_hi; /* exact, strict (processLC.cpp:287-288) */
-    float chi2, nclo2, ntlo, thi;     /* pre-filter (prefilter.h): chi2, -clo2, -tlo, thi */
-    unsigned int* t_idx;              /* temp records: particle index inside the chunk */
-    float *t_th, *t_ph;               /*               theta, phi (arcsec) */
-    float *t_x, *t_y, *t_z;           /*               the position (already in registers here: saves three
-                                                       scattered 4-byte reads per survivor in the gather) */
-    unsigned int region_cap;          /* records per CTA region */
-    unsigned int* cta_used;           /* [grid] records the CTA appended (> region_cap means overflow) */
-    unsigned long long* tile_info;    /* [ntiles] (temp position << 32) | survivors of the tile */
-    unsigned long long* result;       /* [1] += pre-filter candidates, [3] = max records any CTA wanted */
-    unsigned int ntiles;
-    unsigned int drain_at;            /* queued candidates that trigger the exact path (32 = a full warp) */
-};
-
 /* Branch-free on purpose: eight of these run back to back per lane and divergent early-outs cost more than the
  * arithmetic they skip.  Each window condition is turned into a difference by ONE fma -- fma(a,b,-c) has exactly the
  * sign of a*b - c, so `d > 0` is the exact comparison a*b > c -- and the four differences are reduced with min, so the
  * whole window is one compare instead of four compare+select pairs (the compiler has 7 predicate registers for 8
  * particles x 7 conditions).  A NaN difference is dropped by min, which can only ADD candidates; the exact path
  * rejects them (the reference's x>0 && y>0 && z>0 is false for a NaN). */
-__device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const ScanArgs& a) {
+template <class Args>
+__device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const Args& a) {
     const float mn = fminf(x, fminf(y, z));
     const float r2 = fmaf(z, z, fmaf(y, y, x * x));
     const float z2 = z * z;
@@ -197,177 +164,157 @@ __device__ __forceinline__ bool k1_prefilter(float x, float y, float z, const Sc
     return sane ? (score > 0.0f) : (mn > 0.0f); /* mn > 0 is the octant test, processLC.cpp:279 */
 }
 
-/* Per-warp candidate queue, kept ACROSS tiles: the exact path costs ~1000 warp instructions whether 1 or 32 lanes
- * are active, and a narrow window leaves 0-2 candidates per tile, so candidates are batched until a warp's worth is
- * queued and only then run through the exact arithmetic (whole tiles only, so that every tile's records stay
- * contiguous in the temp region).  The queue is deliberately small: shared memory is carved out of the same 228 KB
- * as the L1 that buffers the in-flight streaming loads, and the scan slows down measurably when the L1 share
- * shrinks (profiles/r01: 40 -> 52 KB of shared memory per CTA cost 9 % of the bandwidth).  Tiles with more
- * candidates than the queue can take go through k1_dense_tile instead. */
-constexpr int K1_QCAP = 160;                /* drained once 32 are queued: at most 31 + K1_QMAX_TILE */
-constexpr int K1_QMAX_TILE = K1_QCAP - 32;  /* candidates one tile may queue */
-constexpr int K1_QTILES = 34;               /* tiles per batch: each contributes >= 1 of the < 32 queued, + 1 tile */
-struct K1WarpQueue {
-    float x[K1_QCAP], y[K1_QCAP], z[K1_QCAP], th[K1_QCAP], ph[K1_QCAP];
-    unsigned short where[K1_QCAP];          /* (slot of the tile in tile_id[] << 8) | index inside the tile */
-    unsigned int tile_id[K1_QTILES];        /* tiles of the batch, in processing order */
-    unsigned short tile_q[K1_QTILES];       /* queue offset of each tile's first candidate */
-};
+constexpr int TSCAN_THREADS = 256;
+constexpr int TSCAN_ITEMS = 16; /* tiles per thread */
+constexpr int TSCAN_BLOCK = TSCAN_THREADS * TSCAN_ITEMS;
+constexpr unsigned long long TS_AGG = 1ull << 62;
+constexpr unsigned long long TS_PREFIX = 2ull << 62;
+constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
 
-/* use case 1 membership + angles of one particle: the reference's arithmetic (processLC.cpp:279-288) */
-__device__ __forceinline__ bool k1_exact(const ScanArgs& a, float x, float y, float z, float& th, float& ph) {
+/* ================================================================================================
+ * K1  use case 1, three phases; the unit of ORDER is a segment of K1S_TILES consecutive 256-particle tiles that one
+ *     warp streams front to back (segments are dealt round-robin to the warps)
+ *
+ *   k1s_scan     the bandwidth-bound pass.  Per tile: coalesced float4 loads of x,y,z -> branch-free pre-filter ->
+ *                candidates appended in input order to the warp's shared-memory ring (position + index).  Whenever 32
+ *                are queued the OLDEST 32 take the exact reference arithmetic, one per lane -- always a full warp,
+ *                whatever the tile boundaries (the exact path costs the same ~210 warp instructions for 1 lane as for
+ *                32).  Survivors are appended as (index, theta, phi, x, y, z) records to the WARP's private region of a
+ *                temp buffer through a cursor the warp owns (no atomics); the ring is first-in-first-out, so the records
+ *                of a segment are consecutive there and in input order.  Segment boundaries are found by comparing the
+ *                segment of neighbouring lanes: the lane that holds the first candidate of a segment closes the
+ *                previous one: seg_info[segment] = (first record in the region, survivor count).  No block barrier,
+ *                no inter-warp wait.
+ *   k1s_seg_scan exclusive scan of the segment counts (one 8-byte word per 2048 particles): single pass, decoupled
+ *                look-back across blocks.
+ *   k1s_gather   a CTA owns K1G_SEGS consecutive segments = a contiguous block of OUTPUT rows; thread i of the block
+ *                fetches the record of row i (consecutive inside a segment: coalesced), the survivor's 32-byte payload,
+ *                and writes row i of all 12 columns (coalesced; processLC.cpp:291-307).  k1s_gather_bulk is the same
+ *                kernel with the rows staged in shared memory and written by the bulk-copy engine
+ *                (cp.async.bulk shared -> global).
+ *
+ * History (profiles/r01, profiles/r02): a first version chained the look-back through the particle tiles themselves and
+ * was capped at 14 % of the HBM bandwidth by the chain; round 1 ordered by TILE (per-CTA record regions, a scan over
+ * 2 M tile counts, one row index per record): at 4.5 % survivors it spent 525 warp instructions per tile where the
+ * arithmetic needs ~200 (a second, almost empty round of the exact path per drain, per-tile bookkeeping).
+ * ================================================================================================ */
+constexpr int K1S_TILES = 8;                                  /* tiles per segment */
+constexpr int K1S_SEG = K1S_TILES * SCAN_TILE;                /* particles per segment (2048) */
+constexpr int K1S_SEG_SHIFT = 11;
+static_assert((1 << K1S_SEG_SHIFT) == K1S_SEG, "segment of a particle = index >> K1S_SEG_SHIFT");
+constexpr int K1S_QCAP = 256;                                 /* ring entries per warp: < 32 waiting + up to 128 per half tile */
+static_assert((K1S_QCAP & (K1S_QCAP - 1)) == 0 && K1S_QCAP >= 31 + SCAN_TILE / 2, "ring size");
+
+struct SegScanArgs {
+    const float *x, *y, *z;
+    long long n;                      /* particles in this chunk */
+    float th_lo, th_hi, ph_lo, ph_hi; /* exact, strict (processLC.cpp:287-288) */
+    float chi2, nclo2, ntlo, thi;     /* pre-filter (prefilter.h) */
+    unsigned int* t_idx;              /* records: particle index inside the chunk, theta, phi, position */
+    float *t_th, *t_ph, *t_x, *t_y, *t_z;
+    unsigned int region_cap;          /* records per WARP region */
+    unsigned long long* seg_info;     /* [nseg] (first record inside the warp's region << 32) | survivors */
+    unsigned long long* result;       /* [1] += pre-filter candidates, [3] = max records any warp wanted */
+    unsigned int nseg, ntiles;
+};
+/* The ring keeps the candidate's position, not only its index: reading x,y,z again in the drain was measured (an
+ * index-only ring, 8 KB instead of 32 KB per CTA): the streaming loads are evict-first, the re-reads missed the L2 and
+ * cost 4 GB of extra DRAM traffic on 500 M particles at 4.5 % survivors (profiles/r02). */
+struct __align__(16) K1SRing {
+    unsigned int idx[K1S_QCAP];       /* particle index inside the chunk */
+    float x[K1S_QCAP], y[K1S_QCAP], z[K1S_QCAP];
+};
+struct K1SState {                     /* warp-uniform, in shared memory so that the drain can be a real call */
+    unsigned int head, count;         /* ring */
+    unsigned int cursor;              /* records this warp has appended */
+    unsigned int open_seg, open_start;/* segment whose records are being appended, and its first record */
+    unsigned int n_cand;              /* pre-filter candidates (statistics); < 2^32 per warp */
+};
+constexpr unsigned int K1S_NONE = 0xffffffffu;
+
+__device__ __forceinline__ bool k1s_exact(const SegScanArgs& a, float x, float y, float z, float& th, float& ph) {
     if (!(x > 0.0f && y > 0.0f && z > 0.0f)) return false; /* :279 */
     th = ccref::theta_arcsec(x, y, z);                       /* :282-283 */
     ph = ccref::phi_arcsec_plain(x, y);                      /* :284 */
     return th > a.th_lo && th < a.th_hi && ph > a.ph_lo && ph < a.ph_hi; /* :287-288 */
 }
 
-/* warp-collective: exact test of the queued candidates, survivors -> CTA temp region, (position,count) per tile.
- * noinline: called from one hot and one cold site; `a` points at the __grid_constant__ kernel parameter */
-__device__ __noinline__ void k1_drain(const ScanArgs* __restrict__ ap, K1WarpQueue* __restrict__ qp, unsigned int nent,
-                                      unsigned int ntile_b, unsigned int* s_cursor, unsigned long long region0) {
-    const ScanArgs& a = *ap;
-    K1WarpQueue& q = *qp;
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    const unsigned int lane_lt = (1u << lane) - 1u;
-    constexpr int NW = K1_QCAP / 32;
-    unsigned int bits[NW];
-    unsigned int K = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        bits[w] = 0;
-        if ((unsigned)(w * 32) < nent) { /* warp-uniform */
-            const unsigned int j = w * 32 + lane;
-            bool pass = false;
-            if (j < nent) {
-                float th, ph;
-                pass = k1_exact(a, q.x[j], q.y[j], q.z[j], th, ph);
-                if (pass) { q.th[j] = th; q.ph[j] = ph; }
-            }
-            bits[w] = __ballot_sync(0xffffffffu, pass);
-            K += __popc(bits[w]);
-        }
-    }
-    unsigned int pos0 = 0;
-    if (K) { /* one reservation for the whole batch: records of all its tiles are contiguous and in input order */
-        if (lane == 0) pos0 = atomicAdd(s_cursor, K);
-        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-        unsigned int before = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            if ((unsigned)(w * 32) < nent) {
-                const unsigned int b = bits[w];
-                if ((b >> lane) & 1u) {
-                    const unsigned int j = w * 32 + lane;
-                    const unsigned long long slot = (unsigned long long)pos0 + before + __popc(b & lane_lt);
-                    if (slot < a.region_cap) {
-                        const unsigned int wh = q.where[j];
-                        a.t_idx[region0 + slot] = q.tile_id[wh >> 8] * SCAN_TILE + (wh & 0xffu);
-                        a.t_th[region0 + slot] = q.th[j];
-                        a.t_ph[region0 + slot] = q.ph[j];
-                        a.t_x[region0 + slot] = q.x[j];
-                        a.t_y[region0 + slot] = q.y[j];
-                        a.t_z[region0 + slot] = q.z[j];
-                    }
-                }
-                before += __popc(b);
-            }
-        }
-    }
-    /* survivors in front of queue position p */
-    auto rank = [&](unsigned int p) {
-        unsigned int r = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const unsigned int lo = w * 32;
-            if (p >= lo + 32) r += __popc(bits[w]);
-            else if (p > lo) r += __popc(bits[w] & ((1u << (p - lo)) - 1u));
-        }
-        return r;
-    };
-    for (unsigned int t = lane; t < ntile_b; t += 32) {
-        const unsigned int qs = q.tile_q[t], qe = (t + 1 < ntile_b) ? (unsigned int)q.tile_q[t + 1] : nent;
-        const unsigned int rs = rank(qs), re = rank(qe);
-        a.tile_info[q.tile_id[t]] = ((region0 + pos0 + rs) << 32) | (unsigned long long)(re - rs);
-    }
-    __syncwarp();
-}
-
-/* warp-collective, cold: a tile with more candidates than the queue takes (a window covering a third of the octant
- * or more).  No staging: the tile is re-read (it is still in L2), every particle takes the exact test, once to count
- * and once to write -- survivors of a tile must be contiguous, and nothing is kept between the two rounds. */
-__device__ __noinline__ void k1_dense_tile(const ScanArgs* __restrict__ ap, unsigned int tile, unsigned int* s_cursor,
-                                           unsigned long long region0) {
-    const ScanArgs& a = *ap;
+/* warp-collective: the oldest min(count, 32) candidates of the ring take the exact path, one per lane */
+__device__ __noinline__ void k1s_drain(const SegScanArgs* __restrict__ ap, K1SRing* __restrict__ rp, K1SState* __restrict__ sp,
+                                       unsigned long long region0) {
+    const SegScanArgs& a = *ap;
     const int lane = threadIdx.x & 31;
     const unsigned int lane_lt = (1u << lane) - 1u;
-    const long long base = (long long)tile * SCAN_TILE;
-    unsigned int K = 0, pos0 = 0, before = 0;
-    for (int round = 0; round < 2; ++round) {
-        for (int w = 0; w < SCAN_TILE / 32; ++w) {
-            const long long g = base + w * 32 + lane;
-            bool pass = false;
-            float x = 0.0f, y = 0.0f, z = 0.0f, th = 0.0f, ph = 0.0f;
-            if (g < a.n) {
-                x = a.x[g]; y = a.y[g]; z = a.z[g];
-                pass = k1_exact(a, x, y, z, th, ph);
-            }
-            const unsigned int b = __ballot_sync(0xffffffffu, pass);
-            if (round == 0) {
-                K += __popc(b);
-            } else {
-                if (pass) {
-                    const unsigned long long slot = (unsigned long long)pos0 + before + __popc(b & lane_lt);
-                    if (slot < a.region_cap) {
-                        a.t_idx[region0 + slot] = (unsigned int)g;
-                        a.t_th[region0 + slot] = th;
-                        a.t_ph[region0 + slot] = ph;
-                        a.t_x[region0 + slot] = x;
-                        a.t_y[region0 + slot] = y;
-                        a.t_z[region0 + slot] = z;
-                    }
-                }
-                before += __popc(b);
-            }
-        }
-        if (round == 0) {
-            if (K == 0) break;
-            if (lane == 0) pos0 = atomicAdd(s_cursor, K);
-            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-        }
+    __syncwarp();
+    const unsigned int head = sp->head, cnt = min(sp->count, 32u), cursor = sp->cursor;
+    const unsigned int open_seg = sp->open_seg, open_start = sp->open_start;
+    const bool live = (unsigned int)lane < cnt;
+    const unsigned int e = (head + lane) & (K1S_QCAP - 1);
+    float x = 0.0f, y = 0.0f, z = 0.0f, th = 0.0f, ph = 0.0f;
+    unsigned int idx = 0;
+    bool pass = false;
+    if (live) {
+        idx = rp->idx[e];
+        x = rp->x[e]; y = rp->y[e]; z = rp->z[e];
+        pass = k1s_exact(a, x, y, z, th, ph);
     }
-    if (lane == 0) a.tile_info[tile] = ((region0 + pos0) << 32) | (unsigned long long)K;
+    const unsigned int B = __ballot_sync(0xffffffffu, pass);
+    const unsigned int my_seg = idx >> K1S_SEG_SHIFT;
+    unsigned int prev_seg = __shfl_up_sync(0xffffffffu, my_seg, 1);
+    if (lane == 0) prev_seg = open_seg;
+    const bool is_first = live && my_seg != prev_seg; /* first candidate of its segment */
+    const unsigned int F = __ballot_sync(0xffffffffu, is_first);
+    const unsigned int my_start = cursor + __popc(B & lane_lt);
+    if (is_first && prev_seg != K1S_NONE) { /* close the previous segment: its records end where mine begin */
+        const unsigned int pl = F & lane_lt;
+        const unsigned int ps = pl ? cursor + __popc(B & ((1u << (31 - __clz(pl))) - 1u)) : open_start;
+        a.seg_info[prev_seg] = ((unsigned long long)ps << 32) | (unsigned long long)(my_start - ps);
+    }
+    if (pass && my_start < a.region_cap) {
+        const unsigned long long s = region0 + my_start;
+        a.t_idx[s] = idx; a.t_th[s] = th; a.t_ph[s] = ph;
+        a.t_x[s] = x; a.t_y[s] = y; a.t_z[s] = z;
+    }
+    if (F) { /* warp-uniform */
+        const int last = 31 - __clz(F);
+        const unsigned int seg_l = __shfl_sync(0xffffffffu, my_seg, last);
+        if (lane == 0) { sp->open_seg = seg_l; sp->open_start = cursor + __popc(B & ((1u << last) - 1u)); }
+    }
+    if (lane == 0) { sp->head = head + cnt; sp->count = sp->count - cnt; sp->cursor = cursor + __popc(B); }
+    __syncwarp();
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k1_scan(const __grid_constant__ ScanArgs a) {
-    __shared__ K1WarpQueue s_q[SCAN_WARPS];
-    __shared__ unsigned int s_cursor;
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k1s_scan(const __grid_constant__ SegScanArgs a) {
+    __shared__ K1SRing s_ring[SCAN_WARPS];
+    __shared__ K1SState s_state[SCAN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    K1WarpQueue& q = s_q[warp];
-    const unsigned int total_warps = gridDim.x * SCAN_WARPS;
-    const unsigned long long region0 = (unsigned long long)blockIdx.x * a.region_cap;
-    unsigned long long n_cand = 0;
-    unsigned int qcount = 0, ntile_b = 0; /* warp-uniform */
-    if (threadIdx.x == 0) s_cursor = 0;
-    __syncthreads();
+    K1SRing& q = s_ring[warp];
+    K1SState& st = s_state[warp];
+    const unsigned int total_warps = gridDim.x * SCAN_WARPS, gwarp = blockIdx.x * SCAN_WARPS + warp;
+    if (lane == 0) { st.head = 0; st.count = 0; st.cursor = 0; st.open_seg = K1S_NONE; st.open_start = 0; st.n_cand = 0; }
+    __syncwarp();
+    unsigned int qcount = 0, qtail = 0; /* warp-uniform copies: entries queued, next ring position */
+    auto drain_to_31 = [&]() {
+        while (qcount >= 32u) { k1s_drain(&a, &q, &st, (unsigned long long)gwarp * a.region_cap); qcount -= 32u; }
+    };
 
-    for (unsigned int tile = blockIdx.x * SCAN_WARPS + warp; tile < a.ntiles; tile += total_warps) {
-        if (qcount >= a.drain_at) { /* a warp's worth of candidates is queued: run them through the exact path */
-            k1_drain(&a, &q, qcount, ntile_b, &s_cursor, region0);
-            qcount = 0; ntile_b = 0;
-        }
-        const long long base = (long long)tile * SCAN_TILE;
-        float px[8], py[8], pz[8];
-        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
-        /* ---- pre-filter ---- */
-        unsigned int m = 0;
+    for (unsigned int seg = gwarp; seg < a.nseg; seg += total_warps) {
+        /* a segment without survivors keeps this 0; otherwise the lane that finds the segment's end overwrites it
+         * (k1s_drain; the __syncwarp()s in between order the two stores) */
+        if (lane == 0) a.seg_info[seg] = 0ull;
+        const unsigned int tile_end = min(a.ntiles, (seg + 1) * K1S_TILES);
+        for (unsigned int tile = seg * K1S_TILES; tile < tile_end; ++tile) {
+            drain_to_31();
+            const long long base = (long long)tile * SCAN_TILE;
+            float px[8], py[8], pz[8];
+            const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+            unsigned int m = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m |= (unsigned)k1_prefilter(px[j], py[j], pz[j], a) << j;
-        m &= valid;
-        if (__any_sync(0xffffffffu, m != 0)) {
-            /* ---- ordered candidate compaction into the warp's queue (chunk, lane, element = input order) ---- */
+            for (int j = 0; j < 8; ++j) m |= (unsigned)k1_prefilter(px[j], py[j], pz[j], a) << j;
+            m &= valid;
+            if (!__any_sync(0xffffffffu, m != 0)) continue;
+            /* candidates in input order: chunk A (elements 0-3 of every lane), then chunk B */
             const unsigned int cnt = __popc(m & 0xfu) | (__popc(m >> 4) << 16);
             unsigned int inc = cnt;
 #pragma unroll
@@ -376,57 +323,56 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k1_scan(const __grid_constant
                 if (lane >= d) inc += t;
             }
             const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
-            const unsigned int totalA = total & 0xffffu, C = totalA + (total >> 16);
-            n_cand += C;
-            if (C > K1_QMAX_TILE) { /* cold */
-                k1_dense_tile(&a, tile, &s_cursor, region0);
-                continue;
-            }
-            if (lane == 0) { q.tile_id[ntile_b] = tile; q.tile_q[ntile_b] = (unsigned short)qcount; }
             const unsigned int ex = inc - cnt;
-            unsigned int posA = qcount + (ex & 0xffffu), posB = qcount + totalA + (ex >> 16);
+            /* a tile can carry up to 256 candidates, the ring has room for 225: push it half by half */
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (m & (1u << j)) {
-                    unsigned int& pos = (j < 4) ? posA : posB;
-                    q.x[pos] = px[j]; q.y[pos] = py[j]; q.z[pos] = pz[j];
-                    q.where[pos] = (unsigned short)((ntile_b << 8) | tile_local(lane, j));
+            for (int half = 0; half < 2; ++half) {
+                const unsigned int add = half ? (total >> 16) : (total & 0xffffu);
+                if (half == 1 && qcount + add > (unsigned)K1S_QCAP) drain_to_31();
+                unsigned int pos = qtail + (half ? (ex >> 16) : (ex & 0xffffu));
+                unsigned int mm = half ? (m >> 4) : (m & 0xfu);
+                while (mm) { /* 0.4 candidates per lane even in a wide field: a loop over the set bits, not 8 predicated pushes */
+                    const int j = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const unsigned int p = pos & (K1S_QCAP - 1);
+                    /* px[j] with a runtime j would go through local memory: select from registers instead */
+                    float vx = px[4 * half], vy = py[4 * half], vz = pz[4 * half];
+                    if (j == 1) { vx = px[4 * half + 1]; vy = py[4 * half + 1]; vz = pz[4 * half + 1]; }
+                    if (j == 2) { vx = px[4 * half + 2]; vy = py[4 * half + 2]; vz = pz[4 * half + 2]; }
+                    if (j == 3) { vx = px[4 * half + 3]; vy = py[4 * half + 3]; vz = pz[4 * half + 3]; }
+                    q.x[p] = vx; q.y[p] = vy; q.z[p] = vz;
+                    q.idx[p] = (unsigned int)base + tile_local(lane, j + 4 * half);
                     ++pos;
                 }
-            ++ntile_b;
-            qcount += C; /* <= 31 + K1_QMAX_TILE < K1_QCAP */
-        } else if (lane == 0) {
-            a.tile_info[tile] = 0ull;
+                qtail += add;
+                qcount += add;
+                if (lane == 0) { st.count = qcount; st.n_cand += add; }
+                __syncwarp();
+            }
         }
     }
-    if (ntile_b) k1_drain(&a, &q, qcount, ntile_b, &s_cursor, region0);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        a.cta_used[blockIdx.x] = s_cursor;
-        atomicMax(a.result + 3, (unsigned long long)s_cursor);
+    while (qcount) { /* the last, partial round */
+        k1s_drain(&a, &q, &st, (unsigned long long)gwarp * a.region_cap);
+        qcount -= min(qcount, 32u);
     }
-    if (lane == 0 && n_cand) atomicAdd(a.result + 1, n_cand);
+    if (lane == 0) {
+        if (st.open_seg != K1S_NONE)
+            a.seg_info[st.open_seg] = ((unsigned long long)st.open_start << 32) | (unsigned long long)(st.cursor - st.open_start);
+        atomicMax(a.result + 3, (unsigned long long)st.cursor);
+        if (st.n_cand) atomicAdd(a.result + 1, (unsigned long long)st.n_cand);
+    }
 }
 
-/* ---- phase B: exclusive scan of the tile counts (single pass, decoupled look-back across blocks) ---- */
-constexpr int TSCAN_THREADS = 256;
-constexpr int TSCAN_ITEMS = 16; /* tiles per thread */
-constexpr int TSCAN_BLOCK = TSCAN_THREADS * TSCAN_ITEMS;
-constexpr unsigned long long TS_AGG = 1ull << 62;
-constexpr unsigned long long TS_PREFIX = 2ull << 62;
-constexpr unsigned long long TS_MASK = (1ull << 62) - 1;
-
-struct TileScanArgs {
-    const unsigned long long* tile_info; /* [ntiles] (temp position << 32) | count */
-    unsigned int* t_row;                 /* per temp record: output row inside the chunk (streamed by the gather) */
-    unsigned long long temp_cap;         /* records the temp buffer holds (regions x region_cap) */
-    unsigned long long* block_state;     /* [nblocks] zeroed before launch */
-    unsigned int* ticket;                /* zeroed before launch */
-    unsigned long long* result;          /* [0] survivors so far (in: carry, out: carry + chunk total), [2] = carry */
-    unsigned int ntiles, nblocks;
+/* ---- phase B: exclusive scan of the segment counts (single pass, decoupled look-back across blocks) ---- */
+struct SegPrefixArgs {
+    const unsigned long long* seg_info; /* [nseg] (position << 32) | count */
+    unsigned int* seg_row;              /* [nseg] out: output row of the segment's first record, inside the chunk */
+    unsigned long long* block_state;    /* [nblocks] zeroed before launch */
+    unsigned int* ticket;               /* zeroed before launch */
+    unsigned long long* result;         /* [0] survivors so far (in: carry, out: carry + chunk total), [2] = carry */
+    unsigned int nseg, nblocks;
 };
-
-__global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs a) {
+__global__ void __launch_bounds__(TSCAN_THREADS) k1s_seg_scan(const SegPrefixArgs a) {
     __shared__ unsigned int s_warp[TSCAN_THREADS / 32];
     __shared__ unsigned int s_block;
     __shared__ unsigned long long s_excl;
@@ -435,12 +381,10 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
     __syncthreads();
     const unsigned int blk = s_block;
     const unsigned int first = blk * TSCAN_BLOCK + tid * TSCAN_ITEMS;
-    unsigned int c[TSCAN_ITEMS], p0[TSCAN_ITEMS], sum = 0;
+    unsigned int c[TSCAN_ITEMS], sum = 0;
 #pragma unroll
     for (int i = 0; i < TSCAN_ITEMS; ++i) {
-        const unsigned long long info = (first + i < a.ntiles) ? a.tile_info[first + i] : 0ull;
-        c[i] = (unsigned int)(info & 0xffffffffull);
-        p0[i] = (unsigned int)(info >> 32);
+        c[i] = (first + i < a.nseg) ? (unsigned int)(a.seg_info[first + i] & 0xffffffffull) : 0u;
         sum += c[i];
     }
     unsigned int inc = sum;
@@ -458,7 +402,7 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
         if (w < warp) before += t;
         block_total += t;
     }
-    if (warp == 0) { /* decoupled look-back: ballot for the first published prefix, popc-free sum by shuffles */
+    if (warp == 0) {
         unsigned long long exclusive = 0;
         if (blk == 0) {
             if (lane == 0) st_relaxed_u64(a.block_state, TS_PREFIX | block_total);
@@ -467,14 +411,14 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
             long long look = (long long)blk - 1;
             while (true) {
                 const long long idx = look - lane;
-                unsigned long long st = TS_PREFIX;
+                unsigned long long stt = TS_PREFIX;
                 if (idx >= 0) {
-                    st = ld_relaxed_u64(a.block_state + idx);
-                    while ((st >> 62) == 0) st = ld_relaxed_u64(a.block_state + idx);
+                    stt = ld_relaxed_u64(a.block_state + idx);
+                    while ((stt >> 62) == 0) stt = ld_relaxed_u64(a.block_state + idx);
                 }
-                const unsigned int pmask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                const unsigned int pmask = __ballot_sync(0xffffffffu, (stt >> 62) == 2);
                 const int firstp = pmask ? (__ffs(pmask) - 1) : 31;
-                unsigned long long v = (lane <= firstp) ? (st & TS_MASK) : 0ull;
+                unsigned long long v = (lane <= firstp) ? (stt & TS_MASK) : 0ull;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
                 exclusive += v;
@@ -493,75 +437,170 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1_tile_scan(const TileScanArgs
         }
     }
     __syncthreads();
-    /* rows of every tile's records: consecutive, in input order */
     unsigned int run = (unsigned int)s_excl + before + inc - sum;
 #pragma unroll
     for (int i = 0; i < TSCAN_ITEMS; ++i) {
-        const bool big = c[i] > 8;
-        if (!big) { /* the usual case of a narrow window: a handful of rows, written by the owning thread */
-            for (unsigned int k = 0; k < c[i]; ++k)
-                if ((unsigned long long)p0[i] + k < a.temp_cap) a.t_row[p0[i] + k] = run + k;
-        }
-        unsigned int nz = __ballot_sync(0xffffffffu, big);
-        while (nz) { /* dense tiles: the whole warp writes one tile's rows, coalesced */
-            const int src = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const unsigned int cnt = __shfl_sync(0xffffffffu, c[i], src);
-            const unsigned long long pos = __shfl_sync(0xffffffffu, p0[i], src);
-            const unsigned int r0 = __shfl_sync(0xffffffffu, run, src);
-            for (unsigned int k = lane; k < cnt; k += 32)
-                if (pos + k < a.temp_cap) a.t_row[pos + k] = r0 + k;
-        }
+        if (first + i < a.nseg) a.seg_row[first + i] = run;
         run += c[i];
     }
 }
 
-/* ---- phase C: one thread per survivor record ---- */
-struct GatherConstArgs {
+/* ---- phase C: a CTA owns K1G_SEGS consecutive segments = a contiguous block of output rows ---- */
+constexpr int K1G_SEGS = 32;
+constexpr int K1G_THREADS = 256;
+struct SegGatherArgs {
     ColsIn in;   /* columns other than x,y,z: pointers already offset to the chunk start */
     ColsOut out;
-    const unsigned int *t_idx, *t_row;
+    const unsigned int* t_idx;
     const float *t_th, *t_ph, *t_x, *t_y, *t_z;
-    const unsigned int* cta_used;     /* [nregions] */
+    const unsigned long long* seg_info;
+    const unsigned int* seg_row;
     const unsigned long long* result; /* [2] = carry: rows written by earlier chunks of a streamed step */
-    const Payload* payload;           /* interleaved gather columns of a resident step, or NULL (streamed step) */
-    unsigned int region_cap;
+    const Payload* payload;           /* interleaved gather columns of a resident step, or NULL */
+    unsigned int region_cap, total_warps, nseg;
     long long cap;                    /* rows available in `out` */
     long long index_base;             /* global index of the chunk's first particle */
 };
 
-/* grid = (blocks per region, regions); every per-record input is a coalesced stream, only the seven columns
- * that the scan never touched (vx,vy,vz,a,id,rotation,replication) are gathered */
-__global__ void __launch_bounds__(256) k1_gather(const GatherConstArgs a) {
-    const unsigned long long carry = a.result[2];
-    const unsigned int region = blockIdx.y;
-    const unsigned int used = min(a.cta_used[region], a.region_cap);
-    const unsigned long long slot0 = (unsigned long long)region * a.region_cap;
-    for (unsigned int off = blockIdx.x * blockDim.x + threadIdx.x; off < used; off += gridDim.x * blockDim.x) {
-        const unsigned long long slot = slot0 + off;
-        const long long r = (long long)(carry + a.t_row[slot]);
-        if (r >= a.cap) continue;
-        const long long g = a.t_idx[slot];
-        a.out.theta[r] = a.t_th[slot];
-        a.out.phi[r] = a.t_ph[slot];
-        a.out.x[r] = a.t_x[slot];
-        a.out.y[r] = a.t_y[slot];
-        a.out.z[r] = a.t_z[slot];
-        if (a.payload) {
-            const Payload p = load_payload(a.payload + g);
-            a.out.vx[r] = p.vx; a.out.vy[r] = p.vy; a.out.vz[r] = p.vz;
-            a.out.redshift[r] = a_to_z_dev(p.a);
-            a.out.id[r] = p.id; a.out.rot[r] = p.rot; a.out.rep[r] = p.rep;
-        } else if (a.in.a) { /* NULL: a streamed step whose other columns the host gathers itself (capi.cu fetch_rows) */
-            a.out.vx[r] = a.in.vx[g];
-            a.out.vy[r] = a.in.vy[g];
-            a.out.vz[r] = a.in.vz[g];
-            a.out.redshift[r] = a_to_z_dev(a.in.a[g]);
-            a.out.id[r] = a.in.id[g];
-            a.out.rot[r] = a.in.rot[g];
-            a.out.rep[r] = a.in.rep[g];
+struct K1GRow { /* everything one output row holds */
+    float th, ph, x, y, z, vx, vy, vz, red;
+    long long id, index;
+    int rot, rep;
+};
+/* record + payload of local row i of the CTA's block (s_pref/s_pos: the block's segment table in shared memory) */
+__device__ __forceinline__ bool k1g_fetch(const SegGatherArgs& a, unsigned int g0, const unsigned int* s_pref,
+                                          const unsigned int* s_pos, unsigned int i, K1GRow& r) {
+    unsigned int s = 0; /* largest s with s_pref[s] <= i */
+#pragma unroll
+    for (int d = K1G_SEGS / 2; d > 0; d >>= 1)
+        if (s_pref[s + d] <= i) s += d;
+    const unsigned int k = s_pos[s] + (i - s_pref[s]);
+    if (k >= a.region_cap) return false; /* the warp's region overflowed: the host re-runs with larger regions */
+    const unsigned long long slot = (unsigned long long)((g0 + s) % a.total_warps) * a.region_cap + k;
+    const long long g = a.t_idx[slot];
+    r.th = a.t_th[slot]; r.ph = a.t_ph[slot];
+    r.x = a.t_x[slot]; r.y = a.t_y[slot]; r.z = a.t_z[slot];
+    r.index = a.index_base + g;
+    if (a.payload) {
+        const Payload p = load_payload(a.payload + g);
+        r.vx = p.vx; r.vy = p.vy; r.vz = p.vz; r.red = a_to_z_dev(p.a);
+        r.id = p.id; r.rot = p.rot; r.rep = p.rep;
+    } else if (a.in.a) { /* NULL: a streamed step whose other columns the host gathers itself (capi.cu fetch_rows) */
+        r.vx = a.in.vx[g]; r.vy = a.in.vy[g]; r.vz = a.in.vz[g];
+        r.red = a_to_z_dev(a.in.a[g]);
+        r.id = a.in.id[g]; r.rot = a.in.rot[g]; r.rep = a.in.rep[g];
+    }
+    return true;
+}
+/* the CTA's segment table; returns the number of rows of the block, *row0 = its first row inside the chunk */
+__device__ __forceinline__ unsigned int k1g_table(const SegGatherArgs& a, unsigned int g0, unsigned int* s_pref,
+                                                  unsigned int* s_pos, unsigned int* row0) {
+    if (threadIdx.x < 32) {
+        const unsigned int seg = g0 + threadIdx.x;
+        const unsigned long long info = seg < a.nseg ? a.seg_info[seg] : 0ull;
+        const unsigned int c = (unsigned int)(info & 0xffffffffull);
+        unsigned int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (threadIdx.x >= (unsigned)d) inc += t;
         }
-        if (a.out.index) a.out.index[r] = a.index_base + g;
+        s_pref[threadIdx.x] = inc - c;
+        s_pos[threadIdx.x] = (unsigned int)(info >> 32);
+        if (threadIdx.x == 31) { s_pref[32] = inc; s_pref[33] = a.seg_row[g0]; }
+    }
+    __syncthreads();
+    *row0 = s_pref[33];
+    return s_pref[32];
+}
+static_assert(K1G_SEGS == 32, "k1g_table scans the block's segments with one warp");
+
+__global__ void __launch_bounds__(K1G_THREADS) k1s_gather(const SegGatherArgs a) {
+    __shared__ unsigned int s_pref[K1G_SEGS + 2], s_pos[K1G_SEGS];
+    const unsigned int g0 = blockIdx.x * K1G_SEGS;
+    unsigned int row0;
+    const unsigned int total = k1g_table(a, g0, s_pref, s_pos, &row0);
+    const long long first = (long long)a.result[2] + row0;
+    const bool full = a.payload || a.in.a;
+    for (unsigned int i = threadIdx.x; i < total; i += K1G_THREADS) {
+        const long long r = first + i;
+        K1GRow v;
+        if (r >= a.cap || !k1g_fetch(a, g0, s_pref, s_pos, i, v)) continue;
+        a.out.theta[r] = v.th; a.out.phi[r] = v.ph;
+        a.out.x[r] = v.x; a.out.y[r] = v.y; a.out.z[r] = v.z;
+        if (full) {
+            a.out.vx[r] = v.vx; a.out.vy[r] = v.vy; a.out.vz[r] = v.vz; a.out.redshift[r] = v.red;
+            a.out.id[r] = v.id; a.out.rot[r] = v.rot; a.out.rep[r] = v.rep;
+        }
+        if (a.out.index) a.out.index[r] = v.index;
+    }
+}
+
+/* The same gather with the output rows staged in shared memory, column by column, and written by the bulk-copy engine
+ * (cp.async.bulk.global.shared::cta; north star: "the gather writes output columns with TMA bulk stores").  A staged
+ * block covers K1GB_ROWS consecutive output rows starting at a multiple of 4 rows, so that every column's run starts on
+ * a 16-byte boundary both in shared memory and in HBM; the rows in front of / behind the 16-byte aligned interior of
+ * the CTA's range (< 4 each) are stored by threads. */
+constexpr int K1GB_ROWS = 1024;
+constexpr int K1GB_NCOL4 = 11; /* theta phi x y z vx vy vz redshift rot rep */
+constexpr size_t K1GB_SMEM = (size_t)K1GB_ROWS * (K1GB_NCOL4 * 4 + 2 * 8);
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"((unsigned int)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(K1G_THREADS) k1s_gather_bulk(const SegGatherArgs a) {
+    extern __shared__ __align__(128) unsigned char s_stage[];
+    __shared__ unsigned int s_pref[K1G_SEGS + 2], s_pos[K1G_SEGS];
+    float* s4 = reinterpret_cast<float*>(s_stage);                                         /* [11][ROWS] */
+    long long* s8 = reinterpret_cast<long long*>(s_stage + (size_t)K1GB_ROWS * K1GB_NCOL4 * 4); /* [2][ROWS] */
+    const unsigned int g0 = blockIdx.x * K1G_SEGS;
+    unsigned int row0;
+    const unsigned int total = k1g_table(a, g0, s_pref, s_pos, &row0);
+    const long long lo = (long long)a.result[2] + row0, hi = min(lo + (long long)total, a.cap);
+    const bool full = a.payload || a.in.a;
+    float* const o4[K1GB_NCOL4] = {a.out.theta, a.out.phi, a.out.x, a.out.y, a.out.z, a.out.vx, a.out.vy, a.out.vz,
+                                   a.out.redshift, reinterpret_cast<float*>(a.out.rot), reinterpret_cast<float*>(a.out.rep)};
+    long long* const o8[2] = {a.out.id, a.out.index};
+    for (long long A = lo & ~3ll; A < hi; A += K1GB_ROWS) { /* staged block = rows [A, A + ROWS) of the CTA's range */
+        const long long b0 = max(A, lo), b1 = min(A + K1GB_ROWS, hi);
+        for (long long r = b0 + threadIdx.x; r < b1; r += K1G_THREADS) {
+            K1GRow v = {};
+            const unsigned int j = (unsigned int)(r - A);
+            if (!k1g_fetch(a, g0, s_pref, s_pos, (unsigned int)(r - lo), v)) continue; /* overflow: the host re-runs */
+            s4[0 * K1GB_ROWS + j] = v.th; s4[1 * K1GB_ROWS + j] = v.ph;
+            s4[2 * K1GB_ROWS + j] = v.x; s4[3 * K1GB_ROWS + j] = v.y; s4[4 * K1GB_ROWS + j] = v.z;
+            s4[5 * K1GB_ROWS + j] = v.vx; s4[6 * K1GB_ROWS + j] = v.vy; s4[7 * K1GB_ROWS + j] = v.vz;
+            s4[8 * K1GB_ROWS + j] = v.red;
+            s4[9 * K1GB_ROWS + j] = __int_as_float(v.rot); s4[10 * K1GB_ROWS + j] = __int_as_float(v.rep);
+            s8[j] = v.id; s8[K1GB_ROWS + j] = v.index;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes -> visible to the bulk engine */
+        __syncthreads();
+        const long long i0 = (b0 + 3) & ~3ll, i1 = b1 & ~3ll; /* 16-byte aligned interior */
+        if (threadIdx.x == 0 && i1 > i0) {
+            const unsigned int j0 = (unsigned int)(i0 - A), nr = (unsigned int)(i1 - i0);
+#pragma unroll
+            for (int c = 0; c < K1GB_NCOL4; ++c)
+                if (c < 5 || full) bulk_s2g(o4[c] + i0, s4 + (size_t)c * K1GB_ROWS + j0, nr * 4u);
+            if (full) bulk_s2g(o8[0] + i0, s8 + j0, nr * 8u);
+            if (o8[1]) bulk_s2g(o8[1] + i0, s8 + K1GB_ROWS + j0, nr * 8u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        { /* head and tail rows (at most 3 + 3), by threads */
+            const long long h1 = min(i0, b1), t0 = max(i1, h1);
+            const long long nh = h1 - b0, nt = b1 - t0;
+            if ((long long)threadIdx.x < nh + nt) {
+                const long long r = (long long)threadIdx.x < nh ? b0 + threadIdx.x : t0 + (threadIdx.x - nh);
+                const unsigned int j = (unsigned int)(r - A);
+#pragma unroll
+                for (int c = 0; c < K1GB_NCOL4; ++c)
+                    if (c < 5 || full) o4[c][r] = s4[(size_t)c * K1GB_ROWS + j];
+                if (full) o8[0][r] = s8[j];
+                if (o8[1]) o8[1][r] = s8[K1GB_ROWS + j];
+            }
+        }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* staging may be refilled */
+        __syncthreads();
     }
 }
 
@@ -607,6 +646,7 @@ struct HaloArgs {
     unsigned long long* rec_count;   /* appended records (may exceed rec_cap: overflow is detected on the host) */
     unsigned long long* counts;      /* [2*H_total]: survivors per halo, then rough survivors per halo */
     unsigned long long* n_cand;      /* pre-filter candidates (stat) */
+    unsigned long long* nan_count;   /* scanned particles whose un-rotated theta is NaN (stat; capi.cu cc_last_stats_ex) */
     int total_halos;
     unsigned int ntiles;
 };
@@ -700,6 +740,24 @@ __device__ __forceinline__ void k2_drain(const HaloArgs& a, const K2WarpQueue& q
     __syncwarp();
 }
 
+/* Out-of-range positions are rare; among them are the ones whose un-rotated theta is NaN (NaN coordinate, z = +-Inf,
+ * the origin).  Such a key breaks the ordering contract of the reference's stable_sort / lower_bound
+ * (processLC.cpp:1214-1221, :1334-1337), so they are counted -- once per particle -- and reported (cc_last_stats_ex). */
+template <int NP>
+__device__ __forceinline__ void count_nan_theta(unsigned int insane, const float (&px)[NP], const float (&py)[NP],
+                                                const float (&pz)[NP], unsigned long long* nan_count) {
+    if (!__any_sync(0xffffffffu, insane != 0)) return;
+    unsigned int c = 0;
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+        if ((insane >> j) & 1u) {
+            /* theta = acosf(z/d) scaled: NaN exactly when z/d is NaN or beyond +-1 (d == 0, or z, d both infinite) */
+            const float q = CC_FDIV(pz[j], ccref::radius(px[j], py[j], pz[j]));
+            c += !(fabsf(q) <= 1.0f) ? 1u : 0u;
+        }
+    if (c) atomicAdd(nan_count, (unsigned long long)c);
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs a) {
     extern __shared__ float4 s_pre[]; /* [nhalos] */
@@ -728,6 +786,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs
             pt[j] = py[j] * rcp_fast(px[j]);
         }
         insane &= valid;
+        count_nan_theta<8>(insane, px, py, pz, a.nan_count);
         for (int h = 0; h < a.nhalos; ++h) {
             const float4 P = s_pre[h];
             bool mine = insane != 0;
@@ -874,6 +933,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) k2_cutout_halo_tma(const Halo
             pt[j] = py[j] * rcp_fast(px[j]);
         }
         insane &= valid;
+        count_nan_theta<8>(insane, px, py, pz, a.nan_count);
         for (int h = 0; h < a.nhalos; ++h) {
             const float4 P = s_pre[h];
             bool mine = insane != 0;
@@ -1080,6 +1140,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
                 hit |= ((s_bits[bit >> 5] >> (bit & 31u)) & 1u) << j;
             }
             insane &= valid;
+            if (w0 == 0) count_nan_theta<4>(insane, px, py, pz, a.nan_count);
             hit &= valid & ~insane;
             uint2 rg[4];
             unsigned int mine = 0;

@@ -205,6 +205,25 @@ int64_t cc_launch_count(cc_ctx* ctx);
 /* statistics of the last cutout: [0] particles scanned, [1] pre-filter candidates (exact path taken),
  * [2] survivors, [3] rough survivors */
 int cc_last_stats(cc_ctx* ctx, int64_t out[4]);
+/* the same and more, first n of: [0..3] as cc_last_stats; [4] use case 2: scanned particles whose un-rotated theta is
+ * NaN (NaN coordinate, z = +-Inf, or x = y = z = 0).  The reference orders particles by that angle with
+ * std::stable_sort and std::lower_bound (processLC.cpp:1214-1221, :1334-1337); a NaN key breaks their ordering
+ * contract and what the reference then returns for the OTHER particles is unspecified, so parity is only claimed for
+ * steps where this is 0 (lc_cutout warns otherwise); [5] 1 when the interleaved gather payload of the resident step
+ * exists; [6] microseconds the last cutout call spent building it (0: it did not); [7] use case 2: particles of this
+ * shard behind n_limit_global (the reference's tail drop, util.cpp:106-108). */
+#define CC_STATS_EX_FIELDS 8
+int cc_last_stats_ex(cc_ctx* ctx, int64_t* out, int n);
+
+/* ------------------------------------------------------------------ tuning switches (defaults are the measured best)
+ * key "payload":  "auto" (default) | "always" | "never" -- the 32 B/particle interleaved copy of the seven gather-only
+ *                 columns of a resident step; auto builds it inside the first cutout that follows a cutout with at
+ *                 least max(65536, n/512) survivors on the same resident step
+ * key "exchange": "auto" (default: NVLink peer mailboxes when attached, else NCCL) | "nccl" | "peer"
+ * key "gather":   "auto" (default) | "ldst" | "bulk" -- use case 1 gather: plain coalesced stores, or rows staged in
+ *                 shared memory and written with cp.async.bulk (TMA bulk stores); auto picks bulk stores for dense
+ *                 cutouts (profiles/r02 has the A/B numbers) */
+int cc_set_option(cc_ctx* ctx, const char* key, const char* value);
 
 /* ------------------------------------------------------------------ test hooks (device arithmetic)
  * Evaluate the device restatement of the reference arithmetic element-wise on HOST arrays (copied to the
