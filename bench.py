@@ -2,28 +2,36 @@
 """bench.py -- throughput of the lightcone cutout hot path (BASELINE.json metric: Gparticles/s filtered, and the
 achieved fraction of the HBM roofline), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg4|const1b|cfg5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3|cfg4|const1b|cfg5] [--impl reference]
 
 A "step" is one complete cutout of one synthetic lightcone step: scan of x,y,z (pre-filter + exact reference
-arithmetic), compaction/ordering, column gather of the survivors and -- for N > 1 -- the NCCL all-gather of the
-per-GPU survivor counts that yields each GPU's file offsets.  Default workload = BASELINE.json configs[1]:
-use case 2 halo cutout (--halo 150 20 12 --boxLength 10), 100 M-particle step per GPU (weak scaling: every GPU
-holds its own 100 M-particle index shard of a N*100 M-particle step).
+arithmetic), compaction/ordering, column gather of the survivors and -- for N > 1 -- the exchange of the per-GPU
+survivor counts that yields each GPU's file offsets.  Headline workload = BASELINE.json configs[1]: use case 2 halo
+cutout (--halo 150 20 12 --boxLength 10), 100 M-particle step per GPU (weak scaling: every GPU holds its own
+100 M-particle index shard of a N*100 M-particle step).
 
 Printed JSON (one line, rank 0):
-  value      whole-job Gparticles/s with the step resident in HBM (CUDA events on the cutout stream, max over ranks)
-  e2e        same metric through the C ABI with HOST (pinned) columns: x,y,z streamed H2D double-buffered inside
-             the timed region, survivors copied back to host inside the timed region
-  dtype      "f32": the path computes in the reference's own arithmetic (fp32 products/libm, one fp64 scaling per
-             angle), bit-exact -- not a reduced-precision variant
-  roofline   dominant kernel (the scan): algorithmic bytes (12 B per particle scanned + 84 B per survivor;
-             44 B with posOnly) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  value         whole-job Gparticles/s with the step resident in HBM (CUDA events on the cutout stream, max over ranks)
+  e2e           same metric through the C ABI with HOST (pinned) columns: x,y,z streamed H2D double-buffered inside
+                the timed region, survivors copied back to host inside the timed region
+  dtype         "f32": the path computes in the reference's own arithmetic (fp32 products/libm, one fp64 scaling per
+                angle), bit-exact -- not a reduced-precision variant
+  roofline      dominant kernel (the scan): algorithmic bytes / its CUDA-event duration against MEASURED_PEAKS.json
+                hbm_gbs; `whole_pass` = 12 B per particle + 84 B per survivor over scan+ordering+gather
+  residency     what it cost to make the step resident, and the FIRST cutout on it (cold: buffers sized, no payload)
+  configs       the other BASELINE.json configs at this N, each driver-timed the same way (cfg1, the 1 B-particle
+                north-star size, cfg3 streamed depth, cfg4 wide field, cfg5 1000 halos in boxLength groups)
+  parity_check  untimed: every rank cuts its shard for both use cases, exchanges counts over NCCL AND over the NVLink
+                peer mailboxes, and compares offsets, counts and every survivor column byte for byte with the oracle
+                (oracle/liboracle.so, the CHECKER; never timed) run on the shard's candidate set; non-zero exit on a
+                mismatch
   cpu_baseline  the real reference (oracle/_ref, single rank = 1 core, as shipped it has no threading) on a
-             bounded sample of the same workload, timed on this box's host
+                bounded sample of the same workload, timed on this box's host
 --impl reference: the reference's own CPU implementation on all host cores (one single-rank reference process per
 core on disjoint index slices -- the reference's own decomposition is one MPI rank per core), same metric/config.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -38,22 +46,26 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
+SEED = 20261019
+BOX_GROUPS = (5.0, 10.0, 20.0, 30.0)  # cfg5: boxLength (arcmin) of the four 250-halo processLC calls
+
 WORKLOADS = {
     # name: (use case, particles per GPU, description, parameters)
-    "cfg2": dict(uc=2, n=100_000_000, halos=[((150.0, 20.0, 12.0), 10.0)], kind=0, box=300.0,
+    "cfg2": dict(uc=2, n=100_000_000, halos=[((150.0, 20.0, 12.0), 10.0)], kind=0, box=300.0, scaling="weak",
                  desc="BASELINE cfg2: use case 2 halo cutout --halo 150 20 12 --boxLength 10, 100M-particle synthetic step per GPU"),
-    "cfg1": dict(uc=1, n=10_000_000, theta=(87.0, 2.0), phi=(2.0, 2.0), kind=0, box=300.0,
+    "cfg1": dict(uc=1, n=10_000_000, theta=(87.0, 2.0), phi=(2.0, 2.0), kind=0, box=300.0, scaling="weak",
                  desc="BASELINE cfg1: use case 1 theta=87+-2 phi=2+-2 deg, 10M-particle synthetic step per GPU"),
-    "const1b": dict(uc=1, n=1_000_000_000, theta=(87.0, 2.0), phi=(2.0, 2.0), kind=0, box=300.0,
+    "const1b": dict(uc=1, n=1_000_000_000, theta=(87.0, 2.0), phi=(2.0, 2.0), kind=0, box=300.0, scaling="weak",
                     desc="north-star size: use case 1 theta=87+-2 phi=2+-2 deg, 1B-particle resident step per GPU"),
-    "cfg4": dict(uc=1, n=500_000_000, theta=(90.0, 20.0), phi=(0.0, 20.0), kind=0, box=300.0,
-                 desc="BASELINE cfg4: wide field theta=90+-20 phi=0+-20 deg, 500M-particle resident shell per GPU"),
-    "cfg3": dict(uc=2, n=1_000_000_000 // 30, halos=[((150.0, 20.0, 12.0), 10.0)], kind=0, box=300.0,
-                 desc="BASELINE cfg3: full-depth halo cutout, 30 streamed lightcone steps, 1B particles total"),
-    "cfg5": dict(uc=2, n=125_000_000, halos="random1000", kind=0, box=300.0,
-                 desc="BASELINE cfg5: 1000 halo cutouts (boxLength 15) in one pass, 125M-particle resident shard per GPU"),
+    "cfg4": dict(uc=1, n=500_000_000, theta=(90.0, 20.0), phi=(0.0, 20.0), kind=0, box=300.0, scaling="weak",
+                 desc="BASELINE cfg4: wide field theta=90+-20 phi=0+-20 deg, 500M-particle resident shell per GPU (4B on 8 GPUs)"),
+    "cfg3": dict(uc=2, n=1_000_000_000 // 30, halos=[((150.0, 20.0, 12.0), 10.0)], kind=0, box=300.0, scaling="strong",
+                 desc="BASELINE cfg3: full-depth halo cutout, 30 lightcone steps, 1B particles total, every step streamed "
+                      "from pinned host (x,y,z H2D double-buffered, other columns picked for survivors)"),
+    "cfg5": dict(uc=2, n=125_000_000, halos="random1000", kind=0, box=300.0, scaling="weak",
+                 desc="BASELINE cfg5: 1000 halo cutouts, boxLength 5/10/20/30 arcmin (250 halos each = four processLC-style "
+                      "passes, one boxLength per pass), 125M-particle resident shard per GPU (1B on 8 GPUs)"),
 }
-
 
 _OUT = sys.stdout
 
@@ -123,248 +135,317 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def halo_list(cc, wl):
+def halo_groups(wl):
+    """[(boxLength, [(pos, boxLength), ...]), ...]: one entry per processLC-style pass"""
     if wl["halos"] == "random1000":
         rng = np.random.default_rng(1000)
         pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
-        return [(tuple(float(v) for v in p), 15.0) for p in pos]
-    return wl["halos"]
+        per = len(pos) // len(BOX_GROUPS)
+        return [(b, [(tuple(float(v) for v in p), b) for p in pos[g * per:(g + 1) * per]]) for g, b in enumerate(BOX_GROUPS)]
+    return [(wl["halos"][0][1], wl["halos"])]
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from __graft_entry__ import load_package
-    cc = load_package()
+class Env:
+    """one process = one GPU: context, communicator (NCCL + NVLink peer mailboxes), torch only for the process group"""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        log(f"note: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-
-    wl = WORKLOADS[args.workload]
-    n = int(args.particles) if args.particles else wl["n"]
-    n_total = n * world
-    ctx = cc.Context(local_rank)
-    if world > 1:  # our own communicator for the count exchange; torch.distributed only ships the id
-        ident = [cc.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        ctx.comm_init(world, rank, ident[0])
-        if args.peer:  # count exchange by NVLink peer stores (mailboxes shared through CUDA IPC) instead of NCCL
-            handles = [None] * world
-            dist.all_gather_object(handles, ctx.comm_peer_handle(world, rank))
-            ctx.comm_peer_attach(handles)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from __graft_entry__ import load_package
+        self.torch, self.dist = torch, dist
+        self.cc = cc = load_package()
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            log(f"note: WORLD_SIZE={self.world} but --gpus {args.gpus}; using WORLD_SIZE")
+        # launchers pin OMP_NUM_THREADS to 1: the host-side helpers (synthetic columns, survivor pick) get this rank's share
+        os.environ.setdefault("CC_HOST_THREADS", str(max(1, len(os.sched_getaffinity(0)) // self.world)))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group(backend="nccl", device_id=self.dev)
+        self.ctx = cc.Context(self.local_rank)
+        self.exchange = "none (1 GPU)"
+        if self.world > 1:  # our own communicator for the count exchange; torch.distributed only ships the ids
+            ident = [cc.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(ident, src=0)
+            self.ctx.comm_init(self.world, self.rank, ident[0])
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.ctx.comm_peer_handle(self.world, self.rank))
+            self.ctx.comm_peer_attach(handles)
             dist.barrier()
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+            if args.nccl:
+                self.ctx.set_option("exchange", "nccl")
+                self.exchange = "NCCL all-gather enqueued behind the cutout kernels (--nccl)"
+            else:
+                self.exchange = "NVLink peer stores (k4_exchange_peer) behind the cutout kernels; NCCL path checked in parity_check"
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=self.dev)
 
-    ctx.synth(n, seed=20261019, index_base=rank * n, kind=wl["kind"], box=wl["box"])
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allreduce(self, vals, op="max"):
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN}[op])
+        return [float(v) for v in t.tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def make_step_fn(env, wl, n, n_total):
+    """the cutout call sequence of one step of a resident workload -> (step(), passes per step, halo count)"""
+    cc, ctx = env.cc, env.ctx
     if wl["uc"] == 1:
         tc, pc = cc.cli_bounds(*wl["theta"]), cc.cli_bounds(*wl["phi"])
-        halos, pos_only = None, False
-        bytes_per_survivor = 84
-    else:
-        halos = [cc.halo_setup(p, b).halo for (p, b) in halo_list(cc, wl)]
-        pos_only = False
-        bytes_per_survivor = 84
-        n_limit = cc.ref_scatter_kept(n_total, 1)  # the reference's tail drop
+
+        def step():
+            ctx.cutout_const(tc, pc)
+            if env.world > 1:
+                ctx.exchange_counts()
+            else:
+                ctx.sync()
+        return step, 1, 0
+    groups = [[cc.halo_setup(p, b).halo for (p, b) in hl] for (_b, hl) in halo_groups(wl)]
+    n_limit = cc.ref_scatter_kept(n_total, 1)  # the reference's tail drop (SURVEY.md App. A Q7)
 
     def step():
-        if wl["uc"] == 1:
-            ctx.cutout_const(tc, pc)
-        else:
-            ctx.cutout_halo(halos, pos_only=pos_only, n_limit_global=n_limit)
-        if world > 1:
-            ctx.exchange_counts()
-        else:
-            ctx.sync()
+        for halos in groups:
+            ctx.cutout_halo(halos, pos_only=False, n_limit_global=n_limit)
+            if env.world > 1:
+                ctx.exchange_counts()
+            else:
+                ctx.sync()
+    return step, len(groups), sum(len(g) for g in groups)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+def run_resident(env, args, name, steps, warmup, with_e2e):
+    """one resident workload at this N -> result dict (rank 0) or None"""
+    torch, cc, ctx = env.torch, env.cc, env.ctx
+    wl = WORKLOADS[name]
+    n = int(args.particles) if (args.particles and name == args.workload) else wl["n"]
+    n_total = n * env.world
+    step, passes, nhalos = make_step_fn(env, wl, n, n_total)
+    ctx.release()
+    ctx.set_option("payload", "auto")
+    env.barrier()
+    # ---- residency + the first (cold) cutout on the resident step: no payload yet, survivor buffers at their first guess
+    t0 = time.perf_counter()
+    ctx.synth(n, seed=SEED, index_base=env.rank * n, kind=wl["kind"], box=wl["box"])
+    torch.cuda.synchronize()
+    residency_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    step()
+    first_ms = (time.perf_counter() - t0) * 1e3
+    first_dev_ms = ctx.last_total_ms() if passes == 1 else None
+    payload_ms = 0.0
+    for _ in range(max(warmup, 3)):
         step()
+        payload_ms += ctx.stats_ex()["payload_build_ms"]
     # per-kernel times (the roofline numerator's denominator) are read from the library's own CUDA events in a
     # separate untimed pass: reading them costs two synchronising calls per step that do not belong in the timed loop
     scan_ms, pass_ms = [], []
-    for _ in range(max(3, min(args.steps, 10))):
+    for _ in range(max(3, min(steps, 10))):
         step()
-        scan_ms.append(ctx.last_scan_ms())
+        scan_ms.append(ctx.last_scan_ms())   # of the last pass of the step
         pass_ms.append(ctx.last_total_ms())
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    env.barrier()
+    sampler = ClockSampler(env.local_rank) if (env.rank == 0 and name == args.workload) else None
     if sampler:
         time.sleep(0.25)
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    survivors, scanned = 0, 0
-    barrier()
+    env.barrier()
     t0 = time.time()
-    ev0.record(stream)
-    for _ in range(args.steps):
+    ev0.record(env.stream)
+    for _ in range(steps):
         step()
-    ev1.record(stream)
-    barrier()
+    ev1.record(env.stream)
+    env.barrier()
     t1 = time.time()
     launches = ctx.launch_count() - launches0
-    st = ctx.stats()
-    survivors, scanned = st["survivors"], st["scanned"]
+    st = ctx.stats_ex()  # of the last pass
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t0, t1) if sampler else None
+    # survivors of a whole step (all passes)
+    surv_step, scanned_step = 0, 0
+    if passes == 1:
+        surv_step, scanned_step = st["survivors"], st["scanned"]
+    else:
+        groups = [[cc.halo_setup(p, b).halo for (p, b) in hl] for (_b, hl) in halo_groups(wl)]
+        for halos in groups:
+            ctx.cutout_halo(halos, n_limit_global=cc.ref_scatter_kept(n_total, 1))
+            if env.world > 1:
+                ctx.exchange_counts()
+            else:
+                ctx.sync()
+            s2 = ctx.stats()
+            surv_step += s2["survivors"]
+            scanned_step += s2["scanned"]
 
-    # ---- e2e: HOST (pinned) columns through the C ABI, H2D + D2H inside the timed region
+    e2e = None
+    if with_e2e:
+        e2e = run_e2e(env, args, wl, n)
+
+    ms_total, scan_avg, pass_avg, first_ms, residency_ms = env.allreduce(
+        [ms_total, float(np.mean(scan_ms)), float(np.mean(pass_ms)), first_ms, residency_ms], "max")
+    launches_all, surv_all, scanned_all = [int(v) for v in env.allreduce([launches, surv_step, scanned_step], "sum")]
+    if env.rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    ms_per_step = ms_total / steps
+    value = n_total / (ms_per_step * 1e-3) / 1e9
+    # roofline of the dominant kernel (the scan), per launch on this GPU (rank 0's shard): it reads x,y,z of every
+    # particle (12 B) and writes one 24-byte (index, theta, phi, x, y, z) record per survivor (use case 1) or one
+    # 32-byte record (use case 2); the whole pass (scan + ordering + 12-column gather) moves 12 B per particle +
+    # 84 B per survivor (SURVEY.md 8d) and is reported next to it
+    rec_bytes = 24 if wl["uc"] == 1 else 32
+    alg_bytes = 12.0 * st["scanned"] + rec_bytes * st["survivors"]
+    achieved = alg_bytes / (float(np.mean(scan_ms)) * 1e-3) / 1e9
+    pass_bytes = 12.0 * st["scanned"] + 84.0 * st["survivors"]
+    pass_gbs = pass_bytes / (float(np.mean(pass_ms)) * 1e-3) / 1e9
+    step_bytes = 12.0 * scanned_step + 84.0 * surv_step  # rank 0's shard, all passes of a step
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(name)
+        except Exception:
+            traffic = None
+    kernel = {1: "k1s_scan", 2: "k2_cutout_halo_cells" if nhalos >= 8 else "k2_cutout_halo"}[wl["uc"]]
+    out = {
+        "metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": env.world,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "particles_per_gpu": n, "particles_total": n_total,
+                   "survivors_total": surv_all, "passes_per_step": passes, "halos": nhalos,
+                   "l2": "inputs (12 B x particles per GPU) exceed the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the cutout stream around all timed steps, max over ranks",
+                   "count_exchange": env.exchange},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src, "kernel": kernel,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(float(np.mean(scan_ms)), 4),
+                     "whole_pass": {"bytes": pass_bytes, "ms": round(float(np.mean(pass_ms)), 4),
+                                    "achieved": round(pass_gbs, 1), "frac": round(pass_gbs / peak, 4),
+                                    "what": "scan + ordering + gather kernels of one pass (CUDA events inside the library), "
+                                            "12 B/particle + 84 B/survivor"},
+                     "whole_step": {"bytes": step_bytes, "ms": round(ms_per_step, 4),
+                                    "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                                    "what": "all passes of a step incl. launch gaps, host turnaround and the count exchange"}},
+        "residency": {"resident_ms": round(residency_ms, 3), "how": "cc_step_synth (device generator) incl. allocation, host clock",
+                      "first_cutout_ms": round(first_ms, 3),
+                      "first_cutout_device_ms": None if first_dev_ms is None else round(first_dev_ms, 4),
+                      "first_cutout": "first step() on the newly resident step, host clock incl. synchronisation: survivor "
+                                      "buffers at their first guess, no interleaved payload (gather from the 7 SoA columns)",
+                      "payload_build_ms": round(payload_ms, 3), "payload_resident": st["payload_resident"],
+                      "payload": "built lazily inside the first cutout that follows a dense one (>= max(65536, n/512) "
+                                 "survivors); never for sparse cutouts"},
+        "gpu_launches": launches_all,
+    }
+    if nhalos:
+        out["halos_per_s"] = round(nhalos / (ms_per_step * 1e-3), 1)
+    if e2e is not None:
+        out["e2e"] = e2e
+    if clocks is not None:
+        out["clocks"] = clocks
+    return out
+
+
+def run_e2e(env, args, wl, n):
+    """HOST (pinned) columns through the C ABI, H2D + D2H inside the timed region -> dict (rank 0) or None"""
+    import ctypes as C
+    torch, cc, ctx = env.torch, env.cc, env.ctx
     e2e_n = int(args.e2e_particles) if args.e2e_particles else min(n, 100_000_000)
     if args.no_e2e:
         e2e_n = 1 << 20
     ctx.release()
-    host = {}
-    addrs = []
+    host, addrs = {}, []
     for k in cc.IN_COLS:
         a, addr = cc.pinned_empty(e2e_n, cc.COL_DTYPES[k])
         host[k] = a
         addrs.append(addr)
-    import ctypes as C
-    cc._check(cc.lib().cc_synth_host(e2e_n, 20261019, rank * e2e_n, wl["kind"], C.c_float(wl["box"]),
+    cc._check(cc.lib().cc_synth_host(e2e_n, SEED, env.rank * e2e_n, wl["kind"], C.c_float(wl["box"]),
                                      *[host[k].ctypes.data_as(C.c_void_p) for k in cc.IN_COLS]))
-    e2e_limit = cc.ref_scatter_kept(e2e_n * world, 1)
+    e2e_limit = cc.ref_scatter_kept(e2e_n * env.world, 1)
+    if wl["uc"] == 1:
+        tc, pc = cc.cli_bounds(*wl["theta"]), cc.cli_bounds(*wl["phi"])
+    else:
+        halos = [cc.halo_setup(p, b).halo for (_b, hl) in halo_groups(wl) for (p, b) in hl]
 
     def e2e_step():
         if wl["uc"] == 1:
-            ctx.cutout_const_streamed(host, tc, pc, index_base=rank * e2e_n)
+            ctx.cutout_const_streamed(host, tc, pc, index_base=env.rank * e2e_n)
         else:
-            ctx.cutout_halo_streamed(host, halos, pos_only=pos_only, n_limit_global=e2e_limit, index_base=rank * e2e_n)
-        if world > 1:
+            ctx.cutout_halo_streamed(host, halos, n_limit_global=e2e_limit, index_base=env.rank * e2e_n)
+        if env.world > 1:
             ctx.exchange_counts()
         counts, _ = ctx.sync()
         out, _off = ctx.fetch_all(counts)  # every halo's survivors, one device->host copy per column
-        nbytes = sum(v.nbytes for v in out.values())
-        return int(counts.sum()), nbytes
+        return int(counts.sum()), sum(v.nbytes for v in out.values())
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(min(args.warmup, 3)):
+    for _ in range(min(max(args.warmup, 3), 3)):
         e2e_step()
-    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
     tw0 = time.perf_counter()
-    ev0.record(stream)
+    ev0.record(env.stream)
     d2h = 0
     for _ in range(e2e_steps):
-        k_e2e, d2h = e2e_step()
-    ev1.record(stream)
-    barrier()
+        _k, d2h = e2e_step()
+    ev1.record(env.stream)
+    env.barrier()
     tw1 = time.perf_counter()
     e2e_ms = max(ev0.elapsed_time(ev1), (tw1 - tw0) * 1e3)
+    (e2e_ms,) = env.allreduce([e2e_ms], "max")
+    ctx.release()
+    del host
     for a in addrs:
-        pass  # pinned buffers are freed with the process (numpy views still reference them)
-
-    # ---- max over ranks
-    times = torch.tensor([ms_total, e2e_ms, float(np.mean(scan_ms))], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(launches), float(survivors), float(scanned)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, scan_avg_ms = [float(v) for v in times.tolist()]
-    launches, survivors_all, scanned_all = [int(v) for v in cnt.tolist()]
-
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        ms_per_step = ms_total / args.steps
-        value = n_total / (ms_per_step * 1e-3) / 1e9
-        # roofline of the dominant kernel (the scan), per launch on this GPU (rank 0's shard): it reads x,y,z of
-        # every particle (12 B) and writes one 12-byte (index, theta, phi) record per survivor (use case 1) or one
-        # 24-byte record per survivor (use case 2); the whole pass (scan + ordering + 12-column gather) moves
-        # 12 B per particle + 84 B per survivor and is reported next to it
-        rec_bytes = 12 if wl["uc"] == 1 else 24
-        alg_bytes = 12.0 * scanned + rec_bytes * survivors
-        achieved = alg_bytes / (float(np.mean(scan_ms)) * 1e-3) / 1e9
-        pass_bytes = 12.0 * scanned + bytes_per_survivor * survivors
-        pass_gbs = pass_bytes / (float(np.mean(pass_ms)) * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(REPO, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get(args.workload)
-            except Exception:
-                traffic = None
-        out = {
-            "metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": wl["desc"], "particles_per_gpu": n, "particles_total": n_total,
-                       "survivors_total": survivors_all, "l2": "inputs (12 B x particles per GPU) exceed the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the cutout stream around all timed steps, max over ranks",
-                       "count_exchange": ("none (1 GPU)" if world == 1 else
-                                          ("NVLink peer stores (k4_exchange_peer)" if args.peer else
-                                           "NCCL all-gather enqueued behind the cutout kernels"))},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k2_cutout_halo" if wl["uc"] == 2 else "k1_scan",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(float(np.mean(scan_ms)), 4),
-                         "whole_pass": {"bytes": pass_bytes, "ms": round(float(np.mean(pass_ms)), 4),
-                                        "achieved": round(pass_gbs, 1), "frac": round(pass_gbs / peak, 4),
-                                        "what": "scan + ordering + gather kernels, 12 B/particle + 84 B/survivor"}},
-            "e2e": {"value": round(e2e_n * world / (e2e_ms / e2e_steps * 1e-3) / 1e9, 4), "unit": "Gparticles/s",
-                    "h2d_bytes_per_step": 12 * e2e_n, "d2h_bytes_per_step": d2h, "particles_per_gpu": e2e_n,
-                    "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
-                    "api": "cc_cutout_halo_streamed/cc_cutout_const_streamed + cc_cutout_sync + cc_cutout_fetch_all on pinned host columns"},
-            "gpu_launches": launches,
-            "clocks": clocks,
-        }
-        if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(args, wl, single_core=True)
-        print(json.dumps(out), file=_OUT, flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        cc.pinned_free(a)
+    if env.rank != 0:
+        return None
+    return {"value": round(e2e_n * env.world / (e2e_ms / e2e_steps * 1e-3) / 1e9, 4), "unit": "Gparticles/s",
+            "h2d_bytes_per_step": 12 * e2e_n, "d2h_bytes_per_step": d2h, "particles_per_gpu": e2e_n,
+            "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
+            "api": "cc_cutout_halo_streamed/cc_cutout_const_streamed + cc_cutout_sync + cc_cutout_fetch_all on pinned host columns"}
 
 
 # ------------------------------------------------------------------------------------------------ cfg3: streamed depth
-def run_cfg3(args):
+def run_cfg3(env, args, steps, warmup):
     """BASELINE configs[2]: full-depth cutout, ~30 lightcone steps, 1 B particles in total, every step streamed from
-    pinned host memory (x,y,z by double-buffered cudaMemcpyAsync, the other columns read in place for survivors).
+    pinned host memory (x,y,z by double-buffered cudaMemcpyAsync, the other columns picked for survivors).
     Strong scaling: the 1 B particles are index-sharded over the GPUs.  PCIe-bound by construction (12 B/particle)."""
     import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from __graft_entry__ import load_package
-    cc = load_package()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    ctx = cc.Context(local_rank)
-    if world > 1:
-        ident = [cc.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        ctx.comm_init(world, rank, ident[0])
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
-    n_total = int(args.particles) if args.particles else 1_000_000_000
+    torch, cc, ctx = env.torch, env.cc, env.ctx
+    wl = WORKLOADS["cfg3"]
+    n_total = int(args.particles) if (args.particles and args.workload == "cfg3") else 1_000_000_000
     lc_steps = 30
     m_step = n_total // lc_steps          # particles of one lightcone step (all GPUs)
-    lo, hi = cc.shard_range(m_step, world, rank)
+    lo, hi = cc.shard_range(m_step, env.world, env.rank)
     m = hi - lo                           # this GPU's shard of every step
+    ctx.release()
     # distinct x,y,z per lightcone step; the seven gather-only columns are shared between steps (they are only read
     # at survivor indices, any step's values exercise the same path) to keep pinned memory at 12 B x particles
-    shared = {}
+    shared, addrs = {}, []
     for k in cc.IN_COLS[3:]:
-        shared[k], _ = cc.pinned_empty(m, cc.COL_DTYPES[k])
+        shared[k], a = cc.pinned_empty(m, cc.COL_DTYPES[k])
+        addrs.append(a)
     xs = []
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     for s_ in range(lc_steps):
         cols = dict(shared)
         for k in ("x", "y", "z"):
-            cols[k], _ = cc.pinned_empty(m, np.float32)
-        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+            cols[k], a = cc.pinned_empty(m, np.float32)
+            addrs.append(a)
         others = [ptr(shared[k]) if s_ == 0 else None for k in cc.IN_COLS[3:]]
-        cc._check(cc.lib().cc_synth_host(m, 20261019 + s_, lo, 0, C.c_float(300.0), ptr(cols["x"]), ptr(cols["y"]),
+        cc._check(cc.lib().cc_synth_host(m, SEED + s_, lo, 0, C.c_float(300.0), ptr(cols["x"]), ptr(cols["y"]),
                                          ptr(cols["z"]), *others))
         xs.append(cols)
     halo = cc.halo_setup((150.0, 20.0, 12.0), 10.0).halo
@@ -374,7 +455,7 @@ def run_cfg3(args):
         tot, nbytes = 0, 0
         for cols in xs:
             ctx.cutout_halo_streamed(cols, [halo], n_limit_global=limit, index_base=lo)
-            if world > 1:
+            if env.world > 1:
                 ctx.exchange_counts()
             counts, _ = ctx.sync()
             if counts[0]:
@@ -383,101 +464,200 @@ def run_cfg3(args):
             tot += int(counts[0])
         return tot, nbytes
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    steps = max(1, min(args.steps, 5))
-    for _ in range(max(1, min(args.warmup, 2))):
+    steps = max(1, min(steps, 3))
+    for _ in range(1):
         step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    env.barrier()
+    sampler = ClockSampler(env.local_rank) if (env.rank == 0 and args.workload == "cfg3") else None
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     tw0 = time.perf_counter()
-    ev0.record(stream)
+    ev0.record(env.stream)
     for _ in range(steps):
         surv, d2h = step()
-    ev1.record(stream)
-    barrier()
+    ev1.record(env.stream)
+    env.barrier()
     tw1 = time.perf_counter()
     t1 = time.time()
     ms = max(ev0.elapsed_time(ev1), (tw1 - tw0) * 1e3) / steps
-    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(ctx.launch_count() - launches0), float(surv)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms = float(tms.item())
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        value = m_step * lc_steps / (ms * 1e-3) / 1e9
-        scan_ms = ctx.last_scan_ms()
-        out = {"metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": world,
-               "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
-               "scaling": "strong", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "BASELINE cfg3: full-depth halo cutout, 30 lightcone steps, 1B particles total, every "
-                                      "step streamed from pinned host (x,y,z H2D double-buffered, other columns read in "
-                                      "place for survivors)", "particles_total": m_step * lc_steps,
-                          "particles_per_gpu_per_lc_step": m, "lc_steps": lc_steps, "survivors_total": int(cnt[1].item()),
-                          "l2": "every chunk comes over PCIe; nothing is reused", "timing": "max(CUDA events, host clock), max over ranks"},
-               "roofline": {"bound": "pcie", "achieved": round(12.0 * m * lc_steps / (ms * 1e-3) / 1e9, 2), "peak": 63.0,
-                            "unit": "GB/s", "frac": round(12.0 * m * lc_steps / (ms * 1e-3) / 1e9 / 63.0, 4), "traffic": None,
-                            "peak_source": "PCIe gen5 x16 nominal per GPU (host->device), the scan kernel itself runs at the HBM "
-                                           "roofline (see the resident workloads)", "kernel": "k2_cutout_halo",
-                            "kernel_ms_last_chunk": round(scan_ms, 4)},
-               "e2e": {"value": round(value, 3), "unit": "Gparticles/s", "h2d_bytes_per_step": 12 * m * lc_steps,
-                       "d2h_bytes_per_step": d2h, "api": "cc_cutout_halo_streamed + cc_cutout_sync + cc_cutout_fetch"},
-               "gpu_launches": int(cnt[0].item()), "clocks": sampler.stop(t0, t1) if sampler else None}
-        print(json.dumps(out), file=_OUT, flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    (ms,) = env.allreduce([ms], "max")
+    launches, surv_all = [int(v) for v in env.allreduce([ctx.launch_count() - launches0, surv], "sum")]
+    scan_ms = ctx.last_scan_ms()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ctx.release()
+    xs.clear()
+    shared.clear()
+    for a in addrs:
+        cc.pinned_free(a)
+    if env.rank != 0:
+        return None
+    value = m_step * lc_steps / (ms * 1e-3) / 1e9
+    gbs = 12.0 * m * lc_steps / (ms * 1e-3) / 1e9
+    out = {"metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": env.world,
+           "steps": steps, "warmup": 1, "ms_per_step": round(ms, 3), "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl["desc"], "particles_total": m_step * lc_steps,
+                      "particles_per_gpu_per_lc_step": m, "lc_steps": lc_steps, "survivors_total": surv_all,
+                      "l2": "every chunk comes over PCIe; nothing is reused",
+                      "timing": "max(CUDA events, host clock), max over ranks", "count_exchange": env.exchange},
+           "roofline": {"bound": "pcie", "achieved": round(gbs, 2), "peak": 63.0, "unit": "GB/s", "frac": round(gbs / 63.0, 4),
+                        "traffic": None,
+                        "peak_source": "PCIe gen5 x16 nominal per GPU (host->device); the scan kernel itself runs at the HBM "
+                                       "roofline (see the resident workloads)", "kernel": "k2_cutout_halo",
+                        "kernel_ms_last_chunk": round(scan_ms, 4)},
+           "e2e": {"value": round(value, 3), "unit": "Gparticles/s", "h2d_bytes_per_step": 12 * m * lc_steps,
+                   "d2h_bytes_per_step": d2h, "api": "cc_cutout_halo_streamed + cc_cutout_sync + cc_cutout_fetch"},
+           "gpu_launches": launches}
+    if clocks is not None:
+        out["clocks"] = clocks
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ parity leg (untimed)
+def _sha(cols, names):
+    h = hashlib.sha256()
+    for k in names:
+        h.update(np.ascontiguousarray(cols[k]).tobytes())
+    return h.hexdigest()
+
+
+def parity_check(env, n=None):
+    """Every rank: cut its own shard of a synthetic step (use case 1 and use case 2, several halos), exchange the counts
+    over NCCL and over the peer mailboxes, and compare with the oracle (oracle/liboracle.so -- the checker, never the
+    thing measured) run on the shard's candidate set: a loose float64 window selects every particle that could possibly
+    survive, the oracle decides among those with the reference's own arithmetic."""
+    import harness as H
+    cc, ctx = env.cc, env.ctx
+    n = n or 20_000_000
+    n_total = n * env.world
+    base = env.rank * n
+    ctx.release()
+    ctx.synth(n, seed=SEED + 7, index_base=base, kind=0, box=300.0)
+    host = cc.synth_host(n, SEED + 7, index_base=base, kind=0, box=300.0)
+    x64, y64, z64 = (host[k].astype(np.float64) for k in ("x", "y", "z"))
+    r = np.sqrt(x64 * x64 + y64 * y64 + z64 * z64)
+    th64 = np.degrees(np.arccos(np.clip(z64 / r, -1, 1))) * 3600.0
+    ph64 = np.degrees(np.arctan(y64 / x64)) * 3600.0
+    del x64, y64, z64, r
+    res = {"particles_per_gpu": n, "ranks": env.world, "checks": []}
+    ok_all = True
+    modes = ["auto"] if env.world == 1 else ["peer", "nccl"]
+
+    def offsets_ok(allc, off):
+        want = allc[:env.rank].sum(axis=0)
+        return bool(np.array_equal(np.asarray(off), want))
+
+    # ---- use case 1
+    tc, pc = cc.cli_bounds(87.0, 2.0), cc.cli_bounds(2.0, 2.0)
+    sel = np.nonzero((th64 > tc[0] - 30) & (th64 < tc[1] + 30) & (ph64 > pc[0] - 30) & (ph64 < pc[1] + 30))[0]
+    sub = {k: np.ascontiguousarray(host[k][sel]) for k in cc.IN_COLS}
+    want = H.oracle_cutout_const(sub, tc, pc)
+    for mode in modes:
+        ctx.set_option("exchange", mode)
+        ctx.cutout_const(tc, pc)
+        if env.world > 1:
+            allc, _allr, off = ctx.exchange_counts()
+        else:
+            allc, off = np.array([[int(ctx.sync()[0][0])]]), np.zeros(1, np.int64)
+        got = ctx.fetch(0)
+        same = all(np.ascontiguousarray(got[k]).tobytes() == want[k].tobytes() for k in cc.OUT_COLS)
+        ok = same and int(allc[env.rank][0]) == want["id"].shape[0] and offsets_ok(allc, off)
+        tot = env.allreduce([want["id"].shape[0]], "sum")[0]
+        ok = ok and int(allc.sum()) == int(tot)
+        ok_all &= ok
+        res["checks"].append({"what": f"use case 1, exchange={mode}", "ok_rank0": bool(ok), "survivors_total": int(allc.sum()),
+                              "oracle_total": int(tot), "sha256_rank0": _sha(got, cc.OUT_COLS)[:16]})
+    # ---- use case 2: nine halos (cell-index kernel) + one (plain kernel); the reference's tail drop applies to the step
+    limit = cc.ref_scatter_kept(n_total, 1)
+    rng = np.random.default_rng(11)
+    pos = np.vstack([[150.0, 20.0, 12.0], rng.uniform(40, 250, (8, 3))]).astype(np.float32)
+    for label, hp, box in (("1 halo", pos[:1], 10.0), ("9 halos", pos, 30.0)):
+        infos = [cc.halo_setup(p, box) for p in hp]
+        wants = []
+        for p, info in zip(hp, infos):
+            hh = info.halo
+            s2 = np.nonzero((th64 >= hh.theta_rough[0] - 30) & (th64 < hh.theta_rough[1] + 30) &
+                            (ph64 > hh.phi_rough[0] - 30) & (ph64 < hh.phi_rough[1] + 30))[0]
+            s2 = s2[s2 + base < limit]
+            sub = {k: np.ascontiguousarray(host[k][s2]) for k in cc.IN_COLS}
+            wants.append(H.oracle_cutout_halo(sub, H.oracle_halo_setup(p, box)))
+        for mode in modes:
+            ctx.set_option("exchange", mode)
+            ctx.cutout_halo([i.halo for i in infos], n_limit_global=limit)
+            if env.world > 1:
+                allc, allr, off = ctx.exchange_counts()
+                counts, rough = allc[env.rank], allr[env.rank]
+            else:
+                counts, rough = ctx.sync()
+                allc, off = counts.reshape(1, -1), np.zeros(len(hp), np.int64)
+            everything, offs = ctx.fetch_all(counts)
+            ok = offsets_ok(allc, off)
+            for h, (w, w_rough) in enumerate(wants):
+                g = {k: v[offs[h]:offs[h + 1]] for k, v in everything.items()}
+                ok = ok and int(rough[h]) == w_rough and int(counts[h]) == w["id"].shape[0]
+                ok = ok and all(np.ascontiguousarray(g[k]).tobytes() == w[k].tobytes() for k in cc.OUT_COLS)
+            tot = env.allreduce([sum(w["id"].shape[0] for w, _ in wants)], "sum")[0]
+            ok = ok and int(allc.sum()) == int(tot) and ctx.stats_ex()["nan_theta"] == 0
+            ok_all &= ok
+            res["checks"].append({"what": f"use case 2, {label}, exchange={mode}", "ok_rank0": bool(ok),
+                                  "survivors_total": int(allc.sum()), "oracle_total": int(tot),
+                                  "sha256_rank0": _sha(everything, cc.OUT_COLS)[:16]})
+    ctx.set_option("exchange", "auto")
+    ctx.release()
+    (mn,) = env.allreduce([1.0 if ok_all else 0.0], "min")
+    res["ok"] = bool(mn == 1.0)
+    res["how"] = ("byte-for-byte: all 12 survivor columns of every rank's shard vs oracle/liboracle.so on the shard's candidate "
+                  "set; counts == oracle's; offsets == exclusive scan over ranks of the gathered counts; min over ranks")
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def _synth_np(n, seed, first, box):
+    import harness as H
+    return H.synth_numpy(n, seed, index_base=first, kind=0, box=box)
+
+
 def _ref_worker(task):
-    """one single-rank reference process on one contiguous index slice (runs in a child process)"""
+    """one single-rank reference process on one contiguous index slice (runs in a child process); uses only the
+    reference build (oracle/_ref) or the oracle port, never the product library"""
     (wl_name, first, count, seed, repeat) = task
     import harness as H
-    from __graft_entry__ import load_package
-    cc = load_package()
     wl = WORKLOADS[wl_name]
-    cols = cc.synth_host(count, seed, index_base=first, kind=wl["kind"], box=wl["box"])
+    cols = _synth_np(count, seed, first, wl["box"])
     kind = "reference" if H.ref_available() else "port"
     dts = []
+    hl = halo_groups(wl)[0][1] if wl["uc"] == 2 else None
     for _ in range(repeat):
         t0 = time.perf_counter()
         if kind == "reference":
             with H.RefRun(cols) as r:
                 if wl["uc"] == 1:
-                    out = r.const(cc.cli_bounds(*wl["theta"]), cc.cli_bounds(*wl["phi"]))
+                    out = r.const(H.oracle_cli_bounds(*wl["theta"]), H.oracle_cli_bounds(*wl["phi"]))
                     k = out["id"].shape[0]
                 else:
                     k = 0
-                    for (p, b) in halo_list(cc, wl)[:1]:
+                    for (p, b) in hl[:1]:
                         out = r.halo(p, b)
                         k += out["id"].shape[0]
         else:
             if wl["uc"] == 1:
-                k = H.oracle_cutout_const(cols, cc.cli_bounds(*wl["theta"]), cc.cli_bounds(*wl["phi"]))["id"].shape[0]
+                k = H.oracle_cutout_const(cols, H.oracle_cli_bounds(*wl["theta"]), H.oracle_cli_bounds(*wl["phi"]))["id"].shape[0]
             else:
-                p, b = halo_list(cc, wl)[0]
+                p, b = hl[0]
                 k = H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, b))[0]["id"].shape[0]
         dts.append(time.perf_counter() - t0)
     return kind, dts, k
 
 
-def cpu_baseline(args, wl, single_core):
+def cpu_baseline(args, wl_name):
     import multiprocessing as mp
+    wl = WORKLOADS[wl_name]
     sample = int(args.cpu_sample) if args.cpu_sample else (10_000_000 if wl["uc"] == 2 else 100_000_000)
     sample = min(sample, wl["n"])
     ctx = mp.get_context("spawn")
     with ctx.Pool(1) as pool:
-        kind, dts, k = pool.map(_ref_worker, [(args.workload, 0, sample, 20261019, 1)])[0]
+        kind, dts, k = pool.map(_ref_worker, [(wl_name, 0, sample, SEED, 1)])[0]
     v = sample / dts[0] / 1e9
     return {"value": round(v, 6), "unit": "Gparticles/s", "cores": 1, "kind": kind,
             "sample": f"first {sample} particles of the workload's step, one reference rank (the reference has no "
@@ -493,11 +673,12 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = len(os.sched_getaffinity(0))
     # the reference's own decomposition of this workload on this box: one MPI rank per core, each reading its block
     per = int(args.cpu_sample) if args.cpu_sample else min(wl["n"] // cores, 8_000_000 if wl["uc"] == 2 else 25_000_000)
     ctx = mp.get_context("spawn")
-    tasks = [(args.workload, i * per, per, 20261019, 1) for i in range(cores)]
+    tasks = [(args.workload, i * per, per, SEED, 1) for i in range(cores)]
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
             pool.map(_ref_worker, tasks[:cores])
@@ -509,18 +690,63 @@ def run_reference(args):
     # rate of the compute inside the workers (excludes process start-up and synthetic column generation)
     slowest = max(max(r[1]) for r in res)
     v = cores * per / slowest / 1e9
+    n = wl["n"]
     out = {"impl": "reference", "metric": "Gparticles/s filtered", "value": round(v, 6), "unit": "Gparticles/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(slowest * 1e3, 3),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": wl["desc"], "sample_particles_per_step": cores * per},
+           "config": {"workload": wl["desc"], "particles_per_gpu": n, "particles_total": n * world},
            "cpu_baseline": {"value": round(v, 6), "unit": "Gparticles/s", "cores": cores, "kind": kind,
-                            "sample": f"{cores} single-rank reference processes x {per} particles each (disjoint index "
-                                      f"slices of the workload's step), slowest process {slowest:.2f} s per step; wall "
-                                      f"{dt / max(args.steps, 1):.2f} s per step incl. column generation"},
+                            "sample": f"each step = {cores} single-rank reference processes x {per} particles (disjoint index "
+                                      f"slices of the workload's step; {cores * per} particles per step), slowest process "
+                                      f"{slowest:.2f} s per step; wall {dt / max(args.steps, 1):.2f} s per step incl. column generation"},
            "e2e": {"value": round(v, 6), "unit": "Gparticles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), file=_OUT, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ driver
+def run_ours(args):
+    env = Env(args)
+    cc = env.cc
+    # load every kernel once (module load, first allocations) on a small step before anything is timed
+    env.ctx.synth(1 << 20, seed=1, index_base=0, kind=0, box=300.0)
+    env.ctx.cutout_const(cc.cli_bounds(87.0, 2.0), cc.cli_bounds(2.0, 2.0))
+    env.ctx.sync()
+    env.ctx.cutout_halo([cc.halo_setup((150.0, 20.0, 12.0), 10.0).halo])
+    env.ctx.sync()
+    sub_steps, sub_warm = max(3, min(args.steps, 10)), 3
+    if args.workload == "cfg3":
+        out = run_cfg3(env, args, args.steps, args.warmup)
+    else:
+        out = run_resident(env, args, args.workload, args.steps, args.warmup, with_e2e=True)
+    if not args.no_configs and args.workload == "cfg2":
+        configs = {}
+        for name in ("cfg1", "const1b", "cfg4", "cfg5", "cfg3"):
+            t0 = time.perf_counter()
+            try:
+                r = run_cfg3(env, args, 2, 1) if name == "cfg3" else run_resident(env, args, name, sub_steps, sub_warm, with_e2e=False)
+            except Exception as e:  # e.g. not enough HBM / pinned memory on this box: say so, keep the headline
+                log(f"config {name} failed: {e!r}")
+                r = {"error": repr(e)} if env.rank == 0 else None
+            if env.rank == 0:
+                r["bench_wall_s"] = round(time.perf_counter() - t0, 1)
+                configs[name] = r
+        if env.rank == 0:
+            out["configs"] = configs
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(env)
+        if env.rank == 0:
+            out["parity_check"] = parity
+    if env.rank == 0:
+        if not args.no_cpu_baseline and env.world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, args.workload)
+        print(json.dumps(out), file=_OUT, flush=True)
+    env.close()
+    if parity is not None and not parity["ok"]:
+        log("parity_check FAILED")
+        sys.exit(3)
 
 
 def _claim_stdout():
@@ -539,22 +765,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--particles", default=None, help="override particles per GPU")
+    ap.add_argument("--particles", default=None, help="override particles per GPU of --workload")
     ap.add_argument("--e2e-particles", default=None)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
-    ap.add_argument("--peer", action="store_true",
-                    help="count exchange by NVLink peer stores (k4_exchange_peer) instead of the NCCL all-gather; "
-                         "measured equal within noise at 2 GPUs once both sit behind the kernels on the stream")
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the `configs` block)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity_check leg")
+    ap.add_argument("--nccl", action="store_true",
+                    help="count exchange by the NCCL all-gather instead of the NVLink peer stores (k4_exchange_peer)")
     args = ap.parse_args()
     global _OUT
     _OUT = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "cfg3":
-        run_cfg3(args)
     else:
         run_ours(args)
     _OUT.flush()

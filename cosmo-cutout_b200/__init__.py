@@ -53,7 +53,7 @@ SYMBOLS = (
     "cc_version", "cc_last_error", "cc_device_count", "cc_create", "cc_destroy", "cc_stream",
     "cc_halo_setup", "cc_cli_bounds", "cc_ref_scatter_kept",
     "cc_step_upload", "cc_step_attach", "cc_step_synth", "cc_synth_host", "cc_step_download", "cc_step_size",
-    "cc_step_release",
+    "cc_step_release", "cc_step_select", "cc_device_mem", "cc_bytes_uploaded",
     "cc_cutout_const", "cc_cutout_halo", "cc_cutout_sync", "cc_cutout_fetch", "cc_cutout_fetch_all", "cc_cutout_device_cols",
     "cc_cutout_const_streamed", "cc_cutout_halo_streamed", "cc_host_alloc", "cc_host_free", "cc_host_register",
     "cc_host_unregister",
@@ -93,6 +93,10 @@ def lib():
         L.cc_step_size.restype = C.c_int64
         L.cc_step_size.argtypes = [C.c_void_p]
         L.cc_step_release.argtypes = [C.c_void_p]
+        L.cc_step_select.argtypes = [C.c_void_p, C.c_int]
+        L.cc_device_mem.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cc_bytes_uploaded.restype = C.c_int64
+        L.cc_bytes_uploaded.argtypes = [C.c_void_p]
         L.cc_cutout_const.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cc_cutout_halo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64]
         L.cc_cutout_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -276,6 +280,18 @@ class Context:
 
     def release(self):
         _check(lib().cc_step_release(self._h))
+
+    def select(self, slot):
+        """cc_step_select: make resident-step slot `slot` the current one"""
+        _check(lib().cc_step_select(self._h, int(slot)))
+
+    def device_mem(self):
+        f, t = C.c_int64(0), C.c_int64(0)
+        _check(lib().cc_device_mem(self._h, C.byref(f), C.byref(t)))
+        return int(f.value), int(t.value)
+
+    def bytes_uploaded(self):
+        return int(lib().cc_bytes_uploaded(self._h))
 
     # cutouts
     def cutout_const(self, theta_cut, phi_cut):

@@ -123,6 +123,18 @@ const size_t OUT_COL_SIZE[N_OUT_COLS] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 8, 4, 4, 4, 
 
 enum Pending { P_NONE = 0, P_CONST = 1, P_HALO = 2 };
 
+/* a resident step that is not the context's current one (cc_step_select) */
+struct StepSlot {
+    bool valid = false, owned = false;
+    int64_t n = 0, index_base = 0;
+    const void* col[N_IN_COLS] = {};
+    DevBuf col_buf[N_IN_COLS];
+    DevBuf payload;
+    bool payload_valid = false;
+    int64_t last_survivors = -1;
+    void release() { for (auto& b : col_buf) b.release(); payload.release(); *this = StepSlot(); }
+};
+
 }  // namespace
 
 struct cc_ctx {
@@ -152,7 +164,10 @@ struct cc_ctx {
     int k1s_occupancy[2] = {0, 0};
     DevBuf t_idx, t_th, t_ph, t_x, t_y, t_z;
 
-    /* resident step */
+    /* resident steps: the fields below are the CURRENT one; the others wait in `slots` (cc_step_select) */
+    std::vector<StepSlot> slots;
+    int cur_slot = 0;
+    int64_t bytes_uploaded = 0; /* input-column bytes copied host -> device so far (cc_bytes_uploaded) */
     bool step_valid = false, step_owned = false;
     int64_t n = 0, index_base = 0;
     const void* col[N_IN_COLS] = {};
@@ -706,6 +721,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
             CU(cudaGetLastError());
             cck::RankArgs r;
+            r.rec_count = rec_count;
             r.recs = (const cck::Rec*)c->rec_b.p;
             r.seg_begin = hs_seg(c, H);
             r.rec_cap = (unsigned long long)c->rec_cap;
@@ -777,6 +793,7 @@ int run_streamed(cc_ctx* c) {
         const float* src[3] = {c->host_cols.x, c->host_cols.y, c->host_cols.z};
         for (int k = 0; k < 3 && len > 0; ++k)
             CU(cudaMemcpyAsync(c->stage[s][k].p, src[k] + start, (size_t)len * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        c->bytes_uploaded += 12 * len;
         CU(cudaEventRecord(c->ev_copied[s], c->copy_stream));
         CU(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
         Chunk ch;
@@ -898,7 +915,10 @@ void cc_destroy(cc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->xchg_stream) cudaStreamSynchronize(c->xchg_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto& sl : c->slots) sl.release();
     for (int r = 0; r < cck::XCHG_MAX_RANKS; ++r)
         if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_mb[r]);
     c->mailbox.release();
@@ -955,6 +975,43 @@ int cc_step_release(cc_ctx* c) {
     return CC_OK;
 }
 
+int cc_step_select(cc_ctx* c, int slot) {
+    if (!c || slot < 0 || slot > 65535) return fail(CC_ERR_ARG, "cc_step_select: bad argument");
+    int rc = use_device(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream)); /* a pending cutout may still read the current step */
+    c->pending = P_NONE;
+    if (slot == c->cur_slot) return CC_OK;
+    const size_t need = (size_t)std::max(slot, c->cur_slot) + 1;
+    if (c->slots.size() < need) c->slots.resize(need);
+    StepSlot& out = c->slots[(size_t)c->cur_slot];
+    out.valid = c->step_valid; out.owned = c->step_owned; out.n = c->n; out.index_base = c->index_base;
+    out.payload = c->payload; out.payload_valid = c->payload_valid; out.last_survivors = c->step_last_survivors;
+    for (int i = 0; i < N_IN_COLS; ++i) { out.col[i] = c->col[i]; out.col_buf[i] = c->col_buf[i]; }
+    StepSlot& in = c->slots[(size_t)slot];
+    c->step_valid = in.valid; c->step_owned = in.owned; c->n = in.n; c->index_base = in.index_base;
+    c->payload = in.payload; c->payload_valid = in.payload_valid; c->step_last_survivors = in.last_survivors;
+    for (int i = 0; i < N_IN_COLS; ++i) { c->col[i] = in.col[i]; c->col_buf[i] = in.col_buf[i]; }
+    in = StepSlot(); /* the buffers now belong to the context's current-step fields */
+    c->cur_slot = slot;
+    c->streamed = false;
+    c->payload_timed = false;
+    return CC_OK;
+}
+
+int cc_device_mem(cc_ctx* c, int64_t* free_bytes, int64_t* total_bytes) {
+    if (!c) return fail(CC_ERR_ARG, "ctx is NULL");
+    int rc = use_device(c);
+    if (rc) return rc;
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return CC_OK;
+}
+
+int64_t cc_bytes_uploaded(cc_ctx* c) { return c ? c->bytes_uploaded : 0; }
+
 int cc_step_upload(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_base) {
     if (!c || !host || n < 0) return fail(CC_ERR_ARG, "cc_step_upload: bad argument");
     if (!host->x || !host->y || !host->z || !host->a || !host->id) return fail(CC_ERR_ARG, "cc_step_upload: x,y,z,a,id are required");
@@ -964,8 +1021,10 @@ int cc_step_upload(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_b
     if ((rc = step_alloc(c, n, with_vel))) return rc;
     const void* src[N_IN_COLS] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->a, host->id, host->rotation, host->replication};
     for (int i = 0; i < N_IN_COLS; ++i)
-        if (c->col[i] && n > 0)
+        if (c->col[i] && n > 0) {
             CU(cudaMemcpyAsync(const_cast<void*>(c->col[i]), src[i], (size_t)n * IN_COL_SIZE[i], cudaMemcpyHostToDevice, c->stream));
+            c->bytes_uploaded += n * (int64_t)IN_COL_SIZE[i];
+        }
     CU(cudaStreamSynchronize(c->stream));
     c->n = n;
     c->index_base = index_base;

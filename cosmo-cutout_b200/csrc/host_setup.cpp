@@ -174,6 +174,7 @@ int64_t cc_ref_scatter_kept(int64_t np, int numranks) {
      * processLC.cpp:1003-1006 counts only entries < numranks, so entries that round up to numranks are never
      * sent.  float(j) is monotone in j, hence the kept set is a prefix: bisect for its length. */
     if (np <= 0 || numranks <= 0) return np < 0 ? 0 : np;
+    if (np > 2147483647ll) return np; /* the reference counts particles in `int` (processLC.cpp:897): no such run exists */
     const float np_per_rank = (float)((size_t)np) / numranks;
     int64_t lo = 0, hi = np;
     while (lo < hi) {

@@ -221,8 +221,7 @@ struct SegScanArgs {
  * index-only ring, 8 KB instead of 32 KB per CTA): the streaming loads are evict-first, the re-reads missed the L2 and
  * cost 4 GB of extra DRAM traffic on 500 M particles at 4.5 % survivors (profiles/r02). */
 struct __align__(16) K1SRing {
-    unsigned int idx[K1S_QCAP];       /* particle index inside the chunk */
-    float x[K1S_QCAP], y[K1S_QCAP], z[K1S_QCAP];
+    float4 e[K1S_QCAP];               /* x, y, z, particle index inside the chunk (bits): one 16-byte store per push */
 };
 struct K1SState {                     /* warp-uniform, in shared memory so that the drain can be a real call */
     unsigned int head, count;         /* ring */
@@ -254,8 +253,8 @@ __device__ __noinline__ void k1s_drain(const SegScanArgs* __restrict__ ap, K1SRi
     unsigned int idx = 0;
     bool pass = false;
     if (live) {
-        idx = rp->idx[e];
-        x = rp->x[e]; y = rp->y[e]; z = rp->z[e];
+        const float4 c4 = rp->e[e];
+        x = c4.x; y = c4.y; z = c4.z; idx = __float_as_uint(c4.w);
         pass = k1s_exact(a, x, y, z, th, ph);
     }
     const unsigned int B = __ballot_sync(0xffffffffu, pass);
@@ -330,20 +329,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k1s_scan(const __grid_constan
                 const unsigned int add = half ? (total >> 16) : (total & 0xffffu);
                 if (half == 1 && qcount + add > (unsigned)K1S_QCAP) drain_to_31();
                 unsigned int pos = qtail + (half ? (ex >> 16) : (ex & 0xffffu));
-                unsigned int mm = half ? (m >> 4) : (m & 0xfu);
-                while (mm) { /* 0.4 candidates per lane even in a wide field: a loop over the set bits, not 8 predicated pushes */
-                    const int j = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const unsigned int p = pos & (K1S_QCAP - 1);
-                    /* px[j] with a runtime j would go through local memory: select from registers instead */
-                    float vx = px[4 * half], vy = py[4 * half], vz = pz[4 * half];
-                    if (j == 1) { vx = px[4 * half + 1]; vy = py[4 * half + 1]; vz = pz[4 * half + 1]; }
-                    if (j == 2) { vx = px[4 * half + 2]; vy = py[4 * half + 2]; vz = pz[4 * half + 2]; }
-                    if (j == 3) { vx = px[4 * half + 3]; vy = py[4 * half + 3]; vz = pz[4 * half + 3]; }
-                    q.x[p] = vx; q.y[p] = vy; q.z[p] = vz;
-                    q.idx[p] = (unsigned int)base + tile_local(lane, j + 4 * half);
-                    ++pos;
-                }
+                /* straight-line, predicated: one 16-byte shared-memory store per candidate (a loop over the set bits
+                 * with register selects was measured at 195 warp instructions per tile, profiles/r02) */
+#pragma unroll
+                for (int j = 4 * half; j < 4 * half + 4; ++j)
+                    if (m & (1u << j)) {
+                        q.e[pos & (K1S_QCAP - 1)] = make_float4(px[j], py[j], pz[j], __uint_as_float((unsigned int)base + tile_local(lane, j)));
+                        ++pos;
+                    }
                 qtail += add;
                 qcount += add;
                 if (lane == 0) { st.count = qcount; st.n_cand += add; }
@@ -657,6 +650,10 @@ __device__ __forceinline__ void k2_exact(const HaloArgs& a, int h, float x, floa
     const unsigned int hg = (unsigned int)(a.halo0 + h);
     const float thu = ccref::theta_arcsec(x, y, z);       /* processLC.cpp:899-900 */
     const float phu = ccref::phi_arcsec_guarded(x, y);    /* :903-908 */
+    /* A NaN un-rotated theta (NaN coordinate, z = +-Inf, the origin) breaks the ordering contract of the reference's
+     * stable_sort / lower_bound on that key (:1214-1221, :1334-1337); such positions are out of the pre-filter's range,
+     * so they are paired with EVERY halo and reach this point: count each once (first halo), cc_last_stats_ex */
+    if (thu != thu && hg == 0u) atomicAdd(a.nan_count, 1ull);
     if (!(thu >= Hp->rth_lo && thu < Hp->rth_hi)) return; /* :1334-1340 (two lower_bounds) */
     if (!(phu > Hp->rph_lo && phu < Hp->rph_hi)) return;  /* :1400 */
     atomicAdd(a.counts + a.total_halos + hg, 1ull);       /* rough_cutout_size, :1436 */
@@ -696,6 +693,7 @@ __device__ __forceinline__ void k2_exact_warp(const HaloArgs& a, bool live, int 
     const unsigned int hg = (unsigned int)(a.halo0 + h);
     const float thu = ccref::theta_arcsec(x, y, z);       /* processLC.cpp:899-900 */
     const float phu = ccref::phi_arcsec_guarded(x, y);    /* :903-908 */
+    if (live && thu != thu && hg == 0u) atomicAdd(a.nan_count, 1ull); /* see k2_exact */
     const bool rough = live && (thu >= rth_lo && thu < rth_hi) /* :1334-1340 (two lower_bounds) */
                             && (phu > rph_lo && phu < rph_hi); /* :1400 */
     if (!__any_sync(0xffffffffu, rough)) return;
@@ -740,24 +738,6 @@ __device__ __forceinline__ void k2_drain(const HaloArgs& a, const K2WarpQueue& q
     __syncwarp();
 }
 
-/* Out-of-range positions are rare; among them are the ones whose un-rotated theta is NaN (NaN coordinate, z = +-Inf,
- * the origin).  Such a key breaks the ordering contract of the reference's stable_sort / lower_bound
- * (processLC.cpp:1214-1221, :1334-1337), so they are counted -- once per particle -- and reported (cc_last_stats_ex). */
-template <int NP>
-__device__ __forceinline__ void count_nan_theta(unsigned int insane, const float (&px)[NP], const float (&py)[NP],
-                                                const float (&pz)[NP], unsigned long long* nan_count) {
-    if (!__any_sync(0xffffffffu, insane != 0)) return;
-    unsigned int c = 0;
-#pragma unroll
-    for (int j = 0; j < NP; ++j)
-        if ((insane >> j) & 1u) {
-            /* theta = acosf(z/d) scaled: NaN exactly when z/d is NaN or beyond +-1 (d == 0, or z, d both infinite) */
-            const float q = CC_FDIV(pz[j], ccref::radius(px[j], py[j], pz[j]));
-            c += !(fabsf(q) <= 1.0f) ? 1u : 0u;
-        }
-    if (c) atomicAdd(nan_count, (unsigned long long)c);
-}
-
 template <bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs a) {
     extern __shared__ float4 s_pre[]; /* [nhalos] */
@@ -786,7 +766,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs
             pt[j] = py[j] * rcp_fast(px[j]);
         }
         insane &= valid;
-        count_nan_theta<8>(insane, px, py, pz, a.nan_count);
         for (int h = 0; h < a.nhalos; ++h) {
             const float4 P = s_pre[h];
             bool mine = insane != 0;
@@ -933,7 +912,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) k2_cutout_halo_tma(const Halo
             pt[j] = py[j] * rcp_fast(px[j]);
         }
         insane &= valid;
-        count_nan_theta<8>(insane, px, py, pz, a.nan_count);
         for (int h = 0; h < a.nhalos; ++h) {
             const float4 P = s_pre[h];
             bool mine = insane != 0;
@@ -1140,7 +1118,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
                 hit |= ((s_bits[bit >> 5] >> (bit & 31u)) & 1u) << j;
             }
             insane &= valid;
-            if (w0 == 0) count_nan_theta<4>(insane, px, py, pz, a.nan_count);
             hit &= valid & ~insane;
             uint2 rg[4];
             unsigned int mine = 0;
@@ -1306,8 +1283,12 @@ struct BucketArgs {
                                             one line queue up in the L2) */
     Rec* out;
 };
+/* More survivors than record slots (*rec_count > rec_cap): the host grows the buffers and runs the cutout again, so the
+ * ordering kernels do nothing at all -- the per-halo segments would be partly filled with whatever an earlier cutout
+ * left in the buffers, and following such records' halo / rank fields reads out of bounds. */
 __global__ void k3_bucket(const BucketArgs a) {
-    const unsigned long long nrec = min(*a.rec_count, a.rec_cap);
+    if (*a.rec_count > a.rec_cap) return;
+    const unsigned long long nrec = *a.rec_count;
     const unsigned int lane = threadIdx.x & 31u;
     /* warp-uniform trip count; lanes holding records of the same halo claim their slots with one atomic (the
      * records of a large cutout would otherwise queue up on its one cursor) */
@@ -1369,6 +1350,7 @@ static_assert(K3_NB == K3_THREADS, "k3_rank scans one bucket count per thread");
 constexpr size_t K3_SMEM_BYTES = (size_t)K3_CHUNK * (2 * sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
                                  (size_t)(K3_NB + 1) * sizeof(unsigned int);
 struct RankArgs {
+    const unsigned long long* rec_count; /* > rec_cap: overflow, nothing to do */
     const Rec* recs;                     /* bucketed */
     const unsigned long long* seg_begin; /* [H+1] */
     unsigned long long rec_cap;
@@ -1385,6 +1367,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
     unsigned int* s_start = reinterpret_cast<unsigned int*>(s_slot + K3_CHUNK);         /* [K3_NB + 1] */
     __shared__ unsigned int s_min, s_max, s_warp[K3_THREADS / 32];
     const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (*a.rec_count > a.rec_cap) return;
     for (int h = blockIdx.y; h < a.H; h += gridDim.y) {
         const unsigned long long b = a.seg_begin[h], e = min(a.seg_begin[h + 1], a.rec_cap);
         if (e <= b) continue;
@@ -1477,7 +1460,8 @@ struct GatherArgs {
     int pos_only;
 };
 __global__ void k3_gather_halo(const GatherArgs a) {
-    const unsigned long long nrec = min(*a.rec_count, a.rec_cap);
+    if (*a.rec_count > a.rec_cap) return; /* overflow: see k3_bucket */
+    const unsigned long long nrec = *a.rec_count;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         Rec r = a.recs[i]; /* every record of a segment names the segment's halo */

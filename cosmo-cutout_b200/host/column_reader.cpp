@@ -228,11 +228,15 @@ void ColumnReader::readGioVar(const Var& v, std::string* err) const {
     }
 }
 
+void ColumnReader::allocate() {
+    for (const Var& v : vars_) v.dst->ensure(nelems_ * v.elem_size);
+}
+
 void ColumnReader::readData() {
     std::vector<std::string> errs(vars_.size());
     std::vector<std::thread> th;
     for (size_t i = 0; i < vars_.size(); ++i) {
-        void* dst = vars_[i].dst->ensure(nelems_ * vars_[i].elem_size);
+        void* dst = vars_[i].dst->data();
         if (gio_) th.emplace_back(&ColumnReader::readGioVar, this, std::cref(vars_[i]), &errs[i]);
         else th.emplace_back(read_whole, path_ + "#" + vars_[i].name, dst, nelems_ * vars_[i].elem_size, &errs[i]);
     }
@@ -241,8 +245,10 @@ void ColumnReader::readData() {
         if (!e.empty()) die("column reader: " + e);
 }
 
-void StepColumns::read(const std::string& header_path, bool positionOnly) {
-    ColumnReader rd(header_path);
+void StepColumns::prepare(const std::string& header_path, bool positionOnly) {
+    reader_.clear();
+    reader_.emplace_back(header_path);
+    ColumnReader& rd = reader_[0];
     rd.openAndReadHeader();
     n = rd.readNumElems();
     position_only = positionOnly;
@@ -258,7 +264,13 @@ void StepColumns::read(const std::string& header_path, bool positionOnly) {
         rd.addVariable("rotation", &rotation, 4);
         rd.addVariable("replication", &replication, 4);
     }
-    rd.readData();
+    rd.allocate();
+}
+
+void StepColumns::load() {
+    if (reader_.empty()) die("column reader: load() without prepare()");
+    reader_[0].readData();
+    reader_.clear();
 }
 
 cc_cols_in StepColumns::view(size_t first) const {

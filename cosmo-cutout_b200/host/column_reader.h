@@ -56,7 +56,9 @@ public:
     bool isGenericIO() const { return gio_; }
     size_t readNumElems() const { return nelems_; }
     void addVariable(const std::string& name, PinnedBuffer* dst, size_t elem_size);
-    /* reads every registered variable (one thread per variable) */
+    /* sizes the destination buffers (pinned allocation) */
+    void allocate();
+    /* reads every registered variable (one thread per variable); buffers must have been allocated */
     void readData();
 
 private:
@@ -88,8 +90,15 @@ struct StepColumns {
     size_t n = 0;
     bool position_only = false;
     /* processLC.cpp:102-139 (all ten) / :861-889 (five when positionOnly) */
-    void read(const std::string& header_path, bool positionOnly);
+    void read(const std::string& header_path, bool positionOnly) { prepare(header_path, positionOnly); load(); }
+    /* read = prepare (open, parse the header, size the pinned buffers: may call cudaHostAlloc / cudaFreeHost, so only
+     * on a thread and at a time where no GPU work waits on another GPU) + load (file I/O only: any thread) */
+    void prepare(const std::string& header_path, bool positionOnly);
+    void load();
     cc_cols_in view(size_t first) const;
+
+private:
+    std::vector<ColumnReader> reader_; /* 0 or 1: the prepared read */
 };
 
 }  // namespace cchost

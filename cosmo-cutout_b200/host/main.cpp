@@ -8,6 +8,11 @@
  *             | --haloFile <file> --boxLength <arcmin> [--massDef sod|fof] }  (use case 2, many halos)
  *             [--verbose] [--timeit] [--overwrite] [--posOnly] [--forceWriteProps] [--propsOnly]
  *
+ * Extension: --boxLength takes one value like the reference, or SEVERAL (--boxLength 5 10 20 30).  With several, the
+ * run is what separate invocations with each value would be -- the reference's processLC has one boxLength per call
+ * (processLC.h:46) -- except that each size writes under <output dir>/boxLength_<value>/ and that the lightcone steps
+ * read for the first size stay resident in HBM for the others (no second file read, no second upload).
+ *
  * Where the reference is started under mpirun with one rank per core, this is ONE process that drives every
  * visible GPU (or CC_NGPUS of them); "ranks" in its log lines are GPUs.
  */
@@ -83,6 +88,8 @@ int main(int argc, char** argv) {
     vector<float> theta_cut(2), phi_cut(2), haloPos, haloProps;
     vector<string> haloTags;
     float boxLength = 0;
+    vector<float> boxLengths;
+    vector<string> boxLabels;
     bool verbose = false, timeit = false, overwrite = false, positionOnly = false, forceWriteProps = false, propsOnly = false;
     string massDef = "sod";
 
@@ -122,6 +129,15 @@ int main(int argc, char** argv) {
         } else if (!strcmp(a, "-b") || !strcmp(a, "--boxLength")) {
             need(i, 1);
             boxLength = strtof(argv[++i], NULL);
+            boxLengths.assign(1, boxLength);
+            boxLabels.assign(1, argv[i]);
+            while (i + 1 < argc && argv[i + 1][0] != '-') { /* extension: further box sizes */
+                char* end = NULL;
+                const float b = strtof(argv[i + 1], &end);
+                if (end == argv[i + 1] || *end != 0) break;
+                boxLengths.push_back(b);
+                boxLabels.push_back(argv[++i]);
+            }
         } else if (!strcmp(a, "-m") || !strcmp(a, "--massDef")) {
             need(i, 1);
             massDef = argv[++i];
@@ -140,21 +156,34 @@ int main(int argc, char** argv) {
         else if (!strcmp(a, "--propsOnly")) propsOnly = true;
     }
 
-    /* one output sub-directory per halo of a halo file (main.cpp:320-349) */
-    vector<string> halo_out_dirs;
-    if (customHaloFile) {
-        for (size_t h = 0; h < haloTags.size(); ++h) {
-            const string sub = out_dir + "halo_" + haloTags[h] + "/";
-            DIR* d = opendir(sub.c_str());
-            if (d) closedir(d);
-            else {
-                mkdir(sub.c_str(), S_IRWXU | S_IRGRP | S_IXGRP | S_IXOTH);
-                if (h % 100 == 0) cout << "Created output directory: " << sub << endl;
+    /* one output sub-directory per halo of a halo file (main.cpp:320-349); with several box sizes, one tree per size */
+    auto halo_dirs_under = [&](const string& root) {
+        vector<string> dirs;
+        if (customHaloFile) {
+            for (size_t h = 0; h < haloTags.size(); ++h) {
+                const string sub = root + "halo_" + haloTags[h] + "/";
+                DIR* d = opendir(sub.c_str());
+                if (d) closedir(d);
+                else {
+                    mkdir(sub.c_str(), S_IRWXU | S_IRGRP | S_IXGRP | S_IXOTH);
+                    if (h % 100 == 0) cout << "Created output directory: " << sub << endl;
+                }
+                dirs.push_back(sub);
             }
-            halo_out_dirs.push_back(sub);
+        } else if (customHalo) {
+            dirs.push_back(root);
         }
-    } else if (customHalo) {
-        halo_out_dirs.push_back(out_dir);
+        return dirs;
+    };
+    vector<vector<string>> halo_out_dirs_of;
+    if (boxLengths.size() <= 1) {
+        halo_out_dirs_of.push_back(halo_dirs_under(out_dir));
+    } else {
+        for (const string& label : boxLabels) {
+            const string root = out_dir + "boxLength_" + label + "/";
+            mkdir(root.c_str(), S_IRWXU | S_IRGRP | S_IXGRP | S_IXOTH);
+            halo_out_dirs_of.push_back(halo_dirs_under(root));
+        }
     }
 
     if (customHalo || customHaloFile) {
@@ -166,7 +195,12 @@ int main(int argc, char** argv) {
                 for (int i = 0; i < 3; ++i) cout << cart[i] << "=" << haloPos[3 * k + i] << " ";
             }
         }
-        cout << endl << "box length: " << boxLength << " arcmin" << endl;
+        if (boxLengths.size() <= 1) cout << endl << "box length: " << boxLength << " arcmin" << endl;
+        else {
+            cout << endl << "box lengths:";
+            for (float b : boxLengths) cout << " " << b;
+            cout << " arcmin (one pass each; lightcone steps stay resident in HBM between passes)" << endl;
+        }
     } else {
         cout << "theta bounds: " << theta_cut[0] / ARCSEC << " -> " << theta_cut[1] / ARCSEC << " deg" << endl;
         cout << "phi bounds: " << phi_cut[0] / ARCSEC << " -> " << phi_cut[1] / ARCSEC << " deg" << endl;
@@ -177,13 +211,19 @@ int main(int argc, char** argv) {
     cout << "posOnly is set to " << positionOnly << endl;
 
     const double start = wall_seconds();
+    if (const char* e = getenv("CC_RESIDENT_STEPS")) resident_steps_enable(atoi(e) != 0);
+    if (boxLengths.size() > 1) resident_steps_enable(true);
     if (customHalo || customHaloFile)
-        processLC(input_lc_dir, halo_out_dirs, step_strings, haloPos, haloProps, boxLength, myrank, numranks, verbose,
-                  timeit, overwrite, positionOnly, forceWriteProps, propsOnly);
+        for (size_t b = 0; b < boxLengths.size(); ++b) {
+            if (boxLengths.size() > 1) cout << "\n\n########## box length " << boxLengths[b] << " arcmin ##########" << endl;
+            processLC(input_lc_dir, halo_out_dirs_of[b], step_strings, haloPos, haloProps, boxLengths[b], myrank, numranks,
+                      verbose, timeit, overwrite, positionOnly, forceWriteProps, propsOnly);
+        }
     else
         processLC(input_lc_dir, out_dir, step_strings, theta_cut, phi_cut, myrank, numranks, verbose, timeit, overwrite,
                   positionOnly);
     const double duration = wall_seconds() - start;
     if (timeit) cout << "\nExecution time: " << duration << " s" << endl;
+    shutdown_gpus();
     return 0;
 }

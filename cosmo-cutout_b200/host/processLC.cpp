@@ -46,7 +46,11 @@ namespace {
 /* ---------------------------------------------------------------- GPUs: one context per "rank" */
 struct GpuPool {
     vector<cc_ctx*> ctx;
-    ~GpuPool() { for (cc_ctx* c : ctx) cc_destroy(c); }
+    /* no destructor: a namespace-scope object would call cc_destroy (stream syncs, ncclCommDestroy, cudaFree) from a
+     * static destructor, after the CUDA runtime's own atexit teardown or -- after die() on a worker thread -- next to
+     * threads still inside a collective.  cchost::shutdown_gpus() tears the pool down explicitly; otherwise the
+     * process exit reclaims everything. */
+    void destroy() { for (cc_ctx* c : ctx) cc_destroy(c); ctx.clear(); }
     void ensure(int numranks) {
         if (numranks < 1 || cc_device_count() < 1) die("lc_cutout: no CUDA device is visible; this build has no CPU path");
         if ((int)ctx.size() == numranks) return;
@@ -63,7 +67,7 @@ struct GpuPool {
         if (numranks > 1 && cc_comm_init_all(ctx.data(), numranks) != CC_OK) die(string("lc_cutout: ") + cc_last_error());
     }
 };
-GpuPool g_pool;
+GpuPool& g_pool = *new GpuPool();
 
 void check(int rc) {
     if (rc != CC_OK) die(string("lc_cutout: ") + cc_last_error());
@@ -141,7 +145,11 @@ public:
         pending_header_ = header;
         pending_pos_ = positionOnly;
         StepColumns* dst = &buf_[1 - slot_];
-        th_ = std::thread([dst, header, positionOnly] { dst->read(header, positionOnly); });
+        /* header parse + pinned (re)allocation happen HERE, on the calling thread and before any GPU work of the
+         * current step is enqueued: cudaHostAlloc / cudaFreeHost synchronise every context and must not run next to
+         * a kernel that waits on another GPU (the count exchange); the background thread only reads the file */
+        dst->prepare(header, positionOnly);
+        th_ = std::thread([dst] { dst->load(); });
         pending_ = true;
     }
 
@@ -153,6 +161,118 @@ private:
     bool pending_pos_ = false;
     std::thread th_;
 };
+
+/* ---------------------------------------------------------------- resident lightcone steps across processLC calls
+ * processLC cuts with ONE boxLength per call (processLC.h:45-48), so a job with several box sizes -- BASELINE config 5,
+ * `lc_cutout --haloFile f --boxLength 5 10 20 30` -- calls it once per size over the same lightcone steps.  With the
+ * cache enabled the first call uploads every step it reads to HBM (all ten columns of each GPU's index shard, one
+ * resident-step slot per lightcone step, cc_step_select) and later calls find them there: no file read, no
+ * host -> device copy, the cutout runs on the resident columns.  Entries are keyed by header path, size and mtime (of
+ * the header and of the x column of a flat store), and replaced least-recently-used first when HBM runs short
+ * (44 B + a possible 32 B payload per particle and GPU).  A step that does not fit is streamed as before. */
+struct ResidentSteps {
+    struct Entry { string key; int slot; size_t n; bool pos_only; uint64_t last_use; };
+    bool enabled = false;
+    vector<Entry> entries;
+    vector<int> free_slots;
+    int next_slot = 1; /* slot 0 is the streaming slot */
+    uint64_t clock = 0;
+    int64_t hits = 0, misses = 0, not_fitting = 0;
+};
+ResidentSteps& g_resident = *new ResidentSteps();
+
+string resident_key(const string& header, int numranks) {
+    std::ostringstream k;
+    struct stat st;
+    k << header << "|" << numranks;
+    const string files[2] = {header, header + "#x"};
+    for (const string& f : files)
+        if (stat(f.c_str(), &st) == 0) k << "|" << (long long)st.st_size << "." << (long long)st.st_mtim.tv_sec << "." << st.st_mtim.tv_nsec;
+    return k.str();
+}
+
+void select_slot_everywhere(int numranks, int slot) {
+    for (int r = 0; r < numranks; ++r) check(cc_step_select(g_pool.ctx[r], slot));
+}
+
+/* the step is resident: make it every GPU's current step */
+bool resident_lookup(const string& header, bool positionOnly, int numranks, size_t* Np) {
+    if (!g_resident.enabled) return false;
+    const string key = resident_key(header, numranks);
+    for (auto& e : g_resident.entries)
+        if (e.key == key && (!e.pos_only || positionOnly)) {
+            e.last_use = ++g_resident.clock;
+            select_slot_everywhere(numranks, e.slot);
+            *Np = e.n;
+            ++g_resident.hits;
+            return true;
+        }
+    return false;
+}
+
+/* upload a step that was just read; false (slot 0 selected) when it does not fit */
+bool resident_insert(const string& header, bool positionOnly, int numranks, const StepColumns& cols) {
+    if (!g_resident.enabled) return false;
+    ++g_resident.misses;
+    const size_t shard = (cols.n + (size_t)numranks - 1) / (size_t)numranks;
+    const int64_t need = (int64_t)shard * ((positionOnly ? 24 : 44) + 32) + ((int64_t)3 << 30);
+    auto fits = [&]() {
+        for (int r = 0; r < numranks; ++r) {
+            int64_t free_b = 0;
+            check(cc_device_mem(g_pool.ctx[r], &free_b, nullptr));
+            if (free_b < need) return false;
+        }
+        return true;
+    };
+    while (!fits() && !g_resident.entries.empty()) { /* replace the least recently used step */
+        size_t victim = 0;
+        for (size_t i = 1; i < g_resident.entries.size(); ++i)
+            if (g_resident.entries[i].last_use < g_resident.entries[victim].last_use) victim = i;
+        const int slot = g_resident.entries[victim].slot;
+        for (int r = 0; r < numranks; ++r) { check(cc_step_select(g_pool.ctx[r], slot)); check(cc_step_release(g_pool.ctx[r])); }
+        g_resident.free_slots.push_back(slot);
+        g_resident.entries.erase(g_resident.entries.begin() + (ptrdiff_t)victim);
+    }
+    if (!fits()) {
+        ++g_resident.not_fitting;
+        select_slot_everywhere(numranks, 0);
+        return false;
+    }
+    int slot;
+    if (!g_resident.free_slots.empty()) { slot = g_resident.free_slots.back(); g_resident.free_slots.pop_back(); }
+    else slot = g_resident.next_slot++;
+    for_each_gpu(numranks, [&](int r) {
+        size_t lo, hi;
+        shard_range(cols.n, numranks, r, &lo, &hi);
+        const cc_cols_in v = cols.view(lo);
+        check(cc_step_select(g_pool.ctx[r], slot));
+        check(cc_step_upload(g_pool.ctx[r], (int64_t)(hi - lo), &v, (int64_t)lo));
+    });
+    g_resident.entries.push_back(ResidentSteps::Entry{resident_key(header, numranks), slot, cols.n, positionOnly, ++g_resident.clock});
+    return true;
+}
+
+bool resident_has(const string& header, bool positionOnly, int numranks) {
+    if (!g_resident.enabled) return false;
+    const string key = resident_key(header, numranks);
+    for (const auto& e : g_resident.entries)
+        if (e.key == key && (!e.pos_only || positionOnly)) return true;
+    return false;
+}
+
+int64_t uploaded_bytes(int numranks) {
+    int64_t b = 0;
+    for (int r = 0; r < numranks && r < (int)g_pool.ctx.size(); ++r) b += cc_bytes_uploaded(g_pool.ctx[r]);
+    return b;
+}
+
+void report_transfers(int numranks, int64_t bytes0, int64_t hits0, int64_t misses0) {
+    cout << "\nstep columns copied host->device in this call: " << (uploaded_bytes(numranks) - bytes0) << " bytes";
+    if (g_resident.enabled)
+        cout << " (resident steps: " << (g_resident.hits - hits0) << " found in HBM, " << (g_resident.misses - misses0)
+             << " read and uploaded, " << g_resident.entries.size() << " resident now)";
+    cout << endl;
+}
 
 /* header file of the next step that will be processed after position i (step 499 is skipped), or "" */
 string next_header(const string& dir_name, const string& subdirPrefix, const vector<string>& step_strings, size_t i) {
@@ -259,6 +379,14 @@ string find_prefix(const string& dir_name, bool print) {
 
 }  // namespace
 
+namespace cchost {
+void resident_steps_enable(bool on) { g_resident.enabled = on; }
+void shutdown_gpus() {
+    g_resident.entries.clear();
+    g_pool.destroy();
+}
+}  // namespace cchost
+
 /* =====================================================================================================
  * use case 1 (reference processLC.cpp:15-429)
  * ===================================================================================================== */
@@ -273,6 +401,7 @@ void processLC(string dir_name, string out_dir, vector<string> step_strings, vec
     const string subdirPrefix = find_prefix(dir_name, true);
 
     StepReadAhead reader; /* two sets of pinned buffers, reused across steps */
+    const int64_t bytes0 = uploaded_bytes(numranks), hits0 = g_resident.hits, misses0 = g_resident.misses;
     for (size_t i = 0; i < step_strings.size(); ++i) {
         const int step = atoi(step_strings[i].c_str());
         if (step == 499) continue; /* z = 0: zero lightcone volume (processLC.cpp:72-73) */
@@ -282,12 +411,19 @@ void processLC(string dir_name, string out_dir, vector<string> step_strings, vec
         getLCFile(step_dir, file_name);
         const string header = step_dir + "/" + file_name;
         cout << "Opening file: " << header << endl;
-        StepColumns& cols = reader.take(header, false);
+        size_t Np = 0;
+        StepColumns* cols = nullptr;
+        bool resident = resident_lookup(header, false, numranks, &Np);
+        if (!resident) {
+            cols = &reader.take(header, false);
+            Np = cols->n;
+            resident = resident_insert(header, false, numranks, *cols);
+            if (!resident && g_resident.enabled) select_slot_everywhere(numranks, 0);
+        }
         {
             const string nxt = next_header(dir_name, subdirPrefix, step_strings, i);
-            if (!nxt.empty()) reader.start(nxt, false);
+            if (!nxt.empty() && !resident_has(nxt, false, numranks)) reader.start(nxt, false);
         }
-        const size_t Np = cols.n;
         cout << "Number of elements in lc step at rank " << myrank << ": " << Np << endl;
 
         /* output sub-directory: must be absent or empty (processLC.cpp:161-184) */
@@ -310,8 +446,12 @@ void processLC(string dir_name, string out_dir, vector<string> step_strings, vec
         for (int r = 0; r < numranks; ++r) { /* enqueue on every GPU, nothing blocks here */
             size_t lo, hi;
             shard_range(Np, numranks, r, &lo, &hi);
-            const cc_cols_in v = cols.view(lo);
-            check(cc_cutout_const_streamed(g_pool.ctx[r], (int64_t)(hi - lo), &v, (int64_t)lo, th, ph));
+            if (resident) {
+                check(cc_cutout_const(g_pool.ctx[r], th, ph));
+            } else {
+                const cc_cols_in v = cols->view(lo);
+                check(cc_cutout_const_streamed(g_pool.ctx[r], (int64_t)(hi - lo), &v, (int64_t)lo, th, ph));
+            }
         }
         vector<int64_t> all_counts((size_t)numranks), offsets((size_t)numranks);
         for_each_gpu(numranks, [&](int r) {
@@ -333,6 +473,7 @@ void processLC(string dir_name, string out_dir, vector<string> step_strings, vec
             files.write_block(s, k, (size_t)offsets[(size_t)r]);
         });
     }
+    report_transfers(numranks, bytes0, hits0, misses0);
 }
 
 /* =====================================================================================================
@@ -420,6 +561,8 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
     const bool keep_tail = getenv("CC_KEEP_TAIL") && string(getenv("CC_KEEP_TAIL")) == "1";
     vector<double> read_times, redist_times, sort_times, cutout_times, write_times;
     StepReadAhead reader;
+    const int64_t bytes0 = uploaded_bytes(numranks), hits0 = g_resident.hits, misses0 = g_resident.misses;
+    int64_t nan_theta_total = 0;
 
     for (size_t i = 0; i < step_strings.size(); ++i) {
         double start = wall_seconds();
@@ -433,12 +576,19 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
         getLCFile(step_dir, file_name);
         const string header = step_dir + "/" + file_name;
         cout << "Opening file: " << header << endl;
-        StepColumns& cols = reader.take(header, positionOnly);
+        size_t Np = 0;
+        StepColumns* cols = nullptr;
+        bool resident = resident_lookup(header, positionOnly, numranks, &Np);
+        if (!resident) {
+            cols = &reader.take(header, positionOnly);
+            Np = cols->n;
+            resident = resident_insert(header, positionOnly, numranks, *cols);
+            if (!resident && g_resident.enabled) select_slot_everywhere(numranks, 0);
+        }
         {
             const string nxt = next_header(dir_name, subdirPrefix, step_strings, i);
-            if (!nxt.empty()) reader.start(nxt, positionOnly);
+            if (!nxt.empty() && !resident_has(nxt, positionOnly, numranks)) reader.start(nxt, positionOnly);
         }
-        const size_t Np = cols.n;
         double duration = wall_seconds() - start;
         if (timeit) cout << "Read time: " << duration << " s" << endl;
         read_times.push_back(duration);
@@ -472,9 +622,13 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
         for (int r = 0; r < numranks; ++r) {
             size_t lo, hi;
             shard_range(Np, numranks, r, &lo, &hi);
-            const cc_cols_in v = cols.view(lo);
-            check(cc_cutout_halo_streamed(g_pool.ctx[r], (int64_t)(hi - lo), &v, (int64_t)lo, A, act_halos.data(),
-                                          positionOnly ? 1 : 0, n_limit));
+            if (resident) {
+                check(cc_cutout_halo(g_pool.ctx[r], A, act_halos.data(), positionOnly ? 1 : 0, n_limit));
+            } else {
+                const cc_cols_in v = cols->view(lo);
+                check(cc_cutout_halo_streamed(g_pool.ctx[r], (int64_t)(hi - lo), &v, (int64_t)lo, A, act_halos.data(),
+                                              positionOnly ? 1 : 0, n_limit));
+            }
         }
         vector<int64_t> all_counts((size_t)numranks * (size_t)A), all_rough((size_t)numranks * (size_t)A);
         for_each_gpu(numranks, [&](int r) {
@@ -482,6 +636,23 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
             check(cc_exchange_counts(g_pool.ctx[r], c.data(), g.data(), off.data()));
             if (r == 0) { all_counts = c; all_rough = g; }
         });
+        {
+            /* positions whose un-rotated theta is NaN (NaN coordinate, z = +-Inf, the origin): the reference orders all
+             * particles by that angle with std::stable_sort / std::lower_bound (processLC.cpp:1214-1221, :1334-1337),
+             * which a NaN key breaks -- what it then writes for the OTHER particles is unspecified, so say so */
+            int64_t nan_step = 0;
+            for (int r = 0; r < numranks; ++r) {
+                int64_t st[CC_STATS_EX_FIELDS] = {};
+                check(cc_last_stats_ex(g_pool.ctx[r], st, CC_STATS_EX_FIELDS));
+                nan_step += st[4];
+            }
+            if (nan_step) {
+                nan_theta_total += nan_step;
+                cout << "WARNING: step " << step_strings[i] << " holds " << nan_step << " particle(s) whose theta is NaN (NaN or "
+                     << "infinite coordinates, or a particle at the origin).  They are in no cutout here; the reference sorts "
+                     << "by theta, and its output for such a step is unspecified -- results may differ from it." << endl;
+            }
+        }
         duration = wall_seconds() - start;
         if (timeit) cout << "cutout computation time (all halos of the step): " << duration << " s" << endl;
 
@@ -577,6 +748,8 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
         }
         cout.flush();
     }
+    report_transfers(numranks, bytes0, hits0, misses0);
+    if (nan_theta_total) cout << "WARNING: " << nan_theta_total << " particle(s) with NaN theta in this run (see above)" << endl;
     if (timeit) { /* reference :1718-1756: arrays ready to paste into python */
         cout << endl;
         print_times("read_times", read_times);

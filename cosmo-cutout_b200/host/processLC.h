@@ -28,4 +28,14 @@ void processLC(std::string dir_name, std::vector<std::string> out_dirs, std::vec
                int numranks, bool verbose, bool timeit, bool overwrite, bool positionOnly,
                bool forceWriteProps, bool propsOnly);
 
+namespace cchost {
+/* Extension (no counterpart in the reference): keep every lightcone step a processLC call reads resident in HBM, so
+ * that later calls in the same process -- another boxLength, another window -- neither read nor upload it again.
+ * Off by default (one call cuts each step once and then streams only x,y,z); lc_cutout turns it on when several
+ * --boxLength values are given; CC_RESIDENT_STEPS=1 in the environment does the same. */
+void resident_steps_enable(bool on);
+/* destroy the GPU contexts (call before main returns; never from a static destructor) */
+void shutdown_gpus();
+}  // namespace cchost
+
 #endif

@@ -112,6 +112,17 @@ int cc_step_download(cc_ctx* ctx, int64_t first, int64_t count, float* x, float*
                      float* vy, float* vz, float* a, int64_t* id, int32_t* rotation, int32_t* replication);
 int64_t cc_step_size(cc_ctx* ctx);
 int cc_step_release(cc_ctx* ctx);
+/* A context can keep SEVERAL steps resident, in numbered slots, and cut any of them: cc_step_select makes `slot` the
+ * current step (slot 0 at creation; a slot never used is empty).  Upload / attach / synth / release and every cutout
+ * act on the current slot; a streamed cutout replaces the current slot's resident step, so stream on a slot kept for
+ * that.  This is what lets consecutive processLC calls (one boxLength each, processLC.h:45-48 -- BASELINE config 5)
+ * find the lightcone steps of the previous call still in HBM instead of reading and uploading them again; it plays
+ * the role of the reference's "sort once, cut many halos" index (processLC.cpp:1214-1221, :1237) across calls. */
+int cc_step_select(cc_ctx* ctx, int slot);
+/* free / total bytes of the context's device (capacity planning for resident steps: 44 B per particle and shard) */
+int cc_device_mem(cc_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
+/* input-column bytes this context has copied host -> device so far (cc_step_upload and the streamed cutouts) */
+int64_t cc_bytes_uploaded(cc_ctx* ctx);
 
 /* ------------------------------------------------------------------ the cutout
  * Use case 1 (constant bounds): replaces the loop processLC.cpp:276-310.  Survivors keep input order.

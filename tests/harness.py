@@ -53,6 +53,38 @@ def shell_fixture(n, seed=20261019, rmin=100.0, rmax=300.0, octant=True):
     return cols
 
 
+def synth_numpy(n, seed, index_base=0, kind=0, box=300.0):
+    """numpy replica of the product's counter-based synthetic lightcone (kernels.cuh synth_one / cc_synth_host), so
+    that the reference arm of bench.py can make its columns without loading the product library;
+    tests/test_host_cpu.py asserts it equals cc_synth_host bit for bit."""
+    g = np.arange(index_base, index_base + n, dtype=np.uint64)
+
+    def mix(col):
+        with np.errstate(over="ignore"):
+            z = np.uint64(seed) + np.uint64(0x9e3779b97f4a7c15) * (g + np.uint64(1)) + \
+                np.uint64(0xd1b54a32d192ed03) * np.uint64(col + 1)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+            return z ^ (z >> np.uint64(31))
+
+    def unit(col):  # (2k+1) * 2^-24, k in [0, 2^23): exact in float32
+        k = (mix(col) >> np.uint64(41)).astype(np.uint32)
+        return (np.uint32(2) * k + np.uint32(1)).astype(np.float32) * np.float32(5.9604644775390625e-08)
+
+    f = np.float32
+    u = [unit(c) for c in range(7)]
+    if kind == 0:
+        x, y, z = (u[i] * f(box) for i in range(3))
+    else:
+        x, y, z = ((f(2.0) * u[i] - f(1.0)) * f(box) for i in range(3))
+    hh = mix(7)
+    return dict(x=x.astype(f), y=y.astype(f), z=z.astype(f),
+                vx=((u[3] - f(0.5)) * f(600.0)).astype(f), vy=((u[4] - f(0.5)) * f(600.0)).astype(f),
+                vz=((u[5] - f(0.5)) * f(600.0)).astype(f), a=(f(0.5) + f(0.5) * u[6]).astype(f),
+                id=g.astype(np.int64), rotation=((hh >> np.uint64(33)) % np.uint64(6)).astype(np.int32),
+                replication=(hh & np.uint64(0xfffff)).astype(np.int32))
+
+
 def f32_neighbours(v, k=2):
     """the 2k+1 floats around v (by ulp steps)"""
     v = np.float32(v)

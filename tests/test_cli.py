@@ -188,3 +188,41 @@ def test_cli_reads_genericio_format_input(tmp_path):
         _run(REF_BIN, [str(flat), o2] + args)
         files = _same_tree(str(o1), str(o2))
         assert len(files) >= 2 * 12 and any("475" in f for f in files) and any("487" in f for f in files)
+
+
+@pytest.mark.gpu
+@needs_ref_bin
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_cli_several_box_lengths_keep_steps_resident(lc_dirs, tmp_path, ngpus):
+    """extension over the reference CLI: --boxLength with several values = one processLC pass per value (the
+    reference's API has one boxLength per call, processLC.h:46; BASELINE config 5).  Each value's tree equals a
+    separate reference run with that value, and after the first pass the lightcone steps are found resident in HBM:
+    the later passes copy ZERO bytes of step columns host->device and read no input file."""
+    if ngpus > cc.lib().cc_device_count():
+        pytest.skip(f"{ngpus} GPUs needed")
+    import re
+    hf = tmp_path / "halos.txt"
+    _halo_file(str(hf), [("1001", (150, 20, 12)), ("1002", (30, 170, 100)), ("77", (100, 100, 100)),
+                         ("5", (10, 10, 250)), ("6", (120, -60, 40)), ("7", (200, 120, 40)), ("8", (60, 60, 20)),
+                         ("9", (250, 30, 160)), ("10", (90, 200, 30))])
+    boxes = ["30", "120", "75.5"]
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    a = _run(cc.CLI_PATH, [lc_dirs, ours, 0.0, 0.06, "-f", hf, "-b"] + boxes, env={"CC_NGPUS": str(ngpus)})
+    for b in boxes:
+        ref = tmp_path / f"ref_{b}"
+        ref.mkdir()
+        _run(REF_BIN, [lc_dirs, ref, 0.0, 0.06, "-f", hf, "-b", b])
+        files = _same_tree(str(ours / f"boxLength_{b}"), str(ref))
+        assert len(files) == 9 * (1 + 2 * 12)
+    moved = [int(m) for m in re.findall(r"step columns copied host->device in this call: (\d+) bytes", a.stdout)]
+    found = re.findall(r"resident steps: (\d+) found in HBM, (\d+) read and uploaded", a.stdout)
+    assert len(moved) == 3 and moved[0] == 2 * 200_000 * 44 and moved[1] == 0 and moved[2] == 0, moved
+    assert found == [("0", "2"), ("2", "0"), ("2", "0")], found
+    # use case 1 shares the cache machinery (CC_RESIDENT_STEPS=1): same bytes as the streamed default
+    o1, o2 = tmp_path / "c1", tmp_path / "c2"
+    o1.mkdir(); o2.mkdir()
+    args = [0.0, 0.06, "--theta", 87, 2, "--phi", 2, 2]
+    _run(cc.CLI_PATH, [lc_dirs, o1] + args, env={"CC_NGPUS": str(ngpus), "CC_RESIDENT_STEPS": "1"})
+    _run(REF_BIN, [lc_dirs, o2] + args)
+    _same_tree(str(o1), str(o2))

@@ -234,3 +234,13 @@ def test_binding_fails_loudly_when_the_library_is_missing(monkeypatch):
     monkeypatch.setattr(cc, "LIB_PATH", os.path.join(REPO, "cosmo-cutout_b200", "lib", "does_not_exist.so"))
     with pytest.raises(cc.CutoutError, match="missing"):
         cc.lib()
+
+
+def test_numpy_replica_of_the_synthetic_lightcone_equals_the_library():
+    """bench.py's reference arm makes its columns with tests/harness.py:synth_numpy so that it never loads the product
+    library; the replica must be the same generator, bit for bit, at any global index"""
+    for kind, base in ((0, 0), (0, 987_654_321_012), (1, 3_999_999_000)):
+        a = cc.synth_host(50_021, 20261019, index_base=base, kind=kind, box=300.0)
+        b = H.synth_numpy(50_021, 20261019, index_base=base, kind=kind, box=300.0)
+        for k in cc.IN_COLS:
+            assert a[k].dtype == b[k].dtype and a[k].tobytes() == b[k].tobytes(), (kind, base, k)
