@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -26,6 +27,11 @@
 namespace {
 
 thread_local std::string g_err;
+/* the last failure of ANY thread: what cc_last_error returns to a thread that has none of its own (a caller that
+ * checks the result of work it handed to another thread) */
+std::mutex g_err_any_mutex;
+std::string g_err_any;
+thread_local std::string g_err_copy;
 
 int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -34,6 +40,10 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     g_err = buf;
+    {
+        std::lock_guard<std::mutex> lock(g_err_any_mutex);
+        g_err_any = buf;
+    }
     return code;
 }
 
@@ -44,6 +54,12 @@ int fail(int code, const char* fmt, ...) {
             return fail(e_ == cudaErrorMemoryAllocation ? CC_ERR_NOMEM : CC_ERR_CUDA, "%s failed: %s (%s:%d)", \
                         #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
     } while (0)
+
+}  // namespace
+namespace ccint {
+int fail_msg(int code, const char* msg) { return fail(code, "%s", msg); } /* for host_setup.cpp */
+}
+namespace {
 
 /* ---------------------------------------------------------------- NCCL, loaded lazily */
 struct NcclApi {
@@ -865,7 +881,12 @@ int check_sm100(int device, int* sm_count) {
 extern "C" {
 
 const char* cc_version(void) { return "cosmo-cutout_b200 0.1 (sm_100a)"; }
-const char* cc_last_error(void) { return g_err.c_str(); }
+const char* cc_last_error(void) {
+    if (!g_err.empty()) return g_err.c_str();
+    std::lock_guard<std::mutex> lock(g_err_any_mutex);
+    g_err_copy = g_err_any;
+    return g_err_copy.c_str();
+}
 
 int cc_device_count(void) {
     int n = 0;

@@ -16,6 +16,10 @@
 
 #include "../../include/cosmo_cutout_b200.h"
 
+namespace ccint {
+int fail_msg(int code, const char* msg); /* capi.cu: records the message cc_last_error() returns */
+}
+
 namespace {
 
 const double kPi = 3.14159265; /* processLC.h:35 */
@@ -196,7 +200,15 @@ void cc_shard_range(int64_t n, int nranks, int rank, int64_t* lo, int64_t* hi) {
 
 int cc_merge_order(int nranks, const int64_t* counts, const float* const* theta_u, const int64_t* const* index,
                    int32_t* src_rank, int64_t* src_row) {
-    if (nranks < 1 || !counts || !theta_u || !index || !src_rank || !src_row) return CC_ERR_ARG;
+    if (nranks < 1 || !counts || !theta_u || !index) return ccint::fail_msg(CC_ERR_ARG, "cc_merge_order: bad argument");
+    int64_t total = 0;
+    for (int r = 0; r < nranks; ++r) {
+        if (counts[r] < 0 || (counts[r] > 0 && (!theta_u[r] || !index[r])))
+            return ccint::fail_msg(CC_ERR_ARG, "cc_merge_order: a rank with survivors has no key columns");
+        total += counts[r];
+    }
+    if (total == 0) return CC_OK; /* a halo without survivors in this step: nothing to order (outputs may be NULL) */
+    if (!src_rank || !src_row) return ccint::fail_msg(CC_ERR_ARG, "cc_merge_order: output arrays are NULL");
     /* k-way merge; theta_u >= 0 and never NaN for a survivor, so its bit pattern orders like its value */
     struct Head { uint32_t key; int64_t idx; int32_t r; int64_t row; };
     std::vector<Head> heap;

@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -64,6 +65,56 @@ struct FileBytes {
     }
 };
 inline uint64_t bswap64(uint64_t v) { return __builtin_bswap64(v); }
+
+/* GenericIO's checksum (its CRC64.h: "ECMA-182 polynomial with -1 initialization, ... the bit-reversed CRC"), i.e.
+ * CRC-64/XZ: reflected polynomial 0xC96C5795D7870F42, initial value and final xor ~0 (check value of "123456789":
+ * 0x995DC9BBDF1939FA, tests/test_host_cpu.py).  The writer appends to every checksummed region the 8 bytes that make
+ * the CRC of region + those bytes equal ~0 (crc64_invert), which is what a reader verifies.  Slice-by-8 tables. */
+struct Crc64 {
+    uint64_t t[8][256];
+    Crc64() {
+        const uint64_t poly = 0xC96C5795D7870F42ull;
+        for (int i = 0; i < 256; ++i) {
+            uint64_t c = (uint64_t)i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ poly : c >> 1;
+            t[0][i] = c;
+        }
+        for (int i = 0; i < 256; ++i)
+            for (int s = 1; s < 8; ++s) t[s][i] = t[0][t[s - 1][i] & 0xff] ^ (t[s - 1][i] >> 8);
+    }
+    /* running register (start with ~0; the CRC is ~register) */
+    uint64_t update(uint64_t c, const unsigned char* p, size_t n) const {
+        while (n && ((uintptr_t)p & 7)) { c = t[0][(c ^ *p++) & 0xff] ^ (c >> 8); --n; }
+        while (n >= 8) {
+            uint64_t w;
+            memcpy(&w, p, 8); /* little-endian host (checked by the caller) */
+            c ^= w;
+            c = t[7][c & 0xff] ^ t[6][(c >> 8) & 0xff] ^ t[5][(c >> 16) & 0xff] ^ t[4][(c >> 24) & 0xff] ^
+                t[3][(c >> 32) & 0xff] ^ t[2][(c >> 40) & 0xff] ^ t[1][(c >> 48) & 0xff] ^ t[0][c >> 56];
+            p += 8;
+            n -= 8;
+        }
+        while (n--) c = t[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+        return c;
+    }
+};
+const Crc64& crc64_tables() { static const Crc64 c; return c; }
+enum CrcMode { CRC_STRICT, CRC_WARN, CRC_OFF };
+CrcMode crc_mode() {
+    const char* e = getenv("CC_GIO_CRC");
+    if (!e || !*e || !strcmp(e, "strict")) return CRC_STRICT;
+    if (!strcmp(e, "warn")) return CRC_WARN;
+    return CRC_OFF;
+}
+/* `reg`: CRC register after region + its 8 trailing bytes; a valid region leaves it at 0 (CRC == ~0) */
+void crc_verdict(uint64_t reg, const std::string& what, std::string* err) {
+    if (reg == 0 || crc_mode() == CRC_OFF) return;
+    const std::string msg = "CRC64 mismatch in " + what + " (the file is corrupt or truncated; CC_GIO_CRC=warn reads it anyway, "
+                            "CC_GIO_CRC=off skips the check)";
+    if (crc_mode() == CRC_WARN) { fprintf(stdout, "WARNING: GenericIO reader: %s\n", msg.c_str()); return; }
+    if (err) *err = msg;
+    else cchost::die("GenericIO reader: " + msg);
+}
 inline void swap_elems(void* p, size_t n, size_t size) {
     if (size == 2) { uint16_t* q = (uint16_t*)p; for (size_t i = 0; i < n; ++i) q[i] = __builtin_bswap16(q[i]); }
     else if (size == 4) { uint32_t* q = (uint32_t*)p; for (size_t i = 0; i < n; ++i) q[i] = __builtin_bswap32(q[i]); }
@@ -95,9 +146,14 @@ void ColumnReader::parseGio(const std::string& file, bool is_main, std::vector<i
     /* PhysOrigin[3], PhysScale[3] are fields 12..17; BlocksSize, BlocksStart 18, 19 */
     uint64_t blocks_size = 0, blocks_start = 0;
     if (global_size >= 8 + 8 * 20) { blocks_size = u64_at(8 + 8 * 18); blocks_start = u64_at(8 + 8 * 19); }
-    if (header_size > fb.size || vars_size < 256 + 16 || ranks_size < 40 || nvars > 4096 || nranks > (1u << 24) ||
-        vars_start + nvars * vars_size > header_size || ranks_start + nranks * ranks_size > header_size)
+    if (header_size > fb.size || header_size < 8 + 8 * 12 + 8 || vars_size < 256 + 16 || ranks_size < 40 || nvars > 4096 ||
+        nranks > (1u << 24) || vars_start + nvars * vars_size > header_size || ranks_start + nranks * ranks_size > header_size)
         die("GenericIO reader: implausible header in " + file);
+    if (crc_mode() != CRC_OFF) { /* HeaderSize counts the header's own 8 CRC bytes */
+        std::vector<unsigned char> hdr((size_t)header_size);
+        if (!fb.get(0, hdr.data(), hdr.size())) die("GenericIO reader: truncated header in " + file);
+        crc_verdict(crc64_tables().update(~0ull, hdr.data(), hdr.size()), "the header of " + file, nullptr);
+    }
     std::vector<GioVar> vars((size_t)nvars);
     for (uint64_t v = 0; v < nvars; ++v) {
         char name[257];
@@ -120,10 +176,16 @@ void ColumnReader::parseGio(const std::string& file, bool is_main, std::vector<i
         if (has_blocks) {
             for (uint64_t v = 0; v < nvars; ++v) {
                 const uint64_t bo = blocks_start + (r * nvars + v) * blocks_size;
-                char filt[8];
+                char filt[9];
                 if (!fb.get(bo, filt, 8)) die("GenericIO reader: truncated block table in " + file);
-                b.var_filtered.push_back(filt[0] != 0);
+                filt[8] = 0;
+                if (filt[0] != 0) /* fail before anything is read or allocated: there is no decoder here */
+                    die("GenericIO reader: variable '" + vars[(size_t)v].name + "' of " + file + " is stored through the '" + filt +
+                        "' filter (compressed GenericIO output).  This build reads uncompressed blocks only: re-write the "
+                        "lightcone with compression off (GENERICIO_COMPRESS=0) or decompress it with GenericIO's own tools.");
+                b.var_filtered.push_back(false);
                 b.var_start.push_back(u64_at(bo + 32));
+                b.var_bytes.push_back(u64_at(bo + 40));
             }
         }
         if (is_main && partitions) {
@@ -223,7 +285,16 @@ void ColumnReader::readGioVar(const Var& v, std::string* err) const {
         if (b.nelems == 0) continue;
         FileBytes fb(b.file);
         char* at = dst + b.first_elem * v.elem_size;
-        if (!fb.get(off, at, (size_t)b.nelems * v.elem_size)) { *err = "short read of " + v.name + " in " + b.file; return; }
+        const size_t nbytes = (size_t)b.nelems * v.elem_size;
+        if (!fb.get(off, at, nbytes)) { *err = "short read of " + v.name + " in " + b.file; return; }
+        if (crc_mode() != CRC_OFF) { /* the block's data is followed by the 8 bytes that close its CRC */
+            unsigned char tail[8];
+            if (!fb.get(off + nbytes, tail, 8)) { *err = "no CRC behind " + v.name + " in " + b.file; return; }
+            uint64_t reg = crc64_tables().update(~0ull, (const unsigned char*)at, nbytes);
+            reg = crc64_tables().update(reg, tail, 8);
+            crc_verdict(reg, "variable " + v.name + ", rank block " + std::to_string(b.global_rank) + " of " + b.file, err);
+            if (!err->empty()) return;
+        }
         if (b.swap) swap_elems(at, (size_t)b.nelems, v.elem_size);
     }
 }

@@ -11,7 +11,10 @@
  *                    after the header and after every data block), optionally partitioned into <header>#<p>
  *                    files through the "$rank"/"$partition" map of the main file.  Ranks are read in global rank
  *                    order, which is the element order a single-rank GenericIO::readData (MismatchRedistribute)
- *                    produces.  Both byte orders; uncompressed blocks only; CRCs are not verified.
+ *                    produces.  Both byte orders.  The CRC64 behind the header and behind every variable block is
+ *                    verified (CRC-64/XZ, GenericIO's CRC64.h; a mismatch is fatal, CC_GIO_CRC=warn|off relaxes it).
+ *                    Uncompressed blocks only: a file written through a compression filter (blosc) is refused with
+ *                    an explanation when its header is parsed.
  *
  * GenericIO itself is an un-vendored, un-pinned external library that is not available here: the
  * second back-end is written from the published on-disk format and is exercised against files produced by an
@@ -71,7 +74,8 @@ private:
         uint64_t global_rank, nelems, start;
         std::vector<GioVar> vars;       /* in file order */
         std::vector<uint64_t> var_start; /* explicit per-variable offsets (block headers) or empty */
-        std::vector<bool> var_filtered;  /* block carries a compression filter */
+        std::vector<bool> var_filtered;  /* block carries a compression filter (refused when the header is parsed) */
+        std::vector<uint64_t> var_bytes; /* block header: stored size of the variable's data */
         uint64_t first_elem;            /* position of the block's first element in the assembled column */
     };
     void parseGio(const std::string& file, bool is_main, std::vector<int32_t>* partitions);

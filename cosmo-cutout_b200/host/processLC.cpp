@@ -69,9 +69,10 @@ struct GpuPool {
 };
 GpuPool& g_pool = *new GpuPool();
 
-void check(int rc) {
-    if (rc != CC_OK) die(string("lc_cutout: ") + cc_last_error());
+void check_at(int rc, const char* what) {
+    if (rc != CC_OK) die(string("lc_cutout: ") + cc_last_error() + " [" + what + " returned " + std::to_string(rc) + "]");
 }
+#define check(call) check_at((call), #call)
 
 /* run f(rank) for every GPU on its own host thread (NCCL collectives of one process must be entered concurrently) */
 template <typename F>

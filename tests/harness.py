@@ -159,11 +159,12 @@ def write_flat_step(root, step, cols, prefix="lc", names=IN_COLS):
 
 
 def write_gio_step(root, step, cols, prefix="lc", names=IN_COLS, nranks=3, big_endian=False, block_headers=False,
-                   partitions=0, old_headers=False, seed=0):
+                   partitions=0, old_headers=False, seed=0, bad_crc=None, filter_name=None):
     """A lightcone step in the GenericIO on-disk format (written here from the format description, independently of
     the reader under test): global header, variable headers, one rank header per writing rank, optional block
-    headers, 8 CRC bytes after the header and after every data block (not a real CRC: the reader does not verify
-    them).  The particles are cut into `nranks` contiguous pieces of uneven size (one of them empty when nranks > 2).
+    headers, the 8 closing CRC64 bytes after the header and after every data block (crc64_closing_bytes; `bad_crc`
+    writes a wrong one behind the named variable's first block, `filter_name` marks every block of the second
+    variable as written through that compression filter).  The particles are cut into `nranks` contiguous pieces of uneven size (one of them empty when nranks > 2).
     partitions > 0: the main file only carries the "$rank"/"$partition" map and the data goes to '<header>#<p>',
     ranks dealt round-robin to partitions and stored there in DESCENDING rank order, so a reader has to restore the
     global rank order.  old_headers: rank headers without GlobalRank, variable headers without ElementSize, global
@@ -199,7 +200,7 @@ def write_gio_step(root, step, cols, prefix="lc", names=IN_COLS, nranks=3, big_e
         header_size = ranks_start + len(ranks) * ranks_size + len(ranks) * nvars * blocks_size + 8
         # data layout
         off = header_size
-        rank_start, block_start, payload = [], [], []
+        rank_start, block_start, payload, bad_done = [], [], [], []
         for (_gr, data) in ranks:
             rank_start.append(off)
             for (name, dt) in variables:
@@ -210,7 +211,11 @@ def write_gio_step(root, step, cols, prefix="lc", names=IN_COLS, nranks=3, big_e
                     off += len(pad)
                 block_start.append((off, a.nbytes))
                 payload.append(a.tobytes())
-                payload.append(b"\xC5" * 8)
+                closing = crc64_closing_bytes(a.tobytes())
+                if bad_crc == name and a.nbytes:
+                    closing = bytes([closing[0] ^ 0x40]) + closing[1:]
+                    bad_done.append(1)
+                payload.append(closing if not (bad_crc == name and len(bad_done) > 1) else crc64_closing_bytes(a.tobytes()))
                 off += a.nbytes + 8
         total = sum(data[variables[0][0]].shape[0] for (_gr, data) in ranks)
         out = [b"HACC01B\0" if big_endian else b"HACC01L\0"]
@@ -226,9 +231,10 @@ def write_gio_step(root, step, cols, prefix="lc", names=IN_COLS, nranks=3, big_e
             ne = data[variables[0][0]].shape[0]
             out.append(u64(gr % 4, gr // 4, 0, ne, rank_start[k]) + (b"" if old_headers else u64(gr)))
         if use_blocks:
-            for (st, sz) in block_start:
-                out.append(b"\0" * 32 + u64(st, sz))
-        out.append(b"\xC5" * 8)
+            for k, (st, sz) in enumerate(block_start):
+                filt = (filter_name or "").encode().ljust(8, b"\0") if (filter_name and k % nvars == 1) else b"\0" * 8
+                out.append(filt + b"\0" * 24 + u64(st, sz))
+        out.append(crc64_closing_bytes(b"".join(out)))
         blob = b"".join(out)
         assert len(blob) == header_size, (len(blob), header_size)
         return blob + b"".join(payload)
@@ -245,6 +251,33 @@ def write_gio_step(root, step, cols, prefix="lc", names=IN_COLS, nranks=3, big_e
             mine = [ranks[r] for r in range(nranks) if part_of[r] == p_][::-1]
             open(header + f"#{p_}", "wb").write(gio_bytes(mine, variables))
     return header
+
+
+_CRC64_TABLE = None
+
+
+def crc64_xz(data, reg=0xFFFFFFFFFFFFFFFF):
+    """CRC-64/XZ register after `data` (start ~0; the CRC is ~register): GenericIO's checksum.  Written here from the
+    catalogue parameters (poly 0x42F0E1EBA9EA3693 reflected, init ~0, xorout ~0, check 0x995DC9BBDF1939FA),
+    independently of the reader under test; byte-at-a-time, vectorised over a block with numpy."""
+    global _CRC64_TABLE
+    if _CRC64_TABLE is None:
+        t = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ 0xC96C5795D7870F42 if c & 1 else c >> 1
+            t.append(c)
+        _CRC64_TABLE = t
+    t = _CRC64_TABLE
+    for b in bytes(data):
+        reg = t[(reg ^ b) & 0xFF] ^ (reg >> 8)
+    return reg
+
+
+def crc64_closing_bytes(data):
+    """the 8 bytes GenericIO's crc64_invert appends: with them the CRC of data + bytes is ~0 (register 0)"""
+    return int(crc64_xz(data)).to_bytes(8, "little")
 
 
 def read_cutout_dir(d, step, names=OUT_COLS):

@@ -102,3 +102,17 @@ def test_merge_order_ties_and_empty_ranks():
     r, j = cc.merge_order(t, i)
     merged = [(float(t[a][b]), int(i[a][b])) for a, b in zip(r, j)]
     assert merged == sorted(merged) == [(1.0, 5), (1.0, 7), (1.0, 9), (2.0, 0), (2.0, 1), (2.0, 3)]
+
+
+def test_merge_order_of_a_halo_without_survivors():
+    """a halo whose cutout is empty on every rank (a small box in a sparse step): nothing to merge, and the empty
+    output arrays a caller passes may have NULL data pointers (std::vector<>::data() of an empty vector)"""
+    import ctypes as C
+    r, j = cc.merge_order([np.zeros(0, np.float32)] * 3, [np.zeros(0, np.int64)] * 3)
+    assert r.shape == (0,) and j.shape == (0,)
+    counts = np.zeros(2, dtype=np.int64)
+    null2 = (C.c_void_p * 2)(None, None)
+    assert cc.lib().cc_merge_order(2, counts.ctypes.data_as(C.c_void_p), null2, null2, None, None) == 0
+    counts[0] = 1  # survivors but no key columns: refused with a message
+    assert cc.lib().cc_merge_order(2, counts.ctypes.data_as(C.c_void_p), null2, null2, None, None) != 0
+    assert b"cc_merge_order" in cc.lib().cc_last_error()

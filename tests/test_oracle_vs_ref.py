@@ -122,3 +122,21 @@ def test_tail_drop_equals_reference():
             assert lib.ref_scatter_kept(n_p, ranks) == o.oracle_scatter_kept(n_p, ranks), (n_p, ranks)
     assert o.oracle_scatter_kept(100_000_000, 1) == 100_000_000 - 4
     assert o.oracle_scatter_kept(1_000_000_000, 1) == 1_000_000_000 - 32
+
+
+def test_checkers_carry_glibc_239_acosf_atanf():
+    """theta/phi are glibc's (not correctly rounded) acosf/atanf results: the oracle and the reference build link
+    glibc 2.39's own objects for the two functions (hidden, from the image's static libm) instead of binding to the
+    libm.so.6 of whatever box runs them, so a newer glibc cannot silently change the checker (oracle/Makefile)"""
+    import os
+    import subprocess
+    if not os.path.exists("/usr/lib/x86_64-linux-gnu/libm-2.39.a") and not os.path.isdir(os.path.join(H.ORACLE_DIR, "pin")):
+        pytest.skip("no static glibc 2.39 libm on this box and no prebuilt pin")
+    libs = [os.path.join(H.ORACLE_DIR, "liboracle.so")]
+    if H.ref_available():
+        libs.append(os.path.join(H.REF_DIR, "libcutout_ref.so"))
+    for lib in libs:
+        syms = subprocess.check_output(["nm", lib]).decode()
+        assert " t __ieee754_acosf" in syms and " t __atanf" in syms, lib          # defined inside, local
+        dyn = subprocess.check_output(["nm", "-D", lib]).decode()
+        assert " U acosf" not in dyn and " U atanf" not in dyn, lib                 # not bound to libm.so.6
