@@ -241,6 +241,13 @@ struct cc_ctx {
     int64_t stats[4] = {};
     int64_t nan_theta = 0;  /* use case 2: scanned particles whose un-rotated theta is NaN (see cc_last_stats_ex) */
     bool have_times = false;
+    bool timing = false;     /* record the per-kernel timing events (cc_last_scan_ms / cc_last_total_ms); cc_set_option
+                                "timing": three event records per cutout sit between the kernels, so it is off unless asked */
+    bool hstate_clean = false; /* use case 2 device state was zeroed by the previous cutout's last kernel (k3_small) */
+    int hstate_clean_H = -1;
+    DevBuf xchg_send;          /* use case 2, k3_small path: {counts, rough counts} saved for the count exchange before the
+                                  device state is zeroed */
+    const void* xchg_src = nullptr; /* what cc_exchange_counts sends for the pending use-case-2 cutout */
 
     /* streamed step (pinned host -> HBM double buffering) */
     bool streamed = false;
@@ -365,7 +372,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
     if (ch.first) CU(cudaMemsetAsync(sp, 0, off_info, c->stream));       /* totals + ticket + block states */
     else CU(cudaMemsetAsync(sp + 32, 0, off_info - 32, c->stream));      /* keep the running totals */
     unsigned long long* result = (unsigned long long*)sp;
-    if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
+    if (ch.first && c->timing) CU(cudaEventRecord(c->ev_scan0, c->stream));
     if (nseg > 0) {
         cck::SegScanArgs a;
         a.x = ch.x; a.y = ch.y; a.z = ch.z;
@@ -386,7 +393,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         a.ntiles = ntiles;
         k1s_scan_variant(vec)<<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
         CU(cudaGetLastError());
-        if (ch.last) CU(cudaEventRecord(c->ev_scan1, c->stream));
+        if (ch.last && c->timing) CU(cudaEventRecord(c->ev_scan1, c->stream));
 
         cck::SegPrefixArgs t;
         t.seg_info = a.seg_info;
@@ -396,6 +403,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         t.result = result;
         t.nseg = nseg;
         t.nblocks = nblocks;
+        t.host_result = ch.last ? c->h_small : nullptr; /* the step's totals go straight to pinned host memory */
         cck::k1s_seg_scan<<<nblocks, cck::TSCAN_THREADS, 0, c->stream>>>(t);
         CU(cudaGetLastError());
         if (ch.last) CU(cudaEventRecord(c->ev_counts, c->stream));
@@ -435,13 +443,13 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         CU(cudaGetLastError());
         c->launches += 3;
     } else if (ch.last) {
-        CU(cudaEventRecord(c->ev_scan1, c->stream));
+        if (c->timing) CU(cudaEventRecord(c->ev_scan1, c->stream));
         CU(cudaEventRecord(c->ev_counts, c->stream));
+        CU(cudaMemcpyAsync(c->h_small, result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     }
     if (ch.last) {
-        CU(cudaEventRecord(c->ev_total1, c->stream));
-        CU(cudaMemcpyAsync(c->h_small, result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        c->have_times = true;
+        if (c->timing) CU(cudaEventRecord(c->ev_total1, c->stream));
+        c->have_times = c->timing;
     }
     return CC_OK;
 }
@@ -476,6 +484,7 @@ int prepare_halo(cc_ctx* c) {
     const int H = (int)c->p_halos.size();
     if (c->n > 0xffffffffll) return fail(CC_ERR_ARG, "step too large for one shard (%lld particles)", (long long)c->n);
     int rc;
+    if (hstate_elems(H) * 8 > c->hstate.bytes) c->hstate_clean = false;
     if ((rc = c->hstate.ensure(hstate_elems(H) * 8))) return rc;
     if (c->rec_cap == 0) c->rec_cap = 1 << 20;
     if ((rc = c->rec_a.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
@@ -595,7 +604,8 @@ int prepare_halo(cc_ctx* c) {
         hs->key = c->p_halos;
         hs->bins = c->use_bins;
     }
-    CU(cudaMemsetAsync(c->hstate.p, 0, hstate_elems(H) * 8, c->stream));
+    if (!(c->hstate_clean && c->hstate_clean_H == H)) CU(cudaMemsetAsync(c->hstate.p, 0, hstate_elems(H) * 8, c->stream));
+    c->hstate_clean = false;
     return CC_OK;
 }
 
@@ -603,7 +613,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
     const int H = (int)c->p_halos.size();
     unsigned long long* rec_count = hs_misc(c);
     unsigned long long* n_cand = rec_count + 1;
-    if (ch.first) CU(cudaEventRecord(c->ev_scan0, c->stream));
+    if (ch.first && c->timing) CU(cudaEventRecord(c->ev_scan0, c->stream));
     /* the n_limit clamp (tail drop of the reference's load balancer) applies to step-local indices */
     const int64_t n_scan = std::max<int64_t>(0, std::min<int64_t>(ch.n, halo_scan_limit(c) - ch.start));
     const bool vec = aligned16(ch.x) && aligned16(ch.y) && aligned16(ch.z);
@@ -689,8 +699,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         }
     }
     if (ch.last) {
-        CU(cudaEventRecord(c->ev_scan1, c->stream));
-        CU(cudaEventRecord(c->ev_counts, c->stream));
+        if (c->timing) CU(cudaEventRecord(c->ev_scan1, c->stream));
         /* ordering + gather, sized on the device: the whole pass is one enqueue, one host synchronisation */
         cck::GatherArgs g;
         g.rank = (const unsigned int*)c->rank_buf.p;
@@ -720,10 +729,22 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             sa.seg_begin = hs_seg(c, H);
             sa.misc = hs_misc(c);
             sa.H = H;
+            /* the last kernel of the pass hands the results to the host itself (pinned memory, no copy command behind
+             * it) and leaves the device state zeroed for the next cutout (no memset in front of the next scan) */
+            sa.host_out = c->h_small;
+            sa.state_elems = (unsigned int)hstate_elems(H);
+            { int rc2 = c->xchg_send.ensure((size_t)2 * H * 8); if (rc2) return rc2; }
+            sa.xchg_send = (unsigned long long*)c->xchg_send.p;
             cck::k3_small<<<1, cck::K3S_THREADS, cck::K3S_SMEM_BYTES, c->stream>>>(sa);
             CU(cudaGetLastError());
             c->launches += 1;
+            c->hstate_clean = true;
+            c->hstate_clean_H = H;
+            c->xchg_src = c->xchg_send.p;
+            CU(cudaEventRecord(c->ev_counts, c->stream)); /* the exchange reads the saved counts: after this kernel */
         } else {
+            c->xchg_src = hs_counts(c);
+            CU(cudaEventRecord(c->ev_counts, c->stream)); /* counts are final: the exchange runs next to ordering + gather */
             cck::k3_scan_counts<<<1, 256, 0, c->stream>>>(hs_counts(c), hs_seg(c, H), H);
             CU(cudaGetLastError());
             const unsigned int g1 = (unsigned int)c->sm_count * 8; /* 2048 threads per SM: every record is a chain of dependent L2 round trips */
@@ -759,10 +780,10 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             CU(cudaGetLastError());
             c->launches += 4;
         }
-        CU(cudaEventRecord(c->ev_total1, c->stream));
-        c->have_times = true;
-        /* misc {rec_count, n_cand, ...}, counts, rough counts, segment starts: one read-back */
-        CU(cudaMemcpyAsync(c->h_small, c->hstate.p, (8 + 3 * (size_t)H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (c->timing) CU(cudaEventRecord(c->ev_total1, c->stream));
+        c->have_times = c->timing;
+        /* misc {rec_count, n_cand, ...}, counts, rough counts, segment starts: one read-back (k3_small wrote it itself) */
+        if (!small) CU(cudaMemcpyAsync(c->h_small, c->hstate.p, (8 + 3 * (size_t)H + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     }
     return CC_OK;
 }
@@ -912,6 +933,7 @@ int cc_create(int device, cc_ctx** out) {
     cc_ctx* c = new cc_ctx();
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("CC_GATHER")) c->gather_mode = !strcmp(e, "bulk") ? 2 : !strcmp(e, "ldst") ? 1 : 0;
+    if (const char* e = getenv("CC_TIMING")) c->timing = atoi(e) != 0;
     if (getenv("CC_NO_PAYLOAD")) c->payload_policy = 2;
     if (const char* e = getenv("CC_PAYLOAD")) c->payload_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
     c->device = device;
@@ -947,7 +969,7 @@ void cc_destroy(cc_ctx* c) {
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
     DevBuf* rest[] = {&c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
-                      &c->hstate, &c->gather_buf, &c->offsets_buf, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
+                      &c->hstate, &c->gather_buf, &c->offsets_buf, &c->xchg_send, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
     for (DevBuf* b : rest) b->release();
     for (auto& e : c->halo_sets) e.release();
     for (auto& sl : c->stage) for (auto& b : sl) b.release();
@@ -1548,7 +1570,7 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         CU(cudaMemcpyAsync(c->counts_buf.p, c->scratch.p, 8, cudaMemcpyDeviceToDevice, xs));
         CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, xs));
     }
-    const void* send = (c->pending == P_CONST) ? c->counts_buf.p : (const void*)hs_counts(c);
+    const void* send = (c->pending == P_CONST) ? c->counts_buf.p : c->xchg_src;
     if (c->xchg_mode == 2 && R > 1 && !(c->peers_ready && 2 * H <= cck::XCHG_PAYLOAD))
         return fail(CC_ERR_STATE, "cc_exchange_counts: exchange=peer but no mailboxes are attached (or more than %d halos)", cck::XCHG_PAYLOAD / 2);
     const bool peer_path = c->peers_ready && R > 1 && 2 * H <= cck::XCHG_PAYLOAD && c->xchg_mode != 1 && !getenv("CC_NO_PEER_XCHG");
@@ -1567,6 +1589,8 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         const char* to = getenv("CC_PEER_TIMEOUT_MS");
         x.timeout_ns = (unsigned long long)(to ? atoll(to) : 10000) * 1000000ull;
         x.n = 2 * H; x.H = H; x.R = R; x.rank = c->rank;
+        x.host_gathered = hg;                         /* results also land in pinned host memory: no copy commands */
+        x.host_offsets = hg + (size_t)R * 2 * H + 1;
         cck::k4_exchange_peer<<<1, 256, 0, xs>>>(x);
         CU(cudaGetLastError());
     } else {
@@ -1581,8 +1605,10 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         CU(cudaGetLastError());
     }
     c->launches += 1;
-    CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8 + 8, cudaMemcpyDeviceToHost, xs)); /* + status */
-    CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H + 1, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, xs));
+    if (!peer_path) {
+        CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8 + 8, cudaMemcpyDeviceToHost, xs)); /* + status */
+        CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H + 1, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, xs));
+    }
     CU(cudaEventRecord(c->ev_xchg, xs));
     CU(cudaStreamWaitEvent(c->stream, c->ev_xchg, 0));
     if (c->synced) CU(cudaStreamSynchronize(c->stream));
@@ -1697,6 +1723,9 @@ int cc_set_option(cc_ctx* c, const char* key, const char* value) {
     } else if (k == "exchange") {
         if (v == "auto") c->xchg_mode = 0; else if (v == "nccl") c->xchg_mode = 1; else if (v == "peer") c->xchg_mode = 2;
         else return fail(CC_ERR_ARG, "cc_set_option: exchange = auto|nccl|peer");
+    } else if (k == "timing") {
+        if (v == "on") c->timing = true; else if (v == "off") c->timing = false;
+        else return fail(CC_ERR_ARG, "cc_set_option: timing = on|off");
     } else if (k == "gather") {
         if (v == "auto") c->gather_mode = 0; else if (v == "ldst") c->gather_mode = 1; else if (v == "bulk") c->gather_mode = 2;
         else return fail(CC_ERR_ARG, "cc_set_option: gather = auto|ldst|bulk");

@@ -363,6 +363,8 @@ struct SegPrefixArgs {
     unsigned long long* block_state;    /* [nblocks] zeroed before launch */
     unsigned int* ticket;               /* zeroed before launch */
     unsigned long long* result;         /* [0] survivors so far (in: carry, out: carry + chunk total), [2] = carry */
+    unsigned long long* host_result;    /* pinned host memory (or NULL): result[0..3] of the step's last chunk, so that no
+                                           copy command has to follow the gather */
     unsigned int nseg, nblocks;
 };
 __global__ void __launch_bounds__(TSCAN_THREADS) k1s_seg_scan(const SegPrefixArgs a) {
@@ -426,6 +428,13 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1s_seg_scan(const SegPrefixArg
                 const unsigned long long carry = a.result[0];
                 a.result[2] = carry;
                 a.result[0] = carry + exclusive + block_total;
+                if (a.host_result) { /* [1] candidates and [3] the largest record region are final since k1s_scan ended */
+                    a.host_result[0] = carry + exclusive + block_total;
+                    a.host_result[1] = a.result[1];
+                    a.host_result[2] = carry;
+                    a.host_result[3] = a.result[3];
+                    __threadfence_system();
+                }
             }
         }
     }
@@ -1521,6 +1530,7 @@ __global__ void k3_gather_halo(const GatherArgs a) {
  * output row -- and gathers.  If the record count turns out larger it sets misc[4] and does nothing; the host then
  * re-runs the cutout through the general kernels. */
 constexpr int K3S_THREADS = 512;
+constexpr int K3S_RANK_MAX = 1024; /* up to here rows come from counting, beyond from the bitonic network */
 constexpr size_t K3S_SMEM_BYTES = (size_t)K3_SORT_MAX * (sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
                                   (size_t)K3S_THREADS * sizeof(unsigned long long);
 struct SmallArgs {
@@ -1528,8 +1538,21 @@ struct SmallArgs {
     const unsigned long long* counts;    /* [H] survivors per halo */
     unsigned long long* seg_begin;       /* [H+1] out */
     unsigned long long* misc;            /* [4] = 1 when the record count does not fit */
+    unsigned long long* host_out;        /* pinned host memory: misc[8], counts[2H], seg_begin[H+1] -- what the host reads */
+    unsigned int state_elems;            /* u64 words of the device state starting at misc: zeroed for the next cutout */
+    unsigned long long* xchg_send;       /* [2H] {counts, rough counts} kept for the count exchange (capi.cu) */
     int H;
 };
+/* last step of k3_small (all threads): results to the host, device state zeroed */
+__device__ __forceinline__ void k3s_publish(const SmallArgs& a) {
+    __syncthreads();
+    const unsigned int nout = 8u + 3u * (unsigned int)a.H + 1u;
+    for (unsigned int i = threadIdx.x; i < nout; i += K3S_THREADS) a.host_out[i] = a.misc[i];
+    for (unsigned int i = threadIdx.x; i < 2u * (unsigned int)a.H; i += K3S_THREADS) a.xchg_send[i] = a.counts[i];
+    __threadfence_system();
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < a.state_elems; i += K3S_THREADS) a.misc[i] = 0ull;
+}
 __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw);
@@ -1540,6 +1563,7 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
     const unsigned long long nrec = *a.g.rec_count;
     if (nrec > K3_SORT_MAX || nrec > a.g.rec_cap) {
         if (tid == 0) a.misc[4] = 1ull;
+        k3s_publish(a);
         return;
     }
     /* exclusive scan of the halo counts -> seg_begin (read back by the host) */
@@ -1580,6 +1604,32 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
         s_idx[i] = (unsigned short)i;
     }
     __syncthreads();
+    if (nrec <= K3S_RANK_MAX) {
+        /* a cluster-sized cutout (a few hundred records): every record counts the records in front of it -- (halo, key)
+         * pairs are unique -- and that count IS its row; two barriers instead of the 45 of a 512-element network */
+        unsigned short row[K3S_RANK_MAX / K3S_THREADS];
+#pragma unroll
+        for (int r = 0; r < K3S_RANK_MAX / K3S_THREADS; ++r) {
+            const unsigned int i = tid + r * K3S_THREADS;
+            unsigned int before = 0;
+            if (i < nrec) {
+                const unsigned long long ki = s_key[i];
+                const unsigned short hi = s_halo[i];
+                for (unsigned int j = 0; j < (unsigned int)nrec; ++j) {
+                    const unsigned short hj = s_halo[j];
+                    before += (hj < hi) || (hj == hi && s_key[j] < ki);
+                }
+            }
+            row[r] = (unsigned short)before;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < K3S_RANK_MAX / K3S_THREADS; ++r) {
+            const unsigned int i = tid + r * K3S_THREADS;
+            if (i < nrec) s_idx[row[r]] = (unsigned short)i;
+        }
+        __syncthreads();
+    } else
     for (unsigned int k = 2; k <= n; k <<= 1) {
         for (unsigned int j = k >> 1; j > 0; j >>= 1) {
             for (unsigned int t = tid; t < (n >> 1); t += K3S_THREADS) {
@@ -1626,6 +1676,7 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
         a.g.out.theta_u[o] = __int_as_float((int)(r.key >> 32));
         a.g.out.index[o] = a.g.index_base + g;
     }
+    k3s_publish(a);
 }
 
 /* ================================================================================================
@@ -1681,6 +1732,8 @@ struct XchgArgs {
     unsigned long long* gathered;        /* [R][n] out */
     unsigned long long* offsets;         /* [H] out: sum of counts of lower ranks */
     unsigned long long* status;          /* [0] set to 1 on time-out */
+    unsigned long long* host_gathered;   /* pinned host copies of gathered (+ the status word behind it) and offsets */
+    unsigned long long* host_offsets;
     unsigned long long epoch;
     unsigned long long timeout_ns;
     int n, H, R, rank;
@@ -1712,18 +1765,25 @@ __global__ void __launch_bounds__(256) k4_exchange_peer(const XchgArgs a) {
     }
     __syncthreads();
     if (s_timeout) {
-        if (tid == 0) *a.status = 1ull;
+        if (tid == 0) { *a.status = 1ull; a.host_gathered[(size_t)a.R * a.n] = 1ull; __threadfence_system(); }
         return;
     }
     for (int r = 0; r < a.R; ++r) {
         const unsigned long long* src = mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8;
-        for (int i = tid; i < a.n; i += blockDim.x) a.gathered[(size_t)r * a.n + i] = ld_relaxed_sys_u64(src + i);
+        for (int i = tid; i < a.n; i += blockDim.x) {
+            const unsigned long long v = ld_relaxed_sys_u64(src + i);
+            a.gathered[(size_t)r * a.n + i] = v;
+            a.host_gathered[(size_t)r * a.n + i] = v;
+        }
     }
+    if (tid == 0) a.host_gathered[(size_t)a.R * a.n] = 0ull; /* status: no time-out */
     for (int h = tid; h < a.H; h += blockDim.x) {
         unsigned long long run = 0;
         for (int r = 0; r < a.rank; ++r) run += ld_relaxed_sys_u64(mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8 + h);
         a.offsets[h] = run;
+        a.host_offsets[h] = run;
     }
+    __threadfence_system();
 }
 
 /* ================================================================================================

@@ -862,3 +862,34 @@ def test_resident_step_slots(ctx):
             fresh.cutout_const(tc, pc)              # slot 0 holds nothing
     finally:
         fresh.close()
+
+
+def test_small_cutout_kernel_sizes_and_timing_switch(ctx):
+    """the single-CTA ordering + gather kernel (k3_small) orders by counting up to 1024 records and with the bitonic
+    network beyond; it hands the counts to the host itself and leaves the device state clean for the next cutout.
+    Cutouts of growing size, each run twice (the second run takes the kernel), several halos, then a size that makes it
+    refuse (> 8192) and fall back; per-kernel timing is off unless asked for"""
+    cols = H.shell_fixture(1_500_000, seed=64)
+    ctx.upload(cols)
+    pos = np.array([[150, 20, 12], [100, 100, 100], [30, 170, 100]], dtype=np.float32)
+    seen = []
+    for box in (40.0, 90.0, 130.0, 170.0, 260.0, 420.0):
+        infos = [cc.halo_setup(p, box) for p in pos]
+        wants = [H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, box)) for p in pos]
+        for rep in range(2):
+            ctx.cutout_halo([i.halo for i in infos])
+            counts, rough = ctx.sync()
+            everything, off = ctx.fetch_all(counts)
+            for h, (w, wr) in enumerate(wants):
+                assert int(rough[h]) == wr
+                H.assert_cols_equal({c: v[off[h]:off[h + 1]] for c, v in everything.items()}, w, what=f"box {box} rep {rep} halo {h}: ")
+        seen.append(int(counts.sum()))
+    assert seen[0] < 1024 < seen[2] and any(1024 < k <= 8192 for k in seen) and seen[-1] > 8192, seen
+    assert ctx.last_scan_ms() < 0  # timing events are not recorded by default
+    try:
+        ctx.set_option("timing", "on")
+        ctx.cutout_halo([cc.halo_setup(pos[0], 40.0).halo])
+        ctx.sync()
+        assert 0 < ctx.last_scan_ms() <= ctx.last_total_ms()
+    finally:
+        ctx.set_option("timing", "off")
