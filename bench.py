@@ -180,7 +180,10 @@ class Env:
                 self.ctx.set_option("exchange", "nccl")
                 self.exchange = "NCCL all-gather enqueued behind the cutout kernels (--nccl)"
             else:
-                self.exchange = "NVLink peer stores (k4_exchange_peer) behind the cutout kernels; NCCL path checked in parity_check"
+                self.ctx.set_option("exchange", "eager")
+                self.exchange = ("NVLink peer stores into the other GPUs' mailboxes: inside the cutout's last kernel for small "
+                                 "use-case-2 cutouts (k3_small), a single-CTA kernel next to the gather otherwise "
+                                 "(k4_exchange_peer); the NCCL all-gather path is checked in parity_check")
         self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=self.dev)
 
     def barrier(self):
@@ -394,6 +397,7 @@ def run_e2e(env, args, wl, n):
         out, _off = ctx.fetch_all(counts)  # every halo's survivors, one device->host copy per column
         return int(counts.sum()), sum(v.nbytes for v in out.values())
 
+    ceiling = h2d_ceiling(env, host["x"])
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(min(max(args.warmup, 3), 3)):
         e2e_step()
@@ -415,10 +419,50 @@ def run_e2e(env, args, wl, n):
         cc.pinned_free(a)
     if env.rank != 0:
         return None
+    achieved = 12.0 * e2e_n / (e2e_ms / e2e_steps * 1e-3) / 1e9  # GB/s per GPU over the whole step
     return {"value": round(e2e_n * env.world / (e2e_ms / e2e_steps * 1e-3) / 1e9, 4), "unit": "Gparticles/s",
             "h2d_bytes_per_step": 12 * e2e_n, "d2h_bytes_per_step": d2h, "particles_per_gpu": e2e_n,
             "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
+            "roofline": {"bound": "host->device copies", "achieved_gbs_per_gpu": round(achieved, 2),
+                         "ceiling_gbs_slowest_gpu": ceiling, "frac": round(achieved / ceiling, 4) if ceiling else None,
+                         "what": "ceiling = plain cudaMemcpyAsync of the same pinned x column, all ranks copying at once, "
+                                 "slowest rank (measured in this run; profiles/r02 has the 1/2/4/8-GPU table of this box)"},
             "api": "cc_cutout_halo_streamed/cc_cutout_const_streamed + cc_cutout_sync + cc_cutout_fetch_all on pinned host columns"}
+
+
+def h2d_ceiling(env, host_col):
+    """GB/s of a plain host->device copy of one pinned column while EVERY rank copies at once (min over ranks): what the
+    box gives the streamed path at this GPU count"""
+    torch = env.torch
+    try:
+        from cuda import cudart
+    except Exception:
+        return None
+    nbytes = host_col.nbytes
+    dev = torch.empty(host_col.shape[0], dtype=torch.float32, device=env.dev)
+    st = torch.cuda.Stream(device=env.dev)
+
+    def copy():
+        (err,) = cudart.cudaMemcpyAsync(dev.data_ptr(), host_col.ctypes.data, nbytes,
+                                        cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, st.cuda_stream)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaMemcpyAsync: {err}")
+
+    try:
+        copy()
+        st.synchronize()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            copy()
+        st.synchronize()
+        gbs = 4 * nbytes / (time.perf_counter() - t0) / 1e9
+    except Exception as e:
+        log(f"h2d_ceiling: {e!r}")
+        gbs = 0.0
+    (mn,) = env.allreduce([gbs], "min")
+    del dev
+    return round(mn, 2) if mn > 0 else None
 
 
 # ------------------------------------------------------------------------------------------------ cfg3: streamed depth
@@ -548,7 +592,7 @@ def parity_check(env, n=None):
     del x64, y64, z64, r
     res = {"particles_per_gpu": n, "ranks": env.world, "checks": []}
     ok_all = True
-    modes = ["auto"] if env.world == 1 else ["peer", "nccl"]
+    modes = ["auto"] if env.world == 1 else ["eager", "peer", "nccl"]
 
     def offsets_ok(allc, off):
         want = allc[:env.rank].sum(axis=0)
@@ -588,7 +632,7 @@ def parity_check(env, n=None):
             s2 = s2[s2 + base < limit]
             sub = {k: np.ascontiguousarray(host[k][s2]) for k in cc.IN_COLS}
             wants.append(H.oracle_cutout_halo(sub, H.oracle_halo_setup(p, box)))
-        for mode in modes:
+        for mode in [m for m in modes for _ in (0, 1)]:  # twice each: the second cutout takes the small-cutout kernel
             ctx.set_option("exchange", mode)
             ctx.cutout_halo([i.halo for i in infos], n_limit_global=limit)
             if env.world > 1:
@@ -611,6 +655,7 @@ def parity_check(env, n=None):
                                   "sha256_rank0": _sha(everything, cc.OUT_COLS)[:16]})
     ctx.set_option("exchange", "auto")
     ctx.release()
+    # the small-cutout kernel (one halo, a few hundred survivors) takes over from the second cutout on: both modes ran it
     (mn,) = env.allreduce([1.0 if ok_all else 0.0], "min")
     res["ok"] = bool(mn == 1.0)
     res["how"] = ("byte-for-byte: all 12 survivor columns of every rank's shard vs oracle/liboracle.so on the shard's candidate "

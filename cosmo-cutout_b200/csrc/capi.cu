@@ -165,6 +165,12 @@ struct cc_ctx {
     int64_t launches = 0;
     int64_t last_const_count = -1;
     int k2_occupancy[2] = {0, 0};
+    bool cells_mono = false;   /* CC_CELLS_MONO=1: the single-kernel cell-index scan (k2_cutout_halo_cells) instead of the
+                                  staged sift -> match -> exact kernels */
+    DevBuf cand, cand_count, pair_p, pair_h, pair_count;
+    unsigned int cand_region_cap = 0; /* candidates per warp region (k2c_sift) */
+    int64_t pair_cap = 0;
+    int sift_occupancy[2] = {0, 0};
     bool k2c_ready = false;
     int k2c_warps = 20; /* warps of the one CTA per SM: 20 at 96 registers, no spills, 161 KB of shared memory (24 at 80
                            registers spill and leave too little L1; 16 hide less latency); CC_K2C_WARPS=24|16 for A/B runs */
@@ -194,7 +200,9 @@ struct cc_ctx {
     int64_t step_last_survivors = -1; /* survivors of the previous cutout on the resident step (-1: none yet) */
     cudaEvent_t ev_pay0 = nullptr, ev_pay1 = nullptr;
     bool payload_timed = false;       /* the pending cutout built the payload: ev_pay0..ev_pay1 is its duration */
-    int xchg_mode = 0;       /* 0 auto (peer mailboxes when attached, else NCCL), 1 NCCL, 2 peer; cc_set_option "exchange" */
+    int xchg_mode = 0;       /* 0 auto (peer mailboxes when attached, else NCCL), 1 NCCL, 2 peer, 3 eager: peer, and a
+                                small use-case-2 cutout does the exchange inside its last kernel; cc_set_option "exchange" */
+    bool eager_done = false; /* the pending cutout's last kernel carried the count exchange */
 
     /* survivors */
     DevBuf out_buf[N_OUT_COLS];
@@ -609,6 +617,31 @@ int prepare_halo(cc_ctx* c) {
     return CC_OK;
 }
 
+/* where the exchanged counts land in the pinned read-back area: behind the cutout's own results */
+size_t xchg_host_off(int H) { return 32 + 3 * (size_t)H; }
+
+int fill_xchg_args(cc_ctx* c, int H, const void* send, int uc1, cck::XchgArgs* x) {
+    const int R = c->nranks;
+    int rc;
+    if ((rc = c->gather_buf.ensure((size_t)R * 2 * H * 8 + 64))) return rc;
+    if ((rc = c->offsets_buf.ensure((size_t)H * 8))) return rc;
+    unsigned long long* hg = c->h_small + xchg_host_off(H);
+    memset(x, 0, sizeof(*x));
+    x->send = (const unsigned long long*)send;
+    for (int r = 0; r < R; ++r) x->peer[r] = c->peer_mb[r];
+    x->gathered = (unsigned long long*)c->gather_buf.p;
+    x->offsets = (unsigned long long*)c->offsets_buf.p;
+    x->status = (unsigned long long*)((char*)c->gather_buf.p + (size_t)R * 2 * H * 8);
+    x->host_gathered = hg;                        /* results also land in pinned host memory: no copy commands */
+    x->host_offsets = hg + (size_t)R * 2 * H + 1;
+    x->uc1 = uc1;
+    x->epoch = ++c->xchg_epoch;
+    const char* to = getenv("CC_PEER_TIMEOUT_MS");
+    x->timeout_ns = (unsigned long long)(to ? atoll(to) : 10000) * 1000000ull;
+    x->n = 2 * H; x->H = H; x->R = R; x->rank = c->rank;
+    return CC_OK;
+}
+
 int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
     const int H = (int)c->p_halos.size();
     unsigned long long* rec_count = hs_misc(c);
@@ -642,7 +675,51 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             if (occ < 1) occ = 1;
         }
         const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
-        if (c->use_bins) { /* one 32-warp CTA per SM: bitmap + windows + pair buffers take 128 KB of its shared memory */
+        if (c->use_bins && !c->cells_mono) { /* staged: sift -> match -> exact (kernels.cuh) */
+            const int bi = h0 / cck::K2_MAX_HALOS;
+            int& socc = c->sift_occupancy[vec ? 1 : 0];
+            if (socc == 0) {
+                const void* fn = vec ? (const void*)cck::k2c_sift<true> : (const void*)cck::k2c_sift<false>;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, fn, cck::SCAN_THREADS, 0));
+                if (socc < 1) socc = 1;
+            }
+            const unsigned int sgrid_max = (unsigned int)(c->sm_count * socc);
+            const unsigned int sgrid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, sgrid_max));
+            const unsigned int warps_max = sgrid_max * cck::SCAN_WARPS, nregions = sgrid * cck::SCAN_WARPS;
+            if (c->cand_region_cap == 0) c->cand_region_cap = (unsigned int)std::min<int64_t>(0x7ffffff0, c->n / 6 / warps_max + 512);
+            if (c->pair_cap == 0) c->pair_cap = 4 << 20;
+            int rc2;
+            if ((rc2 = c->cand.ensure((size_t)warps_max * c->cand_region_cap * sizeof(float4)))) return rc2;
+            if ((rc2 = c->cand_count.ensure((size_t)warps_max * 4))) return rc2;
+            if ((rc2 = c->pair_p.ensure((size_t)c->pair_cap * sizeof(float4)))) return rc2;
+            if ((rc2 = c->pair_h.ensure((size_t)c->pair_cap * 4))) return rc2;
+            if ((rc2 = c->pair_count.ensure(64))) return rc2;
+            CU(cudaMemsetAsync(c->pair_count.p, 0, 8, c->stream));
+            cck::SiftArgs sa;
+            sa.x = a.x; sa.y = a.y; sa.z = a.z; sa.n = a.n; sa.local_base = a.local_base;
+            sa.cell_bits = (const unsigned int*)c->hs->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
+            sa.cand = (float4*)c->cand.p; sa.region_cap = c->cand_region_cap; sa.cand_count = (unsigned int*)c->cand_count.p;
+            sa.misc = hs_misc(c); sa.ntiles = a.ntiles;
+            if (vec) cck::k2c_sift<true><<<sgrid, cck::SCAN_THREADS, 0, c->stream>>>(sa);
+            else cck::k2c_sift<false><<<sgrid, cck::SCAN_THREADS, 0, c->stream>>>(sa);
+            CU(cudaGetLastError());
+            cck::MatchArgs ma;
+            ma.h = a;
+            ma.cell_range = (const uint2*)c->hs->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID);
+            ma.cell_items = (const unsigned short*)c->hs->bin_items_buf.p + c->hs->bin_items_off[(size_t)bi];
+            ma.cand = sa.cand; ma.cand_count = sa.cand_count; ma.region_cap = sa.region_cap; ma.nregions = nregions;
+            ma.pair_p = (float4*)c->pair_p.p; ma.pair_h = (unsigned int*)c->pair_h.p;
+            ma.pair_cap = (unsigned long long)c->pair_cap; ma.pair_count = (unsigned long long*)c->pair_count.p;
+            cck::k2c_match<<<std::min(nregions, (unsigned int)c->sm_count * 8u), cck::K2M_THREADS, 0, c->stream>>>(ma);
+            CU(cudaGetLastError());
+            cck::ExactArgs ea;
+            ea.h = a;
+            ea.pair_p = ma.pair_p; ea.pair_h = ma.pair_h; ea.pair_cap = ma.pair_cap; ea.pair_count = ma.pair_count;
+            ea.misc = hs_misc(c);
+            cck::k2c_exact<<<(unsigned int)c->sm_count * 8u, 256, 0, c->stream>>>(ea);
+            CU(cudaGetLastError());
+            c->launches += 3;
+        } else if (c->use_bins) { /* one 20-warp CTA per SM: bitmap + windows + pair buffers take 161 KB of its shared memory */
             cck::HaloBinArgs b;
             b.h = a;
             const int bi = h0 / cck::K2_MAX_HALOS;
@@ -735,6 +812,15 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             sa.state_elems = (unsigned int)hstate_elems(H);
             { int rc2 = c->xchg_send.ensure((size_t)2 * H * 8); if (rc2) return rc2; }
             sa.xchg_send = (unsigned long long*)c->xchg_send.p;
+            /* eager exchange: this kernel posts the counts to the peers first and collects theirs last */
+            sa.do_xchg = 0;
+            if (c->xchg_mode == 3 && !c->eager_done && c->peers_ready && c->nranks > 1 && 2 * H <= cck::XCHG_PAYLOAD &&
+                c->h_small_elems >= small_elems(H, c->nranks)) {
+                int rc2 = fill_xchg_args(c, H, hs_counts(c), 0, &sa.x);
+                if (rc2) return rc2;
+                sa.do_xchg = 1;
+                c->eager_done = true;
+            }
             cck::k3_small<<<1, cck::K3S_THREADS, cck::K3S_SMEM_BYTES, c->stream>>>(sa);
             CU(cudaGetLastError());
             c->launches += 1;
@@ -934,6 +1020,7 @@ int cc_create(int device, cc_ctx** out) {
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("CC_GATHER")) c->gather_mode = !strcmp(e, "bulk") ? 2 : !strcmp(e, "ldst") ? 1 : 0;
     if (const char* e = getenv("CC_TIMING")) c->timing = atoi(e) != 0;
+    if (const char* e = getenv("CC_CELLS_MONO")) c->cells_mono = atoi(e) != 0;
     if (getenv("CC_NO_PAYLOAD")) c->payload_policy = 2;
     if (const char* e = getenv("CC_PAYLOAD")) c->payload_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
     c->device = device;
@@ -969,7 +1056,7 @@ void cc_destroy(cc_ctx* c) {
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
     DevBuf* rest[] = {&c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
-                      &c->hstate, &c->gather_buf, &c->offsets_buf, &c->xchg_send, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
+                      &c->hstate, &c->gather_buf, &c->offsets_buf, &c->xchg_send, &c->cand, &c->cand_count, &c->pair_p, &c->pair_h, &c->pair_count, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
     for (DevBuf* b : rest) b->release();
     for (auto& e : c->halo_sets) e.release();
     for (auto& sl : c->stage) for (auto& b : sl) b.release();
@@ -1173,6 +1260,7 @@ int cc_cutout_const(cc_ctx* c, const float theta_cut[2], const float phi_cut[2])
     c->synced = false;
     c->streamed = false;
     c->payload_timed = false;
+    c->eager_done = false;
     return run_pending(c);
 }
 
@@ -1191,6 +1279,7 @@ int cc_cutout_halo(cc_ctx* c, int nhalos, const cc_halo* halos, int pos_only, in
     c->synced = false;
     c->streamed = false;
     c->payload_timed = false;
+    c->eager_done = false;
     if (nhalos == 0) { c->counts.clear(); c->rough.clear(); c->seg_begin.assign(1, 0); c->synced = true; return CC_OK; }
     return run_pending(c);
 }
@@ -1224,13 +1313,19 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             c->nan_theta = 0;
         } else {
             const int H = c->nhalos;
-            for (int attempt = 0; attempt < 4; ++attempt) {
+            for (int attempt = 0; attempt < 6; ++attempt) {
                 CU(cudaStreamSynchronize(c->stream));
                 const int64_t nrec = (int64_t)c->h_small[0];
                 const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
                 c->force_general = refused;
-                if (nrec <= c->rec_cap && !refused) break;
-                if (attempt == 3) return fail(CC_ERR_CUDA, "internal: halo survivor buffers still too small after regrowth");
+                /* staged cell-index kernels: a warp's candidate region or the pair buffer was too small */
+                const bool staged = c->use_bins && !c->cells_mono;
+                const bool cand_over = staged && c->h_small[2] > c->cand_region_cap;
+                const bool pair_over = staged && (int64_t)c->h_small[3] > c->pair_cap;
+                if (nrec <= c->rec_cap && !refused && !cand_over && !pair_over) break;
+                if (attempt == 5) return fail(CC_ERR_CUDA, "internal: halo survivor buffers still too small after regrowth");
+                if (cand_over) c->cand_region_cap = (unsigned int)std::min<uint64_t>(0x7ffffff0u, c->h_small[2] + c->h_small[2] / 8 + 512);
+                if (pair_over) c->pair_cap = (int64_t)(c->h_small[3] + c->h_small[3] / 8 + 4096);
                 if (nrec > c->rec_cap) c->rec_cap = nrec + nrec / 64;
                 if ((rc = run_pending(c))) return rc;
             }
@@ -1407,6 +1502,7 @@ int cc_cutout_const_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64
     c->p_ph[0] = phi_cut[0]; c->p_ph[1] = phi_cut[1];
     c->nhalos = 1;
     c->pending = P_CONST;
+    c->eager_done = false;
     return run_pending(c);
 }
 
@@ -1420,6 +1516,7 @@ int cc_cutout_halo_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_
     c->p_n_limit = n_limit_global;
     c->nhalos = nhalos;
     c->pending = P_HALO;
+    c->eager_done = false;
     if (nhalos == 0) { c->counts.clear(); c->rough.clear(); c->seg_begin.assign(1, 0); c->synced = true; return CC_OK; }
     return run_pending(c);
 }
@@ -1564,36 +1661,34 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
      * then waits for the exchange, so stream order (and anything timed on the cutout stream) includes it.  Survivor
      * counts are exact even when a survivor buffer overflowed (only the stored rows are clipped), so a local re-run
      * after the synchronisation never needs a second collective -- every rank issues exactly one all-gather per call. */
+    unsigned long long* hg = c->h_small + hg_off;
+    if (c->pending == P_HALO && c->eager_done) {
+        /* the cutout's last kernel already exchanged the counts (k3_small, exchange=eager): nothing to enqueue */
+        if (c->synced) CU(cudaStreamSynchronize(c->stream));
+        else if ((rc = cc_cutout_sync(c, nullptr, nullptr))) return rc;
+        goto read_back;
+    }
+    {
     cudaStream_t xs = c->xchg_stream;
     CU(cudaStreamWaitEvent(xs, c->ev_counts, 0));
-    if (c->pending == P_CONST) { /* device-resident send buffer {count, 0}; use case 2 already has {counts, rough} */
-        CU(cudaMemcpyAsync(c->counts_buf.p, c->scratch.p, 8, cudaMemcpyDeviceToDevice, xs));
-        CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, xs));
-    }
-    const void* send = (c->pending == P_CONST) ? c->counts_buf.p : c->xchg_src;
-    if (c->xchg_mode == 2 && R > 1 && !(c->peers_ready && 2 * H <= cck::XCHG_PAYLOAD))
+    if (c->xchg_mode >= 2 && R > 1 && !(c->peers_ready && 2 * H <= cck::XCHG_PAYLOAD))
         return fail(CC_ERR_STATE, "cc_exchange_counts: exchange=peer but no mailboxes are attached (or more than %d halos)", cck::XCHG_PAYLOAD / 2);
     const bool peer_path = c->peers_ready && R > 1 && 2 * H <= cck::XCHG_PAYLOAD && c->xchg_mode != 1 && !getenv("CC_NO_PEER_XCHG");
-    unsigned long long* hg = c->h_small + hg_off;
-    unsigned long long* d_status = (unsigned long long*)((char*)c->gather_buf.p + (size_t)R * 2 * H * 8);
-    CU(cudaMemsetAsync(d_status, 0, 8, xs));
-    if (peer_path) { /* NVLink peer stores: one single-CTA kernel, no collective launch */
+    if (peer_path) { /* NVLink peer stores: one single-CTA kernel, no collective launch, results written to pinned memory */
         cck::XchgArgs x;
-        memset(&x, 0, sizeof(x));
-        x.send = (const unsigned long long*)send;
-        for (int r = 0; r < R; ++r) x.peer[r] = c->peer_mb[r];
-        x.gathered = (unsigned long long*)c->gather_buf.p;
-        x.offsets = (unsigned long long*)c->offsets_buf.p;
-        x.status = d_status;
-        x.epoch = ++c->xchg_epoch;
-        const char* to = getenv("CC_PEER_TIMEOUT_MS");
-        x.timeout_ns = (unsigned long long)(to ? atoll(to) : 10000) * 1000000ull;
-        x.n = 2 * H; x.H = H; x.R = R; x.rank = c->rank;
-        x.host_gathered = hg;                         /* results also land in pinned host memory: no copy commands */
-        x.host_offsets = hg + (size_t)R * 2 * H + 1;
+        /* use case 1 sends {survivor total, 0} straight from the scan's result words */
+        const void* send = (c->pending == P_CONST) ? c->scratch.p : c->xchg_src;
+        if ((rc = fill_xchg_args(c, H, send, c->pending == P_CONST ? 1 : 0, &x))) return rc;
         cck::k4_exchange_peer<<<1, 256, 0, xs>>>(x);
         CU(cudaGetLastError());
     } else {
+        if (c->pending == P_CONST) { /* device-resident send buffer {count, 0}; use case 2 already has {counts, rough} */
+            CU(cudaMemcpyAsync(c->counts_buf.p, c->scratch.p, 8, cudaMemcpyDeviceToDevice, xs));
+            CU(cudaMemsetAsync((char*)c->counts_buf.p + 8, 0, 8, xs));
+        }
+        const void* send = (c->pending == P_CONST) ? c->counts_buf.p : c->xchg_src;
+        unsigned long long* d_status = (unsigned long long*)((char*)c->gather_buf.p + (size_t)R * 2 * H * 8);
+        CU(cudaMemsetAsync(d_status, 0, 8, xs));
         if (c->comm && R > 1) {
             NC(g_nccl.AllGather(send, c->gather_buf.p, (size_t)2 * H, ncclUint64, c->comm, xs));
         } else {
@@ -1603,16 +1698,16 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
         cck::k4_offsets<<<(H + 255) / 256, 256, 0, xs>>>((const unsigned long long*)c->gather_buf.p,
                                                               (unsigned long long*)c->offsets_buf.p, H, c->rank);
         CU(cudaGetLastError());
-    }
-    c->launches += 1;
-    if (!peer_path) {
         CU(cudaMemcpyAsync(hg, c->gather_buf.p, (size_t)R * 2 * H * 8 + 8, cudaMemcpyDeviceToHost, xs)); /* + status */
         CU(cudaMemcpyAsync(hg + (size_t)R * 2 * H + 1, c->offsets_buf.p, (size_t)H * 8, cudaMemcpyDeviceToHost, xs));
     }
+    c->launches += 1;
     CU(cudaEventRecord(c->ev_xchg, xs));
     CU(cudaStreamWaitEvent(c->stream, c->ev_xchg, 0));
     if (c->synced) CU(cudaStreamSynchronize(c->stream));
     else if ((rc = cc_cutout_sync(c, nullptr, nullptr))) return rc; /* one synchronisation for cutout + exchange */
+    }
+read_back:
     for (int r = 0; r < R; ++r)
         for (int h = 0; h < H; ++h) {
             if (all_counts) all_counts[(size_t)r * H + h] = (int64_t)hg[(size_t)r * 2 * H + h];
@@ -1722,7 +1817,8 @@ int cc_set_option(cc_ctx* c, const char* key, const char* value) {
         if (c->payload_policy == 2 && c->pending == P_NONE) c->payload_valid = false;
     } else if (k == "exchange") {
         if (v == "auto") c->xchg_mode = 0; else if (v == "nccl") c->xchg_mode = 1; else if (v == "peer") c->xchg_mode = 2;
-        else return fail(CC_ERR_ARG, "cc_set_option: exchange = auto|nccl|peer");
+        else if (v == "eager") c->xchg_mode = 3;
+        else return fail(CC_ERR_ARG, "cc_set_option: exchange = auto|nccl|peer|eager");
     } else if (k == "timing") {
         if (v == "on") c->timing = true; else if (v == "off") c->timing = false;
         else return fail(CC_ERR_ARG, "cc_set_option: timing = on|off");

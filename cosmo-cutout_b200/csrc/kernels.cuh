@@ -1276,6 +1276,207 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
 }
 
+/* ---- many halos, staged: sift -> match -> exact ----------------------------------------------------------------
+ * The same cell index, but every stage is its own full-occupancy kernel and hands the next one a COMPACT work list, so
+ * that each kernel runs with all lanes busy and 32 warps per SM hiding its latencies (k2_cutout_halo_cells keeps the
+ * lanes busy with per-warp stacks instead, at 20 warps per SM because of its 161 KB of shared memory):
+ *
+ *   k2c_sift    streams x,y,z (12 B/particle, the only pass over the step), computes (c, s), looks the particle's
+ *               coarse cell up in the 32 KB occupancy bitmap (L1-resident) and appends the 10-25 % that hit -- and the
+ *               out-of-range positions -- as (x, y, z, index) to the warp's private region of a candidate buffer
+ *               (register cursor, ballot positions, no atomics).
+ *   k2c_match   one thread per candidate: cell -> {first, end} of the halo list -> per list item the (c, s) window of
+ *               that halo, then the second filter (certainly inside the rough window AND certainly outside the fine
+ *               one: only the rough counter, kept per CTA in shared memory); what it cannot decide is a
+ *               (particle, halo) PAIR, staged in shared memory and appended to the pair buffer with one atomic per
+ *               1024 pairs.  The CTA walks the lists in rounds (item k of every candidate's list), so a round emits at
+ *               most one pair per thread.  An out-of-range position is paired with every halo.
+ *   k2c_exact   one thread per pair: the exact path (k2_exact_warp).
+ * ---------------------------------------------------------------------------------------------------------------- */
+struct SiftArgs {
+    const float *x, *y, *z;
+    long long n;                  /* particles to scan (after the n_limit clamp) */
+    long long local_base;         /* index of x[0] inside the step */
+    const unsigned int* cell_bits;
+    float4* cand;                 /* [warps][region_cap] x, y, z, index inside the step (bits) */
+    unsigned int region_cap;
+    unsigned int* cand_count;     /* [warps] */
+    unsigned long long* misc;     /* [2] = max candidates any warp wanted (region overflow check) */
+    unsigned int ntiles;
+};
+template <bool VEC>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k2c_sift(const __grid_constant__ SiftArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const unsigned int total_warps = gridDim.x * SCAN_WARPS, gwarp = blockIdx.x * SCAN_WARPS + warp;
+    float4* __restrict__ region = a.cand + (size_t)gwarp * a.region_cap;
+    unsigned int cursor = 0; /* warp-uniform */
+    for (unsigned int tile = gwarp; tile < a.ntiles; tile += total_warps) {
+        const long long base = (long long)tile * SCAN_TILE;
+        float px[8], py[8], pz[8];
+        const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+        unsigned int m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float pc, ps;
+            bool sane;
+            k2c_coords(px[j], py[j], pz[j], pc, ps, sane);
+            /* NaN -> 0, anything large -> 2^32-1 -> G-1: always a valid cell */
+            const unsigned int ic = min(__float2uint_rz(fmaf(pc, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+            const unsigned int is = min(__float2uint_rz(fmaf(ps, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+            const unsigned int bit = (ic >> K2_CSHIFT) * K2_COARSE + (is >> K2_CSHIFT);
+            const unsigned int hit = (__ldg(a.cell_bits + (bit >> 5)) >> (bit & 31u)) & 1u;
+            m |= (hit | (sane ? 0u : 1u)) << j;
+        }
+        m &= valid;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned int b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
+            if (b) { /* warp-uniform */
+                const unsigned int pos = cursor + __popc(b & lt_mask);
+                if (((m >> j) & 1u) && pos < a.region_cap)
+                    region[pos] = make_float4(px[j], py[j], pz[j], __uint_as_float((unsigned int)(a.local_base + base) + tile_local(lane, j)));
+                cursor += __popc(b);
+            }
+        }
+    }
+    if (lane == 0) {
+        a.cand_count[gwarp] = cursor;
+        atomicMax(a.misc + 2, (unsigned long long)cursor);
+    }
+}
+
+constexpr int K2M_THREADS = 256;
+constexpr int K2M_STAGE = 1024; /* pairs staged per CTA before they go to the pair buffer with one atomic */
+struct MatchArgs {
+    HaloArgs h;                       /* h.pre holds {chi, clo, slo, shi} (prefilter.h uc2_bounds_cells) */
+    const uint2* cell_range;
+    const unsigned short* cell_items;
+    const float4* cand;
+    const unsigned int* cand_count;
+    unsigned int region_cap, nregions;
+    float4* pair_p;                   /* x, y, z, index inside the step (bits) */
+    unsigned int* pair_h;             /* halo inside the launch */
+    unsigned long long pair_cap;
+    unsigned long long* pair_count;   /* appended pairs (may exceed pair_cap: overflow is detected on the host) */
+};
+__global__ void __launch_bounds__(K2M_THREADS) k2c_match(const __grid_constant__ MatchArgs a) {
+    __shared__ unsigned int s_rough[K2_MAX_HALOS];
+    __shared__ float4 s_pp[K2M_STAGE];
+    __shared__ unsigned int s_ph[K2M_STAGE];
+    __shared__ unsigned int s_n;
+    __shared__ unsigned long long s_base;
+    const HaloArgs& H = a.h;
+    const unsigned int tid = threadIdx.x, lane = tid & 31u;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    for (unsigned int i = tid; i < (unsigned int)H.nhalos; i += K2M_THREADS) s_rough[i] = 0u;
+    if (tid == 0) s_n = 0u;
+    __syncthreads();
+    auto flush = [&]() { /* all threads */
+        if (tid == 0) s_base = atomicAdd(a.pair_count, (unsigned long long)s_n);
+        __syncthreads();
+        const unsigned int n = s_n;
+        for (unsigned int i = tid; i < n; i += K2M_THREADS)
+            if (s_base + i < a.pair_cap) { a.pair_p[s_base + i] = s_pp[i]; a.pair_h[s_base + i] = s_ph[i]; }
+        __syncthreads();
+        if (tid == 0) s_n = 0u;
+        __syncthreads();
+    };
+    for (unsigned int r = blockIdx.x; r < a.nregions; r += gridDim.x) {
+        const unsigned int cnt = min(a.cand_count[r], a.region_cap);
+        const float4* __restrict__ region = a.cand + (size_t)r * a.region_cap;
+        for (unsigned int e0 = 0; e0 < cnt; e0 += K2M_THREADS) {
+            const unsigned int e = e0 + tid;
+            float4 c4 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            unsigned int it = 0, left = 0;
+            bool all = false; /* out-of-range position: paired with every halo of the launch */
+            float pc = 0.0f, ps = 0.0f;
+            if (e < cnt) {
+                c4 = region[e];
+                bool sane;
+                k2c_coords(c4.x, c4.y, c4.z, pc, ps, sane);
+                if (!sane) {
+                    all = true;
+                    left = (unsigned int)H.nhalos;
+                } else {
+                    const unsigned int ic = min(__float2uint_rz(fmaf(pc, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+                    const unsigned int is = min(__float2uint_rz(fmaf(ps, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+                    const uint2 rg = __ldg(a.cell_range + ic * K2_GRID + is);
+                    it = rg.x;
+                    left = rg.y - rg.x;
+                }
+            }
+            while (__syncthreads_or(left > 0u)) { /* one list item per thread and round */
+                bool emit = false;
+                unsigned int h = 0;
+                if (left > 0u) {
+                    h = all ? it : (unsigned int)__ldg(a.cell_items + it);
+                    ++it;
+                    --left;
+                    if (all) {
+                        emit = true;
+                    } else {
+                        const float4 W = __ldg(H.pre + h);
+                        if ((pc <= W.x) & (pc >= W.y) & (ps >= W.z) & (ps <= W.w)) {
+                            /* certainly inside the rough window AND certainly outside the fine one: only the rough
+                             * counter (processLC.cpp:1436); everything else takes the exact path */
+                            const float4* __restrict__ Hq = reinterpret_cast<const float4*>(H.halos + h);
+                            const float4 q0 = __ldg(Hq), q1 = __ldg(Hq + 1), q2 = __ldg(Hq + 2), q5 = __ldg(Hq + 5), q6 = __ldg(Hq + 6);
+                            const bool sure_rough = (pc <= q5.x) & (pc >= q5.y) & (ps >= q5.z) & (ps <= q5.w);
+                            const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+                            float rx, ry, rz;
+                            ccref::mat_vec(R, c4.x, c4.y, c4.z, rx, ry, rz); /* the exact path's own rotated position */
+                            const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+                            const bool sane_r = (fabsf(rx) >= CC_SANE_LO) & (r2 <= 1.2089258e24f);
+                            const float cf = rz * rsqrt_fast(r2), tf = ry * rcp_fast(rx);
+                            const bool maybe_fine = !sane_r | ((cf <= q6.x) & (cf >= q6.y) & (tf >= q6.z) & (tf <= q6.w));
+                            if (sure_rough && !maybe_fine) atomicAdd(&s_rough[h], 1u);
+                            else emit = true;
+                        }
+                    }
+                }
+                const unsigned int em = __ballot_sync(0xffffffffu, emit);
+                if (em) { /* warp-uniform: one shared-memory atomic per warp and round */
+                    unsigned int slot = 0;
+                    if (lane == 0) slot = atomicAdd(&s_n, (unsigned int)__popc(em));
+                    slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(em & lt_mask);
+                    if (emit) { s_pp[slot] = c4; s_ph[slot] = h; }
+                }
+                __syncthreads();
+                if (s_n > (unsigned int)(K2M_STAGE - K2M_THREADS)) flush(); /* block-uniform */
+            }
+        }
+    }
+    if (s_n) flush();
+    for (unsigned int i = tid; i < (unsigned int)H.nhalos; i += K2M_THREADS)
+        if (s_rough[i]) atomicAdd(H.counts + H.total_halos + (unsigned int)H.halo0 + i, (unsigned long long)s_rough[i]);
+}
+
+struct ExactArgs {
+    HaloArgs h;
+    const float4* pair_p;
+    const unsigned int* pair_h;
+    unsigned long long pair_cap;
+    const unsigned long long* pair_count;
+    unsigned long long* misc; /* [3] = max pairs any round wanted (pair buffer overflow check) */
+};
+__global__ void __launch_bounds__(256) k2c_exact(const __grid_constant__ ExactArgs a) {
+    const unsigned long long want = *a.pair_count, npairs = min(want, a.pair_cap);
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < npairs;
+         i0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = i0 + lane;
+        const bool live = i < npairs;
+        const float4 c4 = live ? a.pair_p[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        const unsigned int h = live ? a.pair_h[i] : 0u;
+        k2_exact_warp(a.h, live, (int)h, c4.x, c4.y, c4.z, __float_as_uint(c4.w), lane);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(a.h.n_cand, want);
+        atomicMax(a.misc + 3, want);
+    }
+}
+
 /* ================================================================================================
  * K3  survivor ordering + gather (use case 2)
  * ================================================================================================ */
@@ -1522,6 +1723,112 @@ __global__ void k3_gather_halo(const GatherArgs a) {
     }
 }
 
+/* ---- count exchange by peer stores (NVLink / NVSwitch), no library launch ---------------------------------------
+ * Every GPU owns a mailbox in its own HBM: [2 parities][R ranks][1 epoch word + XCHG_PAYLOAD counters].  To exchange,
+ * a GPU STORES its {counts, rough counts} into slot [parity][its rank] of every peer's mailbox (the peers' mailboxes
+ * are mapped through CUDA IPC or peer access, so these are plain st.global over NVLink), fences, publishes the epoch
+ * with a release store, then waits until all R slots of its OWN mailbox carry the epoch, and computes its row offsets
+ * = sum of the counts of lower ranks.  One single-CTA kernel enqueued behind the cutout kernels: the exchange costs
+ * one NVLink store round instead of a collective launch (~3 us instead of ~40 us of a 250 us step).
+ * Parity double-buffering is enough: a rank can only start exchange e+1 after every peer has posted e, and a peer
+ * posts e+1 only after it finished reading e. */
+constexpr int XCHG_PAYLOAD = 4096;              /* u64 counters per slot: 2 x halos */
+constexpr int XCHG_SLOT = XCHG_PAYLOAD + 8;     /* epoch word (+ padding to keep the payload 64-byte aligned) */
+constexpr int XCHG_MAX_RANKS = 32;
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct XchgArgs {
+    const unsigned long long* send;      /* [n] this GPU's {counts[H], rough[H]} */
+    unsigned long long* peer[XCHG_MAX_RANKS]; /* every rank's mailbox as seen from this GPU (peer[rank] = own) */
+    unsigned long long* gathered;        /* [R][n] out */
+    unsigned long long* offsets;         /* [H] out: sum of counts of lower ranks */
+    unsigned long long* status;          /* [0] set to 1 on time-out */
+    unsigned long long* host_gathered;   /* pinned host copies of gathered (+ the status word behind it) and offsets */
+    unsigned long long* host_offsets;
+    int uc1;                             /* use case 1: send {send[0], 0} (send points at the running survivor total) */
+    unsigned long long epoch;
+    unsigned long long timeout_ns;
+    int n, H, R, rank;
+};
+
+/* post: my counters into my slot of every mailbox, then the epoch with a release store (all threads of the CTA) */
+__device__ __forceinline__ void xchg_post(const XchgArgs& a) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned long long parity = a.epoch & 1ull;
+    const size_t my_slot = ((size_t)parity * a.R + a.rank) * XCHG_SLOT;
+    for (int p = 0; p < a.R; ++p) {
+        unsigned long long* dst = a.peer[p] + my_slot + 8;
+        for (int i = tid; i < a.n; i += nt) st_relaxed_sys_u64(dst + i, (a.uc1 && i > 0) ? 0ull : a.send[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < a.R) st_release_sys_u64(a.peer[tid] + my_slot, a.epoch);
+}
+/* wait for every rank's post in MY mailbox, hand everything to the host (pinned memory) and compute my row offsets
+ * (all threads of the CTA; s_timeout: one shared int) */
+__device__ __forceinline__ void xchg_finish(const XchgArgs& a, int* s_timeout) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned long long parity = a.epoch & 1ull;
+    if (tid == 0) *s_timeout = 0;
+    __syncthreads();
+    unsigned long long* mine = a.peer[a.rank];
+    if (tid < a.R) {
+        const unsigned long long* flag = mine + ((size_t)parity * a.R + tid) * XCHG_SLOT;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys_u64(flag) != a.epoch) {
+            if (global_timer_ns() - t0 > a.timeout_ns) { *s_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (*s_timeout) {
+        if (tid == 0) { *a.status = 1ull; a.host_gathered[(size_t)a.R * a.n] = 1ull; __threadfence_system(); }
+        return;
+    }
+    for (int r = 0; r < a.R; ++r) {
+        const unsigned long long* src = mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8;
+        for (int i = tid; i < a.n; i += nt) {
+            const unsigned long long v = ld_relaxed_sys_u64(src + i);
+            a.gathered[(size_t)r * a.n + i] = v;
+            a.host_gathered[(size_t)r * a.n + i] = v;
+        }
+    }
+    if (tid == 0) a.host_gathered[(size_t)a.R * a.n] = 0ull; /* status: no time-out */
+    for (int h = tid; h < a.H; h += nt) {
+        unsigned long long run = 0;
+        for (int r = 0; r < a.rank; ++r) run += ld_relaxed_sys_u64(mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8 + h);
+        a.offsets[h] = run;
+        a.host_offsets[h] = run;
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) k4_exchange_peer(const XchgArgs a) {
+    __shared__ int s_timeout;
+    xchg_post(a);
+    xchg_finish(a, &s_timeout);
+}
+
 /* ---- small cutouts: the four kernels above as ONE single-CTA launch -------------------------------------------
  * A cluster-sized cutout leaves a few hundred survivors; k3_scan_counts + k3_bucket + k3_rank + k3_gather_halo are
  * then four launch-latency-bound kernels (~20 us of a 250 us step).  When the previous cutout on the context left at
@@ -1542,6 +1849,9 @@ struct SmallArgs {
     unsigned int state_elems;            /* u64 words of the device state starting at misc: zeroed for the next cutout */
     unsigned long long* xchg_send;       /* [2H] {counts, rough counts} kept for the count exchange (capi.cu) */
     int H;
+    int do_xchg;                         /* the count exchange over the peer mailboxes is part of this kernel: posted first
+                                            (the counts are final), collected after the rows are written */
+    XchgArgs x;
 };
 /* last step of k3_small (all threads): results to the host, device state zeroed */
 __device__ __forceinline__ void k3s_publish(const SmallArgs& a) {
@@ -1560,9 +1870,12 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
     unsigned short* s_idx = s_halo + K3_SORT_MAX;
     unsigned long long* s_part = reinterpret_cast<unsigned long long*>(s_raw + (size_t)K3_SORT_MAX * 12);
     const unsigned int tid = threadIdx.x;
+    __shared__ int s_xchg_timeout;
     const unsigned long long nrec = *a.g.rec_count;
+    if (a.do_xchg) xchg_post(a.x); /* NVLink stores to every peer; their posts arrive while this CTA orders and gathers */
     if (nrec > K3_SORT_MAX || nrec > a.g.rec_cap) {
         if (tid == 0) a.misc[4] = 1ull;
+        if (a.do_xchg) xchg_finish(a.x, &s_xchg_timeout);
         k3s_publish(a);
         return;
     }
@@ -1676,6 +1989,7 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
         a.g.out.theta_u[o] = __int_as_float((int)(r.key >> 32));
         a.g.out.index[o] = a.g.index_base + g;
     }
+    if (a.do_xchg) xchg_finish(a.x, &s_xchg_timeout);
     k3s_publish(a);
 }
 
@@ -1689,101 +2003,6 @@ __global__ void k4_offsets(const unsigned long long* gathered, unsigned long lon
         for (int r = 0; r < rank; ++r) run += gathered[(size_t)r * 2 * H + h];
         offsets[h] = run;
     }
-}
-
-/* ---- count exchange by peer stores (NVLink / NVSwitch), no library launch ---------------------------------------
- * Every GPU owns a mailbox in its own HBM: [2 parities][R ranks][1 epoch word + XCHG_PAYLOAD counters].  To exchange,
- * a GPU STORES its {counts, rough counts} into slot [parity][its rank] of every peer's mailbox (the peers' mailboxes
- * are mapped through CUDA IPC or peer access, so these are plain st.global over NVLink), fences, publishes the epoch
- * with a release store, then waits until all R slots of its OWN mailbox carry the epoch, and computes its row offsets
- * = sum of the counts of lower ranks.  One single-CTA kernel enqueued behind the cutout kernels: the exchange costs
- * one NVLink store round instead of a collective launch (~3 us instead of ~40 us of a 250 us step).
- * Parity double-buffering is enough: a rank can only start exchange e+1 after every peer has posted e, and a peer
- * posts e+1 only after it finished reading e. */
-constexpr int XCHG_PAYLOAD = 4096;              /* u64 counters per slot: 2 x halos */
-constexpr int XCHG_SLOT = XCHG_PAYLOAD + 8;     /* epoch word (+ padding to keep the payload 64-byte aligned) */
-constexpr int XCHG_MAX_RANKS = 32;
-
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-struct XchgArgs {
-    const unsigned long long* send;      /* [n] this GPU's {counts[H], rough[H]} */
-    unsigned long long* peer[XCHG_MAX_RANKS]; /* every rank's mailbox as seen from this GPU (peer[rank] = own) */
-    unsigned long long* gathered;        /* [R][n] out */
-    unsigned long long* offsets;         /* [H] out: sum of counts of lower ranks */
-    unsigned long long* status;          /* [0] set to 1 on time-out */
-    unsigned long long* host_gathered;   /* pinned host copies of gathered (+ the status word behind it) and offsets */
-    unsigned long long* host_offsets;
-    unsigned long long epoch;
-    unsigned long long timeout_ns;
-    int n, H, R, rank;
-};
-
-__global__ void __launch_bounds__(256) k4_exchange_peer(const XchgArgs a) {
-    const int tid = threadIdx.x;
-    const unsigned long long parity = a.epoch & 1ull;
-    const size_t my_slot = ((size_t)parity * a.R + a.rank) * XCHG_SLOT;
-    /* post: my counters into my slot of every mailbox */
-    for (int p = 0; p < a.R; ++p) {
-        unsigned long long* dst = a.peer[p] + my_slot + 8;
-        for (int i = tid; i < a.n; i += blockDim.x) st_relaxed_sys_u64(dst + i, a.send[i]);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < a.R) st_release_sys_u64(a.peer[tid] + my_slot, a.epoch);
-    /* wait: all ranks' slots of MY mailbox */
-    __shared__ int s_timeout;
-    if (tid == 0) s_timeout = 0;
-    __syncthreads();
-    unsigned long long* mine = a.peer[a.rank];
-    if (tid < a.R) {
-        const unsigned long long* flag = mine + ((size_t)parity * a.R + tid) * XCHG_SLOT;
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys_u64(flag) != a.epoch) {
-            if (global_timer_ns() - t0 > a.timeout_ns) { s_timeout = 1; break; }
-        }
-    }
-    __syncthreads();
-    if (s_timeout) {
-        if (tid == 0) { *a.status = 1ull; a.host_gathered[(size_t)a.R * a.n] = 1ull; __threadfence_system(); }
-        return;
-    }
-    for (int r = 0; r < a.R; ++r) {
-        const unsigned long long* src = mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8;
-        for (int i = tid; i < a.n; i += blockDim.x) {
-            const unsigned long long v = ld_relaxed_sys_u64(src + i);
-            a.gathered[(size_t)r * a.n + i] = v;
-            a.host_gathered[(size_t)r * a.n + i] = v;
-        }
-    }
-    if (tid == 0) a.host_gathered[(size_t)a.R * a.n] = 0ull; /* status: no time-out */
-    for (int h = tid; h < a.H; h += blockDim.x) {
-        unsigned long long run = 0;
-        for (int r = 0; r < a.rank; ++r) run += ld_relaxed_sys_u64(mine + ((size_t)parity * a.R + r) * XCHG_SLOT + 8 + h);
-        a.offsets[h] = run;
-        a.host_offsets[h] = run;
-    }
-    __threadfence_system();
 }
 
 /* ================================================================================================

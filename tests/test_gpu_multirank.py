@@ -21,7 +21,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, use_nccl):
+def _worker(rank, world, port, mode):
+    use_nccl = mode == "nccl"
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests"))
     import torch.distributed as dist
@@ -43,6 +44,7 @@ def _worker(rank, world, port, use_nccl):
             handles = [None] * world
             dist.all_gather_object(handles, ctx.comm_peer_handle(world, rank))
             ctx.comm_peer_attach(handles)
+            ctx.set_option("exchange", mode)
         dist.barrier()
         ctx.upload(H.slice_cols(cols, lo, hi), index_base=lo)
         tc, pc = cc.cli_bounds(70, 15), cc.cli_bounds(40, 15)
@@ -67,15 +69,28 @@ def _worker(rank, world, port, use_nccl):
             assert mine["id"].tobytes() == want["id"][sel].tobytes() and mine["theta"].tobytes() == want["theta"][sel].tobytes()
             tot += want["id"].shape[0]
         assert tot > 1000
+        # cluster-sized cutouts, repeatedly: from the second one on the single-CTA kernel orders + gathers, and with
+        # exchange=eager it also carries the count exchange (posted first, collected after the rows are written)
+        small = [((150, 20, 12), 25.0), ((100, 100, 100), 30.0)]
+        wants = [H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, b)) for p, b in small]
+        for rep in range(4):
+            ctx.cutout_halo([cc.halo_setup(p, b).halo for p, b in small], n_limit_global=n)
+            allc, allr, off = ctx.exchange_counts()
+            for h, (want, want_rough) in enumerate(wants):
+                assert int(allc[:, h].sum()) == want["id"].shape[0] and int(allr[:, h].sum()) == want_rough, (rep, h)
+                assert int(off[h]) == int(allc[:rank, h].sum())
+                mine = ctx.fetch(h, names=("id", "phi"))
+                sel = (want["id"] >= lo) & (want["id"] < hi)
+                assert mine["id"].tobytes() == want["id"][sel].tobytes() and mine["phi"].tobytes() == want["phi"][sel].tobytes()
         dist.barrier()
         ctx.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_nccl", [False, True])
-def test_two_gpus_count_exchange(use_nccl):
+@pytest.mark.parametrize("mode", ["peer", "eager", "nccl"])
+def test_two_gpus_count_exchange(mode):
     if cc.lib().cc_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), use_nccl), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), mode), nprocs=2, join=True)
