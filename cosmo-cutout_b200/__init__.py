@@ -236,6 +236,7 @@ class Context:
         self.kind = None
         self._halo_cache = None
         self._count_bufs = None
+        self._xchg_bufs = None
 
     def close(self):
         if self._h:
@@ -367,22 +368,30 @@ class Context:
         return {k: out[k][:total] for k in names}, off
 
     def exchange_counts(self):
-        n, r = self.comm_size(), max(self.nhalos, 1)
-        allc = np.zeros(n * r, dtype=np.int64)
-        allr = np.zeros(n * r, dtype=np.int64)
-        off = np.zeros(r, dtype=np.int64)
-        _check(lib().cc_exchange_counts(self._h, _ptr(allc), _ptr(allr), _ptr(off)))
-        return allc.reshape(n, r), allr.reshape(n, r), off
+        """cc_exchange_counts -> (counts[rank, halo], rough[rank, halo], offsets[halo]); the arrays are reused by the next
+        call with the same shape (copy them to keep them)"""
+        r = max(self.nhalos, 1)
+        cache = self._xchg_bufs
+        if cache is None or cache[0] != r:
+            n = self.comm_size()
+            allc, allr, off = np.zeros(n * r, dtype=np.int64), np.zeros(n * r, dtype=np.int64), np.zeros(r, dtype=np.int64)
+            cache = self._xchg_bufs = (r, allc.reshape(n, r), allr.reshape(n, r), off, _ptr(allc), _ptr(allr), _ptr(off))
+        rc = lib().cc_exchange_counts(self._h, cache[4], cache[5], cache[6])
+        if rc:
+            _check(rc)
+        return cache[1], cache[2], cache[3]
 
     # communicator
     def comm_init(self, nranks, rank, id_bytes):
         buf = C.create_string_buffer(bytes(id_bytes), 128)
         _check(lib().cc_comm_init(self._h, int(nranks), int(rank), buf))
+        self._xchg_bufs = None
 
     def comm_peer_handle(self, nranks, rank):
         """allocate this GPU's count-exchange mailbox and return its 64-byte IPC handle"""
         buf = C.create_string_buffer(64)
         _check(lib().cc_comm_peer_handle(self._h, int(nranks), int(rank), buf))
+        self._xchg_bufs = None
         return bytes(buf.raw)
 
     def comm_peer_attach(self, handles):

@@ -211,7 +211,7 @@ struct cc_ctx {
     /* scan scratch: [tile_state ... | ticket | result(2) ] */
     DevBuf scratch;
     /* use case 2 scratch */
-    DevBuf rec_a, rec_b, rank_buf, counts_buf;
+    DevBuf rec_a, rec_b, rank_buf, place_buf, counts_buf;
     DevBuf hstate; /* use case 2 device state, one memset / one read-back: [misc 8 | counts 2H | seg H+1 | cursor 16H] u64 */
     /* Device-resident parameters (+ cell index) of the halo sets recently cut on this context.  A processLC call cuts
      * every step with ONE halo set, and a batch job (lc_cutout -f with several box sizes, BASELINE config 5) alternates
@@ -498,6 +498,7 @@ int prepare_halo(cc_ctx* c) {
     if ((rc = c->rec_a.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
     if ((rc = c->rec_b.ensure((size_t)c->rec_cap * sizeof(cck::Rec)))) return rc;
     if ((rc = c->rank_buf.ensure((size_t)c->rec_cap * 4))) return rc;
+    if ((rc = c->place_buf.ensure((size_t)c->rec_cap * 4))) return rc;
     if ((rc = ensure_out_cap(c, c->rec_cap))) return rc;
     if ((rc = ensure_small(c, small_elems(H, c->nranks)))) return rc;
 
@@ -716,7 +717,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             ea.h = a;
             ea.pair_p = ma.pair_p; ea.pair_h = ma.pair_h; ea.pair_cap = ma.pair_cap; ea.pair_count = ma.pair_count;
             ea.misc = hs_misc(c);
-            cck::k2c_exact<<<(unsigned int)c->sm_count * 8u, 256, 0, c->stream>>>(ea);
+            cck::k2c_exact<<<(unsigned int)c->sm_count * 2u, cck::K2X_THREADS, 0, c->stream>>>(ea);
             CU(cudaGetLastError());
             c->launches += 3;
         } else if (c->use_bins) { /* one 20-warp CTA per SM: bitmap + windows + pair buffers take 161 KB of its shared memory */
@@ -780,7 +781,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         /* ordering + gather, sized on the device: the whole pass is one enqueue, one host synchronisation */
         cck::GatherArgs g;
         g.rank = (const unsigned int*)c->rank_buf.p;
-        g.sorted = nullptr;
+        g.place = nullptr;
         g.seg_begin = hs_seg(c, H);
         g.rec_count = rec_count;
         g.rec_cap = (unsigned long long)c->rec_cap;
@@ -841,7 +842,8 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             b.seg_begin = hs_seg(c, H);
             b.cursor = hs_cursor(c, H);
             b.out = (cck::Rec*)c->rec_b.p;
-            cck::k3_bucket<<<g1, 256, 0, c->stream>>>(b);
+            b.H = H;
+            cck::k3_bucket<<<(unsigned int)c->sm_count * 2u, cck::K3B_THREADS, 0, c->stream>>>(b);
             CU(cudaGetLastError());
             cck::RankArgs r;
             r.rec_count = rec_count;
@@ -860,11 +862,21 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             }
             cck::k3_rank<<<dim3(gx, gy), cck::K3_THREADS, cck::K3_SMEM_BYTES, c->stream>>>(r);
             CU(cudaGetLastError());
+            cck::PlaceArgs pl;
+            pl.recs = (const cck::Rec*)c->rec_b.p;
+            pl.rank = (const unsigned int*)c->rank_buf.p;
+            pl.sorted = (const unsigned long long*)c->rec_a.p;
+            pl.seg_begin = hs_seg(c, H);
+            pl.rec_count = rec_count;
+            pl.rec_cap = (unsigned long long)c->rec_cap;
+            pl.place = (unsigned int*)c->place_buf.p;
+            cck::k3_place<<<g1, 256, 0, c->stream>>>(pl);
+            CU(cudaGetLastError());
             g.recs = (const cck::Rec*)c->rec_b.p;
-            g.sorted = (const unsigned long long*)c->rec_a.p;
+            g.place = (const unsigned int*)c->place_buf.p;
             cck::k3_gather_halo<<<g1, 256, 0, c->stream>>>(g);
             CU(cudaGetLastError());
-            c->launches += 4;
+            c->launches += 5;
         }
         if (c->timing) CU(cudaEventRecord(c->ev_total1, c->stream));
         c->have_times = c->timing;
@@ -1055,7 +1067,7 @@ void cc_destroy(cc_ctx* c) {
     for (auto& b : c->col_buf) b.release();
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
-    DevBuf* rest[] = {&c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->counts_buf,
+    DevBuf* rest[] = {&c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->place_buf, &c->counts_buf,
                       &c->hstate, &c->gather_buf, &c->offsets_buf, &c->xchg_send, &c->cand, &c->cand_count, &c->pair_p, &c->pair_h, &c->pair_count, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
     for (DevBuf* b : rest) b->release();
     for (auto& e : c->halo_sets) e.release();

@@ -693,7 +693,8 @@ __device__ __forceinline__ void k2_exact(const HaloArgs& a, int h, float x, floa
  * halo's parameters come in as five 16-byte loads issued together (one L2 round trip instead of three dependent
  * ones), and the survivors of the warp claim their record slots with one atomic. */
 __device__ __forceinline__ void k2_exact_warp(const HaloArgs& a, bool live, int h, float x, float y, float z,
-                                              unsigned int local_n, int lane) {
+                                              unsigned int local_n, int lane, unsigned int* s_rough = nullptr,
+                                              unsigned int* s_fine = nullptr) {
     static_assert(sizeof(HaloDev) == 112 && offsetof(HaloDev, rph_hi) == 64, "five float4 loads below");
     const float4* __restrict__ Hq = reinterpret_cast<const float4*>(a.halos + (live ? h : 0));
     const float4 q0 = __ldg(Hq), q1 = __ldg(Hq + 1), q2 = __ldg(Hq + 2), q3 = __ldg(Hq + 3), q4 = __ldg(Hq + 4);
@@ -706,7 +707,10 @@ __device__ __forceinline__ void k2_exact_warp(const HaloArgs& a, bool live, int 
     const bool rough = live && (thu >= rth_lo && thu < rth_hi) /* :1334-1340 (two lower_bounds) */
                             && (phu > rph_lo && phu < rph_hi); /* :1400 */
     if (!__any_sync(0xffffffffu, rough)) return;
-    if (rough) atomicAdd(a.counts + a.total_halos + hg, 1ull); /* rough_cutout_size, :1436 */
+    if (rough) { /* rough_cutout_size, :1436 (per-CTA shared-memory counters when the caller keeps them) */
+        if (s_rough) atomicAdd(&s_rough[h], 1u);
+        else atomicAdd(a.counts + a.total_halos + hg, 1ull);
+    }
     const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
     float rx, ry, rz;
     ccref::mat_vec(R, x, y, z, rx, ry, rz);               /* :1419-1422 */
@@ -719,7 +723,8 @@ __device__ __forceinline__ void k2_exact_warp(const HaloArgs& a, bool live, int 
     if (lane == 0) slot = atomicAdd(a.rec_count, (unsigned long long)__popc(m));
     slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
     if (fine) {
-        atomicAdd(a.counts + hg, 1ull);
+        if (s_fine) atomicAdd(&s_fine[h], 1u);
+        else atomicAdd(a.counts + hg, 1ull);
         if (slot < a.rec_cap) {
             Rec r;
             r.key = ((unsigned long long)(unsigned int)__float_as_int(thu) << 32) | local_n;
@@ -1307,7 +1312,6 @@ struct SiftArgs {
 template <bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k2c_sift(const __grid_constant__ SiftArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int lt_mask = (1u << lane) - 1u;
     const unsigned int total_warps = gridDim.x * SCAN_WARPS, gwarp = blockIdx.x * SCAN_WARPS + warp;
     float4* __restrict__ region = a.cand + (size_t)gwarp * a.region_cap;
     unsigned int cursor = 0; /* warp-uniform */
@@ -1329,16 +1333,25 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2c_sift(const __grid_constan
             m |= (hit | (sane ? 0u : 1u)) << j;
         }
         m &= valid;
+        /* every lane appends its hits at consecutive slots behind those of the lower lanes (the order inside the region
+         * does not matter): one warp scan + up to 8 predicated 16-byte stores (a ballot per element was measured at
+         * 160 warp instructions per tile, profiles/r02) */
+        const unsigned int cnt = __popc(m);
+        unsigned int inc = cnt;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned int b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
-            if (b) { /* warp-uniform */
-                const unsigned int pos = cursor + __popc(b & lt_mask);
-                if (((m >> j) & 1u) && pos < a.region_cap)
-                    region[pos] = make_float4(px[j], py[j], pz[j], __uint_as_float((unsigned int)(a.local_base + base) + tile_local(lane, j)));
-                cursor += __popc(b);
-            }
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
         }
+        unsigned int pos = cursor + inc - cnt;
+        cursor += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if ((m >> j) & 1u) {
+                if (pos < a.region_cap)
+                    region[pos] = make_float4(px[j], py[j], pz[j], __uint_as_float((unsigned int)(a.local_base + base) + tile_local(lane, j)));
+                ++pos;
+            }
     }
     if (lane == 0) {
         a.cand_count[gwarp] = cursor;
@@ -1347,7 +1360,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2c_sift(const __grid_constan
 }
 
 constexpr int K2M_THREADS = 256;
-constexpr int K2M_STAGE = 1024; /* pairs staged per CTA before they go to the pair buffer with one atomic */
+constexpr int K2M_WARPS = K2M_THREADS / 32;
+constexpr int K2M_STAGE = 128; /* pairs staged per WARP before they go to the pair buffer with one atomic */
 struct MatchArgs {
     HaloArgs h;                       /* h.pre holds {chi, clo, slo, shi} (prefilter.h uc2_bounds_cells) */
     const uint2* cell_range;
@@ -1362,31 +1376,30 @@ struct MatchArgs {
 };
 __global__ void __launch_bounds__(K2M_THREADS) k2c_match(const __grid_constant__ MatchArgs a) {
     __shared__ unsigned int s_rough[K2_MAX_HALOS];
-    __shared__ float4 s_pp[K2M_STAGE];
-    __shared__ unsigned int s_ph[K2M_STAGE];
-    __shared__ unsigned int s_n;
-    __shared__ unsigned long long s_base;
+    __shared__ float4 s_pp[K2M_WARPS][K2M_STAGE];
+    __shared__ unsigned int s_ph[K2M_WARPS][K2M_STAGE];
     const HaloArgs& H = a.h;
-    const unsigned int tid = threadIdx.x, lane = tid & 31u;
+    const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned int lt_mask = (1u << lane) - 1u;
     for (unsigned int i = tid; i < (unsigned int)H.nhalos; i += K2M_THREADS) s_rough[i] = 0u;
-    if (tid == 0) s_n = 0u;
     __syncthreads();
-    auto flush = [&]() { /* all threads */
-        if (tid == 0) s_base = atomicAdd(a.pair_count, (unsigned long long)s_n);
-        __syncthreads();
-        const unsigned int n = s_n;
-        for (unsigned int i = tid; i < n; i += K2M_THREADS)
-            if (s_base + i < a.pair_cap) { a.pair_p[s_base + i] = s_pp[i]; a.pair_h[s_base + i] = s_ph[i]; }
-        __syncthreads();
-        if (tid == 0) s_n = 0u;
-        __syncthreads();
+    unsigned int wn = 0; /* warp-uniform: pairs staged by this warp */
+    auto flush = [&]() { /* all lanes of the warp */
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.pair_count, (unsigned long long)wn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (unsigned int i = lane; i < wn; i += 32u)
+            if (base + i < a.pair_cap) { a.pair_p[base + i] = s_pp[warp][i]; a.pair_h[base + i] = s_ph[warp][i]; }
+        __syncwarp();
+        wn = 0;
     };
+    /* warps take (region, 32-candidate slice) items independently: no block barrier inside the loop */
     for (unsigned int r = blockIdx.x; r < a.nregions; r += gridDim.x) {
         const unsigned int cnt = min(a.cand_count[r], a.region_cap);
         const float4* __restrict__ region = a.cand + (size_t)r * a.region_cap;
-        for (unsigned int e0 = 0; e0 < cnt; e0 += K2M_THREADS) {
-            const unsigned int e = e0 + tid;
+        for (unsigned int e0 = warp * 32u; e0 < cnt; e0 += K2M_THREADS) {
+            const unsigned int e = e0 + lane;
             float4 c4 = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             unsigned int it = 0, left = 0;
             bool all = false; /* out-of-range position: paired with every halo of the launch */
@@ -1406,7 +1419,7 @@ __global__ void __launch_bounds__(K2M_THREADS) k2c_match(const __grid_constant__
                     left = rg.y - rg.x;
                 }
             }
-            while (__syncthreads_or(left > 0u)) { /* one list item per thread and round */
+            while (__any_sync(0xffffffffu, left > 0u)) { /* one list item per lane and round */
                 bool emit = false;
                 unsigned int h = 0;
                 if (left > 0u) {
@@ -1436,18 +1449,20 @@ __global__ void __launch_bounds__(K2M_THREADS) k2c_match(const __grid_constant__
                     }
                 }
                 const unsigned int em = __ballot_sync(0xffffffffu, emit);
-                if (em) { /* warp-uniform: one shared-memory atomic per warp and round */
-                    unsigned int slot = 0;
-                    if (lane == 0) slot = atomicAdd(&s_n, (unsigned int)__popc(em));
-                    slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(em & lt_mask);
-                    if (emit) { s_pp[slot] = c4; s_ph[slot] = h; }
+                if (em) { /* warp-uniform */
+                    if (emit) {
+                        const unsigned int slot = wn + __popc(em & lt_mask);
+                        s_pp[warp][slot] = c4;
+                        s_ph[warp][slot] = h;
+                    }
+                    wn += __popc(em);
+                    if (wn > (unsigned int)(K2M_STAGE - 32)) flush();
                 }
-                __syncthreads();
-                if (s_n > (unsigned int)(K2M_STAGE - K2M_THREADS)) flush(); /* block-uniform */
             }
         }
     }
-    if (s_n) flush();
+    if (wn) flush();
+    __syncthreads();
     for (unsigned int i = tid; i < (unsigned int)H.nhalos; i += K2M_THREADS)
         if (s_rough[i]) atomicAdd(H.counts + H.total_halos + (unsigned int)H.halo0 + i, (unsigned long long)s_rough[i]);
 }
@@ -1460,16 +1475,27 @@ struct ExactArgs {
     const unsigned long long* pair_count;
     unsigned long long* misc; /* [3] = max pairs any round wanted (pair buffer overflow check) */
 };
-__global__ void __launch_bounds__(256) k2c_exact(const __grid_constant__ ExactArgs a) {
+constexpr int K2X_THREADS = 512;
+__global__ void __launch_bounds__(K2X_THREADS) k2c_exact(const __grid_constant__ ExactArgs a) {
+    /* survivors and rough survivors per halo: counted per CTA in shared memory, added to the global counters once
+     * (a global atomic per pair was measured: 4 M atomics on the 32 cache lines of 250 counters = 0.3 ms) */
+    __shared__ unsigned int s_rough[K2_MAX_HALOS], s_fine[K2_MAX_HALOS];
     const unsigned long long want = *a.pair_count, npairs = min(want, a.pair_cap);
     const int lane = threadIdx.x & 31;
+    for (unsigned int i = threadIdx.x; i < (unsigned int)a.h.nhalos; i += K2X_THREADS) { s_rough[i] = 0u; s_fine[i] = 0u; }
+    __syncthreads();
     for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < npairs;
          i0 += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long i = i0 + lane;
         const bool live = i < npairs;
         const float4 c4 = live ? a.pair_p[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         const unsigned int h = live ? a.pair_h[i] : 0u;
-        k2_exact_warp(a.h, live, (int)h, c4.x, c4.y, c4.z, __float_as_uint(c4.w), lane);
+        k2_exact_warp(a.h, live, (int)h, c4.x, c4.y, c4.z, __float_as_uint(c4.w), lane, s_rough, s_fine);
+    }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < (unsigned int)a.h.nhalos; i += K2X_THREADS) {
+        if (s_rough[i]) atomicAdd(a.h.counts + a.h.total_halos + (unsigned int)a.h.halo0 + i, (unsigned long long)s_rough[i]);
+        if (s_fine[i]) atomicAdd(a.h.counts + (unsigned int)a.h.halo0 + i, (unsigned long long)s_fine[i]);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(a.h.n_cand, want);
@@ -1492,32 +1518,47 @@ struct BucketArgs {
     unsigned long long* cursor;          /* [H * K3_CURSOR_STRIDE] zeroed: one 128-byte line per halo (atomics on
                                             one line queue up in the L2) */
     Rec* out;
+    int H;
 };
 /* More survivors than record slots (*rec_count > rec_cap): the host grows the buffers and runs the cutout again, so the
  * ordering kernels do nothing at all -- the per-halo segments would be partly filled with whatever an earlier cutout
- * left in the buffers, and following such records' halo / rank fields reads out of bounds. */
-__global__ void k3_bucket(const BucketArgs a) {
+ * left in the buffers, and following such records' halo / rank fields reads out of bounds.
+ *
+ * Records arrive in particle order, i.e. in random halo order: one global atomic per record on the 250 cursors of a
+ * 250-halo pass serialises in the L2 (1.9 M records: 79 us, profiles/r02).  Every CTA therefore takes a contiguous
+ * slice of the records, counts it per halo in shared memory, claims a range per (CTA, halo) with one global atomic,
+ * and deals its records into those ranges (second read of the slice: L2 hits).  Halos beyond the shared-memory table
+ * (H > K3B_HMAX) take the per-record atomic. */
+constexpr int K3B_THREADS = 512;
+constexpr int K3B_HMAX = 8192;
+__global__ void __launch_bounds__(K3B_THREADS) k3_bucket(const BucketArgs a) {
+    __shared__ unsigned int s_cnt[K3B_HMAX];   /* pass 1: records of the slice per halo; pass 2: next free offset */
     if (*a.rec_count > a.rec_cap) return;
     const unsigned long long nrec = *a.rec_count;
-    const unsigned int lane = threadIdx.x & 31u;
-    /* warp-uniform trip count; lanes holding records of the same halo claim their slots with one atomic (the
-     * records of a large cutout would otherwise queue up on its one cursor) */
-    for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < nrec;
-         i0 += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long i = i0 + lane;
-        const bool live = i < nrec;
-        Rec r;
-        r.halo = 0xffffffffu;
-        if (live) r = a.recs[i];
-        const unsigned int peers = __match_any_sync(0xffffffffu, r.halo);
-        const int leader = __ffs(peers) - 1;
-        unsigned long long first = 0;
-        if (live && (int)lane == leader) first = atomicAdd(a.cursor + (size_t)r.halo * K3_CURSOR_STRIDE, (unsigned long long)__popc(peers));
-        first = __shfl_sync(0xffffffffu, first, leader);
-        if (live) {
-            const unsigned long long p = a.seg_begin[r.halo] + first + __popc(peers & ((1u << lane) - 1u));
-            if (p < a.rec_cap) a.out[p] = r;
+    const unsigned int tid = threadIdx.x;
+    const unsigned long long per = (nrec + gridDim.x - 1) / gridDim.x;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * per, i1 = min(nrec, i0 + per);
+    if (i0 >= i1) return;
+    const bool table = a.H <= K3B_HMAX;
+    if (table) {
+        for (unsigned int h = tid; h < (unsigned int)a.H; h += K3B_THREADS) s_cnt[h] = 0u;
+        __syncthreads();
+        for (unsigned long long i = i0 + tid; i < i1; i += K3B_THREADS) atomicAdd(&s_cnt[a.recs[i].halo], 1u);
+        __syncthreads();
+        for (unsigned int h = tid; h < (unsigned int)a.H; h += K3B_THREADS) {
+            const unsigned int c = s_cnt[h];
+            /* the CTA's range inside the halo's segment; kept as a 32-bit offset from the segment start */
+            s_cnt[h] = c ? (unsigned int)atomicAdd(a.cursor + (size_t)h * K3_CURSOR_STRIDE, (unsigned long long)c) : 0u;
         }
+        __syncthreads();
+    }
+    for (unsigned long long i = i0 + tid; i < i1; i += K3B_THREADS) {
+        const Rec r = a.recs[i];
+        unsigned long long off;
+        if (table) off = atomicAdd(&s_cnt[r.halo], 1u);
+        else off = atomicAdd(a.cursor + (size_t)r.halo * K3_CURSOR_STRIDE, 1ull);
+        const unsigned long long p = a.seg_begin[r.halo] + off;
+        if (p < a.rec_cap) a.out[p] = r;
     }
 }
 
@@ -1554,7 +1595,7 @@ __global__ void k3_scan_counts(const unsigned long long* counts, unsigned long l
  * the segment (one binary search per chunk) and scatters.  grid = (chunk slots, halos). */
 constexpr int K3_THREADS = 512;
 constexpr int K3_SORT_MAX = 8192; /* k3_small: records one CTA sorts */
-constexpr int K3_CHUNK = 4096;
+constexpr int K3_CHUNK = 8192;    /* 164 KB of shared memory per CTA; segments up to here are ordered by ONE CTA and gathered row-major */
 constexpr int K3_NB = 512;        /* buckets per chunk */
 static_assert(K3_NB == K3_THREADS, "k3_rank scans one bucket count per thread");
 constexpr size_t K3_SMEM_BYTES = (size_t)K3_CHUNK * (2 * sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
@@ -1657,8 +1698,8 @@ __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
 
 struct GatherArgs {
     const Rec* recs;
+    const unsigned int* place;        /* multi-chunk segments: record (inside the segment) of every row, from k3_place */
     const unsigned int* rank;
-    const unsigned long long* sorted; /* k3_rank's sorted chunk keys (multi-chunk segments) */
     const unsigned long long* seg_begin;
     const unsigned long long* rec_count;
     unsigned long long rec_cap;
@@ -1669,32 +1710,53 @@ struct GatherArgs {
     long long index_base;
     int pos_only;
 };
-__global__ void k3_gather_halo(const GatherArgs a) {
+/* multi-chunk segments: final row of every record = rank inside its chunk + smaller keys in the other chunks of the
+ * segment (one binary search per other chunk); stored the other way round -- which record belongs to row o -- so that
+ * the gather can run row-major (one scattered 4-byte store here instead of fourteen there) */
+struct PlaceArgs {
+    const Rec* recs;
+    const unsigned int* rank;
+    const unsigned long long* sorted;
+    const unsigned long long* seg_begin;
+    const unsigned long long* rec_count;
+    unsigned long long rec_cap;
+    unsigned int* place;
+};
+__global__ void k3_place(const PlaceArgs a) {
     if (*a.rec_count > a.rec_cap) return; /* overflow: see k3_bucket */
     const unsigned long long nrec = *a.rec_count;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        Rec r = a.recs[i]; /* every record of a segment names the segment's halo */
+        const Rec r = a.recs[i];
         const unsigned long long sb = a.seg_begin[r.halo];
-        const unsigned long long len = min(a.seg_begin[r.halo + 1], a.rec_cap) - sb;
-        unsigned long long o;
-        if (len <= K3_CHUNK) { /* thread = output row: rows are written coalesced */
-            o = i;
-            r = a.recs[sb + a.rank[i]];
-        } else { /* thread = record: rank inside its chunk + smaller keys in the other chunks of the segment */
-            o = sb + a.rank[i];
-            const unsigned long long mine = (i - sb) / K3_CHUNK;
-            for (unsigned long long c = 0; c * K3_CHUNK < len; ++c) {
-                if (c == mine) continue;
-                const unsigned long long* ck = a.sorted + sb + c * K3_CHUNK;
-                unsigned int lo = 0, hi = (unsigned int)min((unsigned long long)K3_CHUNK, len - c * K3_CHUNK);
-                while (lo < hi) {
-                    const unsigned int mid = (lo + hi) >> 1;
-                    if (ck[mid] < r.key) lo = mid + 1; else hi = mid;
-                }
-                o += lo;
+        const unsigned long long len = a.seg_begin[r.halo + 1] - sb;
+        if (len <= K3_CHUNK) continue; /* single chunk: k3_rank already stored row -> record */
+        unsigned long long o = a.rank[i];
+        const unsigned long long mine = (i - sb) / K3_CHUNK;
+        for (unsigned long long c = 0; c * K3_CHUNK < len; ++c) {
+            if (c == mine) continue;
+            const unsigned long long* ck = a.sorted + sb + c * K3_CHUNK;
+            unsigned int lo = 0, hi = (unsigned int)min((unsigned long long)K3_CHUNK, len - c * K3_CHUNK);
+            while (lo < hi) {
+                const unsigned int mid = (lo + hi) >> 1;
+                if (ck[mid] < r.key) lo = mid + 1; else hi = mid;
             }
+            o += lo;
         }
+        a.place[sb + o] = (unsigned int)(i - sb);
+    }
+}
+
+/* thread = output row: rows are written coalesced */
+__global__ void k3_gather_halo(const GatherArgs a) {
+    if (*a.rec_count > a.rec_cap) return; /* overflow: see k3_bucket */
+    const unsigned long long nrec = *a.rec_count;
+    for (unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; o < nrec;
+         o += (unsigned long long)gridDim.x * blockDim.x) {
+        Rec r = a.recs[o]; /* every record of a segment names the segment's halo */
+        const unsigned long long sb = a.seg_begin[r.halo];
+        const unsigned long long len = a.seg_begin[r.halo + 1] - sb;
+        r = a.recs[sb + (len <= K3_CHUNK ? a.rank[o] : a.place[o])];
         if ((long long)o >= a.out_cap) continue;
         const long long g = (long long)(r.key & 0xffffffffull);
         a.out.theta[o] = r.th;                        /* processLC.cpp:1446-1447 */
