@@ -326,7 +326,7 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
             traffic = json.load(open(tp)).get(name)
         except Exception:
             traffic = None
-    kernel = {1: "k1s_scan", 2: "k2_cutout_halo_cells" if nhalos >= 8 else "k2_cutout_halo"}[wl["uc"]]
+    kernel = {1: "k1s_scan", 2: "k2c_sift+k2c_match+k2c_exact" if nhalos >= 8 else "k2_cutout_halo"}[wl["uc"]]
     out = {
         "metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": env.world,
         "steps": steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 4),

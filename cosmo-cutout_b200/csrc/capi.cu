@@ -462,6 +462,7 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
     return CC_OK;
 }
 
+
 /* pinned read-back area: [0,32+3H) the cutout's own results, then the exchanged counts of all ranks + offsets */
 size_t small_elems(int H, int R) { return 32 + 3 * (size_t)H + (size_t)R * 2 * H + H + 24; }
 

@@ -58,6 +58,11 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ float4 ldg_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 /* x86 SSE quiets and propagates a NaN operand's payload; the GPU returns the canonical NaN.  redshift is
  * the only output column computed from a possibly-NaN input, so mirror the host there. */
@@ -1813,11 +1818,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
 }
 
 struct XchgArgs {
