@@ -165,15 +165,10 @@ struct cc_ctx {
     int64_t launches = 0;
     int64_t last_const_count = -1;
     int k2_occupancy[2] = {0, 0};
-    bool cells_mono = false;   /* CC_CELLS_MONO=1: the single-kernel cell-index scan (k2_cutout_halo_cells) instead of the
-                                  staged sift -> match -> exact kernels */
     DevBuf cand, cand_count, pair_p, pair_h, pair_count;
     unsigned int cand_region_cap = 0; /* candidates per warp region (k2c_sift) */
     int64_t pair_cap = 0;
     int sift_occupancy[2] = {0, 0};
-    bool k2c_ready = false;
-    int k2c_warps = 20; /* warps of the one CTA per SM: 20 at 96 registers, no spills, 161 KB of shared memory (24 at 80
-                           registers spill and leave too little L1; 16 hide less latency); CC_K2C_WARPS=24|16 for A/B runs */
     bool k3_smem_set = false, k3s_smem_set = false;
     bool k2_tma = false, k2t_ready = false;
     int k2t_occ = 0;
@@ -503,7 +498,7 @@ int prepare_halo(cc_ctx* c) {
     if ((rc = ensure_out_cap(c, c->rec_cap))) return rc;
     if ((rc = ensure_small(c, small_elems(H, c->nranks)))) return rc;
 
-    /* many halos: (cos theta, sin phi) cell index per launch batch (kernels.cuh, k2_cutout_halo_cells) */
+    /* many halos: (cos theta, sin phi) cell index per launch batch (kernels.cuh, k2c_sift / k2c_match / k2c_exact) */
     c->use_bins = H >= 8 && !getenv("CC_NO_BINS");
     /* repeated cutouts with a known halo set (and the same kernel variant) reuse its device-resident parameters and
      * cell index: nothing is recomputed on the host */
@@ -677,7 +672,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             if (occ < 1) occ = 1;
         }
         const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
-        if (c->use_bins && !c->cells_mono) { /* staged: sift -> match -> exact (kernels.cuh) */
+        if (c->use_bins) { /* cell index, staged: sift -> match -> exact (kernels.cuh) */
             const int bi = h0 / cck::K2_MAX_HALOS;
             int& socc = c->sift_occupancy[vec ? 1 : 0];
             if (socc == 0) {
@@ -721,41 +716,6 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             cck::k2c_exact<<<(unsigned int)c->sm_count * 2u, cck::K2X_THREADS, 0, c->stream>>>(ea);
             CU(cudaGetLastError());
             c->launches += 3;
-        } else if (c->use_bins) { /* one 20-warp CTA per SM: bitmap + windows + pair buffers take 161 KB of its shared memory */
-            cck::HaloBinArgs b;
-            b.h = a;
-            const int bi = h0 / cck::K2_MAX_HALOS;
-            b.cell_range = (const uint2*)c->hs->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID);
-            b.cell_bits = (const unsigned int*)c->hs->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
-            b.cell_items = (const unsigned short*)c->hs->bin_items_buf.p + c->hs->bin_items_off[(size_t)bi];
-            if (!c->k2c_ready) {
-                const void* fns[6] = {(const void*)cck::k2_cutout_halo_cells<true, 24>, (const void*)cck::k2_cutout_halo_cells<false, 24>,
-                                      (const void*)cck::k2_cutout_halo_cells<true, 20>, (const void*)cck::k2_cutout_halo_cells<false, 20>,
-                                      (const void*)cck::k2_cutout_halo_cells<true, 16>, (const void*)cck::k2_cutout_halo_cells<false, 16>};
-                const int ws[3] = {24, 20, 16};
-                for (int i = 0; i < 6; ++i)
-                    CU(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::k2c_smem(ws[i / 2])));
-                const char* e = getenv("CC_K2C_WARPS");
-                const int w = e ? atoi(e) : 20;
-                c->k2c_warps = (w == 16 || w == 24) ? w : 20;
-                c->k2c_ready = true;
-            }
-            const unsigned int cw = (unsigned int)c->k2c_warps;
-            const unsigned int ctiles = (unsigned int)((n_scan + cck::K2C_TILE - 1) / cck::K2C_TILE);
-            const unsigned int cgrid = std::max(1u, std::min((ctiles + cw - 1) / cw, (unsigned int)c->sm_count));
-            const size_t csmem = cck::k2c_smem((int)cw);
-            if (cw == 24) {
-                if (vec) cck::k2_cutout_halo_cells<true, 24><<<cgrid, 768, csmem, c->stream>>>(b);
-                else cck::k2_cutout_halo_cells<false, 24><<<cgrid, 768, csmem, c->stream>>>(b);
-            } else if (cw == 20) {
-                if (vec) cck::k2_cutout_halo_cells<true, 20><<<cgrid, 640, csmem, c->stream>>>(b);
-                else cck::k2_cutout_halo_cells<false, 20><<<cgrid, 640, csmem, c->stream>>>(b);
-            } else {
-                if (vec) cck::k2_cutout_halo_cells<true, 16><<<cgrid, 512, csmem, c->stream>>>(b);
-                else cck::k2_cutout_halo_cells<false, 16><<<cgrid, 512, csmem, c->stream>>>(b);
-            }
-            CU(cudaGetLastError());
-            c->launches += 1;
         } else if (c->k2_tma && vec) { /* bulk-copy fed variant (CC_K2_TMA=1) */
             const size_t smem = cck::K2T_SMEM_BASE + pre_bytes;
             if (!c->k2t_ready) {
@@ -1033,7 +993,6 @@ int cc_create(int device, cc_ctx** out) {
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("CC_GATHER")) c->gather_mode = !strcmp(e, "bulk") ? 2 : !strcmp(e, "ldst") ? 1 : 0;
     if (const char* e = getenv("CC_TIMING")) c->timing = atoi(e) != 0;
-    if (const char* e = getenv("CC_CELLS_MONO")) c->cells_mono = atoi(e) != 0;
     if (getenv("CC_NO_PAYLOAD")) c->payload_policy = 2;
     if (const char* e = getenv("CC_PAYLOAD")) c->payload_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
     c->device = device;
@@ -1332,7 +1291,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
                 const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
                 c->force_general = refused;
                 /* staged cell-index kernels: a warp's candidate region or the pair buffer was too small */
-                const bool staged = c->use_bins && !c->cells_mono;
+                const bool staged = c->use_bins;
                 const bool cand_over = staged && c->h_small[2] > c->cand_region_cap;
                 const bool pair_over = staged && (int64_t)c->h_small[3] > c->pair_cap;
                 if (nrec <= c->rec_cap && !refused && !cand_over && !pair_over) break;
