@@ -65,6 +65,9 @@ WORKLOADS = {
     "cfg5": dict(uc=2, n=125_000_000, halos="random1000", kind=0, box=300.0, scaling="weak",
                  desc="BASELINE cfg5: 1000 halo cutouts, boxLength 5/10/20/30 arcmin (250 halos each = four processLC-style "
                       "passes, one boxLength per pass), 125M-particle resident shard per GPU (1B on 8 GPUs)"),
+    "cfg5_onepass": dict(uc=2, n=125_000_000, halos="random1000_15", kind=0, box=300.0, scaling="weak",
+                         desc="cfg5 through the C ABI instead of processLC: the same 1000 halos, all with boxLength 15 arcmin, in ONE "
+                              "pass over the 125M-particle resident shard (round 1's cfg5 figure; the C ABI takes per-halo bounds)"),
 }
 
 _OUT = sys.stdout
@@ -137,6 +140,10 @@ class ClockSampler:
 
 def halo_groups(wl):
     """[(boxLength, [(pos, boxLength), ...]), ...]: one entry per processLC-style pass"""
+    if wl["halos"] == "random1000_15":
+        rng = np.random.default_rng(1000)
+        pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
+        return [(15.0, [(tuple(float(v) for v in p), 15.0) for p in pos])]
     if wl["halos"] == "random1000":
         rng = np.random.default_rng(1000)
         pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
@@ -337,7 +344,10 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
                    "timing": "CUDA events on the cutout stream around all timed steps, max over ranks",
                    "count_exchange": env.exchange},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src, "kernel": kernel,
+                     "frac": round(achieved / peak, 4), "traffic": traffic,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture "
+                                       "(profiles/traffic.json); not re-measured in this run",
+                     "peak_source": peak_src, "kernel": kernel,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(float(np.mean(scan_ms)), 4),
                      "whole_pass": {"bytes": pass_bytes, "ms": round(float(np.mean(pass_ms)), 4),
                                     "achieved": round(pass_gbs, 1), "frac": round(pass_gbs / peak, 4),
@@ -773,7 +783,7 @@ def run_ours(args):
         out = run_resident(env, args, args.workload, args.steps, args.warmup, with_e2e=True)
     if not args.no_configs and args.workload == "cfg2":
         configs = {}
-        for name in ("cfg1", "const1b", "cfg4", "cfg5", "cfg3"):
+        for name in ("cfg1", "const1b", "cfg4", "cfg5", "cfg5_onepass", "cfg3"):
             t0 = time.perf_counter()
             try:
                 r = run_cfg3(env, args, 2, 1) if name == "cfg3" else run_resident(env, args, name, sub_steps, sub_warm, with_e2e=False)

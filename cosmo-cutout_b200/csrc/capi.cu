@@ -960,7 +960,7 @@ int check_sm100(int device, int* sm_count) {
 
 extern "C" {
 
-const char* cc_version(void) { return "cosmo-cutout_b200 0.1 (sm_100a)"; }
+const char* cc_version(void) { return "cosmo-cutout_b200 0.2 (sm_100a)"; }
 const char* cc_last_error(void) {
     if (!g_err.empty()) return g_err.c_str();
     std::lock_guard<std::mutex> lock(g_err_any_mutex);
