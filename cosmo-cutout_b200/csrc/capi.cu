@@ -165,6 +165,11 @@ struct cc_ctx {
     int64_t launches = 0;
     int64_t last_const_count = -1;
     int k2_occupancy[2] = {0, 0};
+    int cells_mode = 0;        /* many halos: 0 auto (per halo set, from the measured bitmap hit rate), 1 staged
+                                  (k2c_sift / k2c_match / k2c_exact), 2 one kernel (k2_cutout_halo_cells); cc_set_option
+                                  "cells" / CC_CELLS */
+    bool cells_mono_ready = false;
+    bool used_mono = false;    /* the pending cutout ran the one-kernel scan */
     DevBuf cand, cand_count, pair_p, pair_h, pair_count;
     unsigned int cand_region_cap = 0; /* candidates per warp region (k2c_sift) */
     int64_t pair_cap = 0;
@@ -218,6 +223,7 @@ struct cc_ctx {
         DevBuf pre_buf, halo_buf;
         DevBuf bin_start_buf, bin_bits_buf, bin_items_buf; /* cell index: {first,end} per cell, occupancy bitmap, halo lists */
         std::vector<size_t> bin_items_off;                 /* per launch batch: first item */
+        int walker = 0;     /* 0: not measured yet (the staged kernels measure), 1: staged, 2: one kernel */
         uint64_t last_use = 0;
         void release() { pre_buf.release(); halo_buf.release(); bin_start_buf.release(); bin_bits_buf.release(); bin_items_buf.release(); key.clear(); }
     };
@@ -471,6 +477,12 @@ int prepare_const(cc_ctx* c) {
     return CC_OK;
 }
 
+/* bitmap hit rate above which a halo set is walked by the one-kernel scan (profiles/r02: 10 % hits: staged 0.59 ms vs
+ * 0.9 ms; 22 % hits: staged 0.94 ms vs 0.71 ms) */
+#ifndef CC_CELLS_MONO_ABOVE
+#define CC_CELLS_MONO_ABOVE 0.16
+#endif
+
 /* ---------------------------------------------------------------- use case 2 launch */
 size_t hstate_elems(int H) { return 8 + 2 * (size_t)H + ((size_t)H + 1) + (size_t)cck::K3_CURSOR_STRIDE * (size_t)H; }
 unsigned long long* hs_misc(const cc_ctx* c) { return (unsigned long long*)c->hstate.p; }
@@ -608,6 +620,7 @@ int prepare_halo(cc_ctx* c) {
         CU(cudaStreamSynchronize(c->stream)); /* the host vectors are pageable and die here */
         hs->key = c->p_halos;
         hs->bins = c->use_bins;
+        hs->walker = 0;
     }
     if (!(c->hstate_clean && c->hstate_clean_H == H)) CU(cudaMemsetAsync(c->hstate.p, 0, hstate_elems(H) * 8, c->stream));
     c->hstate_clean = false;
@@ -672,7 +685,29 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             if (occ < 1) occ = 1;
         }
         const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
-        if (c->use_bins) { /* cell index, staged: sift -> match -> exact (kernels.cuh) */
+        const bool mono = c->use_bins && (c->cells_mode == 2 || (c->cells_mode == 0 && c->hs->walker == 2));
+        if (c->use_bins) c->used_mono = mono;
+        if (mono) { /* cell index, one kernel: one 20-warp CTA per SM, bitmap + windows + stacks + counters in shared memory */
+            constexpr int W = 20;
+            const size_t csmem = cck::k2c_smem(W) + (size_t)2 * cck::K2_MAX_HALOS * 4;
+            cck::HaloBinArgs b;
+            b.h = a;
+            const int bi = h0 / cck::K2_MAX_HALOS;
+            b.cell_range = (const uint2*)c->hs->bin_start_buf.p + (size_t)bi * ((size_t)cck::K2_GRID * cck::K2_GRID);
+            b.cell_bits = (const unsigned int*)c->hs->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
+            b.cell_items = (const unsigned short*)c->hs->bin_items_buf.p + c->hs->bin_items_off[(size_t)bi];
+            if (!c->cells_mono_ready) {
+                CU(cudaFuncSetAttribute((const void*)cck::k2_cutout_halo_cells<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+                CU(cudaFuncSetAttribute((const void*)cck::k2_cutout_halo_cells<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+                c->cells_mono_ready = true;
+            }
+            const unsigned int ctiles = (unsigned int)((n_scan + cck::K2C_TILE - 1) / cck::K2C_TILE);
+            const unsigned int cgrid = std::max(1u, std::min((ctiles + W - 1) / W, (unsigned int)c->sm_count));
+            if (vec) cck::k2_cutout_halo_cells<true, W><<<cgrid, W * 32, csmem, c->stream>>>(b);
+            else cck::k2_cutout_halo_cells<false, W><<<cgrid, W * 32, csmem, c->stream>>>(b);
+            CU(cudaGetLastError());
+            c->launches += 1;
+        } else if (c->use_bins) { /* cell index, staged: sift -> match -> exact (kernels.cuh) */
             const int bi = h0 / cck::K2_MAX_HALOS;
             int& socc = c->sift_occupancy[vec ? 1 : 0];
             if (socc == 0) {
@@ -993,6 +1028,7 @@ int cc_create(int device, cc_ctx** out) {
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("CC_GATHER")) c->gather_mode = !strcmp(e, "bulk") ? 2 : !strcmp(e, "ldst") ? 1 : 0;
     if (const char* e = getenv("CC_TIMING")) c->timing = atoi(e) != 0;
+    if (const char* e = getenv("CC_CELLS")) c->cells_mode = !strcmp(e, "staged") ? 1 : !strcmp(e, "mono") ? 2 : 0;
     if (getenv("CC_NO_PAYLOAD")) c->payload_policy = 2;
     if (const char* e = getenv("CC_PAYLOAD")) c->payload_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
     c->device = device;
@@ -1291,7 +1327,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
                 const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
                 c->force_general = refused;
                 /* staged cell-index kernels: a warp's candidate region or the pair buffer was too small */
-                const bool staged = c->use_bins;
+                const bool staged = c->use_bins && !c->used_mono;
                 const bool cand_over = staged && c->h_small[2] > c->cand_region_cap;
                 const bool pair_over = staged && (int64_t)c->h_small[3] > c->pair_cap;
                 if (nrec <= c->rec_cap && !refused && !cand_over && !pair_over) break;
@@ -1302,6 +1338,13 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
                 if ((rc = run_pending(c))) return rc;
             }
             const int64_t nrec = (int64_t)c->h_small[0];
+            if (c->use_bins && !c->used_mono && c->hs && c->hs->walker == 0 && halo_scan_limit(c) > 0) {
+                /* the staged pass measured how many particles hit the occupancy bitmap: with many hits the candidate
+                 * buffer's round trip through HBM costs more than the one-kernel scan's lower occupancy (profiles/r02) */
+                const int nbatch = (H + cck::K2_MAX_HALOS - 1) / cck::K2_MAX_HALOS;
+                const double hit = (double)c->h_small[6] / ((double)halo_scan_limit(c) * nbatch);
+                c->hs->walker = hit > CC_CELLS_MONO_ABOVE ? 2 : 1;
+            }
             c->last_nrec = nrec;
             if (!c->streamed) c->step_last_survivors = nrec;
             c->force_general = false;
@@ -1791,6 +1834,9 @@ int cc_set_option(cc_ctx* c, const char* key, const char* value) {
         if (v == "auto") c->xchg_mode = 0; else if (v == "nccl") c->xchg_mode = 1; else if (v == "peer") c->xchg_mode = 2;
         else if (v == "eager") c->xchg_mode = 3;
         else return fail(CC_ERR_ARG, "cc_set_option: exchange = auto|nccl|peer|eager");
+    } else if (k == "cells") {
+        if (v == "auto") c->cells_mode = 0; else if (v == "staged") c->cells_mode = 1; else if (v == "mono") c->cells_mode = 2;
+        else return fail(CC_ERR_ARG, "cc_set_option: cells = auto|staged|mono");
     } else if (k == "timing") {
         if (v == "on") c->timing = true; else if (v == "off") c->timing = false;
         else return fail(CC_ERR_ARG, "cc_set_option: timing = on|off");

@@ -984,15 +984,14 @@ constexpr size_t K2T_SMEM_BASE = sizeof(K2TWarpRing) * SCAN_WARPS;
  * looks up its cell (one 8-byte read from an L2-resident table) and owes one test per halo listed there -- for
  * cluster-sized boxes most cells are empty.  This plays the role of the reference's theta-sorted index
  * (processLC.cpp:1214-1221, :1334-1340) without sorting or re-reading 12 B/particle data.
- * (Round 1 ran the whole index in ONE kernel, k2_cutout_halo_cells: one 20-warp CTA per SM, per-warp stacks in 161 KB of
- * shared memory to keep the lanes busy; the staged kernels below replaced it: profiles/r02/README.md has the A/B.) */
+ * Two walkers: ONE kernel (k2_cutout_halo_cells) and a staged form (k2c_sift / k2c_match / k2c_exact). */
 #ifndef CC_K2_GRID
 #define CC_K2_GRID 2048 /* 1024: 12 % slower on 1000 cluster-sized halos (more pairs per hit); the 32 MB table stays L2-resident */
 #endif
 constexpr int K2_GRID = CC_K2_GRID;
 constexpr int K2_CSHIFT = K2_GRID == 2048 ? 2 : 1;
 constexpr int K2_COARSE = K2_GRID >> K2_CSHIFT;              /* occupancy bitmap: 512 x 512 bits, one per 4 x 4 (2 x 2) cells */
-static_assert(K2_COARSE == 512, "the bitmap is 32 KB: it stays in the L1 of every SM");
+static_assert(K2_COARSE == 512, "the bitmap is 32 KB: shared memory of the one-kernel scan, L1 of the staged one");
 constexpr int K2_BITWORDS = K2_COARSE * K2_COARSE / 32;
 
 /* (c, s) of the cell index */
@@ -1004,6 +1003,299 @@ __device__ __forceinline__ void k2c_coords(float x, float y, float z, float& c, 
     c = z * rsqrt_fast(r2);
     /* sin(phi_u) with phi_u = atan(y/x): y / sqrt(x^2+y^2), negated when x < 0 */
     s = __int_as_float(__float_as_int(y * rsqrt_fast(rxy2)) ^ (__float_as_int(x) & 0x80000000));
+}
+
+/* ---- many halos, one kernel -------------------------------------------------------------------------------------
+ * The cell index walked by ONE kernel: one CTA of 20 warps per SM keeps the occupancy bitmap (32 KB) and the halo
+ * windows in shared memory; hits are pushed -- position included -- onto the warp's shared-memory stack, and whenever
+ * 32 are stacked the warp pops them, one per lane: the next halo of the cell's list, four compares against that halo's
+ * window; a pair that passes goes onto a second stack of tested pairs, a hit with a longer list is pushed back with the
+ * list advanced by one; every 32 tested pairs take the second filter and what it cannot decide the exact path.  Tiles
+ * are 128 particles, fetched one trip ahead with cp.async.  Nothing is staged in HBM, which is what wins when a large
+ * share of the particles hits the bitmap (1000 cluster-sized halos in one pass: 22 %); the staged kernels below win
+ * when few do (profiles/r02/README.md).  capi.cu picks per halo set from the hit rate it measured. */
+/* one CTA per SM shares the bitmap: WARPS warps (template parameter; 20 at 96 registers by default) */
+constexpr int K2C_TILE = 128; /* particles per warp tile */
+constexpr int K2C_HCAP = 64;  /* stacked hits per warp (a tile with more is taken in several passes) */
+constexpr int K2C_CCAP = 64;  /* stacked tested pairs per warp: < 32 waiting + <= 32 from one round */
+struct __align__(16) K2CStacks {
+    float4 hp[K2C_HCAP];         /* hit: x, y, z, particle index inside the chunk (bits) */
+    uint2 hl[K2C_HCAP];          /*      {next item of the cell's list, items left} */
+    float4 cp[K2C_CCAP];         /* tested pair: x, y, z, particle index (bits) */
+    unsigned int ch[K2C_CCAP];   /*              halo inside the launch */
+    float4 xp[K2C_CCAP];         /* pair that needs the exact arithmetic */
+    unsigned int xh[K2C_CCAP];
+    float4 next[3][32];          /* x, y, z of the warp's NEXT tile, filled by cp.async while this one is worked on */
+};
+constexpr size_t k2c_smem(int warps) {
+    return (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4) + sizeof(K2CStacks) * (size_t)warps;
+}
+
+struct HaloBinArgs {
+    HaloArgs h;                       /* h.pre holds {chi, clo, slo, shi} here (prefilter.h uc2_bounds_cells) */
+    const unsigned int* cell_bits;    /* [K2_BITWORDS]: bit set when any of the 2 x 2 cells lists a halo */
+    const uint2* cell_range;          /* [K2_GRID*K2_GRID] {first, end} into cell_items */
+    const unsigned short* cell_items; /* halo index inside the launch */
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/* one out-of-range position against every halo of the launch (rare) */
+__device__ __noinline__ void k2c_exact_all(const HaloArgs& a, float x, float y, float z, unsigned int local_n, int lane) {
+    for (int h0 = 0; h0 < a.nhalos; h0 += 32) {
+        const int h = h0 + lane;
+        k2_exact_warp(a, h < a.nhalos, h < a.nhalos ? h : 0, x, y, z, local_n, lane);
+    }
+}
+
+template <bool VEC, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __grid_constant__ HaloBinArgs b) {
+    constexpr int K2C_THREADS = WARPS * 32, K2C_WARPS = WARPS;
+    extern __shared__ __align__(16) unsigned char s_cells[];
+    unsigned int* s_bits = reinterpret_cast<unsigned int*>(s_cells);
+    float4* s_pre = reinterpret_cast<float4*>(s_cells + (size_t)K2_BITWORDS * 4);
+    K2CStacks* s_st = reinterpret_cast<K2CStacks*>(s_cells + (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4));
+    /* survivors and rough survivors per halo, counted per CTA (a global atomic per pair on 250 counters serialises in
+     * the L2: profiles/r02) */
+    unsigned int* s_rough = reinterpret_cast<unsigned int*>(s_cells + (size_t)K2_BITWORDS * 4 + (size_t)K2_MAX_HALOS * sizeof(float4) +
+                                                            sizeof(K2CStacks) * (size_t)WARPS);
+    unsigned int* s_fine = s_rough + K2_MAX_HALOS;
+    for (int i = threadIdx.x; i < K2_MAX_HALOS; i += K2C_THREADS) { s_rough[i] = 0u; s_fine[i] = 0u; }
+    const HaloArgs& a = b.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    K2CStacks& S = s_st[warp];
+    for (int i = threadIdx.x; i < K2_BITWORDS / 4; i += K2C_THREADS)
+        reinterpret_cast<uint4*>(s_bits)[i] = __ldg(reinterpret_cast<const uint4*>(b.cell_bits) + i);
+    for (int h = threadIdx.x; h < a.nhalos; h += K2C_THREADS) s_pre[h] = a.pre[h];
+    __syncthreads();
+    const unsigned int total_warps = gridDim.x * K2C_WARPS;
+    const unsigned int ntiles = (unsigned int)((a.n + K2C_TILE - 1) / K2C_TILE);
+    unsigned long long n_cand = 0;
+    unsigned int nh = 0, nc = 0, nx = 0; /* warp-uniform stack heights: hits, tested pairs, pairs for the exact path */
+    unsigned int w0 = 0;         /* hits of the current tile already pushed (non-zero: the tile is being re-read) */
+    bool flush = false;
+
+    /* a whole, 16-byte aligned tile is fetched one trip ahead into shared memory (each lane copies, and later reads
+     * back, its own 3 x 16 bytes): the DRAM latency of tile t+1 hides behind the work on tile t without holding
+     * registers across that work */
+    auto whole = [&](unsigned int t) { return VEC && t < ntiles && (long long)(t + 1) * K2C_TILE <= a.n; };
+    auto prefetch = [&](unsigned int t) {
+        const long long o = (long long)t * K2C_TILE + 4 * lane;
+        cp_async16(&S.next[0][lane], a.x + o);
+        cp_async16(&S.next[1][lane], a.y + o);
+        cp_async16(&S.next[2][lane], a.z + o);
+        cp_async_commit();
+    };
+    {
+        const unsigned int first = blockIdx.x * K2C_WARPS + warp;
+        if (whole(first)) prefetch(first);
+    }
+
+    for (unsigned int tile = blockIdx.x * K2C_WARPS + warp; !flush;) {
+        if (tile < ntiles) {
+            /* nothing of the tile stays in registers across the rounds below: a tile with more hits than the
+             * stack has room for is simply read again for its next pass (rare) */
+            const long long base = (long long)tile * K2C_TILE;
+            float px[4], py[4], pz[4];
+            unsigned int valid = 0;
+            if (w0 == 0 && whole(tile)) {
+                cp_async_wait_all();
+                const float4 vx = S.next[0][lane], vy = S.next[1][lane], vz = S.next[2][lane];
+                if (whole(tile + total_warps)) prefetch(tile + total_warps);
+                px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+                py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+                pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+                valid = 0xfu;
+            } else if (VEC && base + K2C_TILE <= a.n) { /* another pass over the same tile */
+                const float4 vx = ldg_stream4(a.x + base + 4 * lane), vy = ldg_stream4(a.y + base + 4 * lane),
+                             vz = ldg_stream4(a.z + base + 4 * lane);
+                px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+                py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+                pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+                valid = 0xfu;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long g = base + 4 * lane + j;
+                    px[j] = py[j] = pz[j] = 1.0f;
+                    if (g < a.n) {
+                        px[j] = __ldcs(a.x + g); py[j] = __ldcs(a.y + g); pz[j] = __ldcs(a.z + g);
+                        valid |= 1u << j;
+                    }
+                }
+            }
+            unsigned int cell[4], insane = 0, hit = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { /* cell of every particle; most are ruled out by the shared-memory bitmap */
+                float pc, ps;
+                bool sane;
+                k2c_coords(px[j], py[j], pz[j], pc, ps, sane);
+                if (!sane) insane |= 1u << j;
+                /* NaN -> 0, anything large -> 2^32-1 -> G-1: always a valid cell */
+                const unsigned int ic = min(__float2uint_rz(fmaf(pc, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+                const unsigned int is = min(__float2uint_rz(fmaf(ps, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+                cell[j] = ic * K2_GRID + is;
+                const unsigned int bit = (ic >> K2_CSHIFT) * K2_COARSE + (is >> K2_CSHIFT);
+                hit |= ((s_bits[bit >> 5] >> (bit & 31u)) & 1u) << j;
+            }
+            insane &= valid;
+            hit &= valid & ~insane;
+            uint2 rg[4];
+            unsigned int mine = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { /* the look-ups that remain are issued together */
+                rg[j] = make_uint2(0u, 0u);
+                if ((hit >> j) & 1u) rg[j] = __ldg(b.cell_range + cell[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mine += rg[j].y != rg[j].x ? 1u : 0u;
+            /* out-of-range positions: the exact path decides, against every halo of the launch, warp-cooperatively */
+            if (w0 == 0 && __any_sync(0xffffffffu, insane != 0)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    unsigned int m = __ballot_sync(0xffffffffu, (insane >> j) & 1u);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float x = __shfl_sync(0xffffffffu, px[j], src), y = __shfl_sync(0xffffffffu, py[j], src),
+                                    z = __shfl_sync(0xffffffffu, pz[j], src);
+                        k2c_exact_all(a, x, y, z, (unsigned int)(a.local_base + base + 4 * src + j), lane);
+                        n_cand += (unsigned int)a.nhalos;
+                    }
+                }
+            }
+            /* position of this lane's hits among the tile's hits */
+            unsigned int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
+            const unsigned int w1 = min(total, w0 + (K2C_HCAP - nh));
+            unsigned int pos = inc - mine;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (rg[j].y != rg[j].x) {
+                    if (pos >= w0 && pos < w1) {
+                        const unsigned int e = nh + (pos - w0);
+                        S.hp[e] = make_float4(px[j], py[j], pz[j], __uint_as_float((unsigned int)(base + 4 * lane + j)));
+                        S.hl[e] = make_uint2(rg[j].x, rg[j].y - rg[j].x);
+                    }
+                    ++pos;
+                }
+            nh += w1 - w0;
+            if (w1 < total) {
+                w0 = w1; /* same tile again after the rounds */
+            } else {
+                w0 = 0;
+                tile += total_warps;
+            }
+            __syncwarp();
+        } else {
+            flush = true; /* past this warp's last tile: empty the stacks */
+        }
+        /* pop 32 hits (whatever is left when the stacks are being emptied), test ONE list item of each, and push
+         * the hits with a longer list back: every round tests with all lanes busy */
+        while (nh >= 32u || (flush && (nh | nc | nx) != 0u)) {
+            const unsigned int m = min(nh, 32u);
+            nh -= m;
+            float4 q = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            uint2 l = make_uint2(0u, 0u);
+            unsigned int h = 0;
+            bool pass = false;
+            if ((unsigned int)lane < m) {
+                q = S.hp[nh + lane];
+                l = S.hl[nh + lane];
+                h = __ldg(b.cell_items + l.x);
+                float pc, ps;
+                bool sane;
+                k2c_coords(q.x, q.y, q.z, pc, ps, sane);
+                const float4 W = s_pre[h];
+                pass = (pc <= W.x) & (pc >= W.y) & (ps >= W.z) & (ps <= W.w);
+            }
+            const unsigned int mm = __ballot_sync(0xffffffffu, l.y > 1u);
+            const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+            __syncwarp(); /* every lane holds its hit in registers: the pushes below may overwrite it */
+            if (l.y > 1u) {
+                const unsigned int e = nh + __popc(mm & lt_mask);
+                S.hp[e] = q;
+                S.hl[e] = make_uint2(l.x + 1u, l.y - 1u);
+            }
+            nh += __popc(mm);
+            if (pass) {
+                const unsigned int e = nc + __popc(pm & lt_mask);
+                S.cp[e] = q;
+                S.ch[e] = h;
+            }
+            nc += __popc(pm);
+            __syncwarp();
+            /* tested pairs, 32 at a time (at the very end, whatever is left): the second filter, then the exact
+             * path for what it cannot decide */
+            const bool last = flush && nh == 0u;
+            for (;;) {
+                if (nx >= 32u || (last && nc == 0u && nx != 0u)) { /* exact arithmetic, newest 32 */
+                    const unsigned int mx = min(nx, 32u);
+                    nx -= mx;
+                    const bool lv = (unsigned int)lane < mx;
+                    const unsigned int e = lv ? nx + lane : 0u;
+                    const float4 c4 = S.xp[e];
+                    k2_exact_warp(a, lv, (int)S.xh[e], c4.x, c4.y, c4.z, (unsigned int)a.local_base + __float_as_uint(c4.w), lane, s_rough, s_fine);
+                    n_cand += mx;
+                    __syncwarp();
+                    continue;
+                }
+                if (nc >= 32u || (last && nc != 0u)) {
+                    /* A pair that is certainly inside the rough window (inner (c, s) window) AND certainly outside
+                     * the fine window (rotated position against the widened fine window) only counts as a rough
+                     * survivor: 5 of 6 pairs of a cluster-sized cutout.  The rest takes the exact path. */
+                    const unsigned int mc = min(nc, 32u);
+                    nc -= mc;
+                    const bool lv = (unsigned int)lane < mc;
+                    const unsigned int e = lv ? nc + lane : 0u;
+                    const float4 c4 = S.cp[e];
+                    const unsigned int h = lv ? S.ch[e] : 0u;
+                    const float4* __restrict__ Hq = reinterpret_cast<const float4*>(a.halos + h);
+                    const float4 q0 = __ldg(Hq), q1 = __ldg(Hq + 1), q2 = __ldg(Hq + 2), q5 = __ldg(Hq + 5), q6 = __ldg(Hq + 6);
+                    float pc, ps;
+                    bool sane;
+                    k2c_coords(c4.x, c4.y, c4.z, pc, ps, sane);
+                    const bool sure_rough = (pc <= q5.x) & (pc >= q5.y) & (ps >= q5.z) & (ps <= q5.w);
+                    const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+                    float rx, ry, rz;
+                    ccref::mat_vec(R, c4.x, c4.y, c4.z, rx, ry, rz); /* the exact path's own rotated position */
+                    const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+                    const bool sane_r = (fabsf(rx) >= CC_SANE_LO) & (r2 <= 1.2089258e24f);
+                    const float cf = rz * rsqrt_fast(r2), tf = ry * rcp_fast(rx);
+                    const bool maybe_fine = !sane_r | ((cf <= q6.x) & (cf >= q6.y) & (tf >= q6.z) & (tf <= q6.w));
+                    const bool counted = lv && sure_rough && !maybe_fine;
+                    if (counted) atomicAdd(&s_rough[h], 1u); /* rough_cutout_size, :1436 */
+                    const bool need = lv && !counted;
+                    const unsigned int xm = __ballot_sync(0xffffffffu, need);
+                    if (need) {
+                        const unsigned int x = nx + __popc(xm & lt_mask);
+                        S.xp[x] = c4;
+                        S.xh[x] = h;
+                    }
+                    nx += __popc(xm);
+                    __syncwarp();
+                    continue;
+                }
+                break;
+            }
+        }
+    }
+    if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.nhalos; i += K2C_THREADS) {
+        if (s_rough[i]) atomicAdd(a.counts + a.total_halos + (unsigned int)a.halo0 + i, (unsigned long long)s_rough[i]);
+        if (s_fine[i]) atomicAdd(a.counts + (unsigned int)a.halo0 + i, (unsigned long long)s_fine[i]);
+    }
 }
 
 /* ---- many halos, staged: sift -> match -> exact ----------------------------------------------------------------
@@ -1080,6 +1372,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2c_sift(const __grid_constan
     }
     if (lane == 0) {
         a.cand_count[gwarp] = cursor;
+        atomicAdd(a.misc + 6, (unsigned long long)cursor); /* candidates of the pass: the hit rate capi.cu decides on */
         atomicMax(a.misc + 2, (unsigned long long)cursor);
     }
 }
