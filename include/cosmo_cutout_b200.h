@@ -208,7 +208,9 @@ int cc_merge_order(int nranks, const int64_t* counts, const float* const* theta_
 
 /* ------------------------------------------------------------------ measurement */
 /* Device time (CUDA events on the context's stream) of the scan kernel of the last cutout, and of the
- * whole enqueued cutout (scan + sort + gather).  ms; negative if none.  Implies a stream synchronize. */
+ * whole enqueued cutout (scan + sort + gather).  ms; negative if none -- the events are only recorded after
+ * cc_set_option(ctx, "timing", "on") (three event records between the kernels of every cutout otherwise).
+ * Implies a stream synchronize. */
 double cc_last_scan_ms(cc_ctx* ctx);
 double cc_last_total_ms(cc_ctx* ctx);
 /* number of kernels this context has launched so far */
@@ -230,7 +232,12 @@ int cc_last_stats_ex(cc_ctx* ctx, int64_t* out, int n);
  * key "payload":  "auto" (default) | "always" | "never" -- the 32 B/particle interleaved copy of the seven gather-only
  *                 columns of a resident step; auto builds it inside the first cutout that follows a cutout with at
  *                 least max(65536, n/512) survivors on the same resident step
- * key "exchange": "auto" (default: NVLink peer mailboxes when attached, else NCCL) | "nccl" | "peer"
+ * key "exchange": "auto" (default: NVLink peer mailboxes when attached, else NCCL) | "nccl" | "peer" | "eager" (peer, and a
+ *                 small use-case-2 cutout posts its counts from inside its last kernel: every rank must then follow
+ *                 every cutout by cc_exchange_counts)
+ * key "cells":    "auto" (default) | "staged" | "mono" -- many halos: the cell index is walked by three staged kernels or by
+ *                 one; auto measures the bitmap hit rate of a halo set on its first pass and picks from it
+ * key "timing":   "off" (default) | "on" -- record the per-kernel CUDA events behind cc_last_scan_ms / cc_last_total_ms
  * key "gather":   "auto" (default) | "ldst" | "bulk" -- use case 1 gather: plain coalesced stores, or rows staged in
  *                 shared memory and written with cp.async.bulk (TMA bulk stores); auto picks bulk stores for dense
  *                 cutouts (profiles/r02 has the A/B numbers) */
