@@ -15,6 +15,7 @@
 #include <iostream>
 #include <iterator>
 #include <sstream>
+#include <thread>
 
 namespace cchost {
 
@@ -23,9 +24,19 @@ using std::endl;
 using std::string;
 using std::vector;
 
+namespace {
+const std::thread::id g_main_thread = std::this_thread::get_id();
+}
+
+/* Fatal: message to stdout, non-zero exit (where the reference calls MPI_Abort / exit(EXIT_FAILURE)).  From a worker
+ * thread -- one host thread per GPU around the count exchange, the per-halo writers, the read-ahead -- exit() would run
+ * the atexit handlers (the CUDA runtime's teardown among them) while the other threads are still inside CUDA calls or a
+ * collective: leave without them. */
 void die(const string& msg) {
     cout << msg << endl;
     cout.flush();
+    fflush(stdout);
+    if (std::this_thread::get_id() != g_main_thread) quick_exit(EXIT_FAILURE);
     exit(EXIT_FAILURE);
 }
 
