@@ -250,6 +250,10 @@ struct cc_ctx {
     int64_t stats[4] = {};
     int64_t nan_theta = 0;  /* use case 2: scanned particles whose un-rotated theta is NaN (see cc_last_stats_ex) */
     bool have_times = false;
+    int prefetch = -1;       /* scan kernels ask the L2 for the warp's next tile while they work on this one: -1 auto, 0 off,
+                                1 on (CC_PREFETCH).  Measured (profiles/r02): it hides DRAM latency where the scan is issue- or
+                                latency-limited (wide field +6 %, 10 M particles +18 %, halo scan +3 %, sift +2 %) and costs
+                                5 % where the scan already saturates HBM (1 B particles, narrow window) */
     bool timing = false;     /* record the per-kernel timing events (cc_last_scan_ms / cc_last_total_ms); cc_set_option
                                 "timing": three event records per cutout sit between the kernels, so it is off unless asked */
     bool hstate_clean = false; /* use case 2 device state was zeroed by the previous cutout's last kernel (k3_small) */
@@ -400,6 +404,9 @@ int launch_const_chunk(cc_ctx* c, const Chunk& ch) {
         a.result = result;
         a.nseg = nseg;
         a.ntiles = ntiles;
+        /* auto: a dense window (survivors of the previous cutout) or a step too short to fill the memory pipeline */
+        a.prefetch = !c->streamed && (c->prefetch == 1 || (c->prefetch < 0 && (ch.n <= (64ll << 20) ||
+                                                                              (c->last_const_count >= 0 && c->last_const_count * 256 >= ch.n))));
         k1s_scan_variant(vec)<<<grid, cck::SCAN_THREADS, 0, c->stream>>>(a);
         CU(cudaGetLastError());
         if (ch.last && c->timing) CU(cudaEventRecord(c->ev_scan1, c->stream));
@@ -677,6 +684,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
         a.nan_count = rec_count + 5;
         a.total_halos = H;
         a.ntiles = (unsigned int)((n_scan + cck::SCAN_TILE - 1) / cck::SCAN_TILE);
+        a.prefetch = c->prefetch != 0 && !c->streamed;
         const size_t pre_bytes = (size_t)a.nhalos * sizeof(float4);
         int& occ = c->k2_occupancy[vec ? 1 : 0];
         if (occ == 0) {
@@ -731,7 +739,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             sa.x = a.x; sa.y = a.y; sa.z = a.z; sa.n = a.n; sa.local_base = a.local_base;
             sa.cell_bits = (const unsigned int*)c->hs->bin_bits_buf.p + (size_t)bi * cck::K2_BITWORDS;
             sa.cand = (float4*)c->cand.p; sa.region_cap = c->cand_region_cap; sa.cand_count = (unsigned int*)c->cand_count.p;
-            sa.misc = hs_misc(c); sa.ntiles = a.ntiles;
+            sa.misc = hs_misc(c); sa.ntiles = a.ntiles; sa.prefetch = a.prefetch;
             if (vec) cck::k2c_sift<true><<<sgrid, cck::SCAN_THREADS, 0, c->stream>>>(sa);
             else cck::k2c_sift<false><<<sgrid, cck::SCAN_THREADS, 0, c->stream>>>(sa);
             CU(cudaGetLastError());
@@ -1028,6 +1036,7 @@ int cc_create(int device, cc_ctx** out) {
     if (const char* e = getenv("CC_K2_TMA")) c->k2_tma = atoi(e) != 0;
     if (const char* e = getenv("CC_GATHER")) c->gather_mode = !strcmp(e, "bulk") ? 2 : !strcmp(e, "ldst") ? 1 : 0;
     if (const char* e = getenv("CC_TIMING")) c->timing = atoi(e) != 0;
+    if (const char* e = getenv("CC_PREFETCH")) c->prefetch = atoi(e);
     if (const char* e = getenv("CC_CELLS")) c->cells_mode = !strcmp(e, "staged") ? 1 : !strcmp(e, "mono") ? 2 : 0;
     if (getenv("CC_NO_PAYLOAD")) c->payload_policy = 2;
     if (const char* e = getenv("CC_PAYLOAD")) c->payload_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
@@ -1407,8 +1416,21 @@ int fetch_rows(cc_ctx* c, int64_t row0, int64_t count, const cc_cols_out* host, 
         nt = std::min(nt, 32);
         if (const char* e = getenv("CC_HOST_THREADS")) nt = std::max(1, atoi(e));
         if (count <= 65536) nt = 1;
+        /* every row costs up to seven cache misses at unrelated addresses: ask for the lines of the row PF ahead while
+         * this one is copied (the survivor indices are known), so that each thread keeps ~PF x 7 misses in flight */
+        const int64_t PF = 12;
 #pragma omp parallel for schedule(static) num_threads(nt)
         for (int64_t r = 0; r < count; ++r) {
+            if (r + PF < count) {
+                const int64_t p = index[r + PF] - base;
+                if (host->vx) __builtin_prefetch(in.vx + p);
+                if (host->vy) __builtin_prefetch(in.vy + p);
+                if (host->vz) __builtin_prefetch(in.vz + p);
+                if (host->redshift) __builtin_prefetch(in.a + p);
+                if (host->id) __builtin_prefetch(in.id + p);
+                if (host->rotation) __builtin_prefetch(in.rotation + p);
+                if (host->replication) __builtin_prefetch(in.replication + p);
+            }
             const int64_t g = index[r] - base;
             if (host->vx) host->vx[r] = in.vx[g];
             if (host->vy) host->vy[r] = in.vy[g];

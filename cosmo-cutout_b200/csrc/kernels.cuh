@@ -145,6 +145,15 @@ __device__ __forceinline__ unsigned int load_tile(const float* __restrict__ x, c
     }
     return valid;
 }
+/* ask the L2 for the 256-particle tile that starts at `base` (3 columns x 8 lines of 128 B: lanes 0-23, one line each), so
+ * that the warp's next load_tile finds it there instead of waiting for DRAM */
+__device__ __forceinline__ void prefetch_tile(const float* __restrict__ x, const float* __restrict__ y,
+                                              const float* __restrict__ z, long long base, long long n, int lane) {
+    if (lane < 24 && base + SCAN_TILE <= n) {
+        const float* col = lane < 8 ? x : (lane < 16 ? y : z);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(col + base + (lane & 7) * 32));
+    }
+}
 /* index inside the tile of element j of this lane */
 __device__ __forceinline__ unsigned int tile_local(int lane, int j) { return (unsigned)((j >> 2) * 128 + 4 * lane + (j & 3)); }
 
@@ -221,6 +230,7 @@ struct SegScanArgs {
     unsigned long long* seg_info;     /* [nseg] (first record inside the warp's region << 32) | survivors */
     unsigned long long* result;       /* [1] += pre-filter candidates, [3] = max records any warp wanted */
     unsigned int nseg, ntiles;
+    int prefetch;                     /* L2-prefetch the warp's next tile while this one is worked on */
 };
 /* The ring keeps the candidate's position, not only its index: reading x,y,z again in the drain was measured (an
  * index-only ring, 8 KB instead of 32 KB per CTA): the streaming loads are evict-first, the re-reads missed the L2 and
@@ -313,6 +323,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k1s_scan(const __grid_constan
             const long long base = (long long)tile * SCAN_TILE;
             float px[8], py[8], pz[8];
             const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+            if (a.prefetch) { /* the tile this warp loads next: the following one, or the first of its next segment */
+                const unsigned int nxt = tile + 1 < tile_end ? tile + 1 : (seg + total_warps) * K1S_TILES;
+                prefetch_tile(a.x, a.y, a.z, (long long)nxt * SCAN_TILE, a.n, lane);
+            }
             unsigned int m = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) m |= (unsigned)k1_prefilter(px[j], py[j], pz[j], a) << j;
@@ -656,6 +670,7 @@ struct HaloArgs {
     unsigned long long* nan_count;   /* scanned particles whose un-rotated theta is NaN (stat; capi.cu cc_last_stats_ex) */
     int total_halos;
     unsigned int ntiles;
+    int prefetch;                    /* L2-prefetch the warp's next tile while this one is worked on */
 };
 
 /* exact path for one (particle, halo) pair */
@@ -773,6 +788,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2_cutout_halo(const HaloArgs
         const long long base = (long long)tile * SCAN_TILE;
         float px[8], py[8], pz[8];
         const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+        if (a.prefetch) prefetch_tile(a.x, a.y, a.z, base + (long long)total_warps * SCAN_TILE, a.n, lane);
         /* per-particle quantities shared by all halos; out-of-range particles are always candidates */
         float pc[8], pt[8];
         unsigned int insane = 0;
@@ -1325,6 +1341,7 @@ struct SiftArgs {
     unsigned int* cand_count;     /* [warps] */
     unsigned long long* misc;     /* [2] = max candidates any warp wanted (region overflow check) */
     unsigned int ntiles;
+    int prefetch;                 /* L2-prefetch the warp's next tile while this one is worked on */
 };
 template <bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k2c_sift(const __grid_constant__ SiftArgs a) {
@@ -1336,6 +1353,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k2c_sift(const __grid_constan
         const long long base = (long long)tile * SCAN_TILE;
         float px[8], py[8], pz[8];
         const unsigned int valid = load_tile<VEC>(a.x, a.y, a.z, base, a.n, lane, px, py, pz);
+        if (a.prefetch) prefetch_tile(a.x, a.y, a.z, base + (long long)total_warps * SCAN_TILE, a.n, lane);
         unsigned int m = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
