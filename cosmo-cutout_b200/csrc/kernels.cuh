@@ -1931,8 +1931,11 @@ __global__ void __launch_bounds__(256) k4_exchange_peer(const XchgArgs a) {
  * re-runs the cutout through the general kernels. */
 constexpr int K3S_THREADS = 512;
 constexpr int K3S_RANK_MAX = 1024; /* up to here rows come from counting, beyond from the bitonic network */
-constexpr size_t K3S_SMEM_BYTES = (size_t)K3_SORT_MAX * (sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
-                                  (size_t)K3S_THREADS * sizeof(unsigned long long);
+constexpr size_t K3S_STAGE_OFF = (size_t)K3_SORT_MAX * (sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
+                                 (size_t)K3S_THREADS * sizeof(unsigned long long);
+/* counting path: every record and the columns gathered for it wait in shared memory at the record's ROW (64 B each) */
+struct __align__(16) K3sRow { Rec rec; Payload cols; };
+constexpr size_t K3S_SMEM_BYTES = K3S_STAGE_OFF + (size_t)K3S_RANK_MAX * sizeof(K3sRow);
 struct SmallArgs {
     GatherArgs g;                        /* recs = the UNbucketed records (rec_a) */
     const unsigned long long* counts;    /* [H] survivors per halo */
@@ -1972,6 +1975,41 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
         k3s_publish(a);
         return;
     }
+    /* counting path (below): the owner's loads go out first, so that they travel while the halo counts are scanned */
+    const bool ranked = nrec <= K3S_RANK_MAX;
+    K3sRow* s_row = reinterpret_cast<K3sRow*>(s_raw + K3S_STAGE_OFF);
+    constexpr int PER = K3S_RANK_MAX / K3S_THREADS;
+    const unsigned int n8 = ((unsigned int)nrec + 7u) & ~7u;
+    Rec rec[PER];
+    Payload cols[PER];
+    if (ranked) {
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const unsigned int i = tid + r * K3S_THREADS;
+            if (i < nrec) {
+                rec[r] = a.g.recs[i];
+                s_key[i] = rec[r].key;
+                s_halo[i] = (unsigned short)rec[r].halo;
+            } else if (i < n8) { s_key[i] = ~0ull; s_halo[i] = 0xffffu; }
+        }
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const unsigned int i = tid + r * K3S_THREADS;
+            cols[r] = Payload{0.f, 0.f, 0.f, 0.f, 0ll, 0, 0};
+            if (i < nrec) {
+                const long long g = (long long)(rec[r].key & 0xffffffffull);
+                if (a.g.payload) cols[r] = load_payload(a.g.payload + g);
+                else if (a.g.in.a) {
+                    cols[r].a = a.g.in.a[g];
+                    cols[r].id = a.g.in.id[g];
+                    if (!a.g.pos_only) {
+                        cols[r].vx = a.g.in.vx[g]; cols[r].vy = a.g.in.vy[g]; cols[r].vz = a.g.in.vz[g];
+                        cols[r].rot = a.g.in.rot[g]; cols[r].rep = a.g.in.rep[g];
+                    }
+                }
+            }
+        }
+    }
     /* exclusive scan of the halo counts -> seg_begin (read back by the host) */
     {
         const int per = (a.H + K3S_THREADS - 1) / K3S_THREADS;
@@ -2002,6 +2040,74 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
         for (int i = tid * per; i < min(a.H, (int)(tid + 1) * per); ++i) { a.seg_begin[i] = run; run += a.counts[i]; }
         if (tid == K3S_THREADS - 1) a.seg_begin[a.H] = run;
     }
+    if (ranked) {
+        /* a cluster-sized cutout (a few hundred records): every record counts the records in front of it -- (halo, key)
+         * pairs are unique -- and that count IS its row.  The kernel is one chain of dependent memory round trips on a
+         * single SM, so the chain is kept short: the thread that owns a record loads it once, asks for its gather
+         * columns BEFORE the counting loop (their DRAM latency hides behind it), and parks both in shared memory at the
+         * record's row; the row-major writer below then touches no global memory but the output. */
+        __syncthreads();
+        unsigned int row[PER];
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const unsigned int i = tid + r * K3S_THREADS;
+            unsigned int before = 0;
+            if (i < nrec) {
+                const unsigned long long ki = rec[r].key;
+                if (a.H == 1) {
+                    /* one halo: keys alone order the records; eight independent comparisons per trip */
+                    for (unsigned int j = 0; j < n8; j += 8) {
+                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(s_key + j);
+                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(s_key + j + 2);
+                        const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(s_key + j + 4);
+                        const ulonglong2 k3 = *reinterpret_cast<const ulonglong2*>(s_key + j + 6);
+                        before += (unsigned int)(k0.x < ki) + (unsigned int)(k0.y < ki) + (unsigned int)(k1.x < ki) +
+                                  (unsigned int)(k1.y < ki) + (unsigned int)(k2.x < ki) + (unsigned int)(k2.y < ki) +
+                                  (unsigned int)(k3.x < ki) + (unsigned int)(k3.y < ki);
+                    }
+                } else {
+                    const unsigned int hi = rec[r].halo & 0xffffu;
+                    for (unsigned int j = 0; j < n8; j += 4) {
+                        const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(s_key + j);
+                        const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(s_key + j + 2);
+                        const uint2 hh = *reinterpret_cast<const uint2*>(s_halo + j);
+                        const unsigned int h0 = hh.x & 0xffffu, h1 = hh.x >> 16, h2 = hh.y & 0xffffu, h3 = hh.y >> 16;
+                        before += (unsigned int)((h0 < hi) | ((h0 == hi) & (k0.x < ki))) +
+                                  (unsigned int)((h1 < hi) | ((h1 == hi) & (k0.y < ki))) +
+                                  (unsigned int)((h2 < hi) | ((h2 == hi) & (k1.x < ki))) +
+                                  (unsigned int)((h3 < hi) | ((h3 == hi) & (k1.y < ki)));
+                    }
+                }
+            }
+            row[r] = before;
+        }
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const unsigned int i = tid + r * K3S_THREADS;
+            if (i < nrec) { s_row[row[r]].rec = rec[r]; s_row[row[r]].cols = cols[r]; }
+        }
+        __syncthreads();
+        for (unsigned int o = tid; o < nrec; o += K3S_THREADS) {
+            if ((long long)o >= a.g.out_cap) continue;
+            const Rec r = s_row[o].rec;
+            const Payload p = s_row[o].cols;
+            a.g.out.theta[o] = r.th;
+            a.g.out.phi[o] = r.ph;
+            a.g.out.x[o] = r.x;
+            a.g.out.y[o] = r.y;
+            a.g.out.z[o] = r.z;
+            if (a.g.payload || a.g.in.a) {
+                a.g.out.redshift[o] = a_to_z_dev(p.a);
+                a.g.out.id[o] = p.id;
+                if (!a.g.pos_only) { a.g.out.vx[o] = p.vx; a.g.out.vy[o] = p.vy; a.g.out.vz[o] = p.vz; a.g.out.rot[o] = p.rot; a.g.out.rep[o] = p.rep; }
+            }
+            a.g.out.theta_u[o] = __int_as_float((int)(r.key >> 32));
+            a.g.out.index[o] = a.g.index_base + (long long)(r.key & 0xffffffffull);
+        }
+        if (a.do_xchg) xchg_finish(a.x, &s_xchg_timeout);
+        k3s_publish(a);
+        return;
+    }
     unsigned int n = 32;
     while (n < nrec) n <<= 1;
     for (unsigned int i = tid; i < n; i += K3S_THREADS) {
@@ -2010,32 +2116,6 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
         s_idx[i] = (unsigned short)i;
     }
     __syncthreads();
-    if (nrec <= K3S_RANK_MAX) {
-        /* a cluster-sized cutout (a few hundred records): every record counts the records in front of it -- (halo, key)
-         * pairs are unique -- and that count IS its row; two barriers instead of the 45 of a 512-element network */
-        unsigned short row[K3S_RANK_MAX / K3S_THREADS];
-#pragma unroll
-        for (int r = 0; r < K3S_RANK_MAX / K3S_THREADS; ++r) {
-            const unsigned int i = tid + r * K3S_THREADS;
-            unsigned int before = 0;
-            if (i < nrec) {
-                const unsigned long long ki = s_key[i];
-                const unsigned short hi = s_halo[i];
-                for (unsigned int j = 0; j < (unsigned int)nrec; ++j) {
-                    const unsigned short hj = s_halo[j];
-                    before += (hj < hi) || (hj == hi && s_key[j] < ki);
-                }
-            }
-            row[r] = (unsigned short)before;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < K3S_RANK_MAX / K3S_THREADS; ++r) {
-            const unsigned int i = tid + r * K3S_THREADS;
-            if (i < nrec) s_idx[row[r]] = (unsigned short)i;
-        }
-        __syncthreads();
-    } else
     for (unsigned int k = 2; k <= n; k <<= 1) {
         for (unsigned int j = k >> 1; j > 0; j >>= 1) {
             for (unsigned int t = tid; t < (n >> 1); t += K3S_THREADS) {
