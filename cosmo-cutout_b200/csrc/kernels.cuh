@@ -451,8 +451,7 @@ __global__ void __launch_bounds__(TSCAN_THREADS) k1s_seg_scan(const SegPrefixArg
                     a.host_result[0] = carry + exclusive + block_total;
                     a.host_result[1] = a.result[1];
                     a.host_result[2] = carry;
-                    a.host_result[3] = a.result[3];
-                    __threadfence_system();
+                    a.host_result[3] = a.result[3]; /* read by the host after the stream has drained: no fence */
                 }
             }
         }
@@ -1913,7 +1912,7 @@ __device__ __forceinline__ void xchg_finish(const XchgArgs& a, int* s_timeout) {
         a.offsets[h] = run;
         a.host_offsets[h] = run;
     }
-    __threadfence_system();
+    /* the host reads its copies after the stream has drained (cc_exchange_counts): no system-wide fence */
 }
 
 __global__ void __launch_bounds__(256) k4_exchange_peer(const XchgArgs a) {
@@ -1955,7 +1954,8 @@ __device__ __forceinline__ void k3s_publish(const SmallArgs& a) {
     const unsigned int nout = 8u + 3u * (unsigned int)a.H + 1u;
     for (unsigned int i = threadIdx.x; i < nout; i += K3S_THREADS) a.host_out[i] = a.misc[i];
     for (unsigned int i = threadIdx.x; i < 2u * (unsigned int)a.H; i += K3S_THREADS) a.xchg_send[i] = a.counts[i];
-    __threadfence_system();
+    /* no system-wide fence: the host reads host_out only after the stream has drained (cc_cutout_sync), which makes
+     * every store of this kernel visible; a fence here made the one CTA wait for the PCIe writes in mid-kernel */
     __syncthreads();
     for (unsigned int i = threadIdx.x; i < a.state_elems; i += K3S_THREADS) a.misc[i] = 0ull;
 }
@@ -1967,27 +1967,35 @@ __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
     unsigned long long* s_part = reinterpret_cast<unsigned long long*>(s_raw + (size_t)K3_SORT_MAX * 12);
     const unsigned int tid = threadIdx.x;
     __shared__ int s_xchg_timeout;
+    /* one CTA on one SM: the kernel is a chain of memory round trips, so everything that can travel together does.
+     * The record count, the first K3S_RANK_MAX records (speculatively: the buffer is at least that large or the load
+     * is skipped) and -- exchange=eager -- the NVLink stores of the counts to every peer all leave before anything
+     * waits; the peers' posts arrive while this CTA orders and gathers. */
     const unsigned long long nrec = *a.g.rec_count;
-    if (a.do_xchg) xchg_post(a.x); /* NVLink stores to every peer; their posts arrive while this CTA orders and gathers */
+    K3sRow* s_row = reinterpret_cast<K3sRow*>(s_raw + K3S_STAGE_OFF);
+    constexpr int PER = K3S_RANK_MAX / K3S_THREADS;
+    Rec rec[PER];
+    Payload cols[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const unsigned int i = tid + r * K3S_THREADS;
+        rec[r] = Rec{0ull, 0u, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (i < a.g.rec_cap) rec[r] = a.g.recs[i];
+    }
+    if (a.do_xchg) xchg_post(a.x);
     if (nrec > K3_SORT_MAX || nrec > a.g.rec_cap) {
         if (tid == 0) a.misc[4] = 1ull;
         if (a.do_xchg) xchg_finish(a.x, &s_xchg_timeout);
         k3s_publish(a);
         return;
     }
-    /* counting path (below): the owner's loads go out first, so that they travel while the halo counts are scanned */
     const bool ranked = nrec <= K3S_RANK_MAX;
-    K3sRow* s_row = reinterpret_cast<K3sRow*>(s_raw + K3S_STAGE_OFF);
-    constexpr int PER = K3S_RANK_MAX / K3S_THREADS;
     const unsigned int n8 = ((unsigned int)nrec + 7u) & ~7u;
-    Rec rec[PER];
-    Payload cols[PER];
     if (ranked) {
 #pragma unroll
         for (int r = 0; r < PER; ++r) {
             const unsigned int i = tid + r * K3S_THREADS;
             if (i < nrec) {
-                rec[r] = a.g.recs[i];
                 s_key[i] = rec[r].key;
                 s_halo[i] = (unsigned short)rec[r].halo;
             } else if (i < n8) { s_key[i] = ~0ull; s_halo[i] = 0xffffu; }
