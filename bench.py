@@ -65,6 +65,10 @@ WORKLOADS = {
     "cfg5": dict(uc=2, n=125_000_000, halos="random1000", kind=0, box=300.0, scaling="weak",
                  desc="BASELINE cfg5: 1000 halo cutouts, boxLength 5/10/20/30 arcmin (250 halos each = four processLC-style "
                       "passes, one boxLength per pass), 125M-particle resident shard per GPU (1B on 8 GPUs)"),
+    "cfg5_shared": dict(uc=2, n=125_000_000, halos="random1000_shared", kind=0, box=300.0, scaling="weak",
+                        desc="BASELINE cfg5 as host/processLC.cpp's processLC_boxes (lc_cutout --boxLength 5 10 20 30) runs it: the "
+                             "same 1000 (halo, boxLength 5/10/20/30) cutouts as cfg5, same results, in ONE pass over the "
+                             "125M-particle resident shard (the device pass takes per-halo bounds)"),
     "cfg5_onepass": dict(uc=2, n=125_000_000, halos="random1000_15", kind=0, box=300.0, scaling="weak",
                          desc="cfg5 through the C ABI instead of processLC: the same 1000 halos, all with boxLength 15 arcmin, in ONE "
                               "pass over the 125M-particle resident shard (round 1's cfg5 figure; the C ABI takes per-halo bounds)"),
@@ -144,6 +148,11 @@ def halo_groups(wl):
         rng = np.random.default_rng(1000)
         pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
         return [(15.0, [(tuple(float(v) for v in p), 15.0) for p in pos])]
+    if wl["halos"] == "random1000_shared":
+        rng = np.random.default_rng(1000)
+        pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
+        per = len(pos) // len(BOX_GROUPS)
+        return [(0.0, [(tuple(float(v) for v in p), BOX_GROUPS[min(i // per, len(BOX_GROUPS) - 1)]) for i, p in enumerate(pos)])]
     if wl["halos"] == "random1000":
         rng = np.random.default_rng(1000)
         pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
@@ -333,7 +342,7 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
             traffic = json.load(open(tp)).get(name)
         except Exception:
             traffic = None
-    kernel = {1: "k1s_scan", 2: "k2c_sift+k2c_match+k2c_exact" if nhalos >= 8 else "k2_cutout_halo"}[wl["uc"]]
+    kernel = st["scan_kernels"]  # of the last pass: the library picks the cell-index walker per halo set
     out = {
         "metric": "Gparticles/s filtered", "value": round(value, 3), "unit": "Gparticles/s", "n_gpus": env.world,
         "steps": steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 4),
@@ -783,7 +792,7 @@ def run_ours(args):
         out = run_resident(env, args, args.workload, args.steps, args.warmup, with_e2e=True)
     if not args.no_configs and args.workload == "cfg2":
         configs = {}
-        for name in ("cfg1", "const1b", "cfg4", "cfg5", "cfg5_onepass", "cfg3"):
+        for name in ("cfg1", "const1b", "cfg4", "cfg5", "cfg5_shared", "cfg5_onepass", "cfg3"):
             t0 = time.perf_counter()
             try:
                 r = run_cfg3(env, args, 2, 1) if name == "cfg3" else run_resident(env, args, name, sub_steps, sub_warm, with_e2e=False)

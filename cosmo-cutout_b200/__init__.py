@@ -422,11 +422,12 @@ class Context:
         return dict(scanned=int(out[0]), candidates=int(out[1]), survivors=int(out[2]), rough=int(out[3]))
 
     def stats_ex(self):
-        out = np.zeros(8, dtype=np.int64)
-        _check(lib().cc_last_stats_ex(self._h, _ptr(out), 8))
+        out = np.zeros(9, dtype=np.int64)
+        _check(lib().cc_last_stats_ex(self._h, _ptr(out), 9))
         return dict(scanned=int(out[0]), candidates=int(out[1]), survivors=int(out[2]), rough=int(out[3]),
                     nan_theta=int(out[4]), payload_resident=bool(out[5]), payload_build_ms=out[6] / 1000.0,
-                    tail_dropped=int(out[7]))
+                    tail_dropped=int(out[7]),
+                    scan_kernels=("k1s_scan", "k2_cutout_halo", "k2c_sift+k2c_match+k2c_exact", "k2_cutout_halo_cells")[int(out[8])])
 
     def set_option(self, key, value):
         """cc_set_option: payload=auto|always|never, exchange=auto|nccl|peer, gather=auto|ldst|bulk"""

@@ -1841,6 +1841,7 @@ int cc_last_stats_ex(cc_ctx* c, int64_t* out, int n) {
         else cudaGetLastError();
     }
     v[7] = (c->pending == P_HALO) ? c->n - c->stats[0] : 0;
+    v[8] = (c->pending != P_HALO) ? 0 : !c->use_bins ? 1 : c->used_mono ? 3 : 2;
     for (int i = 0; i < n && i < CC_STATS_EX_FIELDS; ++i) out[i] = v[i];
     return CC_OK;
 }

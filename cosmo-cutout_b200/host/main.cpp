@@ -9,9 +9,10 @@
  *             [--verbose] [--timeit] [--overwrite] [--posOnly] [--forceWriteProps] [--propsOnly]
  *
  * Extension: --boxLength takes one value like the reference, or SEVERAL (--boxLength 5 10 20 30).  With several, the
- * run is what separate invocations with each value would be -- the reference's processLC has one boxLength per call
- * (processLC.h:46) -- except that each size writes under <output dir>/boxLength_<value>/ and that the lightcone steps
- * read for the first size stay resident in HBM for the others (no second file read, no second upload).
+ * results are what separate invocations with each value would write -- the reference's processLC has one boxLength
+ * per call (processLC.h:46) -- under <output dir>/boxLength_<value>/, but every lightcone step is read, uploaded and
+ * scanned ONCE for all sizes (cchost::processLC_boxes: the device pass takes per-halo bounds).  CC_BOX_PASSES=separate
+ * runs one processLC call per size instead, with the steps of the first call kept resident in HBM for the others.
  *
  * Where the reference is started under mpirun with one rank per core, this is ONE process that drives every
  * visible GPU (or CC_NGPUS of them); "ranks" in its log lines are GPUs.
@@ -175,6 +176,7 @@ int main(int argc, char** argv) {
         }
         return dirs;
     };
+    const bool separate_passes = getenv("CC_BOX_PASSES") && !strcmp(getenv("CC_BOX_PASSES"), "separate");
     vector<vector<string>> halo_out_dirs_of;
     if (boxLengths.size() <= 1) {
         halo_out_dirs_of.push_back(halo_dirs_under(out_dir));
@@ -199,7 +201,8 @@ int main(int argc, char** argv) {
         else {
             cout << endl << "box lengths:";
             for (float b : boxLengths) cout << " " << b;
-            cout << " arcmin (one pass each; lightcone steps stay resident in HBM between passes)" << endl;
+            cout << (separate_passes ? " arcmin (one pass each; lightcone steps stay resident in HBM between passes)"
+                                     : " arcmin (all sizes share one pass over every lightcone step)") << endl;
         }
     } else {
         cout << "theta bounds: " << theta_cut[0] / ARCSEC << " -> " << theta_cut[1] / ARCSEC << " deg" << endl;
@@ -212,8 +215,11 @@ int main(int argc, char** argv) {
 
     const double start = wall_seconds();
     if (const char* e = getenv("CC_RESIDENT_STEPS")) resident_steps_enable(atoi(e) != 0);
-    if (boxLengths.size() > 1) resident_steps_enable(true);
-    if (customHalo || customHaloFile)
+    if (boxLengths.size() > 1 && separate_passes) resident_steps_enable(true);
+    if ((customHalo || customHaloFile) && boxLengths.size() > 1 && !separate_passes)
+        processLC_boxes(input_lc_dir, halo_out_dirs_of, step_strings, haloPos, haloProps, boxLengths, myrank, numranks,
+                        verbose, timeit, overwrite, positionOnly, forceWriteProps, propsOnly);
+    else if (customHalo || customHaloFile)
         for (size_t b = 0; b < boxLengths.size(); ++b) {
             if (boxLengths.size() > 1) cout << "\n\n########## box length " << boxLengths[b] << " arcmin ##########" << endl;
             processLC(input_lc_dir, halo_out_dirs_of[b], step_strings, haloPos, haloProps, boxLengths[b], myrank, numranks,

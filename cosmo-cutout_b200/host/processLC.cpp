@@ -480,13 +480,18 @@ void processLC(string dir_name, string out_dir, vector<string> step_strings, vec
 /* =====================================================================================================
  * use case 2 (reference processLC.cpp:440-1757)
  * ===================================================================================================== */
-void processLC(string dir_name, vector<string> out_dirs, vector<string> step_strings, vector<float> halo_pos,
-               vector<float> halo_props, float boxLength, int myrank, int numranks, bool verbose, bool timeit,
-               bool overwrite, bool positionOnly, bool forceWriteProps, bool propsOnly) {
+/* the body of use case 2 with ONE BOX LENGTH PER HALO: the reference's entry point passes the same value for every
+ * halo; cchost::processLC_boxes passes the (halo, box length) pairs of several calls so that they share one device
+ * pass per step (every pair is an independent cutout with its own bounds, rotation and output directory) */
+static void process_halo_list(const string& dir_name, const vector<string>& out_dirs, const vector<string>& step_strings,
+                              const vector<float>& halo_pos, const vector<float>& halo_props,
+                              const vector<float>& box_of_halo, int myrank, int numranks, bool verbose, bool timeit,
+                              bool overwrite, bool positionOnly, bool forceWriteProps, bool propsOnly) {
     if (myrank != 0) die("processLC: this implementation is one process driving all GPUs; call it with myrank == 0");
     const string subdirPrefix = find_prefix(dir_name, true);
     const int numHalos = (int)(halo_pos.size() / 3);
     if ((int)out_dirs.size() != numHalos) die("processLC: one output directory per halo is required");
+    if ((int)box_of_halo.size() != numHalos) die("processLC: one box length per halo is required");
 
     /* ---------------- per-halo bounds + rotation (host, O(1) per halo; reference :512-770) ---------------- */
     cout << "\n\n---------- Setting up for coordinate rotation ----------" << endl;
@@ -501,7 +506,7 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
         const bool printHalo = (numHalos < 20) || (h % 100 == 0);
         const float pos[3] = {halo_pos[3 * h], halo_pos[3 * h + 1], halo_pos[3 * h + 2]};
         cc_halo_info info;
-        check(cc_halo_setup(pos, boxLength, &info));
+        check(cc_halo_setup(pos, box_of_halo[(size_t)h], &info));
         halos[(size_t)h] = info.halo;
         const cc_halo& H = info.halo;
         if (printHalo) {
@@ -760,3 +765,33 @@ void processLC(string dir_name, vector<string> out_dirs, vector<string> step_str
         print_times("write_times", write_times);
     }
 }
+
+void processLC(string dir_name, vector<string> out_dirs, vector<string> step_strings, vector<float> halo_pos,
+               vector<float> halo_props, float boxLength, int myrank, int numranks, bool verbose, bool timeit,
+               bool overwrite, bool positionOnly, bool forceWriteProps, bool propsOnly) {
+    const vector<float> box_of_halo(halo_pos.size() / 3, boxLength);
+    process_halo_list(dir_name, out_dirs, step_strings, halo_pos, halo_props, box_of_halo, myrank, numranks, verbose,
+                      timeit, overwrite, positionOnly, forceWriteProps, propsOnly);
+}
+
+namespace cchost {
+void processLC_boxes(const string& dir_name, const vector<vector<string>>& out_dirs_of_box,
+                     const vector<string>& step_strings, const vector<float>& halo_pos, const vector<float>& halo_props,
+                     const vector<float>& boxLengths, int myrank, int numranks, bool verbose, bool timeit, bool overwrite,
+                     bool positionOnly, bool forceWriteProps, bool propsOnly) {
+    const size_t H = halo_pos.size() / 3, B = boxLengths.size();
+    if (out_dirs_of_box.size() != B) die("processLC_boxes: one list of output directories per box length is required");
+    const size_t P = H ? halo_props.size() / H : 0;
+    vector<string> out_dirs;
+    vector<float> pos, props, box;
+    for (size_t b = 0; b < B; ++b) {
+        if (out_dirs_of_box[b].size() != H) die("processLC_boxes: one output directory per halo and box length is required");
+        out_dirs.insert(out_dirs.end(), out_dirs_of_box[b].begin(), out_dirs_of_box[b].end());
+        pos.insert(pos.end(), halo_pos.begin(), halo_pos.end());
+        props.insert(props.end(), halo_props.begin(), halo_props.begin() + (ptrdiff_t)(P * H));
+        box.insert(box.end(), H, boxLengths[b]);
+    }
+    process_halo_list(dir_name, out_dirs, step_strings, pos, props, box, myrank, numranks, verbose, timeit, overwrite,
+                      positionOnly, forceWriteProps, propsOnly);
+}
+}  // namespace cchost

@@ -34,6 +34,15 @@ namespace cchost {
  * Off by default (one call cuts each step once and then streams only x,y,z); lc_cutout turns it on when several
  * --boxLength values are given; CC_RESIDENT_STEPS=1 in the environment does the same. */
 void resident_steps_enable(bool on);
+/* Extension: the cutouts of SEVERAL processLC calls that differ only in boxLength (and output directories) as one
+ * call: entry b of out_dirs_of_box lists one directory per halo for boxLengths[b].  Every (halo, box length) pair is an
+ * independent cutout -- files identical to those of the separate calls -- but each lightcone step is read, uploaded and
+ * scanned ONCE for all of them (the device pass takes per-halo bounds; the reference's one-boxLength-per-call signature,
+ * processLC.h:46, is why BASELINE config 5 otherwise needs a pass per size). */
+void processLC_boxes(const std::string& dir_name, const std::vector<std::vector<std::string>>& out_dirs_of_box,
+                     const std::vector<std::string>& step_strings, const std::vector<float>& halo_pos,
+                     const std::vector<float>& halo_props, const std::vector<float>& boxLengths, int myrank, int numranks,
+                     bool verbose, bool timeit, bool overwrite, bool positionOnly, bool forceWriteProps, bool propsOnly);
 /* destroy the GPU contexts (call before main returns; never from a static destructor) */
 void shutdown_gpus();
 }  // namespace cchost

@@ -224,8 +224,10 @@ int cc_last_stats(cc_ctx* ctx, int64_t out[4]);
  * contract and what the reference then returns for the OTHER particles is unspecified, so parity is only claimed for
  * steps where this is 0 (lc_cutout warns otherwise); [5] 1 when the interleaved gather payload of the resident step
  * exists; [6] microseconds the last cutout call spent building it (0: it did not); [7] use case 2: particles of this
- * shard behind n_limit_global (the reference's tail drop, util.cpp:106-108). */
-#define CC_STATS_EX_FIELDS 8
+ * shard behind n_limit_global (the reference's tail drop, util.cpp:106-108); [8] which scan ran: 0 use case 1,
+ * 1 use case 2 every particle against every halo (k2_cutout_halo), 2 the cell index walked by the staged kernels
+ * (k2c_sift, k2c_match, k2c_exact), 3 by one kernel (k2_cutout_halo_cells). */
+#define CC_STATS_EX_FIELDS 9
 int cc_last_stats_ex(cc_ctx* ctx, int64_t* out, int n);
 
 /* ------------------------------------------------------------------ tuning switches (defaults are the measured best)

@@ -192,12 +192,14 @@ def test_cli_reads_genericio_format_input(tmp_path):
 
 @pytest.mark.gpu
 @needs_ref_bin
+@pytest.mark.parametrize("passes", ["shared", "separate"])
 @pytest.mark.parametrize("ngpus", [1, 2])
-def test_cli_several_box_lengths_keep_steps_resident(lc_dirs, tmp_path, ngpus):
-    """extension over the reference CLI: --boxLength with several values = one processLC pass per value (the
-    reference's API has one boxLength per call, processLC.h:46; BASELINE config 5).  Each value's tree equals a
-    separate reference run with that value, and after the first pass the lightcone steps are found resident in HBM:
-    the later passes copy ZERO bytes of step columns host->device and read no input file."""
+def test_cli_several_box_lengths_keep_steps_resident(lc_dirs, tmp_path, ngpus, passes):
+    """extension over the reference CLI: --boxLength with several values (the reference's API has one boxLength per
+    call, processLC.h:46; BASELINE config 5).  Each value's tree equals a separate reference run with that value.
+    Default ("shared"): all (halo, box length) pairs share ONE device pass per lightcone step (processLC_boxes) --
+    every step is read and uploaded once.  CC_BOX_PASSES=separate: one processLC call per value; after the first
+    call the steps are found resident in HBM, the later calls copy ZERO bytes host->device and read no input file."""
     if ngpus > cc.lib().cc_device_count():
         pytest.skip(f"{ngpus} GPUs needed")
     import re
@@ -208,7 +210,10 @@ def test_cli_several_box_lengths_keep_steps_resident(lc_dirs, tmp_path, ngpus):
     boxes = ["30", "120", "75.5"]
     ours = tmp_path / "ours"
     ours.mkdir()
-    a = _run(cc.CLI_PATH, [lc_dirs, ours, 0.0, 0.06, "-f", hf, "-b"] + boxes, env={"CC_NGPUS": str(ngpus)})
+    env = {"CC_NGPUS": str(ngpus)}
+    if passes == "separate":
+        env["CC_BOX_PASSES"] = "separate"
+    a = _run(cc.CLI_PATH, [lc_dirs, ours, 0.0, 0.06, "-f", hf, "-b"] + boxes, env=env)
     for b in boxes:
         ref = tmp_path / f"ref_{b}"
         ref.mkdir()
@@ -217,8 +222,13 @@ def test_cli_several_box_lengths_keep_steps_resident(lc_dirs, tmp_path, ngpus):
         assert len(files) == 9 * (1 + 2 * 12)
     moved = [int(m) for m in re.findall(r"step columns copied host->device in this call: (\d+) bytes", a.stdout)]
     found = re.findall(r"resident steps: (\d+) found in HBM, (\d+) read and uploaded", a.stdout)
-    assert len(moved) == 3 and moved[0] == 2 * 200_000 * 44 and moved[1] == 0 and moved[2] == 0, moved
-    assert found == [("0", "2"), ("2", "0"), ("2", "0")], found
+    if passes == "separate":
+        assert len(moved) == 3 and moved[0] == 2 * 200_000 * 44 and moved[1] == 0 and moved[2] == 0, moved
+        assert found == [("0", "2"), ("2", "0"), ("2", "0")], found
+    else:
+        # one call: x,y,z of both steps streamed once for the 27 cutouts (the other columns are picked on the host)
+        assert len(moved) == 1 and moved[0] == 2 * 200_000 * 12, moved
+        return
     # use case 1 shares the cache machinery (CC_RESIDENT_STEPS=1): same bytes as the streamed default
     o1, o2 = tmp_path / "c1", tmp_path / "c2"
     o1.mkdir(); o2.mkdir()

@@ -709,13 +709,16 @@ def test_many_halos_at_size_sample_parity(ctx):
     pos = rng.uniform(30.0, 280.0, (1000, 3)).astype(np.float32)
     limit = cc.ref_scatter_kept(n, 1)
     checked = 0
+    per_group, all_halos = [], []
     for g, box in enumerate((5.0, 10.0, 20.0, 30.0)):
         hp = pos[g * 250:(g + 1) * 250]
         infos = [cc.halo_setup(p, box) for p in hp]
+        all_halos += [i.halo for i in infos]
         ctx.cutout_halo([i.halo for i in infos], n_limit_global=limit)
         counts, rough = ctx.sync()
         assert ctx.stats_ex()["nan_theta"] == 0 and ctx.stats_ex()["tail_dropped"] == n - limit
         everything, off = ctx.fetch_all(counts)
+        per_group.append((counts.copy(), rough.copy(), everything))
         for h in (3, 77, 128, 201, 249):
             hh = infos[h].halo
             sel = np.nonzero((th64 >= hh.theta_rough[0] - 30.0) & (th64 < hh.theta_rough[1] + 30.0))[0]
@@ -726,6 +729,15 @@ def test_many_halos_at_size_sample_parity(ctx):
             H.assert_cols_equal({c: v[off[h]:off[h + 1]] for c, v in everything.items()}, want, what=f"box {box} halo {h}: ")
             checked += 1
     assert checked == 20
+    # the same 1000 (halo, box length) cutouts in ONE pass (host/processLC.cpp processLC_boxes; bench cfg5_shared): every
+    # halo's counts and rows are those of the four separate passes, bit for bit
+    ctx.cutout_halo(all_halos, n_limit_global=limit)
+    counts, rough = ctx.sync()
+    everything, _ = ctx.fetch_all(counts)
+    assert np.array_equal(counts, np.concatenate([p[0] for p in per_group]))
+    assert np.array_equal(rough, np.concatenate([p[1] for p in per_group]))
+    for c in everything:
+        assert np.array_equal(everything[c].view(np.uint8), np.concatenate([p[2][c] for p in per_group]).view(np.uint8)), c
     ctx.release()
 
 
