@@ -422,15 +422,18 @@ class Context:
         return dict(scanned=int(out[0]), candidates=int(out[1]), survivors=int(out[2]), rough=int(out[3]))
 
     def stats_ex(self):
-        out = np.zeros(9, dtype=np.int64)
-        _check(lib().cc_last_stats_ex(self._h, _ptr(out), 9))
+        out = np.zeros(12, dtype=np.int64)
+        _check(lib().cc_last_stats_ex(self._h, _ptr(out), 12))
         return dict(scanned=int(out[0]), candidates=int(out[1]), survivors=int(out[2]), rough=int(out[3]),
                     nan_theta=int(out[4]), payload_resident=bool(out[5]), payload_build_ms=out[6] / 1000.0,
                     tail_dropped=int(out[7]),
-                    scan_kernels=("k1s_scan", "k2_cutout_halo", "k2c_sift+k2c_match+k2c_exact", "k2_cutout_halo_cells")[int(out[8])])
+                    scan_kernels=("k1s_scan", "k2_cutout_halo", "k2c_sift+k2c_match+k2c_exact", "k2_cutout_halo_cells",
+                                  "k2p_plan+k2p_query")[int(out[8])],
+                    particles_read=int(out[9]), index_resident=bool(out[10]), index_build_ms=out[11] / 1000.0)
 
     def set_option(self, key, value):
-        """cc_set_option: payload=auto|always|never, exchange=auto|nccl|peer, gather=auto|ldst|bulk"""
+        """cc_set_option: payload|index=auto|always|never, exchange=auto|nccl|peer|eager, cells=auto|staged|mono,
+        timing=on|off, gather=auto|ldst|bulk"""
         _check(lib().cc_set_option(self._h, key.encode(), value.encode()))
 
     def stream(self):

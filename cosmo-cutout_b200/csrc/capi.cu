@@ -148,7 +148,11 @@ struct StepSlot {
     DevBuf payload;
     bool payload_valid = false;
     int64_t last_survivors = -1;
-    void release() { for (auto& b : col_buf) b.release(); payload.release(); *this = StepSlot(); }
+    DevBuf pidx_sorted, pidx_start; /* particle index of the step (kernels.cuh k2p_*) */
+    bool pidx_valid = false;
+    uint64_t pidx_gen = 0;
+    int64_t many_halo_cutouts = 0;
+    void release() { for (auto& b : col_buf) b.release(); payload.release(); pidx_sorted.release(); pidx_start.release(); *this = StepSlot(); }
 };
 
 }  // namespace
@@ -200,6 +204,19 @@ struct cc_ctx {
     int64_t step_last_survivors = -1; /* survivors of the previous cutout on the resident step (-1: none yet) */
     cudaEvent_t ev_pay0 = nullptr, ev_pay1 = nullptr;
     bool payload_timed = false;       /* the pending cutout built the payload: ev_pay0..ev_pay1 is its duration */
+    /* Particle index of the resident step (kernels.cuh k2p_*): {x, y, z, index} in (cos theta_u, sin phi_u) cell order +
+     * the first row of every cell.  A many-halo cutout on an indexed step reads only the cells under its halos' windows.
+     * Built lazily like the payload: policy auto = inside the SECOND many-halo cutout on the same resident step (a step
+     * that is cut once is cheaper to scan); 16 B/particle + 2 x 16 MB of HBM; dropped when another step becomes resident. */
+    DevBuf pidx_sorted, pidx_start, pidx_tmp, pidx_partial;
+    bool pidx_valid = false;
+    uint64_t pidx_gen = 0, pidx_gen_clock = 0; /* which build: a halo set keeps its plan (k2p_plan) for one */
+    int index_policy = 0;             /* 0 auto, 1 always, 2 never; cc_set_option "index" / CC_INDEX */
+    int64_t step_many_halo_cutouts = 0;
+    cudaEvent_t ev_idx0 = nullptr, ev_idx1 = nullptr;
+    bool index_timed = false;         /* the pending cutout built the index: ev_idx0..ev_idx1 is its duration */
+    bool used_index = false;          /* the pending cutout walked the particle index */
+    int64_t particles_read = 0;       /* by the scan kernel(s) of the last cutout: all scanned ones, or the index rows */
     int xchg_mode = 0;       /* 0 auto (peer mailboxes when attached, else NCCL), 1 NCCL, 2 peer, 3 eager: peer, and a
                                 small use-case-2 cutout does the exchange inside its last kernel; cc_set_option "exchange" */
     bool eager_done = false; /* the pending cutout's last kernel carried the count exchange */
@@ -223,9 +240,14 @@ struct cc_ctx {
         DevBuf pre_buf, halo_buf;
         DevBuf bin_start_buf, bin_bits_buf, bin_items_buf; /* cell index: {first,end} per cell, occupancy bitmap, halo lists */
         std::vector<size_t> bin_items_off;                 /* per launch batch: first item */
+        DevBuf pidx_items_buf;                             /* particle-index walker: (halo, grid line, columns) items */
+        std::vector<size_t> pidx_items_off;                /* per launch batch: first item, number of items */
+        std::vector<unsigned int> pidx_items_cnt;
+        DevBuf pidx_steps_buf;                             /* k2p_plan's prefix of every batch's items (+1 per batch) ... */
+        uint64_t plan_gen = 0;                             /* ... valid for this build of the particle index (0: none) */
         int walker = 0;     /* 0: not measured yet (the staged kernels measure), 1: staged, 2: one kernel */
         uint64_t last_use = 0;
-        void release() { pre_buf.release(); halo_buf.release(); bin_start_buf.release(); bin_bits_buf.release(); bin_items_buf.release(); key.clear(); }
+        void release() { pre_buf.release(); halo_buf.release(); bin_start_buf.release(); bin_bits_buf.release(); bin_items_buf.release(); pidx_items_buf.release(); pidx_steps_buf.release(); plan_gen = 0; key.clear(); }
     };
     static const int MAX_HALO_SETS = 8;
     HaloSet halo_sets[MAX_HALO_SETS];
@@ -573,6 +595,9 @@ int prepare_halo(cc_ctx* c) {
             std::vector<unsigned int> bits((size_t)nbatch * cck::K2_BITWORDS, 0u);
             std::vector<unsigned short> items;
             hs->bin_items_off.assign((size_t)nbatch, 0);
+            std::vector<uint2> pitems; /* particle-index walker: one item per (halo, grid line), then the out-of-range bin */
+            hs->pidx_items_off.assign((size_t)nbatch, 0);
+            hs->pidx_items_cnt.assign((size_t)nbatch, 0);
             for (int bi = 0; bi < nbatch; ++bi) {
                 const int h0 = bi * cck::K2_MAX_HALOS, hn = std::min(cck::K2_MAX_HALOS, H - h0);
                 unsigned int* st = starts.data();
@@ -592,6 +617,15 @@ int prepare_halo(cc_ctx* c) {
                     for (int ic = bx.c0; ic <= bx.c1; ++ic)
                         for (int is = bx.s0; is <= bx.s1; ++is) st[(size_t)ic * G + is + 1] += 1;
                 }
+                hs->pidx_items_off[(size_t)bi] = pitems.size();
+                for (int h = 0; h < hn; ++h) {
+                    const Box& bx = boxes[(size_t)h];
+                    if (bx.s1 < bx.s0) continue;
+                    for (int ic = bx.c0; ic <= bx.c1; ++ic)
+                        pitems.push_back(make_uint2((unsigned int)h | ((unsigned int)ic << 16), (unsigned int)bx.s0 | ((unsigned int)bx.s1 << 16)));
+                }
+                pitems.push_back(make_uint2(cck::K2P_ALL, 0u));
+                hs->pidx_items_cnt[(size_t)bi] = (unsigned int)(pitems.size() - hs->pidx_items_off[(size_t)bi]);
                 for (size_t i = 0; i < ncell; ++i) st[i + 1] += st[i]; /* st[i] = first item of cell i */
                 const size_t base_item = items.size();
                 hs->bin_items_off[(size_t)bi] = base_item;
@@ -621,6 +655,10 @@ int prepare_halo(cc_ctx* c) {
             CU(cudaMemcpyAsync(hs->bin_bits_buf.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, c->stream));
             if (!items.empty())
                 CU(cudaMemcpyAsync(hs->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
+            if ((rc = hs->pidx_items_buf.ensure(pitems.size() * sizeof(uint2)))) return rc;
+            if ((rc = hs->pidx_steps_buf.ensure((pitems.size() + (size_t)nbatch) * 8))) return rc;
+            hs->plan_gen = 0;
+            CU(cudaMemcpyAsync(hs->pidx_items_buf.p, pitems.data(), pitems.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
         }
         CU(cudaMemcpyAsync(hs->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(hs->halo_buf.p, hd.data(), (size_t)H * sizeof(cck::HaloDev), cudaMemcpyHostToDevice, c->stream));
@@ -693,9 +731,31 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             if (occ < 1) occ = 1;
         }
         const unsigned int grid = std::max(1u, std::min((a.ntiles + cck::SCAN_WARPS - 1) / cck::SCAN_WARPS, (unsigned int)(c->sm_count * occ)));
-        const bool mono = c->use_bins && (c->cells_mode == 2 || (c->cells_mode == 0 && c->hs->walker == 2));
-        if (c->use_bins) c->used_mono = mono;
-        if (mono) { /* cell index, one kernel: one 20-warp CTA per SM, bitmap + windows + stacks + counters in shared memory */
+        const bool indexed = c->use_bins && c->pidx_valid && !c->streamed && c->index_policy != 2;
+        const bool mono = !indexed && c->use_bins && (c->cells_mode == 2 || (c->cells_mode == 0 && c->hs->walker == 2));
+        if (c->use_bins) { c->used_mono = mono; c->used_index = indexed; }
+        if (indexed) { /* particle index: only the cells under the halos' windows are read (kernels.cuh k2p_*) */
+            const int bi = h0 / cck::K2_MAX_HALOS;
+            cck::PidxArgs pa;
+            pa.h = a;
+            pa.sorted = (const float4*)c->pidx_sorted.p;
+            pa.start = (const unsigned int*)c->pidx_start.p;
+            pa.items = (const uint2*)c->hs->pidx_items_buf.p + c->hs->pidx_items_off[(size_t)bi];
+            pa.nitems = c->hs->pidx_items_cnt[(size_t)bi];
+            /* the plan (rows of every item -> prefix of 32-particle steps) depends on the halo set and on the index
+             * only: computed in the set's first pass over this index, reused by the later ones */
+            pa.item_step0 = (unsigned long long*)c->hs->pidx_steps_buf.p + c->hs->pidx_items_off[(size_t)bi] + (size_t)bi;
+            pa.tested = rec_count + 6;
+            if (c->hs->plan_gen != c->pidx_gen) {
+                cck::k2p_plan<<<1, cck::K2P_PLAN_THREADS, 0, c->stream>>>(pa);
+                CU(cudaGetLastError());
+                c->launches += 1;
+                if (h0 + cck::K2_MAX_HALOS >= H) c->hs->plan_gen = c->pidx_gen;
+            }
+            cck::k2p_query<<<(unsigned int)c->sm_count * 5u, cck::K2P_THREADS, 0, c->stream>>>(pa);
+            CU(cudaGetLastError());
+            c->launches += 1;
+        } else if (mono) { /* cell index, one kernel: one 20-warp CTA per SM, bitmap + windows + stacks + counters in shared memory */
             constexpr int W = 20;
             const size_t csmem = cck::k2c_smem(W) + (size_t)2 * cck::K2_MAX_HALOS * 4;
             cck::HaloBinArgs b;
@@ -892,11 +952,13 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
 
 /* ---------------------------------------------------------------- whole-step drivers */
 int maybe_build_payload(cc_ctx* c);
+int maybe_build_index(cc_ctx* c);
 
 int run_resident(cc_ctx* c) {
     int rc = (c->pending == P_CONST) ? prepare_const(c) : prepare_halo(c);
     if (rc) return rc;
     if ((rc = maybe_build_payload(c))) return rc;
+    if ((rc = maybe_build_index(c))) return rc;
     c->gcols = cols_in_of(c);
     Chunk ch;
     ch.x = c->gcols.x; ch.y = c->gcols.y; ch.z = c->gcols.z;
@@ -982,11 +1044,62 @@ int maybe_build_payload(cc_ctx* c) {
     return CC_OK;
 }
 
+/* the particle index of the resident step (kernels.cuh k2p_*): counting sort by (cos theta_u, sin phi_u) cell */
+int maybe_build_index(cc_ctx* c) {
+    if (c->pending != P_HALO || !c->use_bins || c->streamed || c->pidx_valid || c->n == 0 || c->index_policy == 2) return CC_OK;
+    if (c->index_policy == 0 && (c->step_many_halo_cutouts < 1 || c->n < (4ll << 20))) return CC_OK;
+    const size_t nbin = cck::K2P_NBIN;
+    const unsigned int nblocks = (unsigned int)((nbin + cck::K2P_SCAN_BLOCK - 1) / cck::K2P_SCAN_BLOCK);
+    {
+        /* not enough HBM for the extra 16 B/particle: keep scanning */
+        DevBuf* need[] = {&c->pidx_sorted, &c->pidx_start, &c->pidx_tmp, &c->pidx_partial};
+        const size_t bytes[] = {(size_t)c->n * sizeof(float4), (nbin + 1) * 4, (nbin + 1) * 4, (size_t)nblocks * 4};
+        for (int i = 0; i < 4; ++i) {
+            if (need[i]->bytes >= bytes[i]) continue;
+            need[i]->release();
+            if (cudaMalloc(&need[i]->p, bytes[i]) != cudaSuccess) {
+                cudaGetLastError();
+                need[i]->p = nullptr;
+                c->index_policy = 2;
+                return CC_OK;
+            }
+            need[i]->bytes = bytes[i];
+        }
+    }
+    const cck::ColsIn ci = cols_in_of(c);
+    unsigned int* hist = (unsigned int*)c->pidx_tmp.p;
+    unsigned int* start = (unsigned int*)c->pidx_start.p;
+    unsigned int* partial = (unsigned int*)c->pidx_partial.p;
+    CU(cudaEventRecord(c->ev_idx0, c->stream));
+    CU(cudaMemsetAsync(hist, 0, (nbin + 1) * 4, c->stream));
+    const unsigned int grid = (unsigned int)c->sm_count * 16u;
+    cck::k2p_hist<<<grid, 256, 0, c->stream>>>(ci.x, ci.y, ci.z, c->n, hist);
+    CU(cudaGetLastError());
+    cck::k2p_scan_a<<<nblocks, 256, 0, c->stream>>>(hist, partial);
+    CU(cudaGetLastError());
+    cck::k2p_scan_b<<<1, 32, 0, c->stream>>>(partial, nblocks);
+    CU(cudaGetLastError());
+    cck::k2p_scan_c<<<nblocks, 256, 0, c->stream>>>(hist, partial, start);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hist, start, nbin * 4, cudaMemcpyDeviceToDevice, c->stream)); /* fill cursors */
+    cck::k2p_scatter<<<grid, 256, 0, c->stream>>>(ci.x, ci.y, ci.z, c->n, hist, (float4*)c->pidx_sorted.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_idx1, c->stream));
+    c->launches += 5;
+    c->pidx_valid = true;
+    c->pidx_gen = ++c->pidx_gen_clock;
+    c->index_timed = true;
+    return CC_OK;
+}
+
 /* a new step became resident */
 void reset_step_state(cc_ctx* c) {
     c->payload_valid = false;
     c->step_last_survivors = -1;
     c->payload_timed = false;
+    c->pidx_valid = false;
+    c->step_many_halo_cutouts = 0;
+    c->index_timed = false;
 }
 
 int check_sm100(int device, int* sm_count) {
@@ -1038,6 +1151,7 @@ int cc_create(int device, cc_ctx** out) {
     if (const char* e = getenv("CC_TIMING")) c->timing = atoi(e) != 0;
     if (const char* e = getenv("CC_PREFETCH")) c->prefetch = atoi(e);
     if (const char* e = getenv("CC_CELLS")) c->cells_mode = !strcmp(e, "staged") ? 1 : !strcmp(e, "mono") ? 2 : 0;
+    if (const char* e = getenv("CC_INDEX")) c->index_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
     if (getenv("CC_NO_PAYLOAD")) c->payload_policy = 2;
     if (const char* e = getenv("CC_PAYLOAD")) c->payload_policy = !strcmp(e, "always") ? 1 : !strcmp(e, "never") ? 2 : 0;
     c->device = device;
@@ -1046,6 +1160,7 @@ int cc_create(int device, cc_ctx** out) {
         cudaEventCreate(&c->ev_scan0) != cudaSuccess || cudaEventCreate(&c->ev_scan1) != cudaSuccess ||
         cudaEventCreate(&c->ev_total1) != cudaSuccess ||
         cudaEventCreate(&c->ev_pay0) != cudaSuccess || cudaEventCreate(&c->ev_pay1) != cudaSuccess ||
+        cudaEventCreate(&c->ev_idx0) != cudaSuccess || cudaEventCreate(&c->ev_idx1) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_xchg, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->xchg_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1072,7 +1187,7 @@ void cc_destroy(cc_ctx* c) {
     for (auto& b : c->col_buf) b.release();
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
-    DevBuf* rest[] = {&c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->place_buf, &c->counts_buf,
+    DevBuf* rest[] = {&c->pidx_sorted, &c->pidx_start, &c->pidx_tmp, &c->pidx_partial, &c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->place_buf, &c->counts_buf,
                       &c->hstate, &c->gather_buf, &c->offsets_buf, &c->xchg_send, &c->cand, &c->cand_count, &c->pair_p, &c->pair_h, &c->pair_count, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
     for (DevBuf* b : rest) b->release();
     for (auto& e : c->halo_sets) e.release();
@@ -1088,6 +1203,8 @@ void cc_destroy(cc_ctx* c) {
     if (c->ev_total1) cudaEventDestroy(c->ev_total1);
     if (c->ev_pay0) cudaEventDestroy(c->ev_pay0);
     if (c->ev_pay1) cudaEventDestroy(c->ev_pay1);
+    if (c->ev_idx0) cudaEventDestroy(c->ev_idx0);
+    if (c->ev_idx1) cudaEventDestroy(c->ev_idx1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1113,6 +1230,7 @@ int cc_step_release(cc_ctx* c) {
     CU(cudaStreamSynchronize(c->stream));
     for (auto& b : c->col_buf) b.release();
     c->payload.release();
+    c->pidx_sorted.release();
     reset_step_state(c);
     for (auto& p : c->col) p = nullptr;
     c->step_valid = false;
@@ -1134,10 +1252,15 @@ int cc_step_select(cc_ctx* c, int slot) {
     StepSlot& out = c->slots[(size_t)c->cur_slot];
     out.valid = c->step_valid; out.owned = c->step_owned; out.n = c->n; out.index_base = c->index_base;
     out.payload = c->payload; out.payload_valid = c->payload_valid; out.last_survivors = c->step_last_survivors;
+    out.pidx_sorted = c->pidx_sorted; out.pidx_start = c->pidx_start; out.pidx_valid = c->pidx_valid; out.pidx_gen = c->pidx_gen;
+    out.many_halo_cutouts = c->step_many_halo_cutouts;
     for (int i = 0; i < N_IN_COLS; ++i) { out.col[i] = c->col[i]; out.col_buf[i] = c->col_buf[i]; }
     StepSlot& in = c->slots[(size_t)slot];
     c->step_valid = in.valid; c->step_owned = in.owned; c->n = in.n; c->index_base = in.index_base;
     c->payload = in.payload; c->payload_valid = in.payload_valid; c->step_last_survivors = in.last_survivors;
+    c->pidx_sorted = in.pidx_sorted; c->pidx_start = in.pidx_start; c->pidx_valid = in.pidx_valid; c->pidx_gen = in.pidx_gen;
+    c->step_many_halo_cutouts = in.many_halo_cutouts;
+    c->index_timed = false;
     for (int i = 0; i < N_IN_COLS; ++i) { c->col[i] = in.col[i]; c->col_buf[i] = in.col_buf[i]; }
     in = StepSlot(); /* the buffers now belong to the context's current-step fields */
     c->cur_slot = slot;
@@ -1277,6 +1400,7 @@ int cc_cutout_const(cc_ctx* c, const float theta_cut[2], const float phi_cut[2])
     c->synced = false;
     c->streamed = false;
     c->payload_timed = false;
+    c->index_timed = false;
     c->eager_done = false;
     return run_pending(c);
 }
@@ -1296,6 +1420,7 @@ int cc_cutout_halo(cc_ctx* c, int nhalos, const cc_halo* halos, int pos_only, in
     c->synced = false;
     c->streamed = false;
     c->payload_timed = false;
+    c->index_timed = false;
     c->eager_done = false;
     if (nhalos == 0) { c->counts.clear(); c->rough.clear(); c->seg_begin.assign(1, 0); c->synced = true; return CC_OK; }
     return run_pending(c);
@@ -1328,6 +1453,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             c->seg_begin[1] = c->counts[0];
             c->stats[0] = c->n; c->stats[1] = (int64_t)c->h_small[1]; c->stats[2] = c->counts[0]; c->stats[3] = 0;
             c->nan_theta = 0;
+            c->particles_read = c->n;
         } else {
             const int H = c->nhalos;
             for (int attempt = 0; attempt < 6; ++attempt) {
@@ -1336,7 +1462,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
                 const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
                 c->force_general = refused;
                 /* staged cell-index kernels: a warp's candidate region or the pair buffer was too small */
-                const bool staged = c->use_bins && !c->used_mono;
+                const bool staged = c->use_bins && !c->used_mono && !c->used_index;
                 const bool cand_over = staged && c->h_small[2] > c->cand_region_cap;
                 const bool pair_over = staged && (int64_t)c->h_small[3] > c->pair_cap;
                 if (nrec <= c->rec_cap && !refused && !cand_over && !pair_over) break;
@@ -1347,7 +1473,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
                 if ((rc = run_pending(c))) return rc;
             }
             const int64_t nrec = (int64_t)c->h_small[0];
-            if (c->use_bins && !c->used_mono && c->hs && c->hs->walker == 0 && halo_scan_limit(c) > 0) {
+            if (c->use_bins && !c->used_mono && !c->used_index && c->hs && c->hs->walker == 0 && halo_scan_limit(c) > 0) {
                 /* the staged pass measured how many particles hit the occupancy bitmap: with many hits the candidate
                  * buffer's round trip through HBM costs more than the one-kernel scan's lower occupancy (profiles/r02) */
                 const int nbatch = (H + cck::K2_MAX_HALOS - 1) / cck::K2_MAX_HALOS;
@@ -1356,6 +1482,8 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             }
             c->last_nrec = nrec;
             if (!c->streamed) c->step_last_survivors = nrec;
+            if (!c->streamed && c->use_bins) c->step_many_halo_cutouts += 1;
+            c->particles_read = (c->use_bins && c->used_index) ? (int64_t)c->h_small[6] : halo_scan_limit(c);
             c->force_general = false;
             c->counts.resize(H); c->rough.resize(H); c->seg_begin.resize(H + 1);
             int64_t tot = 0, tot_rough = 0;
@@ -1526,6 +1654,7 @@ int begin_streamed(cc_ctx* c, int64_t n, const cc_cols_in* host, int64_t index_b
     c->streamed = true;
     c->synced = false;
     c->payload_timed = false;
+    c->index_timed = false;
     return CC_OK;
 }
 }  // namespace
@@ -1841,7 +1970,16 @@ int cc_last_stats_ex(cc_ctx* c, int64_t* out, int n) {
         else cudaGetLastError();
     }
     v[7] = (c->pending == P_HALO) ? c->n - c->stats[0] : 0;
-    v[8] = (c->pending != P_HALO) ? 0 : !c->use_bins ? 1 : c->used_mono ? 3 : 2;
+    v[8] = (c->pending != P_HALO) ? 0 : !c->use_bins ? 1 : c->used_index ? 4 : c->used_mono ? 3 : 2;
+    v[9] = c->particles_read;
+    v[10] = c->pidx_valid ? 1 : 0;
+    if (c->index_timed) {
+        cudaSetDevice(c->device);
+        float ms = 0.0f;
+        if (cudaStreamSynchronize(c->stream) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev_idx0, c->ev_idx1) == cudaSuccess)
+            v[11] = (int64_t)(ms * 1000.0f);
+        else cudaGetLastError();
+    }
     for (int i = 0; i < n && i < CC_STATS_EX_FIELDS; ++i) out[i] = v[i];
     return CC_OK;
 }
@@ -1849,6 +1987,11 @@ int cc_last_stats_ex(cc_ctx* c, int64_t* out, int n) {
 int cc_set_option(cc_ctx* c, const char* key, const char* value) {
     if (!c || !key || !value) return fail(CC_ERR_ARG, "cc_set_option: bad argument");
     const std::string k = key, v = value;
+    if (k == "index") {
+        if (v == "auto") c->index_policy = 0; else if (v == "always") c->index_policy = 1;
+        else if (v == "never") c->index_policy = 2; else return fail(CC_ERR_ARG, "cc_set_option: index = auto|always|never");
+        return CC_OK;
+    }
     if (k == "payload") {
         if (v == "auto") c->payload_policy = 0; else if (v == "always") c->payload_policy = 1;
         else if (v == "never") c->payload_policy = 2; else return fail(CC_ERR_ARG, "cc_set_option: payload = auto|always|never");

@@ -154,6 +154,7 @@ __device__ __forceinline__ void prefetch_tile(const float* __restrict__ x, const
         asm volatile("prefetch.global.L2 [%0];" ::"l"(col + base + (lane & 7) * 32));
     }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 /* index inside the tile of element j of this lane */
 __device__ __forceinline__ unsigned int tile_local(int lane, int j) { return (unsigned)((j >> 2) * 128 + 4 * lane + (j & 3)); }
 
@@ -1308,6 +1309,315 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
     __syncthreads();
     for (int i = threadIdx.x; i < a.nhalos; i += K2C_THREADS) {
+        if (s_rough[i]) atomicAdd(a.counts + a.total_halos + (unsigned int)a.halo0 + i, (unsigned long long)s_rough[i]);
+        if (s_fine[i]) atomicAdd(a.counts + (unsigned int)a.halo0 + i, (unsigned long long)s_fine[i]);
+    }
+}
+
+/* ---- many halos on an INDEXED resident step -----------------------------------------------------------------------
+ * The reference sorts every step by theta once and then finds each halo's candidates with two binary searches
+ * (processLC.cpp:1214-1221, :1334-1340): per halo it touches the annulus, not the step.  The walkers above and below
+ * do the opposite -- they stream all 12 B/particle for every pass and look the HALOS up -- which is the right trade
+ * for a step that is cut once.  For a step that stays resident and is cut again and again (BASELINE config 5: 1000
+ * halos, several box sizes) the particles themselves are indexed once: a counting sort by the particle's cell of the
+ * same 2048 x 2048 (cos theta_u, sin phi_u) grid writes {x, y, z, index} (16 B) in cell order, with the first row of
+ * every cell in `start`; out-of-range positions (k2c_coords !sane: they must meet every halo) sit in one extra bin
+ * behind the last cell.  A halo's window is a rectangle of cells, i.e. one CONTIGUOUS run of rows per grid line:
+ * a pass reads 16 B for the particles of those runs and nothing else -- 15-20 M of 125 M for the 1000 cutouts of
+ * config 5 -- and hands (particle, halo) pairs to the same second filter and exact path as the cell walkers, so the
+ * records, counts and therefore the cutouts are the same, bit for bit.
+ *
+ *   k2p_hist / k2p_scan_{a,b,c} / k2p_scatter   build (once per resident step, capi.cu maybe_build_index)
+ *   k2p_plan    per pass: rows of every (halo, grid line) item -> prefix of 32-particle steps
+ *   k2p_query   per pass: the steps are cut into equal contiguous slices, one per warp (no atomics, no tail) */
+constexpr unsigned int K2P_NCELL = (unsigned int)K2_GRID * (unsigned int)K2_GRID; /* + 1 bin: out-of-range positions */
+constexpr unsigned int K2P_NBIN = K2P_NCELL + 1u;
+constexpr unsigned int K2P_ALL = 0xffffu; /* item halo: every halo of the launch (the out-of-range bin) */
+constexpr int K2P_SCAN_BLOCK = 4096;
+
+__device__ __forceinline__ unsigned int k2p_cell(float x, float y, float z) {
+    float pc, ps;
+    bool sane;
+    k2c_coords(x, y, z, pc, ps, sane);
+    /* the SAME expressions as the cell walkers (k2_cutout_halo_cells, k2c_sift): the halo lists were rasterised for them */
+    const unsigned int ic = min(__float2uint_rz(fmaf(pc, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+    const unsigned int is = min(__float2uint_rz(fmaf(ps, 0.5f * K2_GRID, 0.5f * K2_GRID)), (unsigned int)(K2_GRID - 1));
+    return sane ? ic * (unsigned int)K2_GRID + is : K2P_NCELL;
+}
+__global__ void k2p_hist(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, long long n,
+                         unsigned int* __restrict__ hist) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(hist + k2p_cell(__ldcs(x + i), __ldcs(y + i), __ldcs(z + i)), 1u);
+}
+/* exclusive scan of the K2P_NBIN bin counts in three small kernels: block sums, scan of the sums, scan + offset */
+__global__ void __launch_bounds__(256) k2p_scan_a(const unsigned int* __restrict__ hist, unsigned int* __restrict__ partial) {
+    __shared__ unsigned int s_w[8];
+    const unsigned int b0 = blockIdx.x * K2P_SCAN_BLOCK;
+    unsigned int sum = 0;
+    for (unsigned int i = threadIdx.x; i < (unsigned int)K2P_SCAN_BLOCK; i += 256)
+        if (b0 + i < K2P_NBIN) sum += hist[b0 + i];
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(32) k2p_scan_b(unsigned int* partial, unsigned int nblocks) {
+    const unsigned int lane = threadIdx.x, per = (nblocks + 31u) / 32u;
+    unsigned int sum = 0;
+    for (unsigned int i = lane * per; i < min(nblocks, (lane + 1u) * per); ++i) sum += partial[i];
+    unsigned int inc = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned int)d) inc += t;
+    }
+    unsigned int run = inc - sum;
+    for (unsigned int i = lane * per; i < min(nblocks, (lane + 1u) * per); ++i) { const unsigned int v = partial[i]; partial[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(256) k2p_scan_c(const unsigned int* __restrict__ hist, const unsigned int* __restrict__ partial,
+                                                  unsigned int* __restrict__ start) {
+    __shared__ unsigned int s_w[8];
+    constexpr int PER = K2P_SCAN_BLOCK / 256;
+    const unsigned int b0 = blockIdx.x * K2P_SCAN_BLOCK + threadIdx.x * PER;
+    unsigned int v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { v[k] = (b0 + k < K2P_NBIN) ? hist[b0 + k] : 0u; sum += v[k]; }
+    const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned int inc = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned int)d) inc += t;
+    }
+    if (lane == 31u) s_w[warp] = inc;
+    __syncthreads();
+    unsigned int run = partial[blockIdx.x] + inc - sum;
+    for (unsigned int w = 0; w < warp; ++w) run += s_w[w];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        if (b0 + k < K2P_NBIN) start[b0 + k] = run;
+        run += v[k];
+        if (b0 + k == K2P_NBIN - 1u) start[K2P_NBIN] = run; /* = n */
+    }
+}
+/* fill: a copy of start; every particle takes the next row of its bin (the order inside a bin is whatever the atomics
+ * make it: survivors are ordered by (theta_u, index) afterwards, k3_*) */
+__global__ void k2p_scatter(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, long long n,
+                            unsigned int* __restrict__ fill, float4* __restrict__ sorted) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float px = __ldcs(x + i), py = __ldcs(y + i), pz = __ldcs(z + i);
+        const unsigned int row = atomicAdd(fill + k2p_cell(px, py, pz), 1u);
+        sorted[row] = make_float4(px, py, pz, __uint_as_float((unsigned int)i));
+    }
+}
+
+struct PidxArgs {
+    HaloArgs h;                      /* x, y, z unused; n = particles in range of the n_limit clamp (index < n) */
+    const float4* sorted;            /* {x, y, z, index bits} in bin order */
+    const unsigned int* start;       /* [K2P_NBIN + 1] first row of every bin */
+    const uint2* items;              /* {halo | grid line << 16, first column | last column << 16}; halo K2P_ALL: the
+                                        out-of-range bin against every halo of the launch */
+    unsigned int nitems;
+    unsigned long long* item_step0;  /* [nitems + 1] exclusive prefix of the items' 32-particle steps (k2p_plan) */
+    unsigned long long* tested;      /* stat: particles read */
+};
+__device__ __forceinline__ void k2p_rows(const PidxArgs& p, uint2 it, unsigned int& begin, unsigned int& end) {
+    if ((it.x & 0xffffu) == K2P_ALL) { begin = __ldg(p.start + K2P_NCELL); end = __ldg(p.start + K2P_NBIN); return; }
+    const unsigned int line = (it.x >> 16) * (unsigned int)K2_GRID;
+    begin = __ldg(p.start + line + (it.y & 0xffffu));
+    end = __ldg(p.start + line + (it.y >> 16) + 1u);
+}
+constexpr int K2P_PLAN_THREADS = 1024;
+__global__ void __launch_bounds__(K2P_PLAN_THREADS) k2p_plan(const PidxArgs p) {
+    __shared__ unsigned long long s_w[K2P_PLAN_THREADS / 32];
+    const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned int per = (p.nitems + K2P_PLAN_THREADS - 1) / K2P_PLAN_THREADS;
+    const unsigned int i0 = min(p.nitems, tid * per), i1 = min(p.nitems, i0 + per);
+    unsigned long long sum = 0;
+    for (unsigned int i = i0; i < i1; ++i) {
+        unsigned int b, e;
+        k2p_rows(p, p.items[i], b, e);
+        sum += (e - b + 31u) >> 5;
+    }
+    unsigned long long inc = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned int)d) inc += t;
+    }
+    if (lane == 31u) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = s_w[lane];
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= (unsigned int)d) w += t;
+        }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    unsigned long long run = inc - sum + (warp ? s_w[warp - 1] : 0ull);
+    for (unsigned int i = i0; i < i1; ++i) {
+        unsigned int b, e;
+        k2p_rows(p, p.items[i], b, e);
+        p.item_step0[i] = run;
+        run += (e - b + 31u) >> 5;
+    }
+    if (tid == K2P_PLAN_THREADS - 1) p.item_step0[p.nitems] = run;
+}
+
+constexpr int K2P_THREADS = 128; /* five CTAs per SM at 96 registers: 20 warps, each with its own slice of the steps */
+struct __align__(16) K2PStacks {
+    float4 cp[K2C_CCAP];         /* tested pair: x, y, z, particle index (bits) */
+    unsigned int ch[K2C_CCAP];   /*              halo inside the launch */
+    float4 xp[K2C_CCAP];         /* pair that needs the exact arithmetic */
+    unsigned int xh[K2C_CCAP];
+};
+__global__ void __launch_bounds__(K2P_THREADS, 5) k2p_query(const __grid_constant__ PidxArgs p) {
+    __shared__ K2PStacks s_st[K2P_THREADS / 32];
+    __shared__ unsigned int s_rough[K2_MAX_HALOS], s_fine[K2_MAX_HALOS];
+    for (int i = threadIdx.x; i < K2_MAX_HALOS; i += K2P_THREADS) { s_rough[i] = 0u; s_fine[i] = 0u; }
+    __syncthreads();
+    const HaloArgs& a = p.h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    K2PStacks& S = s_st[warp];
+    unsigned int nc = 0, nx = 0; /* warp-uniform stack heights: tested pairs, pairs for the exact path */
+    unsigned long long n_cand = 0, n_tested = 0;
+
+    /* tested pairs, 32 at a time (when `last`, whatever is left): the second filter, then the exact path for what it
+     * cannot decide -- the tail of k2_cutout_halo_cells */
+    auto drain = [&](bool last) {
+        for (;;) {
+            if (nx >= 32u || (last && nc == 0u && nx != 0u)) {
+                const unsigned int mx = min(nx, 32u);
+                nx -= mx;
+                const bool lv = (unsigned int)lane < mx;
+                const unsigned int e = lv ? nx + lane : 0u;
+                const float4 c4 = S.xp[e];
+                k2_exact_warp(a, lv, (int)S.xh[e], c4.x, c4.y, c4.z, (unsigned int)a.local_base + __float_as_uint(c4.w), lane, s_rough, s_fine);
+                n_cand += mx;
+                __syncwarp();
+                continue;
+            }
+            if (nc >= 32u || (last && nc != 0u)) {
+                const unsigned int mc = min(nc, 32u);
+                nc -= mc;
+                const bool lv = (unsigned int)lane < mc;
+                const unsigned int e = lv ? nc + lane : 0u;
+                const float4 c4 = S.cp[e];
+                const unsigned int h = lv ? S.ch[e] : 0u;
+                const float4* __restrict__ Hq = reinterpret_cast<const float4*>(a.halos + h);
+                const float4 q0 = __ldg(Hq), q1 = __ldg(Hq + 1), q2 = __ldg(Hq + 2), q5 = __ldg(Hq + 5), q6 = __ldg(Hq + 6);
+                float pc, ps;
+                bool sane;
+                k2c_coords(c4.x, c4.y, c4.z, pc, ps, sane);
+                const bool sure_rough = (pc <= q5.x) & (pc >= q5.y) & (ps >= q5.z) & (ps <= q5.w);
+                const float R[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+                float rx, ry, rz;
+                ccref::mat_vec(R, c4.x, c4.y, c4.z, rx, ry, rz); /* the exact path's own rotated position */
+                const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+                const bool sane_r = (fabsf(rx) >= CC_SANE_LO) & (r2 <= 1.2089258e24f);
+                const float cf = rz * rsqrt_fast(r2), tf = ry * rcp_fast(rx);
+                const bool maybe_fine = !sane_r | ((cf <= q6.x) & (cf >= q6.y) & (tf >= q6.z) & (tf <= q6.w));
+                const bool counted = lv && sure_rough && !maybe_fine;
+                if (counted) atomicAdd(&s_rough[h], 1u); /* rough_cutout_size, :1436 */
+                const bool need = lv && !counted;
+                const unsigned int xm = __ballot_sync(0xffffffffu, need);
+                if (need) {
+                    const unsigned int x = nx + __popc(xm & lt_mask);
+                    S.xp[x] = c4;
+                    S.xh[x] = h;
+                }
+                nx += __popc(xm);
+                __syncwarp();
+                continue;
+            }
+            break;
+        }
+    };
+
+    const unsigned long long total = p.item_step0[p.nitems];
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (K2P_THREADS / 32);
+    const unsigned long long per = (total + total_warps - 1) / total_warps;
+    const unsigned long long wid = (unsigned long long)blockIdx.x * (K2P_THREADS / 32) + warp;
+    const unsigned long long s_begin = min(total, wid * per), s_end = min(total, s_begin + per);
+    if (s_begin < s_end) {
+        /* the item that holds this warp's first step: the last one whose prefix is <= s_begin */
+        unsigned int lo = 0, hi = p.nitems - 1u;
+        while (lo < hi) {
+            const unsigned int mid = (lo + hi + 1u) >> 1;
+            if (p.item_step0[mid] <= s_begin) lo = mid;
+            else hi = mid - 1u;
+        }
+        /* the walk is one step AHEAD of the work: the 512 bytes of step s+1 are requested before step s is worked on
+         * (and the rows four steps further on are pulled into the L2), or every step would wait out a DRAM round trip
+         * with nothing else in flight for the warp */
+        unsigned int item = lo;
+        unsigned long long step0 = p.item_step0[item], step1 = p.item_step0[item + 1];
+        bool fresh = true;
+        unsigned int h_next = 0, row_begin = 0, row_end = 0;
+        float4 W_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 q_next = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        bool live_next = false;
+        auto request = [&](unsigned long long step) {
+            while (step >= step1) { ++item; step0 = step1; step1 = p.item_step0[item + 1]; fresh = true; }
+            if (fresh) {
+                const uint2 it = p.items[item];
+                h_next = it.x & 0xffffu;
+                k2p_rows(p, it, row_begin, row_end);
+                if (h_next != K2P_ALL) W_next = __ldg(a.pre + h_next);
+                fresh = false;
+            }
+            const unsigned long long row = (unsigned long long)row_begin + ((step - step0) << 5) + (unsigned int)lane;
+            live_next = row < (unsigned long long)row_end;
+            q_next = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            if (live_next) q_next = __ldcs(p.sorted + row);
+            if ((lane & 7) == 0 && row + 128u < (unsigned long long)row_end) prefetch_l2(p.sorted + row + 128u);
+        };
+        request(s_begin);
+        for (unsigned long long step = s_begin; step < s_end; ++step) {
+            const float4 q = q_next;
+            const unsigned int h = h_next;
+            const float4 W = W_next;
+            bool live = live_next;
+            if (step + 1 < s_end) request(step + 1);
+            live = live && (long long)__float_as_uint(q.w) < a.n; /* the n_limit clamp (reference tail drop) */
+            n_tested += __popc(__ballot_sync(0xffffffffu, live));
+            if (h == K2P_ALL) { /* out-of-range positions: the exact path decides, against every halo of the launch */
+                unsigned int m = __ballot_sync(0xffffffffu, live);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float x = __shfl_sync(0xffffffffu, q.x, src), y = __shfl_sync(0xffffffffu, q.y, src),
+                                z = __shfl_sync(0xffffffffu, q.z, src);
+                    const unsigned int idx = __shfl_sync(0xffffffffu, __float_as_uint(q.w), src);
+                    k2c_exact_all(a, x, y, z, (unsigned int)a.local_base + idx, lane);
+                    n_cand += (unsigned int)a.nhalos;
+                }
+                continue;
+            }
+            float pc, ps;
+            bool sane;
+            k2c_coords(q.x, q.y, q.z, pc, ps, sane);
+            const bool pass = live & (pc <= W.x) & (pc >= W.y) & (ps >= W.z) & (ps <= W.w);
+            const unsigned int pm = __ballot_sync(0xffffffffu, pass);
+            if (pass) {
+                const unsigned int e = nc + __popc(pm & lt_mask);
+                S.cp[e] = q;
+                S.ch[e] = h;
+            }
+            nc += __popc(pm);
+            __syncwarp();
+            drain(false);
+        }
+    }
+    drain(true);
+    if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);
+    if (lane == 0 && n_tested) atomicAdd(p.tested, n_tested);
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.nhalos; i += K2P_THREADS) {
         if (s_rough[i]) atomicAdd(a.counts + a.total_halos + (unsigned int)a.halo0 + i, (unsigned long long)s_rough[i]);
         if (s_fine[i]) atomicAdd(a.counts + (unsigned int)a.halo0 + i, (unsigned long long)s_fine[i]);
     }

@@ -226,8 +226,11 @@ int cc_last_stats(cc_ctx* ctx, int64_t out[4]);
  * exists; [6] microseconds the last cutout call spent building it (0: it did not); [7] use case 2: particles of this
  * shard behind n_limit_global (the reference's tail drop, util.cpp:106-108); [8] which scan ran: 0 use case 1,
  * 1 use case 2 every particle against every halo (k2_cutout_halo), 2 the cell index walked by the staged kernels
- * (k2c_sift, k2c_match, k2c_exact), 3 by one kernel (k2_cutout_halo_cells). */
-#define CC_STATS_EX_FIELDS 9
+ * (k2c_sift, k2c_match, k2c_exact), 3 by one kernel (k2_cutout_halo_cells), 4 the particle index of the resident
+ * step (k2p_plan, k2p_query); [9] particles the scan read: all scanned ones, or with [8] = 4 only the index rows under the
+ * halos' windows; [10] 1 when the particle index of the resident step exists; [11] microseconds the last cutout call
+ * spent building it (0: it did not). */
+#define CC_STATS_EX_FIELDS 12
 int cc_last_stats_ex(cc_ctx* ctx, int64_t* out, int n);
 
 /* ------------------------------------------------------------------ tuning switches (defaults are the measured best)
@@ -239,6 +242,11 @@ int cc_last_stats_ex(cc_ctx* ctx, int64_t* out, int n);
  *                 every cutout by cc_exchange_counts)
  * key "cells":    "auto" (default) | "staged" | "mono" -- many halos: the cell index is walked by three staged kernels or by
  *                 one; auto measures the bitmap hit rate of a halo set on its first pass and picks from it
+ * key "index":    "auto" (default) | "always" | "never" -- the particle index of a resident step: {x, y, z, index} in
+ *                 (cos theta_u, sin phi_u) cell order (16 B/particle).  A many-halo cutout (>= 8 halos) on an indexed
+ *                 step reads only the cells under its halos' windows instead of the whole step -- what the reference's
+ *                 theta sort + lower_bound does (processLC.cpp:1214-1221, :1334-1340).  auto builds it inside the second
+ *                 many-halo cutout on the same resident step of >= 4 Mi particles; results are identical either way
  * key "timing":   "off" (default) | "on" -- record the per-kernel CUDA events behind cc_last_scan_ms / cc_last_total_ms
  * key "gather":   "auto" (default) | "ldst" | "bulk" -- use case 1 gather: plain coalesced stores, or rows staged in
  *                 shared memory and written with cp.async.bulk (TMA bulk stores); auto picks bulk stores for dense

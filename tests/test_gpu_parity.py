@@ -22,11 +22,20 @@ def ctx():
 
 @pytest.fixture()
 def cells_mode(ctx, request):
-    """many halos: run the test with the staged kernels (k2c_sift / k2c_match / k2c_exact) and with the one-kernel scan
-    (k2_cutout_halo_cells); the library picks between them per halo set from the measured bitmap hit rate"""
-    ctx.set_option("cells", request.getfixturevalue("cells"))
+    """many halos: run the test with the staged kernels (k2c_sift / k2c_match / k2c_exact), with the one-kernel scan
+    (k2_cutout_halo_cells) -- the library picks between them per halo set from the measured bitmap hit rate -- and with
+    the particle index of the resident step (k2p_plan / k2p_query), which it builds for a step that is cut repeatedly"""
+    mode = request.getfixturevalue("cells")
+    if mode == "index":  # the particle index of the resident step (k2p_*), built inside the first many-halo cutout
+        ctx.set_option("index", "always")
+    else:
+        ctx.set_option("index", "never")
+        ctx.set_option("cells", mode)
     yield
+    ran = ctx.stats_ex()["scan_kernels"]
     ctx.set_option("cells", "auto")
+    ctx.set_option("index", "auto")
+    assert ran == {"staged": "k2c_sift+k2c_match+k2c_exact", "mono": "k2_cutout_halo_cells", "index": "k2p_plan+k2p_query"}[mode]
 
 
 def _same_float_bits(a, b):
@@ -309,7 +318,7 @@ def test_halo_sort_keys_and_tail_drop(ctx, halo_cols):
     assert np.array_equal(th_u[got["index"]].view(np.uint32), got["theta_u"].view(np.uint32))
 
 
-@pytest.mark.parametrize("cells", ["staged", "mono"])
+@pytest.mark.parametrize("cells", ["staged", "mono", "index"])
 def test_halo_many_halos_one_pass(ctx, cells_mode, cells):
     """more halos than one launch batch (K2_MAX_HALOS = 1024)"""
     rng = np.random.default_rng(5)
@@ -330,7 +339,7 @@ def test_halo_many_halos_one_pass(ctx, cells_mode, cells):
         ctx.fetch_all(counts[:-1])  # wrong total
 
 
-@pytest.mark.parametrize("cells", ["staged", "mono"])
+@pytest.mark.parametrize("cells", ["staged", "mono", "index"])
 def test_halo_cell_index_overlapping_halos_and_special_positions(ctx, cells_mode, cells):
     """the cell-index kernel (>= 8 halos): 48 halos whose windows all overlap, so a 256-particle tile owes far more
     (particle, halo) pairs than the warp's pair buffer holds (several passes per tile), plus positions the
@@ -362,7 +371,7 @@ def test_halo_cell_index_overlapping_halos_and_special_positions(ctx, cells_mode
         H.assert_cols_equal(ctx.fetch(h), want, what=f"halo {h}: ")
 
 
-@pytest.mark.parametrize("cells", ["staged", "mono"])
+@pytest.mark.parametrize("cells", ["staged", "mono", "index"])
 def test_halo_cell_index_window_edges(ctx, cells_mode, cells):
     """the cell-index kernel's second filter decides most pairs without the exact arithmetic: "certainly inside the
     rough window" and "certainly outside the fine window".  Aim particles at every bound of both windows -- the
@@ -710,6 +719,7 @@ def test_many_halos_at_size_sample_parity(ctx):
     limit = cc.ref_scatter_kept(n, 1)
     checked = 0
     per_group, all_halos = [], []
+    ctx.set_option("index", "never")  # the four passes: the cell walkers (every pass streams the 125 M particles)
     for g, box in enumerate((5.0, 10.0, 20.0, 30.0)):
         hp = pos[g * 250:(g + 1) * 250]
         infos = [cc.halo_setup(p, box) for p in hp]
@@ -731,8 +741,15 @@ def test_many_halos_at_size_sample_parity(ctx):
     assert checked == 20
     # the same 1000 (halo, box length) cutouts in ONE pass (host/processLC.cpp processLC_boxes; bench cfg5_shared): every
     # halo's counts and rows are those of the four separate passes, bit for bit
-    ctx.cutout_halo(all_halos, n_limit_global=limit)
-    counts, rough = ctx.sync()
+    for index in ("never", "always"):  # one pass: cell walker, then the particle index (built inside this cutout)
+        ctx.set_option("index", index)
+        ctx.cutout_halo(all_halos, n_limit_global=limit)
+        counts, rough = ctx.sync()
+        st = ctx.stats_ex()
+        assert st["index_resident"] == (index == "always") and (st["index_build_ms"] > 0) == (index == "always")
+        assert (st["scan_kernels"] == "k2p_plan+k2p_query") == (index == "always")
+        assert st["particles_read"] == limit if index == "never" else 0 < st["particles_read"] < limit // 4
+    ctx.set_option("index", "auto")
     everything, _ = ctx.fetch_all(counts)
     assert np.array_equal(counts, np.concatenate([p[0] for p in per_group]))
     assert np.array_equal(rough, np.concatenate([p[1] for p in per_group]))
@@ -886,6 +903,64 @@ def test_resident_step_slots(ctx):
         fresh.select(0)
         with pytest.raises(cc.CutoutError):
             fresh.cutout_const(tc, pc)              # slot 0 holds nothing
+    finally:
+        fresh.close()
+
+
+def test_particle_index_policy_and_slots():
+    """the particle index of a resident step (k2p_*): policy auto builds it inside the SECOND many-halo cutout on a
+    resident step of >= 4 Mi particles, later many-halo cutouts read only the cells under the halos' windows, and the
+    cutouts are the same bit for bit; cutouts of a few halos keep scanning; the index belongs to the step: another
+    slot has none, coming back finds it, a new step in the slot drops it"""
+    n = 5_000_000
+    rng = np.random.default_rng(99)
+    pos = rng.uniform(30.0, 280.0, (40, 3)).astype(np.float32)
+    boxes = rng.uniform(5.0, 40.0, 40)
+    halos = [cc.halo_setup(p, b).halo for p, b in zip(pos, boxes)]
+    fresh = cc.Context(0)
+
+    def cut(hl, limit=-1):
+        fresh.cutout_halo(hl, n_limit_global=limit)
+        counts, rough = fresh.sync()
+        ev, _ = fresh.fetch_all(counts)
+        return counts.copy(), rough.copy(), ev, fresh.stats_ex()
+
+    def same(a, b):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        for c in a[2]:
+            assert np.array_equal(a[2][c].view(np.uint8), b[2][c].view(np.uint8)), c
+
+    try:
+        fresh.select(1)
+        fresh.synth(n, seed=5, kind=0, box=300.0)
+        res = [cut(halos) for _ in range(3)]
+        assert int(res[0][0].sum()) > 1000
+        for k, r in enumerate(res):
+            st = r[3]
+            assert st["index_resident"] == (k >= 1) and (st["index_build_ms"] > 0) == (k == 1), (k, st)
+            assert (st["scan_kernels"] == "k2p_plan+k2p_query") == (k >= 1), (k, st)
+            assert st["particles_read"] == n if k == 0 else 0 < st["particles_read"] < n // 4
+            same(r, res[0])
+        limit = n - 1_234_567  # the reference's tail drop applies to indexed rows too
+        fresh.set_option("index", "never")
+        want = cut(halos, limit)
+        fresh.set_option("index", "auto")
+        got = cut(halos, limit)
+        assert got[3]["scan_kernels"] == "k2p_plan+k2p_query" and want[3]["scan_kernels"] != "k2p_plan+k2p_query"
+        assert int(want[0].sum()) < int(res[0][0].sum())
+        same(got, want)
+        assert cut(halos[:2])[3]["scan_kernels"] == "k2_cutout_halo"  # below 8 halos: no cell index, plain scan
+        fresh.select(2)
+        fresh.synth(n, seed=6, kind=0, box=300.0)
+        other = cut(halos)
+        assert not other[3]["index_resident"] and other[3]["scan_kernels"] != "k2p_plan+k2p_query"
+        fresh.select(1)
+        back = cut(halos)
+        assert back[3]["index_resident"] and back[3]["index_build_ms"] == 0 and back[3]["scan_kernels"] == "k2p_plan+k2p_query"
+        same(back, res[0])
+        fresh.release()
+        fresh.synth(n, seed=7, kind=0, box=300.0)  # a new step in the slot: its index is gone
+        assert not cut(halos)[3]["index_resident"]
     finally:
         fresh.close()
 
