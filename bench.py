@@ -65,6 +65,9 @@ WORKLOADS = {
     "cfg5": dict(uc=2, n=125_000_000, halos="random1000", kind=0, box=300.0, scaling="weak",
                  desc="BASELINE cfg5: 1000 halo cutouts, boxLength 5/10/20/30 arcmin (250 halos each = four processLC-style "
                       "passes, one boxLength per pass), 125M-particle resident shard per GPU (1B on 8 GPUs)"),
+    "cfg5_scan": dict(uc=2, n=125_000_000, halos="random1000", kind=0, box=300.0, scaling="weak", index="never",
+                      desc="BASELINE cfg5 with the particle index switched off (option index=never): every one of the four "
+                           "passes streams all 125M particles through the cell-index walkers"),
     "cfg5_shared": dict(uc=2, n=125_000_000, halos="random1000_shared", kind=0, box=300.0, scaling="weak",
                         desc="BASELINE cfg5 as host/processLC.cpp's processLC_boxes (lc_cutout --boxLength 5 10 20 30) runs it: the "
                              "same 1000 (halo, boxLength 5/10/20/30) cutouts as cfg5, same results, in ONE pass over the "
@@ -254,6 +257,7 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
     step, passes, nhalos = make_step_fn(env, wl, n, n_total)
     ctx.release()
     ctx.set_option("payload", "auto")
+    ctx.set_option("index", wl.get("index", "auto"))
     ctx.set_option("timing", "on")  # per-kernel CUDA events inside the library: first cutout + the per-kernel pass only
     env.barrier()
     # ---- residency + the first (cold) cutout on the resident step: no payload yet, survivor buffers at their first guess
@@ -266,9 +270,11 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
     first_ms = (time.perf_counter() - t0) * 1e3
     first_dev_ms = ctx.last_total_ms() if passes == 1 else None
     payload_ms = 0.0
+    index_ms = 0.0
     for _ in range(max(warmup, 3)):
         step()
         payload_ms += ctx.stats_ex()["payload_build_ms"]
+        index_ms += ctx.stats_ex()["index_build_ms"]
     # per-kernel times (the roofline numerator's denominator) are read from the library's own CUDA events in a
     # separate untimed pass: reading them costs two synchronising calls per step that do not belong in the timed loop
     scan_ms, pass_ms = [], []
@@ -298,9 +304,11 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t0, t1) if sampler else None
     # survivors of a whole step (all passes)
-    surv_step, scanned_step = 0, 0
+    def in_bytes(s_):  # what the scan has to read: 12 B of every particle, or 16 B of the index rows under the windows
+        return 16.0 * s_["particles_read"] if s_["scan_kernels"].startswith("k2p") else 12.0 * s_["scanned"]
+    surv_step, scanned_step, read_step = 0, 0, 0.0
     if passes == 1:
-        surv_step, scanned_step = st["survivors"], st["scanned"]
+        surv_step, scanned_step, read_step = st["survivors"], st["scanned"], in_bytes(st)
     else:
         groups = [[cc.halo_setup(p, b).halo for (p, b) in hl] for (_b, hl) in halo_groups(wl)]
         for halos in groups:
@@ -309,9 +317,10 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
                 ctx.exchange_counts()
             else:
                 ctx.sync()
-            s2 = ctx.stats()
+            s2 = ctx.stats_ex()
             surv_step += s2["survivors"]
             scanned_step += s2["scanned"]
+            read_step += in_bytes(s2)
 
     e2e = None
     if with_e2e:
@@ -330,11 +339,12 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
     # 32-byte record (use case 2); the whole pass (scan + ordering + 12-column gather) moves 12 B per particle +
     # 84 B per survivor and is reported next to it
     rec_bytes = 24 if wl["uc"] == 1 else 32
-    alg_bytes = 12.0 * st["scanned"] + rec_bytes * st["survivors"]
+    alg_bytes = in_bytes(st) + rec_bytes * st["survivors"]
     achieved = alg_bytes / (float(np.mean(scan_ms)) * 1e-3) / 1e9
-    pass_bytes = 12.0 * st["scanned"] + 84.0 * st["survivors"]
+    pass_bytes = in_bytes(st) + 84.0 * st["survivors"]
     pass_gbs = pass_bytes / (float(np.mean(pass_ms)) * 1e-3) / 1e9
-    step_bytes = 12.0 * scanned_step + 84.0 * surv_step  # rank 0's shard, all passes of a step
+    step_bytes = read_step + 84.0 * surv_step  # rank 0's shard, all passes of a step
+    indexed = st["scan_kernels"].startswith("k2p")
     traffic = None
     tp = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -357,11 +367,11 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture "
                                        "(profiles/traffic.json); not re-measured in this run",
                      "peak_source": peak_src, "kernel": kernel,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(float(np.mean(scan_ms)), 4),
+                     "algorithmic_bytes_per_launch": alg_bytes, "particles_read_per_launch": st["particles_read"], "kernel_ms": round(float(np.mean(scan_ms)), 4),
                      "whole_pass": {"bytes": pass_bytes, "ms": round(float(np.mean(pass_ms)), 4),
                                     "achieved": round(pass_gbs, 1), "frac": round(pass_gbs / peak, 4),
                                     "what": "scan + ordering + gather kernels of one pass (CUDA events inside the library), "
-                                            "12 B/particle + 84 B/survivor"},
+                                            + ("16 B/index row read" if indexed else "12 B/particle") + " + 84 B/survivor"},
                      "whole_step": {"bytes": step_bytes, "ms": round(ms_per_step, 4),
                                     "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
                                     "what": "all passes of a step incl. launch gaps, host turnaround and the count exchange"}},
@@ -372,7 +382,11 @@ def run_resident(env, args, name, steps, warmup, with_e2e):
                                       "buffers at their first guess, no interleaved payload (gather from the 7 SoA columns)",
                       "payload_build_ms": round(payload_ms, 3), "payload_resident": st["payload_resident"],
                       "payload": "built lazily inside the first cutout that follows a dense one (>= max(65536, n/512) "
-                                 "survivors); never for sparse cutouts"},
+                                 "survivors); never for sparse cutouts",
+                      "index_build_ms": round(index_ms, 3), "index_resident": st["index_resident"],
+                      "index": "particle index of the resident step (16 B/particle, cell order), built lazily inside the "
+                               "second many-halo (>= 8) cutout on it; the timed passes then read only the rows under the "
+                               "halos' windows (roofline.particles_read_per_launch of particles_per_gpu)"},
         "gpu_launches": launches_all,
     }
     if nhalos:
@@ -792,7 +806,7 @@ def run_ours(args):
         out = run_resident(env, args, args.workload, args.steps, args.warmup, with_e2e=True)
     if not args.no_configs and args.workload == "cfg2":
         configs = {}
-        for name in ("cfg1", "const1b", "cfg4", "cfg5", "cfg5_shared", "cfg5_onepass", "cfg3"):
+        for name in ("cfg1", "const1b", "cfg4", "cfg5", "cfg5_scan", "cfg5_shared", "cfg5_onepass", "cfg3"):
             t0 = time.perf_counter()
             try:
                 r = run_cfg3(env, args, 2, 1) if name == "cfg3" else run_resident(env, args, name, sub_steps, sub_warm, with_e2e=False)
