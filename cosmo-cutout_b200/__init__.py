@@ -428,7 +428,7 @@ class Context:
                     nan_theta=int(out[4]), payload_resident=bool(out[5]), payload_build_ms=out[6] / 1000.0,
                     tail_dropped=int(out[7]),
                     scan_kernels=("k1s_scan", "k2_cutout_halo", "k2c_sift+k2c_match+k2c_exact", "k2_cutout_halo_cells",
-                                  "k2p_plan+k2p_query")[int(out[8])],
+                                  "k2p_query")[int(out[8])],
                     particles_read=int(out[9]), index_resident=bool(out[10]), index_build_ms=out[11] / 1000.0)
 
     def set_option(self, key, value):

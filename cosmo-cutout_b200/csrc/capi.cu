@@ -208,9 +208,9 @@ struct cc_ctx {
      * the first row of every cell.  A many-halo cutout on an indexed step reads only the cells under its halos' windows.
      * Built lazily like the payload: policy auto = inside the SECOND many-halo cutout on the same resident step (a step
      * that is cut once is cheaper to scan); 16 B/particle + 2 x 16 MB of HBM; dropped when another step becomes resident. */
-    DevBuf pidx_sorted, pidx_start, pidx_tmp, pidx_partial;
+    DevBuf pidx_sorted, pidx_start, pidx_tmp, pidx_partial, pidx_work;
     bool pidx_valid = false;
-    uint64_t pidx_gen = 0, pidx_gen_clock = 0; /* which build: a halo set keeps its plan (k2p_plan) for one */
+    uint64_t pidx_gen = 0, pidx_gen_clock = 0; /* which build of the index this is */
     int index_policy = 0;             /* 0 auto, 1 always, 2 never; cc_set_option "index" / CC_INDEX */
     int64_t step_many_halo_cutouts = 0;
     cudaEvent_t ev_idx0 = nullptr, ev_idx1 = nullptr;
@@ -243,11 +243,9 @@ struct cc_ctx {
         DevBuf pidx_items_buf;                             /* particle-index walker: (halo, grid line, columns) items */
         std::vector<size_t> pidx_items_off;                /* per launch batch: first item, number of items */
         std::vector<unsigned int> pidx_items_cnt;
-        DevBuf pidx_steps_buf;                             /* k2p_plan's prefix of every batch's items (+1 per batch) ... */
-        uint64_t plan_gen = 0;                             /* ... valid for this build of the particle index (0: none) */
         int walker = 0;     /* 0: not measured yet (the staged kernels measure), 1: staged, 2: one kernel */
         uint64_t last_use = 0;
-        void release() { pre_buf.release(); halo_buf.release(); bin_start_buf.release(); bin_bits_buf.release(); bin_items_buf.release(); pidx_items_buf.release(); pidx_steps_buf.release(); plan_gen = 0; key.clear(); }
+        void release() { pre_buf.release(); halo_buf.release(); bin_start_buf.release(); bin_bits_buf.release(); bin_items_buf.release(); pidx_items_buf.release(); key.clear(); }
     };
     static const int MAX_HALO_SETS = 8;
     HaloSet halo_sets[MAX_HALO_SETS];
@@ -621,9 +619,18 @@ int prepare_halo(cc_ctx* c) {
                 for (int h = 0; h < hn; ++h) {
                     const Box& bx = boxes[(size_t)h];
                     if (bx.s1 < bx.s0) continue;
+                    /* runs of at most 4 cells (~500 rows, 15 steps of 32): fine enough for the atomic hand-out to balance */
+                    int run = 4; /* (longer runs for a window that covers a large part of the sky: at most 4096 items per halo) */
+                    while ((int64_t)(bx.c1 - bx.c0 + 1) * ((bx.s1 - bx.s0 + run) / run) > 4096) run *= 2;
                     for (int ic = bx.c0; ic <= bx.c1; ++ic)
-                        pitems.push_back(make_uint2((unsigned int)h | ((unsigned int)ic << 16), (unsigned int)bx.s0 | ((unsigned int)bx.s1 << 16)));
+                        for (int s0 = bx.s0; s0 <= bx.s1; s0 += run)
+                            pitems.push_back(make_uint2((unsigned int)h | ((unsigned int)ic << 16),
+                                                        (unsigned int)s0 | ((unsigned int)std::min(bx.s1, s0 + run - 1) << 16)));
                 }
+                /* widest runs first: the hand-out ends with the short items (longest-processing-time-first) */
+                std::stable_sort(pitems.begin() + (ptrdiff_t)hs->pidx_items_off[(size_t)bi], pitems.end(), [](const uint2& u, const uint2& v) {
+                    return ((u.y >> 16) - (u.y & 0xffffu)) > ((v.y >> 16) - (v.y & 0xffffu));
+                });
                 pitems.push_back(make_uint2(cck::K2P_ALL, 0u));
                 hs->pidx_items_cnt[(size_t)bi] = (unsigned int)(pitems.size() - hs->pidx_items_off[(size_t)bi]);
                 for (size_t i = 0; i < ncell; ++i) st[i + 1] += st[i]; /* st[i] = first item of cell i */
@@ -656,8 +663,6 @@ int prepare_halo(cc_ctx* c) {
             if (!items.empty())
                 CU(cudaMemcpyAsync(hs->bin_items_buf.p, items.data(), items.size() * 2, cudaMemcpyHostToDevice, c->stream));
             if ((rc = hs->pidx_items_buf.ensure(pitems.size() * sizeof(uint2)))) return rc;
-            if ((rc = hs->pidx_steps_buf.ensure((pitems.size() + (size_t)nbatch) * 8))) return rc;
-            hs->plan_gen = 0;
             CU(cudaMemcpyAsync(hs->pidx_items_buf.p, pitems.data(), pitems.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
         }
         CU(cudaMemcpyAsync(hs->pre_buf.p, pre.data(), (size_t)H * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -742,16 +747,13 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             pa.start = (const unsigned int*)c->pidx_start.p;
             pa.items = (const uint2*)c->hs->pidx_items_buf.p + c->hs->pidx_items_off[(size_t)bi];
             pa.nitems = c->hs->pidx_items_cnt[(size_t)bi];
-            /* the plan (rows of every item -> prefix of 32-particle steps) depends on the halo set and on the index
-             * only: computed in the set's first pass over this index, reused by the later ones */
-            pa.item_step0 = (unsigned long long*)c->hs->pidx_steps_buf.p + c->hs->pidx_items_off[(size_t)bi] + (size_t)bi;
+            /* items are handed out through one zeroed counter per launch batch */
+            const int nbatch = (H + cck::K2_MAX_HALOS - 1) / cck::K2_MAX_HALOS;
+            int rc2;
+            if ((rc2 = c->pidx_work.ensure((size_t)nbatch * 4))) return rc2;
+            if (bi == 0) CU(cudaMemsetAsync(c->pidx_work.p, 0, (size_t)nbatch * 4, c->stream));
+            pa.work = (unsigned int*)c->pidx_work.p + bi;
             pa.tested = rec_count + 6;
-            if (c->hs->plan_gen != c->pidx_gen) {
-                cck::k2p_plan<<<1, cck::K2P_PLAN_THREADS, 0, c->stream>>>(pa);
-                CU(cudaGetLastError());
-                c->launches += 1;
-                if (h0 + cck::K2_MAX_HALOS >= H) c->hs->plan_gen = c->pidx_gen;
-            }
             cck::k2p_query<<<(unsigned int)c->sm_count * 5u, cck::K2P_THREADS, 0, c->stream>>>(pa);
             CU(cudaGetLastError());
             c->launches += 1;
@@ -1187,7 +1189,7 @@ void cc_destroy(cc_ctx* c) {
     for (auto& b : c->col_buf) b.release();
     c->payload.release();
     for (auto& b : c->out_buf) b.release();
-    DevBuf* rest[] = {&c->pidx_sorted, &c->pidx_start, &c->pidx_tmp, &c->pidx_partial, &c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->place_buf, &c->counts_buf,
+    DevBuf* rest[] = {&c->pidx_sorted, &c->pidx_start, &c->pidx_tmp, &c->pidx_partial, &c->pidx_work, &c->scratch, &c->rec_a, &c->rec_b, &c->rank_buf, &c->place_buf, &c->counts_buf,
                       &c->hstate, &c->gather_buf, &c->offsets_buf, &c->xchg_send, &c->cand, &c->cand_count, &c->pair_p, &c->pair_h, &c->pair_count, &c->t_idx, &c->t_th, &c->t_ph, &c->t_x, &c->t_y, &c->t_z};
     for (DevBuf* b : rest) b->release();
     for (auto& e : c->halo_sets) e.release();

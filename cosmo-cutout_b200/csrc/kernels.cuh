@@ -1328,8 +1328,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k2_cutout_halo_cells(const __gr
  * records, counts and therefore the cutouts are the same, bit for bit.
  *
  *   k2p_hist / k2p_scan_{a,b,c} / k2p_scatter   build (once per resident step, capi.cu maybe_build_index)
- *   k2p_plan    per pass: rows of every (halo, grid line) item -> prefix of 32-particle steps
- *   k2p_query   per pass: the steps are cut into equal contiguous slices, one per warp (no atomics, no tail) */
+ *   k2p_query   per pass: (halo, grid line) items handed out to the warps by an atomic counter, largest first */
 constexpr unsigned int K2P_NCELL = (unsigned int)K2_GRID * (unsigned int)K2_GRID; /* + 1 bin: out-of-range positions */
 constexpr unsigned int K2P_NBIN = K2P_NCELL + 1u;
 constexpr unsigned int K2P_ALL = 0xffffu; /* item halo: every halo of the launch (the out-of-range bin) */
@@ -1420,7 +1419,7 @@ struct PidxArgs {
     const uint2* items;              /* {halo | grid line << 16, first column | last column << 16}; halo K2P_ALL: the
                                         out-of-range bin against every halo of the launch */
     unsigned int nitems;
-    unsigned long long* item_step0;  /* [nitems + 1] exclusive prefix of the items' 32-particle steps (k2p_plan) */
+    unsigned int* work;              /* zeroed: next item to hand out */
     unsigned long long* tested;      /* stat: particles read */
 };
 __device__ __forceinline__ void k2p_rows(const PidxArgs& p, uint2 it, unsigned int& begin, unsigned int& end) {
@@ -1429,44 +1428,6 @@ __device__ __forceinline__ void k2p_rows(const PidxArgs& p, uint2 it, unsigned i
     begin = __ldg(p.start + line + (it.y & 0xffffu));
     end = __ldg(p.start + line + (it.y >> 16) + 1u);
 }
-constexpr int K2P_PLAN_THREADS = 1024;
-__global__ void __launch_bounds__(K2P_PLAN_THREADS) k2p_plan(const PidxArgs p) {
-    __shared__ unsigned long long s_w[K2P_PLAN_THREADS / 32];
-    const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned int per = (p.nitems + K2P_PLAN_THREADS - 1) / K2P_PLAN_THREADS;
-    const unsigned int i0 = min(p.nitems, tid * per), i1 = min(p.nitems, i0 + per);
-    unsigned long long sum = 0;
-    for (unsigned int i = i0; i < i1; ++i) {
-        unsigned int b, e;
-        k2p_rows(p, p.items[i], b, e);
-        sum += (e - b + 31u) >> 5;
-    }
-    unsigned long long inc = sum;
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= (unsigned int)d) inc += t;
-    }
-    if (lane == 31u) s_w[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = s_w[lane];
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= (unsigned int)d) w += t;
-        }
-        s_w[lane] = w;
-    }
-    __syncthreads();
-    unsigned long long run = inc - sum + (warp ? s_w[warp - 1] : 0ull);
-    for (unsigned int i = i0; i < i1; ++i) {
-        unsigned int b, e;
-        k2p_rows(p, p.items[i], b, e);
-        p.item_step0[i] = run;
-        run += (e - b + 31u) >> 5;
-    }
-    if (tid == K2P_PLAN_THREADS - 1) p.item_step0[p.nitems] = run;
-}
-
 constexpr int K2P_THREADS = 128; /* five CTAs per SM at 96 registers: 20 warps, each with its own slice of the steps */
 struct __align__(16) K2PStacks {
     float4 cp[K2C_CCAP];         /* tested pair: x, y, z, particle index (bits) */
@@ -1538,51 +1499,57 @@ __global__ void __launch_bounds__(K2P_THREADS, 5) k2p_query(const __grid_constan
         }
     };
 
-    const unsigned long long total = p.item_step0[p.nitems];
-    const unsigned long long total_warps = (unsigned long long)gridDim.x * (K2P_THREADS / 32);
-    const unsigned long long per = (total + total_warps - 1) / total_warps;
-    const unsigned long long wid = (unsigned long long)blockIdx.x * (K2P_THREADS / 32) + warp;
-    const unsigned long long s_begin = min(total, wid * per), s_end = min(total, s_begin + per);
-    if (s_begin < s_end) {
-        /* the item that holds this warp's first step: the last one whose prefix is <= s_begin */
-        unsigned int lo = 0, hi = p.nitems - 1u;
-        while (lo < hi) {
-            const unsigned int mid = (lo + hi + 1u) >> 1;
-            if (p.item_step0[mid] <= s_begin) lo = mid;
-            else hi = mid - 1u;
+    /* Items (one halo x one grid line: a contiguous run of rows) are handed out by an atomic counter, largest first
+     * (the host sorts them), one per warp at a time: how much exact arithmetic a row costs depends on where it lies in
+     * its halo's window, so equal static slices left most warps waiting at the final barrier for a few (ncu: 31 % of
+     * the samples).  The hand-out is pipelined two deep -- while item k is worked on, the rows and window of item k+1
+     * are on their way and the ticket of item k+2 has been drawn -- and inside an item the 512 bytes of the next step
+     * are requested before the current step is worked on (+ an L2 prefetch four steps ahead). */
+    auto ticket = [&]() {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(p.work, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    struct Meta { unsigned int h, row_begin, row_end; float4 W; };
+    auto meta_of = [&](unsigned int it) {
+        Meta m;
+        m.h = 0u; m.row_begin = 0u; m.row_end = 0u; m.W = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it < p.nitems) {
+            const uint2 v = __ldg(p.items + it);
+            m.h = v.x & 0xffffu;
+            k2p_rows(p, v, m.row_begin, m.row_end);
+            if (m.h != K2P_ALL) m.W = __ldg(a.pre + m.h);
         }
-        /* the walk is one step AHEAD of the work: the 512 bytes of step s+1 are requested before step s is worked on
-         * (and the rows four steps further on are pulled into the L2), or every step would wait out a DRAM round trip
-         * with nothing else in flight for the warp */
-        unsigned int item = lo;
-        unsigned long long step0 = p.item_step0[item], step1 = p.item_step0[item + 1];
-        bool fresh = true;
-        unsigned int h_next = 0, row_begin = 0, row_end = 0;
-        float4 W_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 q_next = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-        bool live_next = false;
-        auto request = [&](unsigned long long step) {
-            while (step >= step1) { ++item; step0 = step1; step1 = p.item_step0[item + 1]; fresh = true; }
-            if (fresh) {
-                const uint2 it = p.items[item];
-                h_next = it.x & 0xffffu;
-                k2p_rows(p, it, row_begin, row_end);
-                if (h_next != K2P_ALL) W_next = __ldg(a.pre + h_next);
-                fresh = false;
-            }
-            const unsigned long long row = (unsigned long long)row_begin + ((step - step0) << 5) + (unsigned int)lane;
-            live_next = row < (unsigned long long)row_end;
+        return m;
+    };
+    unsigned int it_cur = ticket(), it_next = ticket();
+    Meta cur = meta_of(it_cur);
+    float4 q_next = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    bool have_first = false; /* q_next holds the first 32 rows of `cur` */
+    while (it_cur < p.nitems) {
+        const unsigned int it_after = ticket();
+        const Meta nxt = meta_of(it_next);
+        const unsigned int h = cur.h;
+        const float4 W = cur.W;
+        if (!have_first) {
+            const unsigned int row = cur.row_begin + (unsigned int)lane;
             q_next = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-            if (live_next) q_next = __ldcs(p.sorted + row);
-            if ((lane & 7) == 0 && row + 128u < (unsigned long long)row_end) prefetch_l2(p.sorted + row + 128u);
-        };
-        request(s_begin);
-        for (unsigned long long step = s_begin; step < s_end; ++step) {
+            if (row < cur.row_end) q_next = __ldcs(p.sorted + row);
+        }
+        have_first = false;
+        for (unsigned int r0 = cur.row_begin; r0 < cur.row_end; r0 += 32u) {
             const float4 q = q_next;
-            const unsigned int h = h_next;
-            const float4 W = W_next;
-            bool live = live_next;
-            if (step + 1 < s_end) request(step + 1);
+            const unsigned int row = r0 + (unsigned int)lane;
+            bool live = row < cur.row_end;
+            q_next = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            if (r0 + 32u < cur.row_end) {
+                if (row + 32u < cur.row_end) q_next = __ldcs(p.sorted + row + 32u);
+            } else { /* last step of the item: the first rows of the next one */
+                const unsigned int rn = nxt.row_begin + (unsigned int)lane;
+                if (rn < nxt.row_end) q_next = __ldcs(p.sorted + rn);
+                have_first = true;
+            }
+            if ((lane & 7) == 0 && row + 160u < cur.row_end) prefetch_l2(p.sorted + row + 160u);
             live = live && (long long)__float_as_uint(q.w) < a.n; /* the n_limit clamp (reference tail drop) */
             n_tested += __popc(__ballot_sync(0xffffffffu, live));
             if (h == K2P_ALL) { /* out-of-range positions: the exact path decides, against every halo of the launch */
@@ -1612,6 +1579,9 @@ __global__ void __launch_bounds__(K2P_THREADS, 5) k2p_query(const __grid_constan
             __syncwarp();
             drain(false);
         }
+        it_cur = it_next;
+        it_next = it_after;
+        cur = nxt;
     }
     drain(true);
     if (lane == 0 && n_cand) atomicAdd(a.n_cand, n_cand);

@@ -227,7 +227,7 @@ int cc_last_stats(cc_ctx* ctx, int64_t out[4]);
  * shard behind n_limit_global (the reference's tail drop, util.cpp:106-108); [8] which scan ran: 0 use case 1,
  * 1 use case 2 every particle against every halo (k2_cutout_halo), 2 the cell index walked by the staged kernels
  * (k2c_sift, k2c_match, k2c_exact), 3 by one kernel (k2_cutout_halo_cells), 4 the particle index of the resident
- * step (k2p_plan, k2p_query); [9] particles the scan read: all scanned ones, or with [8] = 4 only the index rows under the
+ * step (k2p_query); [9] particles the scan read: all scanned ones, or with [8] = 4 only the index rows under the
  * halos' windows; [10] 1 when the particle index of the resident step exists; [11] microseconds the last cutout call
  * spent building it (0: it did not). */
 #define CC_STATS_EX_FIELDS 12

@@ -1,0 +1,4 @@
+# cfg5_shared with the particle index: full-set capture of k2p_query and the ordering kernels
+set -x
+B="python bench.py --workload cfg5_shared --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-configs"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k2p_query|k3_bucket|k3_rank|k3_place|k3_gather_halo" -s 20 -c 5 -o gpurun_out/r02c24_prof_cfg5_shared_idx -f $B > gpurun_out/r02c24_ncu.log 2>&1; echo full rc=$?

@@ -24,7 +24,7 @@ def ctx():
 def cells_mode(ctx, request):
     """many halos: run the test with the staged kernels (k2c_sift / k2c_match / k2c_exact), with the one-kernel scan
     (k2_cutout_halo_cells) -- the library picks between them per halo set from the measured bitmap hit rate -- and with
-    the particle index of the resident step (k2p_plan / k2p_query), which it builds for a step that is cut repeatedly"""
+    the particle index of the resident step (k2p_query), which it builds for a step that is cut repeatedly"""
     mode = request.getfixturevalue("cells")
     if mode == "index":  # the particle index of the resident step (k2p_*), built inside the first many-halo cutout
         ctx.set_option("index", "always")
@@ -35,7 +35,7 @@ def cells_mode(ctx, request):
     ran = ctx.stats_ex()["scan_kernels"]
     ctx.set_option("cells", "auto")
     ctx.set_option("index", "auto")
-    assert ran == {"staged": "k2c_sift+k2c_match+k2c_exact", "mono": "k2_cutout_halo_cells", "index": "k2p_plan+k2p_query"}[mode]
+    assert ran == {"staged": "k2c_sift+k2c_match+k2c_exact", "mono": "k2_cutout_halo_cells", "index": "k2p_query"}[mode]
 
 
 def _same_float_bits(a, b):
@@ -747,7 +747,7 @@ def test_many_halos_at_size_sample_parity(ctx):
         counts, rough = ctx.sync()
         st = ctx.stats_ex()
         assert st["index_resident"] == (index == "always") and (st["index_build_ms"] > 0) == (index == "always")
-        assert (st["scan_kernels"] == "k2p_plan+k2p_query") == (index == "always")
+        assert (st["scan_kernels"] == "k2p_query") == (index == "always")
         assert st["particles_read"] == limit if index == "never" else 0 < st["particles_read"] < limit // 4
     ctx.set_option("index", "auto")
     everything, _ = ctx.fetch_all(counts)
@@ -938,7 +938,7 @@ def test_particle_index_policy_and_slots():
         for k, r in enumerate(res):
             st = r[3]
             assert st["index_resident"] == (k >= 1) and (st["index_build_ms"] > 0) == (k == 1), (k, st)
-            assert (st["scan_kernels"] == "k2p_plan+k2p_query") == (k >= 1), (k, st)
+            assert (st["scan_kernels"] == "k2p_query") == (k >= 1), (k, st)
             assert st["particles_read"] == n if k == 0 else 0 < st["particles_read"] < n // 4
             same(r, res[0])
         limit = n - 1_234_567  # the reference's tail drop applies to indexed rows too
@@ -946,17 +946,17 @@ def test_particle_index_policy_and_slots():
         want = cut(halos, limit)
         fresh.set_option("index", "auto")
         got = cut(halos, limit)
-        assert got[3]["scan_kernels"] == "k2p_plan+k2p_query" and want[3]["scan_kernels"] != "k2p_plan+k2p_query"
+        assert got[3]["scan_kernels"] == "k2p_query" and want[3]["scan_kernels"] != "k2p_query"
         assert int(want[0].sum()) < int(res[0][0].sum())
         same(got, want)
         assert cut(halos[:2])[3]["scan_kernels"] == "k2_cutout_halo"  # below 8 halos: no cell index, plain scan
         fresh.select(2)
         fresh.synth(n, seed=6, kind=0, box=300.0)
         other = cut(halos)
-        assert not other[3]["index_resident"] and other[3]["scan_kernels"] != "k2p_plan+k2p_query"
+        assert not other[3]["index_resident"] and other[3]["scan_kernels"] != "k2p_query"
         fresh.select(1)
         back = cut(halos)
-        assert back[3]["index_resident"] and back[3]["index_build_ms"] == 0 and back[3]["scan_kernels"] == "k2p_plan+k2p_query"
+        assert back[3]["index_resident"] and back[3]["index_build_ms"] == 0 and back[3]["scan_kernels"] == "k2p_query"
         same(back, res[0])
         fresh.release()
         fresh.synth(n, seed=7, kind=0, box=300.0)  # a new step in the slot: its index is gone
