@@ -918,6 +918,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             r.rec_cap = (unsigned long long)c->rec_cap;
             r.rank = (unsigned int*)c->rank_buf.p;
             r.sorted = (unsigned long long*)c->rec_a.p; /* the unbucketed records are dead once k3_bucket ran */
+            r.place = (unsigned int*)c->place_buf.p;
             r.H = H;
             /* few halos: many chunk slots per halo; many halos: a few, the y dimension provides the parallelism */
             const unsigned int gy = (unsigned int)std::min(H, 8192);
@@ -936,7 +937,13 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             pl.rec_count = rec_count;
             pl.rec_cap = (unsigned long long)c->rec_cap;
             pl.place = (unsigned int*)c->place_buf.p;
-            cck::k3_place<<<g1, 256, 0, c->stream>>>(pl);
+            pl.H = H;
+            {
+                /* few halos: many slices per segment; many halos: the y dimension provides the parallelism */
+                const unsigned int py = (unsigned int)std::min(H, 4096);
+                const unsigned int px = (unsigned int)std::max(2, std::min(1024, (c->sm_count * 8) / (int)py));
+                cck::k3_place<<<dim3(px, py), 256, 0, c->stream>>>(pl);
+            }
             CU(cudaGetLastError());
             g.recs = (const cck::Rec*)c->rec_b.p;
             g.place = (const unsigned int*)c->place_buf.p;

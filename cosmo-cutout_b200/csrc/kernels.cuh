@@ -1908,26 +1908,29 @@ __global__ void k3_scan_counts(const unsigned long long* counts, unsigned long l
  * k3_gather_halo writes its rows coalesced.  For a longer segment it stores the record's rank inside its chunk and
  * the chunk's sorted keys, and k3_gather_halo adds, per record, the number of smaller keys in the OTHER chunks of
  * the segment (one binary search per chunk) and scatters.  grid = (chunk slots, halos). */
-constexpr int K3_THREADS = 512;
+constexpr int K3_THREADS = 1024;
 constexpr int K3_SORT_MAX = 8192; /* k3_small: records one CTA sorts */
-constexpr int K3_CHUNK = 8192;    /* 164 KB of shared memory per CTA; segments up to here are ordered by ONE CTA and gathered row-major */
-constexpr int K3_NB = 512;        /* buckets per chunk */
+constexpr int K3_CHUNK = 16384;   /* segments up to here are ordered by ONE CTA and gathered row-major; a thread keeps its
+                                     16 keys in registers (all loads in flight at once), shared memory holds the grouped
+                                     copy: 196 KB per CTA */
+constexpr int K3_PER = K3_CHUNK / K3_THREADS;
+constexpr int K3_NB = 1024;       /* buckets per chunk */
 static_assert(K3_NB == K3_THREADS, "k3_rank scans one bucket count per thread");
-constexpr size_t K3_SMEM_BYTES = (size_t)K3_CHUNK * (2 * sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
+constexpr size_t K3_SMEM_BYTES = (size_t)K3_CHUNK * (sizeof(unsigned long long) + 2 * sizeof(unsigned short)) +
                                  (size_t)(K3_NB + 1) * sizeof(unsigned int);
 struct RankArgs {
     const unsigned long long* rec_count; /* > rec_cap: overflow, nothing to do */
     const Rec* recs;                     /* bucketed */
     const unsigned long long* seg_begin; /* [H+1] */
     unsigned long long rec_cap;
-    unsigned int* rank;                  /* [nrec] single-chunk segment: record of row i; else: rank inside the chunk */
+    unsigned int* rank;                  /* [nrec] multi-chunk segment: rank of the record inside its chunk */
     unsigned long long* sorted;          /* [nrec] sorted keys of every chunk of a multi-chunk segment */
+    unsigned int* place;                 /* [nrec] single-chunk segment: the record (index into recs) of every output row */
     int H;
 };
 __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw);          /* as loaded */
-    unsigned long long* s_grp = s_key + K3_CHUNK;                                       /* grouped by bucket */
+    unsigned long long* s_grp = reinterpret_cast<unsigned long long*>(s_raw);           /* grouped by bucket */
     unsigned short* s_src = reinterpret_cast<unsigned short*>(s_grp + K3_CHUNK);        /* grouped: position as loaded */
     unsigned short* s_slot = s_src + K3_CHUNK;                                          /* as loaded: slot inside the bucket */
     unsigned int* s_start = reinterpret_cast<unsigned int*>(s_slot + K3_CHUNK);         /* [K3_NB + 1] */
@@ -1942,14 +1945,20 @@ __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
             const unsigned int m = (unsigned int)min((unsigned long long)K3_CHUNK, len - c0);
             if (tid == 0) { s_min = 0xffffffffu; s_max = 0u; }
             for (unsigned int i = tid; i <= K3_NB; i += K3_THREADS) s_start[i] = 0u;
-            __syncthreads();
+            unsigned long long key[K3_PER];
             unsigned int lo = 0xffffffffu, hi = 0u;
-            for (unsigned int i = tid; i < m; i += K3_THREADS) {
-                const unsigned long long k = a.recs[b + c0 + i].key;
-                s_key[i] = k;
-                lo = min(lo, (unsigned int)(k >> 32));
-                hi = max(hi, (unsigned int)(k >> 32));
+#pragma unroll
+            for (int k = 0; k < K3_PER; ++k) {
+                const unsigned int i = tid + k * K3_THREADS;
+                key[k] = ~0ull;
+                if (i < m) key[k] = a.recs[b + c0 + i].key;
             }
+#pragma unroll
+            for (int k = 0; k < K3_PER; ++k) {
+                const unsigned int i = tid + k * K3_THREADS;
+                if (i < m) { lo = min(lo, (unsigned int)(key[k] >> 32)); hi = max(hi, (unsigned int)(key[k] >> 32)); }
+            }
+            __syncthreads();
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
             if (lane == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); }
@@ -1957,9 +1966,13 @@ __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
             const unsigned int kmin = s_min;
             unsigned int shift = 0; /* bucket = (theta bits - min) >> shift, < K3_NB */
             while (((s_max - kmin) >> shift) >= (unsigned int)K3_NB) ++shift;
-            for (unsigned int i = tid; i < m; i += K3_THREADS) {
-                const unsigned int bk = ((unsigned int)(s_key[i] >> 32) - kmin) >> shift;
-                s_slot[i] = (unsigned short)atomicAdd(&s_start[bk + 1], 1u); /* counts land one to the right */
+#pragma unroll
+            for (int k = 0; k < K3_PER; ++k) {
+                const unsigned int i = tid + k * K3_THREADS;
+                if (i < m) {
+                    const unsigned int bk = ((unsigned int)(key[k] >> 32) - kmin) >> shift;
+                    s_slot[i] = (unsigned short)atomicAdd(&s_start[bk + 1], 1u); /* counts land one to the right */
+                }
             }
             __syncthreads();
             /* inclusive scan of the counts: s_start[bk] = first position of bucket bk (one entry per thread,
@@ -1986,11 +1999,14 @@ __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
                 s_start[tid + 1] = v + (warp ? s_warp[warp - 1] : 0u);
             }
             __syncthreads();
-            for (unsigned int i = tid; i < m; i += K3_THREADS) {
-                const unsigned long long k = s_key[i];
-                const unsigned int p = s_start[((unsigned int)(k >> 32) - kmin) >> shift] + s_slot[i];
-                s_grp[p] = k;
-                s_src[p] = (unsigned short)i;
+#pragma unroll
+            for (int k = 0; k < K3_PER; ++k) {
+                const unsigned int i = tid + k * K3_THREADS;
+                if (i < m) {
+                    const unsigned int p = s_start[((unsigned int)(key[k] >> 32) - kmin) >> shift] + s_slot[i];
+                    s_grp[p] = key[k];
+                    s_src[p] = (unsigned short)i;
+                }
             }
             __syncthreads();
             for (unsigned int p = tid; p < m; p += K3_THREADS) {
@@ -2000,7 +2016,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_rank(const RankArgs a) {
                 unsigned int r = q0;
                 for (unsigned int q = q0; q < q1; ++q) r += s_grp[q] < k;
                 if (len <= K3_CHUNK) {
-                    a.rank[b + r] = s_src[p];
+                    a.place[b + r] = (unsigned int)b + s_src[p];
                 } else {
                     a.rank[b + c0 + s_src[p]] = r;
                     a.sorted[b + c0 + r] = k;
@@ -2035,30 +2051,35 @@ struct PlaceArgs {
     const unsigned long long* seg_begin;
     const unsigned long long* rec_count;
     unsigned long long rec_cap;
-    unsigned int* place;
+    unsigned int* place;                 /* the record (index into recs) of every output row */
+    int H;
 };
-__global__ void k3_place(const PlaceArgs a) {
+/* grid = (slices, segments): a single-chunk segment (nearly all of them in a job of cluster-sized cutouts) costs its
+ * CTAs one read of two segment starts -- the kernel used to read every record to learn its segment -- and the records
+ * of a multi-chunk segment are spread over gridDim.x CTAs (each is a chain of binary searches through the L2) */
+__global__ void __launch_bounds__(256) k3_place(const PlaceArgs a) {
     if (*a.rec_count > a.rec_cap) return; /* overflow: see k3_bucket */
-    const unsigned long long nrec = *a.rec_count;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrec;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const Rec r = a.recs[i];
-        const unsigned long long sb = a.seg_begin[r.halo];
-        const unsigned long long len = a.seg_begin[r.halo + 1] - sb;
+    for (int h = blockIdx.y; h < a.H; h += gridDim.y) {
+        const unsigned long long sb = a.seg_begin[h];
+        const unsigned long long len = a.seg_begin[h + 1] - sb;
         if (len <= K3_CHUNK) continue; /* single chunk: k3_rank already stored row -> record */
-        unsigned long long o = a.rank[i];
-        const unsigned long long mine = (i - sb) / K3_CHUNK;
-        for (unsigned long long c = 0; c * K3_CHUNK < len; ++c) {
-            if (c == mine) continue;
-            const unsigned long long* ck = a.sorted + sb + c * K3_CHUNK;
-            unsigned int lo = 0, hi = (unsigned int)min((unsigned long long)K3_CHUNK, len - c * K3_CHUNK);
-            while (lo < hi) {
-                const unsigned int mid = (lo + hi) >> 1;
-                if (ck[mid] < r.key) lo = mid + 1; else hi = mid;
+        for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < len;
+             j += (unsigned long long)gridDim.x * blockDim.x) {
+            const unsigned long long key = a.recs[sb + j].key;
+            unsigned long long o = a.rank[sb + j];
+            const unsigned long long mine = j / K3_CHUNK;
+            for (unsigned long long c = 0; c * K3_CHUNK < len; ++c) {
+                if (c == mine) continue;
+                const unsigned long long* ck = a.sorted + sb + c * K3_CHUNK;
+                unsigned int lo = 0, hi = (unsigned int)min((unsigned long long)K3_CHUNK, len - c * K3_CHUNK);
+                while (lo < hi) {
+                    const unsigned int mid = (lo + hi) >> 1;
+                    if (ck[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                o += lo;
             }
-            o += lo;
+            a.place[sb + o] = (unsigned int)(sb + j);
         }
-        a.place[sb + o] = (unsigned int)(i - sb);
     }
 }
 
@@ -2068,10 +2089,7 @@ __global__ void k3_gather_halo(const GatherArgs a) {
     const unsigned long long nrec = *a.rec_count;
     for (unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; o < nrec;
          o += (unsigned long long)gridDim.x * blockDim.x) {
-        Rec r = a.recs[o]; /* every record of a segment names the segment's halo */
-        const unsigned long long sb = a.seg_begin[r.halo];
-        const unsigned long long len = a.seg_begin[r.halo + 1] - sb;
-        r = a.recs[sb + (len <= K3_CHUNK ? a.rank[o] : a.place[o])];
+        const Rec r = a.recs[a.place[o]]; /* row -> record: k3_rank (single-chunk segments) or k3_place */
         if ((long long)o >= a.out_cap) continue;
         const long long g = (long long)(r.key & 0xffffffffull);
         a.out.theta[o] = r.th;                        /* processLC.cpp:1446-1447 */
