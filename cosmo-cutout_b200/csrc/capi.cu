@@ -922,7 +922,8 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             r.H = H;
             /* few halos: many chunk slots per halo; many halos: a few, the y dimension provides the parallelism */
             const unsigned int gy = (unsigned int)std::min(H, 8192);
-            const unsigned int gx = (unsigned int)std::max(8, std::min(64, (c->sm_count * 8) / (int)gy));
+            /* (a CTA holds 196 KB of shared memory, i.e. an SM: idle chunk slots of a many-halo pass cost as much as busy ones) */
+            const unsigned int gx = (unsigned int)std::max(1, std::min(64, (c->sm_count * 2) / (int)gy));
             if (!c->k3_smem_set) {
                 CU(cudaFuncSetAttribute((const void*)cck::k3_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cck::K3_SMEM_BYTES));
                 c->k3_smem_set = true;

@@ -1855,23 +1855,50 @@ __global__ void __launch_bounds__(K3B_THREADS) k3_bucket(const BucketArgs a) {
     const unsigned long long i0 = (unsigned long long)blockIdx.x * per, i1 = min(nrec, i0 + per);
     if (i0 >= i1) return;
     const bool table = a.H <= K3B_HMAX;
+    const unsigned int lane = tid & 31u;
+    /* the scans emit a halo's records in runs (a warp works on one halo at a time): when all 32 records of a warp's
+     * load name the same halo, one shared-memory atomic stands for 32 conflicting ones */
     if (table) {
         for (unsigned int h = tid; h < (unsigned int)a.H; h += K3B_THREADS) s_cnt[h] = 0u;
         __syncthreads();
-        for (unsigned long long i = i0 + tid; i < i1; i += K3B_THREADS) atomicAdd(&s_cnt[a.recs[i].halo], 1u);
+        for (unsigned long long i = i0 + tid; i - tid < i1; i += K3B_THREADS) {
+            const bool live = i < i1;
+            const unsigned int halo = live ? a.recs[i].halo : 0xffffffffu;
+            const unsigned int first = __shfl_sync(0xffffffffu, halo, 0);
+            if (__all_sync(0xffffffffu, halo == first)) {
+                if (lane == 0 && live) atomicAdd(&s_cnt[halo], 32u);
+            } else if (live) {
+                atomicAdd(&s_cnt[halo], 1u);
+            }
+        }
         __syncthreads();
         for (unsigned int h = tid; h < (unsigned int)a.H; h += K3B_THREADS) {
             const unsigned int c = s_cnt[h];
-            /* the CTA's range inside the halo's segment; kept as a 32-bit offset from the segment start */
-            s_cnt[h] = c ? (unsigned int)atomicAdd(a.cursor + (size_t)h * K3_CURSOR_STRIDE, (unsigned long long)c) : 0u;
+            /* the CTA's range inside the halo's segment, as a 32-bit position in the output (record counts fit 32 bits:
+             * the row -> record map is 32-bit) */
+            s_cnt[h] = c ? (unsigned int)(a.seg_begin[h] + atomicAdd(a.cursor + (size_t)h * K3_CURSOR_STRIDE, (unsigned long long)c)) : 0u;
         }
         __syncthreads();
+        for (unsigned long long i = i0 + tid; i - tid < i1; i += K3B_THREADS) {
+            const bool live = i < i1;
+            Rec r;
+            r.halo = 0xffffffffu;
+            if (live) r = a.recs[i];
+            const unsigned int first = __shfl_sync(0xffffffffu, r.halo, 0);
+            unsigned int p = 0;
+            if (__all_sync(0xffffffffu, r.halo == first)) {
+                if (lane == 0 && live) p = atomicAdd(&s_cnt[r.halo], 32u);
+                p = __shfl_sync(0xffffffffu, p, 0) + lane;
+            } else if (live) {
+                p = atomicAdd(&s_cnt[r.halo], 1u);
+            }
+            if (live && p < a.rec_cap) a.out[p] = r;
+        }
+        return;
     }
     for (unsigned long long i = i0 + tid; i < i1; i += K3B_THREADS) {
         const Rec r = a.recs[i];
-        unsigned long long off;
-        if (table) off = atomicAdd(&s_cnt[r.halo], 1u);
-        else off = atomicAdd(a.cursor + (size_t)r.halo * K3_CURSOR_STRIDE, 1ull);
+        const unsigned long long off = atomicAdd(a.cursor + (size_t)r.halo * K3_CURSOR_STRIDE, 1ull);
         const unsigned long long p = a.seg_begin[r.halo] + off;
         if (p < a.rec_cap) a.out[p] = r;
     }
