@@ -909,7 +909,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             b.cursor = hs_cursor(c, H);
             b.out = (cck::Rec*)c->rec_b.p;
             b.H = H;
-            cck::k3_bucket<<<(unsigned int)c->sm_count * 2u, cck::K3B_THREADS, 0, c->stream>>>(b);
+            cck::k3_bucket<<<(unsigned int)c->sm_count * 4u, cck::K3B_THREADS, 0, c->stream>>>(b); /* 4 CTAs x 512 threads x 32 KB per SM */
             CU(cudaGetLastError());
             cck::RankArgs r;
             r.rec_count = rec_count;

@@ -17,7 +17,7 @@ print("parity ok", d.get("parity_check",{}).get("ok"), "cpu", d.get("cpu_baselin
 PY
 ( time timeout 900 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/r02f1_bench_reference.json 2> gpurun_out/r02f1_bench_reference.err ) 2>&1 | tail -3; echo ref rc=$?; cut -c1-400 gpurun_out/r02f1_bench_reference.json
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active"
-for w in cfg2 const1b cfg4 cfg5 cfg1; do
+for w in cfg2 const1b cfg4 cfg5 cfg5_shared cfg1; do
   B="python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-configs"
   timeout 600 ncu --metrics $M --clock-control none -c 160 --csv --log-file gpurun_out/r02f1_launches_$w.csv $B > gpurun_out/r02f1_ncu_$w.log 2>&1; echo launches $w rc=$?
 done
@@ -28,4 +28,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k1s_
 B="python bench.py --workload cfg4 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-configs"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k1s_ -s 12 -c 3 -o gpurun_out/r02f1_prof_cfg4 -f $B > gpurun_out/r02f1_ncu_full_cfg4.log 2>&1; echo full cfg4 rc=$?
 B="python bench.py --workload cfg5 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --no-configs"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k2c_ -s 33 -c 3 -o gpurun_out/r02f1_prof_cfg5 -f $B > gpurun_out/r02f1_ncu_full_cfg5.log 2>&1; echo full cfg5 rc=$?
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k2p_query|k3_bucket|k3_rank|k3_gather_halo" -s 16 -c 4 -o gpurun_out/r02f1_prof_cfg5 -f $B > gpurun_out/r02f1_ncu_full_cfg5.log 2>&1; echo full cfg5 rc=$?
