@@ -1,6 +1,6 @@
 # round 2 evidence, 8 GPUs: default bench line at N=8 and N=4 (all configs + parity over eager / peer / NCCL exchange)
 set -x
-for n in 8 4; do
+for n in ${NLIST:-8 4}; do
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2971$n"
 ( time timeout 1200 $TR bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r02f8_bench_${n}gpu.json 2> gpurun_out/r02f8_bench_${n}gpu.err ) 2>&1 | tail -3; echo bench$n rc=$?
 python - <<PY
