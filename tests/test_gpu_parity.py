@@ -416,14 +416,16 @@ def test_halo_cell_index_window_edges(ctx, cells_mode, cells):
 
 
 def test_halo_large_segment(ctx):
-    """a 10-degree box: tens of thousands of survivors in one halo -- beyond the shared-memory sort (K3_SORT_MAX =
-    8192), so the counting fallback orders the segment; a second, small halo in the same pass takes the sort"""
+    """a 10-degree box: tens of thousands of survivors in one halo -- beyond the single-CTA kernel (K3_SORT_MAX = 8192)
+    and beyond one chunk of the general ordering kernel (K3_CHUNK = 16384: three chunks, the last one partial, merged
+    by k3_place); a 5.7-degree box in the same pass fills most of one chunk (more than 8 of a thread's 16 key
+    registers); a small halo takes a handful of records"""
     cols = H.shell_fixture(2_000_000, seed=77)
-    specs = [((150, 120, 90), 600.0), ((150, 20, 12), 30.0)]
+    specs = [((150, 120, 90), 600.0), ((150, 20, 12), 30.0), ((60, 200, 80), 340.0)]
     ctx.upload(cols)
     ctx.cutout_halo([cc.halo_setup(p, b).halo for p, b in specs])
     counts, rough = ctx.sync()
-    assert int(counts[0]) > 8192 > int(counts[1]) > 0
+    assert int(counts[0]) > 2 * 16384 and 16384 >= int(counts[2]) > 8192 > int(counts[1]) > 0
     for h, (p, b) in enumerate(specs):
         want, want_rough = H.oracle_cutout_halo(cols, H.oracle_halo_setup(p, b))
         assert int(rough[h]) == want_rough
@@ -432,7 +434,7 @@ def test_halo_large_segment(ctx):
 
 def test_halo_huge_segment_regrows_and_merges_hundreds_of_chunks(ctx):
     """a 60-degree box: more than 2^20 survivors in ONE halo -- beyond the initial record capacity (the pass is re-run
-    at the exact size) and hundreds of 4096-record chunks, each ordered by one CTA and merged by binary searches"""
+    at the exact size) and dozens of 16384-record chunks, each ordered by one CTA and merged by binary searches"""
     cols = H.shell_fixture(5_000_000, seed=91)
     p, b = (100, 100, 100), 3600.0
     fresh = cc.Context(0)  # a context whose buffers still have their initial sizes
