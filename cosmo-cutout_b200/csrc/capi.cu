@@ -216,6 +216,7 @@ struct cc_ctx {
     cudaEvent_t ev_idx0 = nullptr, ev_idx1 = nullptr;
     bool index_timed = false;         /* the pending cutout built the index: ev_idx0..ev_idx1 is its duration */
     bool used_index = false;          /* the pending cutout walked the particle index */
+    unsigned long long small_seq = 0; /* k3_small launches so far: the value its last launch writes to h_small[7] */
     int64_t particles_read = 0;       /* by the scan kernel(s) of the last cutout: all scanned ones, or the index rows */
     int xchg_mode = 0;       /* 0 auto (peer mailboxes when attached, else NCCL), 1 NCCL, 2 peer, 3 eager: peer, and a
                                 small use-case-2 cutout does the exchange inside its last kernel; cc_set_option "exchange" */
@@ -343,6 +344,7 @@ int ensure_small(cc_ctx* c, size_t elems) {
     c->h_small = nullptr;
     c->h_small_elems = 0;
     CU(cudaMallocHost((void**)&c->h_small, elems * sizeof(unsigned long long)));
+    memset(c->h_small, 0, elems * sizeof(unsigned long long));
     c->h_small_elems = elems;
     return CC_OK;
 }
@@ -876,6 +878,7 @@ int launch_halo_chunk(cc_ctx* c, const Chunk& ch) {
             /* the last kernel of the pass hands the results to the host itself (pinned memory, no copy command behind
              * it) and leaves the device state zeroed for the next cutout (no memset in front of the next scan) */
             sa.host_out = c->h_small;
+            sa.seq = ++c->small_seq;
             sa.state_elems = (unsigned int)hstate_elems(H);
             { int rc2 = c->xchg_send.ensure((size_t)2 * H * 8); if (rc2) return rc2; }
             sa.xchg_send = (unsigned long long*)c->xchg_send.p;
@@ -1436,6 +1439,25 @@ int cc_cutout_halo(cc_ctx* c, int nhalos, const cc_halo* halos, int pos_only, in
     return run_pending(c);
 }
 
+/* wait for the results of a cutout whose last kernel was k3_small: that kernel writes everything the host reads to
+ * pinned memory itself and then raises h_small[7]; spinning on the flag returns a few microseconds before the
+ * driver reports the stream idle (the kernel is still zeroing device state; whatever is enqueued next is ordered
+ * behind it by the stream) */
+static int wait_small(cc_ctx* c) {
+    volatile unsigned long long* flag = c->h_small + 7;
+    for (unsigned int spins = 1;; ++spins) {
+        if (*flag == c->small_seq) break;
+        if ((spins & 0xfffu) == 0) { /* now and then: did the stream end (or fail) without raising the flag? */
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorNotReady) return fail(CC_ERR_CUDA, "CUDA error while waiting for a cutout: %s", cudaGetErrorString(e));
+        }
+        __builtin_ia32_pause();
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return CC_OK;
+}
+
 int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
     if (!c) return fail(CC_ERR_ARG, "ctx is NULL");
     if (c->pending == P_NONE) return fail(CC_ERR_STATE, "cc_cutout_sync: no cutout pending");
@@ -1467,7 +1489,9 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
         } else {
             const int H = c->nhalos;
             for (int attempt = 0; attempt < 6; ++attempt) {
-                CU(cudaStreamSynchronize(c->stream));
+                static const bool no_flag_wait = getenv("CC_NO_FLAG_WAIT") != nullptr; /* A/B switch (profiles/r02) */
+                if (c->used_small && !c->timing && !no_flag_wait) { if ((rc = wait_small(c))) return rc; }
+                else CU(cudaStreamSynchronize(c->stream));
                 const int64_t nrec = (int64_t)c->h_small[0];
                 const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
                 c->force_general = refused;

@@ -2269,6 +2269,8 @@ struct SmallArgs {
     unsigned int state_elems;            /* u64 words of the device state starting at misc: zeroed for the next cutout */
     unsigned long long* xchg_send;       /* [2H] {counts, rough counts} kept for the count exchange (capi.cu) */
     int H;
+    unsigned long long seq;              /* written to host_out[7] once everything the host reads is on its way: the host
+                                            spins on it instead of waiting for the stream to drain (capi.cu wait_small) */
     int do_xchg;                         /* the count exchange over the peer mailboxes is part of this kernel: posted first
                                             (the counts are final), collected after the rows are written */
     XchgArgs x;
@@ -2279,9 +2281,13 @@ __device__ __forceinline__ void k3s_publish(const SmallArgs& a) {
     const unsigned int nout = 8u + 3u * (unsigned int)a.H + 1u;
     for (unsigned int i = threadIdx.x; i < nout; i += K3S_THREADS) a.host_out[i] = a.misc[i];
     for (unsigned int i = threadIdx.x; i < 2u * (unsigned int)a.H; i += K3S_THREADS) a.xchg_send[i] = a.counts[i];
-    /* no system-wide fence: the host reads host_out only after the stream has drained (cc_cutout_sync), which makes
-     * every store of this kernel visible; a fence here made the one CTA wait for the PCIe writes in mid-kernel */
+    /* one thread makes the CTA's stores to the host visible (the barrier orders them before its fence) and raises the
+     * flag the host spins on; the others go on zeroing the device state */
     __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(a.host_out + 7) = a.seq;
+    }
     for (unsigned int i = threadIdx.x; i < a.state_elems; i += K3S_THREADS) a.misc[i] = 0ull;
 }
 __global__ void __launch_bounds__(K3S_THREADS) k3_small(const SmallArgs a) {
