@@ -217,6 +217,7 @@ struct cc_ctx {
     bool index_timed = false;         /* the pending cutout built the index: ev_idx0..ev_idx1 is its duration */
     bool used_index = false;          /* the pending cutout walked the particle index */
     unsigned long long small_seq = 0; /* k3_small launches so far: the value its last launch writes to h_small[7] */
+    bool sync_whole_stream = false;   /* cc_cutout_sync: wait for the stream even when the flag would do (cc_exchange_counts) */
     int64_t particles_read = 0;       /* by the scan kernel(s) of the last cutout: all scanned ones, or the index rows */
     int xchg_mode = 0;       /* 0 auto (peer mailboxes when attached, else NCCL), 1 NCCL, 2 peer, 3 eager: peer, and a
                                 small use-case-2 cutout does the exchange inside its last kernel; cc_set_option "exchange" */
@@ -1490,7 +1491,7 @@ int cc_cutout_sync(cc_ctx* c, int64_t* counts, int64_t* rough_counts) {
             const int H = c->nhalos;
             for (int attempt = 0; attempt < 6; ++attempt) {
                 static const bool no_flag_wait = getenv("CC_NO_FLAG_WAIT") != nullptr; /* A/B switch (profiles/r02) */
-                if (c->used_small && !c->timing && !no_flag_wait) { if ((rc = wait_small(c))) return rc; }
+                if (c->used_small && !c->timing && !no_flag_wait && !c->sync_whole_stream) { if ((rc = wait_small(c))) return rc; }
                 else CU(cudaStreamSynchronize(c->stream));
                 const int64_t nrec = (int64_t)c->h_small[0];
                 const bool refused = c->used_small && c->h_small[4] != 0; /* k3_small found too many records */
@@ -1905,7 +1906,14 @@ int cc_exchange_counts(cc_ctx* c, int64_t* all_counts, int64_t* all_rough, int64
     CU(cudaEventRecord(c->ev_xchg, xs));
     CU(cudaStreamWaitEvent(c->stream, c->ev_xchg, 0));
     if (c->synced) CU(cudaStreamSynchronize(c->stream));
-    else if ((rc = cc_cutout_sync(c, nullptr, nullptr))) return rc; /* one synchronisation for cutout + exchange */
+    else {
+        /* one synchronisation for cutout + exchange: the exchange ran on its own stream, so the flag a small cutout's
+         * last kernel raises says nothing about it -- wait for the cutout stream, which waits for the exchange */
+        c->sync_whole_stream = true;
+        rc = cc_cutout_sync(c, nullptr, nullptr);
+        c->sync_whole_stream = false;
+        if (rc) return rc;
+    }
     }
 read_back:
     for (int r = 0; r < R; ++r)
